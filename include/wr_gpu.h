@@ -1,0 +1,167 @@
+/* wr_gpu.h — C ABI of libwrgpu.so, the B200 (sm_100a) device layer of the welding-robot
+ * ACS hot path.
+ *
+ * The reference (mhsitu/welding_robot) has no FFI: its boundary is a header-only C++ class
+ * surface.  This header is the C-ABI a replacement must export for that
+ * surface; every entry point names the reference code it replaces (paths relative to the
+ * reference root).  The C++ facade in include/welding_robot_b200/ re-creates the reference's
+ * class and method names on top of these calls; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain C types only; all buffers are caller-owned HOST memory unless a name says `dev`;
+ *  - every call returns a wr_status (0 = ok, negative = error); wr_last_error() gives the
+ *    message of the calling thread's last failure; nothing throws or exits;
+ *  - a handle is used by one host thread at a time; different handles may be used from
+ *    different threads / on different devices; a handle lives on the device that was
+ *    current (wr_set_device) when it was created;
+ *  - there is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *    WR_ERR_CUDA.
+ */
+#ifndef WR_GPU_H
+#define WR_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    WR_OK = 0,
+    WR_ERR_INVALID = -1,  /* bad argument */
+    WR_ERR_CUDA = -2,     /* CUDA runtime error / no device */
+    WR_ERR_NOMEM = -3,
+    WR_ERR_STATE = -4,    /* call order (e.g. iterate before endpoints are set) */
+    WR_ERR_NOTFOUND = -5, /* route point does not snap to a free node */
+    WR_ERR_CAPACITY = -6, /* caller buffer too small */
+    WR_ERR_FORMAT = -7    /* malformed STL / grid / graph input */
+} wr_status;
+
+typedef struct wr_grid wr_grid;   /* bit-packed occupancy grid + axis coordinates, resident in HBM */
+typedef struct wr_acs wr_acs;     /* one rank-based 3-D ant-colony search (pheromone field in HBM) */
+typedef struct wr_gtsp wr_gtsp;   /* a batch of seam-ordering colonies */
+
+const char* wr_last_error(void);
+int wr_version(void);
+int wr_device_count(int* count);
+int wr_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * STL — replaces STLReader::readFile / ReadBinary (core/read_STL.hpp:26-77, 131-174).
+ * buf/len: the whole file.  tris12: 12 floats per triangle (normal, v0, v1, v2).
+ * *ntri receives the triangle count in the file; at most `cap` triangles are written.
+ * The ASCII branch (read_STL.hpp:99-129) is not supported -> WR_ERR_FORMAT.
+ * ---------------------------------------------------------------------------------------- */
+int wr_stl_parse(const uint8_t* buf, size_t len, float* tris12, int cap, int* ntri);
+
+/* ------------------------------------------------------------------------------------------
+ * Voxel grid — replaces GridMap<T>::creatGridMap (core/model_grid_map.hpp:151-273).
+ * Node id = z*ry*rx + y*rx + x (model_grid_map.hpp:214); occupancy is bit-packed, bit
+ * (id & 31) of word (id >> 5), 1 = occupied (isFree == false).
+ * ---------------------------------------------------------------------------------------- */
+int wr_grid_create_from_triangles(const float* tris12, int ntri, float precision, int wall, wr_grid** out);
+/* synthetic / reloaded grids: isfree is N bytes in z,y,x order (what readGridMap,
+ * model_grid_map.hpp:300-356, produces); xs/ys/zs are the per-axis node coordinates. */
+int wr_grid_create_from_occupancy(const uint8_t* isfree, int rx, int ry, int rz, const float* xs, const float* ys,
+                                  const float* zs, float precision, wr_grid** out);
+int wr_grid_destroy(wr_grid* g);
+int wr_grid_dims(const wr_grid* g, int dims[3]);                       /* rangeX, rangeY, rangeZ (:381-383) */
+int wr_grid_precision(const wr_grid* g, float* precision, int* wall);
+int wr_grid_bbox(const wr_grid* g, float mn[3], float mx[3]);          /* global mesh box (:165-181) */
+int wr_grid_coords(const wr_grid* g, float* xs, float* ys, float* zs); /* node coordinates (:204-211) */
+int wr_grid_download_bits(const wr_grid* g, uint32_t* bits, size_t nwords);
+int wr_grid_download_isfree(const wr_grid* g, uint8_t* isfree, size_t n);
+/* occupied nodes, triangle-node predicate evaluations, device ms of the voxelise kernel */
+int wr_grid_stats(const wr_grid* g, uint64_t* occupied, uint64_t* tests, float* kernel_ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Rank-based 3-D ant colony search — replaces ACS_Rank (core/ACSRank_3D.hpp).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int alpha;            /* pheromone exponent, ACSRank_3D.hpp:319 (1)            */
+    float beta;           /* heuristic weight in tau^alpha*(1+beta*cos), :320 (0.6) */
+    float rho;            /* evaporation factor, :321 (0.8)                        */
+    float tau0;           /* initial pheromone, :324 (1)                           */
+    int fixed_colony;     /* 0: adaptive colony_num of :247; >0: that many ants    */
+    int step_cap;         /* 0: auto (min(N-1, 65534)); else max steps per ant     */
+    int K;                /* neighbourhood: 6 (reference)                          */
+    uint64_t seed;        /* Philox key; draw = f(seed; iteration, ant, step)      */
+    int update_mode;      /* WR_UPDATE_*                                           */
+    int walk_table_log2;  /* log2 of per-ant shared-memory visited-tile slots (0: default 9) */
+} wr_acs_params;
+
+enum {
+    WR_UPDATE_FUSED = 0,   /* one HBM pass: TMA tile in, evaporate + rank-ordered deposits, TMA tile out */
+    WR_UPDATE_SPLIT = 1,   /* float4 evaporation pass, then rank-ordered deposit pass (same bits) */
+    WR_UPDATE_ATOMIC = 2   /* evaporation pass + atomicAdd deposits (fast, order not reproducible) */
+};
+
+int wr_acs_default_params(wr_acs_params* p);                        /* literals of initFromGridMap :319-325 */
+int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out); /* initFromGridMap :317-410 */
+int wr_acs_destroy(wr_acs* a);
+/* setPoints :537-565 — snap two world points to the last free node (z,y,x scan order) within
+ * 1.2*precision on every axis.  ids[0]/ids[1] = start/goal node id (-1 if none). */
+int wr_acs_set_points(wr_acs* a, const float start[3], const float goal[3], int64_t ids[2]);
+int wr_acs_set_endpoints(wr_acs* a, int64_t start_id, int64_t goal_id);
+/* computeSolution :220-305 = wr_acs_begin(predict) + wr_acs_iterate(max_iteration) */
+int wr_acs_begin(wr_acs* a, float predict_path_len);                /* :229-233 */
+int wr_acs_iterate(wr_acs* a, int n_iterations);                    /* loop body :237-299, n times; asynchronous */
+int wr_acs_sync(wr_acs* a);
+int wr_acs_reset(wr_acs* a);                                        /* reset() :307-315 */
+/* getSolution :506-509 / Agent::getPath, nodeIndex :93-100.  *n = node count of the best path
+ * (0 if none yet); ids gets min(*n, cap) node ids, dirs min(*n-1, cap) slot indices; *L = best.L
+ * (+inf if none). */
+int wr_acs_best(wr_acs* a, int64_t* ids, int* dirs, int cap, int* n, float* L);
+int wr_acs_download_pheromone(wr_acs* a, float* tau, size_t n);     /* N*K floats, node-major, slots [-z,-y,-x,+x,+y,+z] */
+int wr_acs_upload_pheromone(wr_acs* a, const float* tau, size_t n);
+/* last iteration's colony (parity checks): size, lambda, Q of :247-249 */
+int wr_acs_last_colony(wr_acs* a, int* colony, float* lambda, float* Q);
+/* ant k of the last iteration: node ids visited (start first), *n = node count, *L = its length
+ * (+inf if it died), *order = 1-based rank after the sort of :273 */
+int wr_acs_last_ant(wr_acs* a, int k, int64_t* ids, int* dirs, int cap, int* n, float* L, int* order);
+/* cumulative counters: [0] ant-steps [1] ants [2] arrived [3] dead: no candidate [4] dead: roulette
+ * fall-through/NaN [5] dead: step cap [6] iterations [7] deposit records [8] visited-table overflows */
+int wr_acs_counters(wr_acs* a, uint64_t out[9]);
+/* cumulative device milliseconds per kernel since begin (CUDA events on the handle's stream):
+ * [0] walk [1] rank+best [2] deposit build+sort [3] update (evaporate+deposit) [4] whole iterations */
+int wr_acs_kernel_ms(wr_acs* a, float out[5]);
+int wr_acs_set_timing(wr_acs* a, int enabled);
+/* use an existing CUDA stream (cudaStream_t as void*); default: a private non-blocking stream */
+int wr_acs_set_stream(wr_acs* a, void* cuda_stream);
+
+/* ---- ant sharding across ranks: one process per GPU ----------------------
+ * With a shard set, wr_acs_walk() constructs only ants [first, first+count) of the global colony
+ * (Philox is keyed by the GLOBAL ant index, so results do not depend on the rank count);
+ * the host exchanges the packed results (torch.distributed / NCCL all_gather) and every rank
+ * applies the identical global update with wr_acs_update_from_gathered(). */
+int wr_acs_set_shard(wr_acs* a, int rank, int nranks);
+int wr_acs_walk(wr_acs* a);                                  /* iter_begin + local ant construction */
+int wr_acs_local_steps_dev(wr_acs* a, int** dev_steps, int* first, int* count); /* device int32[count], -1 = dead */
+/* all ranks' steps, global ant order, as a DEVICE int32[colony] buffer -> global ranking */
+int wr_acs_rank_global(wr_acs* a, const int* dev_all_steps);
+/* pack this rank's ants that are in the global top-w into a device buffer; *dev_buf, *bytes */
+int wr_acs_pack_top(wr_acs* a, void** dev_buf, size_t* bytes, size_t* max_bytes);
+/* gathered = concatenation over ranks of max_bytes-sized packs (device) */
+int wr_acs_update_from_gathered(wr_acs* a, const void* dev_gathered, int nranks, size_t stride_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Seam ordering — replaces ACS_GTSP (core/ACS_GTSP.hpp), batched: B independent colonies on
+ * the same distance matrix, colony b drawing from Philox stream (seed, colony_first + b).
+ * ---------------------------------------------------------------------------------------- */
+/* dis: n*n doubles, symmetric, diagonal ignored (readFromGraphFile :224-253 + init_param :187-218);
+ * cnt = the edge count used in tau0 = cnt/(sum*n) (:249). */
+int wr_gtsp_create(const double* dis, int n, int cnt, int batch, int colony_first, uint64_t seed, wr_gtsp** out);
+int wr_gtsp_destroy(wr_gtsp* g);
+int wr_gtsp_iterate(wr_gtsp* g, int iterations);   /* loop body of computeSolution :261-276, no early stop */
+int wr_gtsp_sync(wr_gtsp* g);
+/* best tour of colony b: 2 ints per edge (r, s), n edges (closing edge last); L excludes the
+ * closing edge (ACS_Tour::calc :36-44). */
+int wr_gtsp_best(wr_gtsp* g, int colony, int* tour_pairs, int* nedges, double* L);
+int wr_gtsp_download_pheromone(wr_gtsp* g, int colony, double* out); /* n*n */
+int wr_gtsp_tau0(wr_gtsp* g, double* tau0);
+int wr_gtsp_kernel_ms(wr_gtsp* g, float out[3]); /* [0] info rebuild [1] construction [2] update */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WR_GPU_H */

@@ -1,0 +1,204 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, and against the committed reference fixtures.  Bit-exact for grids, visited-node
+sequences and — in the rank-ordered update modes — the pheromone field."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import C1_NAN_PAIR, C1_POINTS
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def wr():
+    import welding_robot_b200 as wr
+    return wr
+
+
+def gpu_grid(wr, tris, precision, wall, cls=None, **kw):
+    g = (cls or wr.GridMap)(**kw)
+    g.creatGridMap(tris, precision, wall)
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 voxeliser
+# ---------------------------------------------------------------------------------------------
+def test_voxel_grid_matches_reference_fixtures(wr, meshes, kat):
+    for k in kat["grids"]:
+        g = gpu_grid(wr, meshes[k["mesh"]], k["precision"], k["wall"])
+        assert [g.rangeX, g.rangeY, g.rangeZ] == k["dims"]
+        free = g.isfree()
+        assert int((free == 0).sum()) == k["occupied"] == g.stats()["occupied"]
+        assert sha(free) == k["sha256_isfree"], k
+        xs, ys, zs = g.coords()
+        assert (sha(xs), sha(ys), sha(zs)) == (k["sha256_xs"], k["sha256_ys"], k["sha256_zs"])
+
+
+@pytest.mark.parametrize("mesh,precision,wall", [("simplified_piece", 0.0061, 4), ("origin_piece", 0.0047, 6), ("cubic", 0.0123, 1),
+                                                 ("simplified_piece", 0.0034981, 10)])
+def test_voxel_grid_matches_oracle(wr, oracle, meshes, mesh, precision, wall):
+    G = oracle.Grid.from_triangles(meshes[mesh], precision, wall, oracle.VOX_AABB)
+    g = gpu_grid(wr, meshes[mesh], precision, wall)
+    assert (g.rangeX, g.rangeY, g.rangeZ) == G.dims
+    assert np.array_equal(g.isfree(), G.isfree())
+    assert g.stats()["tests"] == G.tests()   # same set of (triangle, node) pairs passes the box test
+    bits = g.bits()
+    assert np.array_equal(np.unpackbits(bits.view(np.uint8), bitorder="little")[:g.size_of_map()], 1 - G.isfree())
+
+
+def test_occupancy_entry_point_round_trip(wr):
+    rng = np.random.default_rng(5)
+    rx, ry, rz = 37, 21, 13
+    free = (rng.random(rx * ry * rz) > 0.3).astype(np.uint8)
+    g = wr.GridMap().creatFromOccupancy(free, np.arange(rx), np.arange(ry), np.arange(rz), 1.0)
+    assert np.array_equal(g.isfree(), free)
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 walk + ranking + K3 update against the oracle (keyed Philox, total order)
+# ---------------------------------------------------------------------------------------------
+def make_pair(wr, oracle, tris, precision, wall, **params):
+    G = oracle.Grid.from_triangles(tris, precision, wall, oracle.VOX_AABB)
+    op = {k: v for k, v in params.items() if k in ("alpha", "beta", "rho", "tau0", "fixed_colony", "step_cap", "seed")}
+    A = oracle.Acs(G, **op)
+    g = wr.ACS_Rank(**params)
+    g.creatGridMap(tris, precision, wall)
+    g.initFromGridMap()
+    return A, g
+
+
+def compare_iteration(A, g, check_tau=True, exact_tau=True):
+    oc, olam, oq = A.last_colony()
+    gc, glam, gq = g.lastColony()
+    assert (oc, np.float32(olam).tobytes(), np.float32(oq).tobytes()) == (gc, np.float32(glam).tobytes(), np.float32(gq).tobytes())
+    for k in range(oc):
+        oid, odir, oL, oorder = A.last_ant(k)
+        gid, gdir, gL, gorder = g.lastAnt(k)
+        assert gorder == oorder, (k, gorder, oorder)
+        if np.isinf(oL):
+            assert np.isinf(gL), k
+        else:
+            assert np.float32(oL).tobytes() == np.float32(gL).tobytes(), (k, oL, gL)
+            assert np.array_equal(oid, gid), k          # visited-node sequence, bit-exact
+            assert np.array_equal(odir, gdir), k
+    ob, gb = A.best(), g.bestPath()
+    assert np.float32(ob[2]).tobytes() == np.float32(gb[2]).tobytes()
+    if not np.isinf(ob[2]):
+        assert np.array_equal(ob[0], gb[0]) and np.array_equal(ob[1], gb[1])
+    if check_tau:
+        to, tg = A.pheromone(), g.pheromone()
+        if exact_tau:
+            assert np.array_equal(to.view(np.uint32), tg.view(np.uint32)), "pheromone field differs: max |d| = %g" % np.abs(to - tg).max()
+        else:
+            assert np.allclose(to, tg, rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("update_mode", [0, 1])
+def test_c1_adaptive_colony_bit_exact(wr, oracle, meshes, update_mode):
+    """cubic.stl @ (0.005, 10), reference defaults (adaptive colony), pair (0,5): every ant of
+    every iteration, the best path and the whole pheromone field, bit for bit."""
+    A, g = make_pair(wr, oracle, meshes["cubic"], 0.005, 10, seed=0x5EED, update_mode=update_mode)
+    ok, s, e = A.set_points(C1_POINTS[0], C1_POINTS[5])
+    assert g.setPoints(C1_POINTS[0], C1_POINTS[5]) and ok
+    assert (g._start_id, g._goal_id) == (s, e)
+    A.begin(0.5); g.begin(0.5)
+    for it in range(12):
+        A.iterate(1); g.iterate(1)
+        compare_iteration(A, g, check_tau=it in (0, 1, 9, 11))
+    A.iterate(40); g.iterate(40)
+    compare_iteration(A, g)
+    oc, gc = A.counters(), g.counters()
+    for key in ("ant_steps", "ants", "arrived", "dead_no_candidate", "dead_fallthrough", "dead_step_cap", "iterations"):
+        assert oc[key] == gc[key], key
+    assert gc["table_overflows"] == 0
+
+
+def test_c1_all_pairs_lengths_and_nan_plane(wr, oracle, meshes):
+    """searchBestPathOfPoints' pair loop (ACSRank_3D.hpp:472-499) incl. reset() between pairs, and
+    the pair beyond the duplicate-coordinate plane: NaN must propagate and every ant must die."""
+    A, g = make_pair(wr, oracle, meshes["cubic"], 0.005, 10, seed=0x5EED)
+    for (i, j) in [(0, 1), (2, 5), (1, 4)]:
+        A.set_points(C1_POINTS[i], C1_POINTS[j]); assert g.setPoints(C1_POINTS[i], C1_POINTS[j])
+        A.begin(0.5); A.iterate(150); g.computeSolution(0.5)
+        compare_iteration(A, g)
+        A.reset(); g.reset()
+        assert np.array_equal(A.pheromone().view(np.uint32), g.pheromone().view(np.uint32))
+    ok, s, e = A.set_points(*C1_NAN_PAIR)
+    assert g.setPoints(*C1_NAN_PAIR) and (g._start_id, g._goal_id) == (s, e)
+    A.begin(0.5); A.iterate(5); g.begin(0.5); g.iterate(5)
+    compare_iteration(A, g)
+    assert np.isinf(g.bestPath()[2]) and g.counters()["dead_fallthrough"] > 0
+
+
+@pytest.mark.parametrize("table_log2", [4, 9])
+def test_fixed_colony_step_cap_and_table_overflow(wr, oracle, meshes, table_log2):
+    """Fixed colony of 512 ants, step cap 300 (some ants hit it), and — with a 16-slot visited table —
+    the exact re-run path (pass 2 with tables in HBM)."""
+    A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=7, fixed_colony=512, step_cap=300, walk_table_log2=table_log2)
+    G = A.grid
+    free = G.isfree()
+    ids = np.flatnonzero(free)
+    s, e = int(ids[10]), int(ids[-10])
+    A.set_endpoints(s, e); g.setEndpoints(s, e)
+    A.begin(1.0); g.begin(1.0)
+    for it in range(6):
+        A.iterate(1); g.iterate(1)
+        compare_iteration(A, g)
+    gc = g.counters()
+    assert (gc["table_overflows"] > 0) == (table_log2 == 4)
+    assert gc["dead_step_cap"] == A.counters()["dead_step_cap"]
+
+
+def test_atomic_update_within_tolerance(wr, oracle, meshes):
+    A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=9, fixed_colony=256, step_cap=400, update_mode=2)
+    ids = np.flatnonzero(A.grid.isfree())
+    s, e = int(ids[5]), int(ids[-5])
+    A.set_endpoints(s, e); g.setEndpoints(s, e)
+    A.begin(1.0); g.begin(1.0)
+    A.iterate(1); g.iterate(1)
+    compare_iteration(A, g, exact_tau=False)   # tolerance 1e-5 relative (north_star) for the atomic mode
+
+
+def test_path_properties_full_size(wr, meshes):
+    """BASELINE configs[1] scale (256-long grid, 4096 ants): properties that need no oracle —
+    6-connected, self-avoiding, free cells only, starts/ends at the endpoints, L = steps * precision."""
+    precision = 0.823812 / 235.5
+    g = wr.ACS_Rank(seed=1, fixed_colony=4096, step_cap=4096)
+    g.creatGridMap(meshes["simplified_piece"], precision, 10)
+    assert max(g.rangeX, g.rangeY, g.rangeZ) == 256
+    free = g.isfree()
+    rx, ry, rz = g.rangeX, g.rangeY, g.rangeZ
+    nid = lambda x, y, z: (z * ry + y) * rx + x  # noqa: E731
+    s, e = nid(5, 5, 5), nid(rx - 6, ry - 6, rz - 6)
+    assert free[s] and free[e]
+    g.setEndpoints(s, e)
+    g.begin(1.0); g.iterate(3)
+    c = g.counters()
+    assert c["ants"] == 3 * 4096 and c["arrived"] > 0
+    strides = {0: -rx * ry, 1: -rx, 2: -1, 3: 1, 4: rx, 5: rx * ry}
+    checked = 0
+    for k in list(range(0, 4096, 97)):
+        ids, dirs, L, order = g.lastAnt(k)
+        if np.isinf(L):
+            continue
+        assert ids[0] == s and ids[-1] == e
+        assert len(set(ids.tolist())) == len(ids)
+        assert free[ids].all()
+        assert np.array_equal(np.diff(ids), np.array([strides[d] for d in dirs]))
+        x = ids % rx
+        assert (np.abs(np.diff(x)) <= 1).all()     # no wrap across a row
+        Lacc = np.float32(0)
+        for _ in range(len(dirs)):
+            Lacc = np.float32(Lacc + np.float32(precision))
+        assert np.float32(L) == Lacc
+        checked += 1
+    assert checked > 5
+    ids, dirs, L = g.bestPath()
+    assert ids[0] == s and ids[-1] == e and len(ids) == len(dirs) + 1

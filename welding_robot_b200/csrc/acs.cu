@@ -1,0 +1,541 @@
+// Host side of the rank-based 3-D ant colony search: handle, buffers in HBM, the per-iteration
+// kernel sequence, and the C ABI (include/wr_gpu.h) that stands in for ACS_Rank
+// (core/ACSRank_3D.hpp).  An iteration is a fixed sequence of launches whose sizes live on the
+// device (IterState), so wr_acs_iterate(n) never synchronises with the host.
+#include <stdarg.h>
+#include <stddef.h>
+
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+#include "acs_kernels.cuh"
+#include "wr_internal.cuh"
+
+namespace wr {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+static int ceil_log2(unsigned long long v)
+{
+    int b = 0;
+    while ((1ull << b) < v) b++;
+    return b;
+}
+
+struct PhaseTimer {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    float ms[5] = {0, 0, 0, 0, 0};
+    bool enabled = false;
+    cudaEvent_t next()
+    {
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+        return ev[used++];
+    }
+    void resolve()
+    {   // groups of 5 events: [begin, after walk, after rank, after deposit build, end]
+        for (size_t i = 0; i + 5 <= used; i += 5) {
+            float t;
+            for (int k = 0; k < 4; k++) { if (cudaEventElapsedTime(&t, ev[i + k], ev[i + k + 1]) == cudaSuccess) ms[k] += t; }
+            if (cudaEventElapsedTime(&t, ev[i], ev[i + 4]) == cudaSuccess) ms[4] += t;
+        }
+        used = 0;
+    }
+    ~PhaseTimer() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+
+}  // namespace wr
+
+using namespace wr;
+
+struct wr_acs {
+    wr_grid* g = nullptr;
+    wr_acs_params p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    size_t N = 0, n_slots = 0, n_slots_pad = 0;
+    unsigned ntiles = 0;
+    int cap = 0, rank_bits = 0, slot_bits = 0;
+    int table_log2 = 9, gtable_log2 = 0;
+    int64_t start = -1, goal = -1;
+    bool begun = false;
+    int colony_max = 0, w_max = 0;
+    // shard (multi-rank)
+    int rank = 0, nranks = 1, chunk = 0;
+
+    float* d_tau = nullptr;
+    IterState* d_state = nullptr;
+    uint32_t* d_onbest = nullptr;
+    float* d_Ltab = nullptr;
+    std::vector<float> h_Ltab;
+    int* d_best_n = nullptr;
+    uint32_t* d_best_ids = nullptr;
+    uint8_t* d_best_dirs = nullptr;
+    // per-colony buffers (sized at begin)
+    int* d_ant_steps = nullptr;
+    uint32_t* d_path_ids = nullptr;
+    uint8_t* d_path_dirs = nullptr;
+    uint32_t* d_overflow = nullptr;
+    uint32_t* d_gkeys = nullptr;
+    unsigned long long* d_gmasks = nullptr;
+    int walk2_blocks = 0;
+    uint32_t* d_rec_off = nullptr;
+    int* d_order = nullptr;
+    uint32_t* d_tile_off = nullptr;
+    SortPlan sort_ants, sort_recs;
+    bool ants_in_b = false, recs_in_b = false;
+    size_t alloc_colony = 0;
+    PhaseTimer timer;
+
+    const int* dptr_colony() const { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + offsetof(IterState, colony)); }
+    const int* dptr_nrec() const { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + offsetof(IterState, n_records)); }
+};
+
+static void free_colony_buffers(wr_acs* a)
+{
+    cudaFree(a->d_ant_steps); cudaFree(a->d_path_ids); cudaFree(a->d_path_dirs); cudaFree(a->d_overflow);
+    cudaFree(a->d_gkeys); cudaFree(a->d_gmasks); cudaFree(a->d_rec_off); cudaFree(a->d_order);
+    a->d_ant_steps = nullptr; a->d_path_ids = nullptr; a->d_path_dirs = nullptr; a->d_overflow = nullptr;
+    a->d_gkeys = nullptr; a->d_gmasks = nullptr; a->d_rec_off = nullptr; a->d_order = nullptr;
+    sort_plan_destroy(&a->sort_ants); sort_plan_destroy(&a->sort_recs);
+    a->alloc_colony = 0;
+}
+
+static int alloc_colony_buffers(wr_acs* a, int colony_max)
+{
+    if ((size_t)colony_max <= a->alloc_colony && a->alloc_colony) return WR_OK;
+    free_colony_buffers(a);
+    const size_t cm = std::max(colony_max, 1);
+    const size_t cap = a->cap;
+    a->chunk = (int)((cm + a->nranks - 1) / a->nranks);
+    const size_t chunk = a->chunk;
+    a->w_max = (int)(0.2 * (double)cm) + 1;
+    const size_t rec_max = (size_t)a->w_max * cap;
+    if (rec_max >= 0x7fffffffull) { set_error("colony %zu x step cap %zu needs too many deposit records; set step_cap", cm, cap); return WR_ERR_NOMEM; }
+    WR_CUDA(cudaMalloc(&a->d_ant_steps, cm * sizeof(int)));   // sized for the global colony: ranking reads all ranks' steps
+    WR_CUDA(cudaMalloc(&a->d_path_ids, chunk * cap * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&a->d_path_dirs, chunk * cap));
+    WR_CUDA(cudaMalloc(&a->d_overflow, chunk * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&a->d_rec_off, cm * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&a->d_order, cm * sizeof(int)));
+    WR_CUDA(cudaMemsetAsync(a->d_order, 0, cm * sizeof(int), a->stream));
+    // pass-2 visited tables in HBM: every tile an ant can touch fits (tiles <= steps+1 <= cap+1)
+    a->gtable_log2 = ceil_log2((unsigned long long)cap + 3);
+    a->walk2_blocks = (int)std::min<size_t>((chunk + kAntsPerCta - 1) / kAntsPerCta, 32);
+    const size_t gslots = (size_t)a->walk2_blocks * kAntsPerCta << a->gtable_log2;
+    WR_CUDA(cudaMalloc(&a->d_gkeys, gslots * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&a->d_gmasks, gslots * sizeof(unsigned long long)));
+    int st = sort_plan_create(&a->sort_ants, cm);
+    if (st != WR_OK) return st;
+    st = sort_plan_create(&a->sort_recs, rec_max);
+    if (st != WR_OK) return st;
+    a->alloc_colony = cm;
+    return WR_OK;
+}
+
+extern "C" const char* wr_last_error(void) { return g_err.c_str(); }
+extern "C" int wr_version(void) { return 100; }
+extern "C" int wr_device_count(int* count)
+{
+    WR_REQUIRE(count, WR_ERR_INVALID, "wr_device_count: null");
+    *count = 0;
+    WR_CUDA(cudaGetDeviceCount(count));
+    return WR_OK;
+}
+extern "C" int wr_set_device(int device)
+{
+    WR_CUDA(cudaSetDevice(device));
+    return WR_OK;
+}
+
+extern "C" int wr_acs_default_params(wr_acs_params* p)
+{
+    WR_REQUIRE(p, WR_ERR_INVALID, "wr_acs_default_params: null");
+    p->alpha = 1; p->beta = 0.6; p->rho = 0.8; p->tau0 = 1;   // ACSRank_3D.hpp:319-324
+    p->fixed_colony = 0; p->step_cap = 0; p->K = 6; p->seed = 0;
+    p->update_mode = WR_UPDATE_FUSED; p->walk_table_log2 = 0;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_destroy(wr_acs* a)
+{
+    if (!a) return WR_OK;
+    if (a->stream) cudaStreamSynchronize(a->stream);
+    free_colony_buffers(a);
+    cudaFree(a->d_tau); cudaFree(a->d_state); cudaFree(a->d_onbest); cudaFree(a->d_Ltab);
+    cudaFree(a->d_best_n); cudaFree(a->d_best_ids); cudaFree(a->d_best_dirs); cudaFree(a->d_tile_off);
+    if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
+    delete a;
+    return WR_OK;
+}
+
+// initFromGridMap, ACSRank_3D.hpp:317-410: the 6-slot adjacency in order [-z,-y,-x,+x,+y,+z],
+// every in-bounds slot at tau0, out-of-bounds slots at 0.  The node cuboid itself is never
+// materialised: coordinates and neighbours are recomputed from indices.
+extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
+{
+    WR_REQUIRE(g && p && out, WR_ERR_INVALID, "wr_acs_create: null");
+    *out = nullptr;
+    WR_REQUIRE(p->K == 6, WR_ERR_INVALID, "wr_acs_create: only K = 6 (the reference's neighbourhood) is implemented");
+    WR_REQUIRE(p->alpha >= 0 && p->alpha < 64, WR_ERR_INVALID, "wr_acs_create: alpha out of range");
+    WR_REQUIRE(p->update_mode >= WR_UPDATE_FUSED && p->update_mode <= WR_UPDATE_ATOMIC, WR_ERR_INVALID, "wr_acs_create: bad update_mode");
+    WR_REQUIRE((unsigned long long)g->N * 6 < 0xFFFFFFFFull - kUpdTile, WR_ERR_INVALID, "wr_acs_create: grid too large for 32-bit slot ids");
+    WR_REQUIRE(g->N >= 2, WR_ERR_INVALID, "wr_acs_create: grid too small");
+    wr_acs* a = new wr_acs();
+    a->g = g; a->p = *p; a->N = g->N;
+    a->n_slots = g->N * 6;
+    a->n_slots_pad = (a->n_slots + kUpdTile - 1) / kUpdTile * kUpdTile;
+    a->ntiles = (unsigned)(a->n_slots_pad / kUpdTile);
+    a->slot_bits = ceil_log2(a->n_slots);
+    a->cap = p->step_cap > 0 ? p->step_cap : (int)std::min<size_t>(g->N - 1, 65532);
+    a->rank_bits = ceil_log2((unsigned long long)a->cap + 2);
+    a->table_log2 = p->walk_table_log2 > 0 ? p->walk_table_log2 : 9;
+    if (a->table_log2 < 4 || a->table_log2 > 10) { delete a; set_error("wr_acs_create: walk_table_log2 must be in [4,10]"); return WR_ERR_INVALID; }
+#define WR_CUDA_A(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); wr_acs_destroy(a); return WR_ERR_CUDA; } } while (0)
+    WR_CUDA_A(cudaGetDevice(&a->device));
+    WR_CUDA_A(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+    a->own_stream = true;
+    int st = grid_ensure_open6(g, a->stream);
+    if (st != WR_OK) { wr_acs_destroy(a); return st; }
+    WR_CUDA_A(cudaMalloc(&a->d_tau, a->n_slots_pad * sizeof(float)));
+    WR_CUDA_A(cudaMemsetAsync(a->d_tau, 0, a->n_slots_pad * sizeof(float), a->stream));
+    k_tau_init<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, p->tau0);
+    WR_CUDA_A(cudaGetLastError());
+    WR_CUDA_A(cudaMalloc(&a->d_state, sizeof(IterState)));
+    WR_CUDA_A(cudaMemsetAsync(a->d_state, 0, sizeof(IterState), a->stream));
+    k_begin<<<1, 1, 0, a->stream>>>(a->d_state, 0.0f);
+    WR_CUDA_A(cudaMalloc(&a->d_onbest, (a->N / 32 + 2) * sizeof(uint32_t)));
+    WR_CUDA_A(cudaMemsetAsync(a->d_onbest, 0, (a->N / 32 + 2) * sizeof(uint32_t), a->stream));
+    // L after s steps: precision added s times in float (Agent::addNextNode :78)
+    a->h_Ltab.resize((size_t)a->cap + 2);
+    { float L = 0; a->h_Ltab[0] = 0; for (int s = 1; s <= a->cap + 1; s++) { L += g->precision; a->h_Ltab[s] = L; } }
+    WR_CUDA_A(cudaMalloc(&a->d_Ltab, a->h_Ltab.size() * sizeof(float)));
+    WR_CUDA_A(cudaMemcpyAsync(a->d_Ltab, a->h_Ltab.data(), a->h_Ltab.size() * sizeof(float), cudaMemcpyHostToDevice, a->stream));
+    WR_CUDA_A(cudaMalloc(&a->d_best_n, sizeof(int)));
+    WR_CUDA_A(cudaMemsetAsync(a->d_best_n, 0, sizeof(int), a->stream));
+    WR_CUDA_A(cudaMalloc(&a->d_best_ids, ((size_t)a->cap + 2) * sizeof(uint32_t)));
+    WR_CUDA_A(cudaMalloc(&a->d_best_dirs, (size_t)a->cap + 2));
+    WR_CUDA_A(cudaMalloc(&a->d_tile_off, ((size_t)a->ntiles + 2) * sizeof(uint32_t)));
+    {
+        size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
+        WR_CUDA_A(cudaFuncSetAttribute(k_update_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        size_t ws = (((size_t)(g->rx + g->ry + g->rz) * 4 + 15) & ~(size_t)15) + ((size_t)kAntsPerCta << a->table_log2) * 12;
+        if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+    }
+    WR_CUDA_A(cudaStreamSynchronize(a->stream));
+#undef WR_CUDA_A
+    *out = a;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_set_stream(wr_acs* a, void* cuda_stream)
+{
+    WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_set_stream: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    if (a->own_stream) cudaStreamDestroy(a->stream);
+    a->stream = (cudaStream_t)cuda_stream;
+    a->own_stream = false;
+    return WR_OK;
+}
+
+// setPoints, ACSRank_3D.hpp:537-565.  The reference scans every node; the per-axis test is
+// separable, so the match set is a product of (tiny) per-axis index lists and "last match in
+// z,y,x order" is the largest free id in it.
+static int64_t snap_point(const wr_grid* g, const float p[3])
+{
+    const float t = 1.2 * g->precision;   // double product rounded to float, as `float t = 1.2*precision`
+    std::vector<int> cx, cy, cz;
+    auto wabs = [](float v) { return v > 0 ? v : -v; };
+    for (int x = 0; x < g->rx; x++) if (wabs(p[0] - g->h_xs[x]) < t) cx.push_back(x);
+    for (int y = 0; y < g->ry; y++) if (wabs(p[1] - g->h_ys[y]) < t) cy.push_back(y);
+    for (int z = 0; z < g->rz; z++) if (wabs(p[2] - g->h_zs[z]) < t) cz.push_back(z);
+    int64_t last = -1;
+    for (int z : cz) for (int y : cy) for (int x : cx) {
+        int64_t id = ((int64_t)z * g->ry + y) * g->rx + x;
+        if (grid_is_free_host(g, (size_t)id) && id > last) last = id;
+    }
+    return last;
+}
+
+extern "C" int wr_acs_set_points(wr_acs* a, const float s[3], const float e[3], int64_t ids[2])
+{
+    WR_REQUIRE(a && s && e && ids, WR_ERR_INVALID, "wr_acs_set_points: null");
+    int st = grid_ensure_host_bits(a->g);
+    if (st != WR_OK) return st;
+    ids[0] = snap_point(a->g, s);
+    ids[1] = snap_point(a->g, e);
+    a->start = ids[0]; a->goal = ids[1];
+    if (ids[0] < 0 || ids[1] < 0) { set_error("route point does not snap to a free node"); return WR_ERR_NOTFOUND; }
+    return WR_OK;
+}
+
+extern "C" int wr_acs_set_endpoints(wr_acs* a, int64_t s, int64_t e)
+{
+    WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_set_endpoints: null");
+    WR_REQUIRE(s >= 0 && e >= 0 && (size_t)s < a->N && (size_t)e < a->N, WR_ERR_INVALID, "wr_acs_set_endpoints: id out of range");
+    a->start = s; a->goal = e;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_begin(wr_acs* a, float predict)
+{
+    WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_begin: null");
+    WR_REQUIRE(a->start >= 0 && a->goal >= 0, WR_ERR_STATE, "wr_acs_begin: endpoints not set");
+    int cm = a->p.fixed_colony > 0 ? a->p.fixed_colony : (int)(0.35 * (double)predict / (double)a->g->precision);   // :247 with best = inf
+    WR_REQUIRE(cm >= 0 && cm < (1 << 24), WR_ERR_INVALID, "wr_acs_begin: colony size out of range");
+    WR_CUDA(cudaSetDevice(a->device));
+    int st = alloc_colony_buffers(a, cm);
+    if (st != WR_OK) return st;
+    a->colony_max = cm;
+    k_begin<<<1, 1, 0, a->stream>>>(a->d_state, predict);
+    WR_CUDA(cudaGetLastError());
+    a->begun = true;
+    a->timer.used = 0;
+    for (float& m : a->timer.ms) m = 0;
+    return WR_OK;
+}
+
+static int launch_walk(wr_acs* a)
+{
+    const wr_grid* g = a->g;
+    WalkArgs w;
+    w.st = a->d_state; w.tau = a->d_tau; w.open6 = g->d_open6; w.coords = g->d_coords;
+    w.rx = g->rx; w.ry = g->ry; w.rz = g->rz;
+    w.start = (int)a->start; w.goal = (int)a->goal;
+    w.seed_lo = (uint32_t)a->p.seed; w.seed_hi = (uint32_t)(a->p.seed >> 32);
+    w.alpha = a->p.alpha; w.beta = a->p.beta; w.cap = a->cap;
+    w.shard_first = a->rank * a->chunk; w.shard_chunk = a->chunk;
+    w.ant_steps = a->d_ant_steps + (a->nranks > 1 ? 0 : 0);
+    w.path_ids = a->d_path_ids; w.path_dirs = a->d_path_dirs;
+    w.table_log2 = a->table_log2; w.overflow_list = a->d_overflow;
+    w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks;
+    const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz) * 4 + 15) & ~(size_t)15;
+    const size_t smem1 = coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
+    const int per_sm = std::max(1, (int)((227 * 1024) / (smem1 + 1024)));
+    const int blocks1 = std::max(1, std::min((a->chunk + kAntsPerCta - 1) / kAntsPerCta, kNumSMs * std::min(per_sm, 16)));
+    k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+    // pass 2: ants whose shared-memory table overflowed (usually none: the kernel exits at once)
+    k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
+    w.table_log2 = a->gtable_log2;
+    k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+static int launch_rank_and_update(wr_acs* a, const int* d_all_steps)
+{
+    const int cm = std::max(a->colony_max, 1);
+    cudaStream_t s = a->stream;
+    k_rank_keys<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->cap, a->sort_ants.keys_a, a->sort_ants.vals_a);
+    int st = sort_pairs(&a->sort_ants, a->dptr_colony(), a->rank_bits, s, &a->ants_in_b);
+    if (st != WR_OK) return st;
+    const uint32_t* rk = a->ants_in_b ? a->sort_ants.keys_b : a->sort_ants.keys_a;
+    const uint32_t* rv = a->ants_in_b ? a->sort_ants.vals_b : a->sort_ants.vals_a;
+    k_rank_finish<<<1, 1024, 0, s>>>(a->d_state, rk, rv, a->cap, a->d_Ltab, a->d_rec_off, a->d_order);
+    k_best_clear<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_onbest);
+    k_best_copy<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_path_ids, a->d_path_dirs, a->cap,
+                                  a->rank * a->chunk, (int)a->goal);
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    const int evap_blocks = kNumSMs * 8;
+    if (a->p.update_mode == WR_UPDATE_ATOMIC) {
+        k_evaporate<<<evap_blocks, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
+        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+        k_deposit_gen<true><<<a->w_max, 128, 0, s>>>(a->d_state, rk, rv, a->d_rec_off, a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal,
+                                                     a->d_Ltab, a->d_onbest, nullptr, nullptr, a->d_tau);
+    } else {
+        k_deposit_gen<false><<<a->w_max, 128, 0, s>>>(a->d_state, rk, rv, a->d_rec_off, a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal,
+                                                      a->d_Ltab, a->d_onbest, a->sort_recs.keys_a, a->sort_recs.vals_a, nullptr);
+        st = sort_pairs(&a->sort_recs, a->dptr_nrec(), a->slot_bits, s, &a->recs_in_b);
+        if (st != WR_OK) return st;
+        const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
+        const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
+        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+        if (a->p.update_mode == WR_UPDATE_FUSED) {
+            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
+            const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
+            const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * 2);
+            k_update_fused<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
+        } else {
+            k_evaporate<<<evap_blocks, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
+            k_deposit_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, ck, cv, a->d_tau);
+        }
+    }
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+extern "C" int wr_acs_iterate(wr_acs* a, int n)
+{
+    WR_REQUIRE(a && n >= 0, WR_ERR_INVALID, "wr_acs_iterate: bad argument");
+    WR_REQUIRE(a->begun, WR_ERR_STATE, "wr_acs_iterate: call wr_acs_begin first");
+    WR_REQUIRE(a->nranks == 1, WR_ERR_STATE, "wr_acs_iterate: sharded handles iterate through wr_acs_walk / wr_acs_update_from_gathered");
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    for (int it = 0; it < n; it++) {
+        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+        k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0);
+        int st = launch_walk(a);
+        if (st != WR_OK) return st;
+        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+        st = launch_rank_and_update(a, a->d_ant_steps);
+        if (st != WR_OK) return st;
+        k_iter_end<<<1, 1, 0, s>>>(a->d_state);
+        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    }
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+extern "C" int wr_acs_sync(wr_acs* a)
+{
+    WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_sync: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    if (a->timer.enabled) a->timer.resolve();
+    return WR_OK;
+}
+
+extern "C" int wr_acs_reset(wr_acs* a)
+{   // reset() :307-315: every slot (out-of-bounds ones included) back to tau0
+    WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_reset: null");
+    WR_CUDA(cudaSetDevice(a->device));
+    k_tau_fill<<<kNumSMs * 8, 256, 0, a->stream>>>(a->d_tau, a->n_slots, a->p.tau0);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+extern "C" int wr_acs_best(wr_acs* a, int64_t* ids, int* dirs, int cap, int* n, float* L)
+{
+    WR_REQUIRE(a && n && L, WR_ERR_INVALID, "wr_acs_best: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    IterState st;
+    WR_CUDA(cudaMemcpy(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost));
+    *L = st.best_L;
+    if (st.best_steps == INT_MAX) { *n = 0; return WR_OK; }
+    const int nodes = st.best_steps + 1;
+    *n = nodes;
+    if (ids && cap > 0) {
+        std::vector<uint32_t> h(nodes);
+        WR_CUDA(cudaMemcpy(h.data(), a->d_best_ids, nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nodes && i < cap; i++) ids[i] = h[i];
+    }
+    if (dirs && cap > 0 && nodes > 1) {
+        std::vector<uint8_t> h(nodes - 1);
+        WR_CUDA(cudaMemcpy(h.data(), a->d_best_dirs, nodes - 1, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nodes - 1 && i < cap; i++) dirs[i] = h[i];
+    }
+    return WR_OK;
+}
+
+extern "C" int wr_acs_download_pheromone(wr_acs* a, float* tau, size_t n)
+{
+    WR_REQUIRE(a && tau, WR_ERR_INVALID, "wr_acs_download_pheromone: null");
+    WR_REQUIRE(n >= a->n_slots, WR_ERR_CAPACITY, "wr_acs_download_pheromone: buffer too small");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    WR_CUDA(cudaMemcpy(tau, a->d_tau, a->n_slots * sizeof(float), cudaMemcpyDeviceToHost));
+    return WR_OK;
+}
+extern "C" int wr_acs_upload_pheromone(wr_acs* a, const float* tau, size_t n)
+{
+    WR_REQUIRE(a && tau, WR_ERR_INVALID, "wr_acs_upload_pheromone: null");
+    WR_REQUIRE(n == a->n_slots, WR_ERR_INVALID, "wr_acs_upload_pheromone: size mismatch");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    WR_CUDA(cudaMemcpy(a->d_tau, tau, a->n_slots * sizeof(float), cudaMemcpyHostToDevice));
+    return WR_OK;
+}
+
+extern "C" int wr_acs_last_colony(wr_acs* a, int* colony, float* lambda, float* Q)
+{
+    WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_last_colony: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    IterState st;
+    WR_CUDA(cudaMemcpy(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost));
+    if (colony) *colony = st.colony;
+    if (lambda) *lambda = st.lambda;
+    if (Q) *Q = st.Q;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_last_ant(wr_acs* a, int k, int64_t* ids, int* dirs, int cap, int* n, float* L, int* order)
+{
+    WR_REQUIRE(a && n && L, WR_ERR_INVALID, "wr_acs_last_ant: null");
+    WR_REQUIRE(a->begun, WR_ERR_STATE, "wr_acs_last_ant: no iteration yet");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    IterState st;
+    WR_CUDA(cudaMemcpy(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost));
+    WR_REQUIRE(k >= 0 && k < st.colony, WR_ERR_INVALID, "wr_acs_last_ant: ant index out of range");
+    const int first = a->rank * a->chunk;
+    WR_REQUIRE(k >= first && k < first + a->chunk, WR_ERR_INVALID, "wr_acs_last_ant: ant lives on another rank");
+    int steps = 0, ord = 0;
+    WR_CUDA(cudaMemcpy(&steps, a->d_ant_steps + k, sizeof(int), cudaMemcpyDeviceToHost));
+    WR_CUDA(cudaMemcpy(&ord, a->d_order + k, sizeof(int), cudaMemcpyDeviceToHost));
+    if (order) *order = ord;
+    if (steps < 0) { *L = INFINITY; *n = 0; return WR_OK; }   // the trail of a dead ant is not kept
+    *L = a->h_Ltab[steps];
+    *n = steps + 1;
+    const size_t off = (size_t)(k - first) * a->cap;
+    if (ids && cap > 0) {
+        std::vector<uint32_t> h(steps);
+        WR_CUDA(cudaMemcpy(h.data(), a->d_path_ids + off, steps * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < steps && i < cap; i++) ids[i] = h[i];
+        if (steps < cap) ids[steps] = a->goal;
+    }
+    if (dirs && cap > 0) {
+        std::vector<uint8_t> h(steps);
+        WR_CUDA(cudaMemcpy(h.data(), a->d_path_dirs + off, steps, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < steps && i < cap; i++) dirs[i] = h[i];
+    }
+    return WR_OK;
+}
+
+extern "C" int wr_acs_counters(wr_acs* a, uint64_t out[9])
+{
+    WR_REQUIRE(a && out, WR_ERR_INVALID, "wr_acs_counters: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    IterState st;
+    WR_CUDA(cudaMemcpy(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 9; i++) out[i] = st.cnt[i];
+    return WR_OK;
+}
+
+extern "C" int wr_acs_set_timing(wr_acs* a, int enabled)
+{
+    WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_set_timing: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    a->timer.resolve();
+    a->timer.enabled = enabled != 0;
+    return WR_OK;
+}
+extern "C" int wr_acs_kernel_ms(wr_acs* a, float out[5])
+{
+    WR_REQUIRE(a && out, WR_ERR_INVALID, "wr_acs_kernel_ms: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    a->timer.resolve();
+    for (int i = 0; i < 5; i++) out[i] = a->timer.ms[i];
+    return WR_OK;
+}
+
+// ---- ant sharding (filled in with the multi-GPU step) ---------------------------------------
+extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks)
+{
+    WR_REQUIRE(a && nranks >= 1 && rank >= 0 && rank < nranks, WR_ERR_INVALID, "wr_acs_set_shard: bad argument");
+    WR_REQUIRE(!a->begun || (a->rank == rank && a->nranks == nranks), WR_ERR_STATE, "wr_acs_set_shard: set the shard before wr_acs_begin");
+    a->rank = rank; a->nranks = nranks;
+    return WR_OK;
+}
+extern "C" int wr_acs_walk(wr_acs*) { set_error("wr_acs_walk: not implemented yet"); return WR_ERR_STATE; }
+extern "C" int wr_acs_local_steps_dev(wr_acs*, int**, int*, int*) { set_error("not implemented yet"); return WR_ERR_STATE; }
+extern "C" int wr_acs_rank_global(wr_acs*, const int*) { set_error("not implemented yet"); return WR_ERR_STATE; }
+extern "C" int wr_acs_pack_top(wr_acs*, void**, size_t*, size_t*) { set_error("not implemented yet"); return WR_ERR_STATE; }
+extern "C" int wr_acs_update_from_gathered(wr_acs*, const void*, int, size_t) { set_error("not implemented yet"); return WR_ERR_STATE; }

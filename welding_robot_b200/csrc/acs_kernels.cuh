@@ -1,0 +1,536 @@
+// Device kernels of the rank-based 3-D ant colony search (ACS_Rank, core/ACSRank_3D.hpp).
+//   K2  k_walk            ant construction (selectNext :134-193 + the ant loop :252-265)
+//   --  k_rank_*          colony ranking, best tracking (:263-264, :273-274)
+//   --  k_deposit_gen     deposit records of update_pheromone (:198-215)
+//   K3  k_update_fused    evaporation (:268-272) + rank-ordered deposits in ONE HBM pass (TMA)
+//       k_evaporate / k_deposit_apply / atomic: the split variants
+// All float arithmetic that reaches a comparison or the pheromone field uses explicit
+// round-to-nearest intrinsics in the reference's operation order (no FMA contraction).
+#pragma once
+#include <limits.h>
+#include <math.h>
+
+#include "tma.cuh"
+#include "wr_common.cuh"
+
+namespace wr {
+
+constexpr int kWalkThreads = 128;
+constexpr int kGroup = 8;                                  // lanes per ant (6 neighbour lanes + 2 idle) for K = 6
+constexpr int kAntsPerCta = kWalkThreads / kGroup;         // 16
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+constexpr int kUpdTile = 4096;                             // floats per TMA tile (16 KB)
+constexpr int kUpdStages = 4;
+constexpr int kUpdThreads = 256;
+
+struct WalkArgs {
+    IterState* st;
+    const float* tau;        // [N][6] node-major ("edge-major": a node's 6 directed slots are contiguous)
+    const uint8_t* open6;    // [N]
+    const float* coords;     // xs | ys | zs
+    int rx, ry, rz;
+    int start, goal;
+    uint32_t seed_lo, seed_hi;
+    int alpha;
+    float beta;
+    int cap;                 // max steps per ant
+    int shard_first, shard_chunk;  // this rank constructs global ants [first, first+chunk) /\ [0, colony)
+    int* ant_steps;          // [chunk]  steps, -1 dead, -2 pending (table overflow -> pass 2)
+    uint32_t* path_ids;      // [chunk][cap]   node the ant stood on before step i
+    uint8_t* path_dirs;      // [chunk][cap]   slot chosen at step i
+    int table_log2;          // shared-memory (pass 1) or global (pass 2) visited-tile table size
+    uint32_t* overflow_list; // [chunk]
+    uint32_t* gkeys;         // pass 2: [groups][1<<table_log2]
+    unsigned long long* gmasks;
+};
+
+__device__ __forceinline__ float pow_int(float x, int y)
+{   // power<T>() ACSRank_3D.hpp:48-60 (square-and-multiply, same multiplication order)
+    float ans = 1.0f;
+    while (y) {
+        if (y & 1) ans = __fmul_rn(ans, x);
+        x = __fmul_rn(x, x);
+        y >>= 1;
+    }
+    return ans;
+}
+
+__global__ void k_begin(IterState* st, float predict)
+{   // computeSolution :229-233
+    st->iter = 0;
+    st->predict = predict;
+    st->best_steps = INT_MAX;
+    st->best_L = INFINITY;
+    st->best_changed = 0;
+    st->best_ant = -1;
+    st->colony = 0; st->lambda = 0; st->Q = 0;
+    st->n_eligible = 0; st->n_records = 0;
+}
+
+__global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, float precision, float tau0)
+{   // :247-249
+    float best_L = st->best_L, predict = st->predict;
+    int colony = fixed_colony > 0 ? fixed_colony : (int)(0.35 * (double)(best_L < predict ? best_L : predict) / (double)precision);
+    colony = max(0, min(colony, colony_max));
+    float lambda = (float)(0.2 * (double)colony);
+    float Q = __fmul_rn(__fdiv_rn(tau0, lambda), (best_L == INFINITY ? predict : best_L));
+    st->colony = colony; st->lambda = lambda; st->Q = Q;
+    st->queue = 0; st->overflow_n = 0; st->best_changed = 0;
+    st->n_eligible = 0; st->n_records = 0;
+}
+
+__global__ void k_iter_end(IterState* st)
+{
+    st->iter++;
+    st->cnt[6]++;
+}
+
+__global__ void k_queue_reset(IterState* st) { st->queue = 0; }
+
+// ------------------------------------------------------------------------------------------
+// K2: one ant per 8-lane group, 4 ants per warp, 16 per CTA; persistent groups pull ants from a
+// device-side queue.  Lane k < 6 owns neighbour slot k: it loads tau[cur][k] (the six lanes of a
+// group read 24 contiguous bytes: one coalesced request), probes the visited set for its
+// neighbour and evaluates tau^alpha * (1 + beta*cos).  The roulette needs the reference's exact
+// summation order (ascending for `total`, descending for `prob_sum`), so the six scores are
+// exchanged with shuffles and every lane re-adds them sequentially — 11 dependent FADDs, cheap
+// next to the pheromone gather.  The Philox draw for (iteration, ant, step) does not depend on
+// the loads and overlaps them.
+//
+// Visited set ("tabu", std::set at :70): an open-addressed hash of 4x4x4-node tiles, 64-bit
+// occupancy mask per tile, in shared memory.  A lattice walk re-visits the same few tiles, so a
+// 512-slot table (6 KB) holds walks of thousands of steps.  An ant that fills its table to 3/4 is
+// re-run from scratch by pass 2 (GLOBAL = true) with a table in HBM sized for the step cap —
+// exact, because its draws are a pure function of (iteration, ant, step).
+// ------------------------------------------------------------------------------------------
+template <bool GLOBAL>
+__global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);
+    float* ys = xs + a.rx;
+    float* zs = ys + a.ry;
+    const int ncoord = a.rx + a.ry + a.rz;
+    for (int i = threadIdx.x; i < ncoord; i += kWalkThreads) xs[i] = a.coords[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane & 24;
+    const unsigned gmask = 0xFFu << gbase;
+    const int k = lane & 7;
+    const int g = threadIdx.x >> 3;
+    const int E = 1 << a.table_log2;
+    const int hshift = 32 - a.table_log2;
+
+    unsigned long long* masks;
+    uint32_t* keys;
+    if (GLOBAL) {
+        size_t slot = (size_t)blockIdx.x * kAntsPerCta + g;
+        keys = a.gkeys + slot * E;
+        masks = a.gmasks + slot * E;
+    } else {
+        unsigned long long* mbase = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)ncoord * 4 + 15) & ~(size_t)15));
+        masks = mbase + (size_t)g * E;
+        keys = reinterpret_cast<uint32_t*>(mbase + (size_t)kAntsPerCta * E) + (size_t)g * E;
+    }
+
+    const int rx = a.rx, ry = a.ry;
+    const int rxy = rx * ry;
+    const int TX = (rx + 3) >> 2, TY = (ry + 3) >> 2;
+    const int dxk = (k == 3) - (k == 2), dyk = (k == 4) - (k == 1), dzk = (k == 5) - (k == 0);
+    const int stride_k = dxk + dyk * rx + dzk * rxy;
+
+    const int sz = a.start / rxy, sy = (a.start % rxy) / rx, sx = a.start % rx;
+    const int gz = a.goal / rxy, gy = (a.goal % rxy) / rx, gx = a.goal % rx;
+    const float gxc = xs[gx], gyc = ys[gy], gzc = zs[gz];
+
+    IterState* st = a.st;
+    const int colony = st->colony;
+    const uint32_t iter = (uint32_t)st->iter;
+    int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
+    if (GLOBAL) local_n = (int)st->overflow_n;
+
+    unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
+
+    while (true) {
+        unsigned q = 0;
+        if (k == 0) q = atomicAdd(&st->queue, 1u);
+        q = __shfl_sync(gmask, q, gbase);
+        if (q >= (unsigned)local_n) break;
+        const int ant_local = GLOBAL ? (int)a.overflow_list[q] : (int)q;
+        const uint32_t ant_global = (uint32_t)(a.shard_first + ant_local);
+
+        for (int i = k; i < E; i += kGroup) keys[i] = kEmptyKey;
+        __syncwarp(gmask);
+        int cur = a.start, x = sx, y = sy, z = sz, steps = 0, ntiles = 1;
+        if (k == 0) {   // addStartNode :81-86
+            uint32_t tile = (uint32_t)(((z >> 2) * TY + (y >> 2)) * TX + (x >> 2));
+            unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
+            unsigned slot = (tile * 2654435761u) >> hshift;
+            keys[slot] = tile; masks[slot] = 1ull << bit;
+        }
+        __syncwarp(gmask);
+
+        int result;  // >=0 steps (arrived), -1 dead, -2 pending
+        uint32_t* pid = a.path_ids + (size_t)ant_local * a.cap;
+        uint8_t* pdir = a.path_dirs + (size_t)ant_local * a.cap;
+        while (true) {
+            if (steps >= a.cap) { result = -1; c_cap++; break; }
+            // ---- issue the loads of this step --------------------------------------------
+            const unsigned open = a.open6[cur];
+            const float tau_k = (k < 6) ? __ldg(a.tau + (size_t)cur * 6 + k) : 0.0f;
+            // ---- Philox draw, rnd = (float)rand()/(float)RAND_MAX (:169) ------------------
+            const uint32_t r31 = rand31(a.seed_lo, a.seed_hi, iter, ant_global, (uint32_t)steps, kStreamAcs3D);
+            const float u = __fdiv_rn(__int2float_rn((int)r31), 2147483648.0f);
+            // ---- neighbour k: bounds+free (open mask), tabu probe ------------------------
+            const int nx = x + dxk, ny = y + dyk, nz = z + dzk;
+            const int nid = cur + stride_k;
+            const bool open_k = (k < 6) && ((open >> k) & 1u);
+            bool found = false;
+            unsigned slot = 0, bit = 0;
+            uint32_t tile = 0;
+            bool vis = false;
+            if (open_k) {
+                tile = (uint32_t)(((nz >> 2) * TY + (ny >> 2)) * TX + (nx >> 2));
+                bit = ((nz & 3) << 4) | ((ny & 3) << 2) | (nx & 3);
+                slot = (tile * 2654435761u) >> hshift;
+                while (true) {
+                    uint32_t kk = keys[slot];
+                    if (kk == tile) { found = true; break; }
+                    if (kk == kEmptyKey) break;
+                    slot = (slot + 1) & (E - 1);
+                }
+                vis = found && ((masks[slot] >> bit) & 1ull);
+            }
+            const bool cand = open_k && !vis;
+            // ---- info = tau^alpha * (1 + beta*cos)  (:151-154) ---------------------------
+            float info = 0.0f;
+            if (cand) {
+                const float cx = xs[x], cy = ys[y], cz = zs[z];
+                const float ax = __fsub_rn(gxc, cx), ay = __fsub_rn(gyc, cy), az = __fsub_rn(gzc, cz);
+                const float bx = __fsub_rn(xs[nx], cx), by = __fsub_rn(ys[ny], cy), bz = __fsub_rn(zs[nz], cz);
+                const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+                const float nb = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz)));
+                const float dot = __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+                const float cosv = __fdiv_rn(dot, __fmul_rn(na, nb));
+                info = __fmul_rn(pow_int(tau_k, a.alpha), __fadd_rn(1.0f, __fmul_rn(a.beta, cosv)));
+            }
+            const unsigned cb = (__ballot_sync(gmask, cand) >> gbase) & 0x3Fu;
+            if (cb == 0) { result = -1; c_nocand++; break; }   // :162-166
+            // ---- roulette in the reference's order (:155, :172-181) ----------------------
+            float v[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) v[j] = __shfl_sync(gmask, info, gbase + j);
+            float total = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 6; j++) if ((cb >> j) & 1u) total = __fadd_rn(total, v[j]);
+            const float rnd = __fmul_rn(u, total);
+            float ps = 0.0f, mine = 0.0f;
+#pragma unroll
+            for (int j = 5; j >= 0; j--) {
+                if ((cb >> j) & 1u) ps = __fadd_rn(ps, v[j]);
+                if (j == k) mine = ps;
+            }
+            const bool pick = cand && (mine >= rnd);
+            const unsigned pb = (__ballot_sync(gmask, pick) >> gbase) & 0x3Fu;
+            if (pb == 0) { result = -1; c_fall++; break; }     // NaN / rounding fall-through (:191-192)
+            const int c = 31 - __clz(pb);                      // first hit scanning 5 -> 0
+            // ---- addNextNode (:73-79) ----------------------------------------------------
+            if (k == 0) { pid[steps] = (uint32_t)cur; pdir[steps] = (uint8_t)c; }
+            if (k == c) {
+                if (found) masks[slot] |= 1ull << bit;
+                else { keys[slot] = tile; masks[slot] = 1ull << bit; }
+            }
+            const int src = gbase + c;
+            cur = __shfl_sync(gmask, nid, src);
+            x = __shfl_sync(gmask, nx, src); y = __shfl_sync(gmask, ny, src); z = __shfl_sync(gmask, nz, src);
+            const int newtile = __shfl_sync(gmask, found ? 0 : 1, src);
+            ntiles += newtile;
+            steps++;
+            __syncwarp(gmask);
+            if (cur == a.goal) { result = steps; c_arrived++; break; }   // :182-186
+            if (!GLOBAL && newtile && ntiles > (E >> 2) * 3) { result = -2; break; }
+        }
+        if (result == -2) {
+            if (k == 0) {
+                unsigned o = atomicAdd(&st->overflow_n, 1u);
+                a.overflow_list[o] = (uint32_t)ant_local;
+                a.ant_steps[ant_local] = -2;
+            }
+            c_over++;
+        } else {
+            if (k == 0) a.ant_steps[ant_local] = result;
+            c_steps += (unsigned long long)steps; c_ants++;
+        }
+        __syncwarp(gmask);
+    }
+    if (k == 0) {
+        if (c_steps) atomicAdd(&st->cnt[0], c_steps);
+        if (c_ants) atomicAdd(&st->cnt[1], c_ants);
+        if (c_arrived) atomicAdd(&st->cnt[2], c_arrived);
+        if (c_nocand) atomicAdd(&st->cnt[3], c_nocand);
+        if (c_fall) atomicAdd(&st->cnt[4], c_fall);
+        if (c_cap) atomicAdd(&st->cnt[5], c_cap);
+        if (c_over) atomicAdd(&st->cnt[8], c_over);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Ranking (:273-280) and best tracking (:263-264)
+// ------------------------------------------------------------------------------------------
+// key = steps for an ant that arrived, cap+1 for a dead one; value = ant index.  L is a strictly
+// increasing function of steps (L = precision added `steps` times, :78), so ordering by
+// (steps, ant) is ordering by (L, ant), the oracle's total order.
+__global__ void k_rank_keys(const IterState* st, const int* __restrict__ ant_steps, int cap, uint32_t* keys, uint32_t* vals)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->colony) return;
+    int s = ant_steps[i];
+    keys[i] = s < 0 ? (uint32_t)(cap + 1) : (uint32_t)s;
+    vals[i] = (uint32_t)i;
+}
+
+// Single CTA.  From the sorted colony: the iteration's best (rank 1; lowest ant index among ties,
+// as the sequential `<` of :263 yields), the deposit eligibility of update_pheromone :200
+// (L finite and order <= lambda-1) and the record offset of every eligible rank.
+__global__ void __launch_bounds__(1024) k_rank_finish(IterState* st, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                       int cap, const float* __restrict__ Ltab, uint32_t* __restrict__ rec_off,
+                                                       int* __restrict__ order_of_ant)
+{
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry, elig_total;
+    const int n = st->colony;
+    const float lambda = st->lambda;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        carry = 0; elig_total = 0;
+        if (n > 0) {
+            int s = (int)keys[0];
+            if (s <= cap && s < st->best_steps) {   // agentK.L < best.L  (:263)
+                st->best_steps = s; st->best_L = Ltab[s]; st->best_changed = 1; st->best_ant = (int)vals[0];
+            }
+        }
+    }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int r = base + threadIdx.x;
+        uint32_t len = 0; bool el = false;
+        if (r < n) {
+            const int s = (int)keys[r];
+            const int order = r + 1;
+            order_of_ant[vals[r]] = order;
+            el = s <= cap && !((float)order > __fsub_rn(lambda, 1.0f));   // :200
+            len = el ? (uint32_t)s : 0u;
+        }
+        uint32_t incl = len;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) warp_sum[w] = incl;
+        unsigned em = __ballot_sync(0xffffffffu, el);
+        if (lane == 0 && em) atomicAdd(&elig_total, (uint32_t)__popc(em));
+        __syncthreads();
+        if (w == 0) {
+            uint32_t s = warp_sum[lane], si = s;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += u; }
+            warp_sum[lane] = si - s;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sum[w] + (incl - len);
+        if (r < n) rec_off[r] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + len;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { st->n_eligible = (int)elig_total; st->n_records = (int)carry; st->cnt[7] += carry; }
+}
+
+// best = agentK (:264): drop the old best path's membership bits ...
+__global__ void k_best_clear(const IterState* st, const int* __restrict__ best_n, const uint32_t* __restrict__ best_ids, uint32_t* onbest)
+{
+    if (!st->best_changed) return;
+    const int n = *best_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t id = best_ids[i];
+        atomicAnd(&onbest[id >> 5], ~(1u << (id & 31)));
+    }
+}
+// ... then copy the new one (path + chosen slots) and set its bits.  src_ids/src_dirs: the path
+// buffers of the ant that produced it (local ant index src_ant).
+__global__ void k_best_copy(const IterState* st, int* best_n, uint32_t* best_ids, uint8_t* best_dirs, uint32_t* onbest,
+                            const uint32_t* __restrict__ path_ids, const uint8_t* __restrict__ path_dirs, int cap, int shard_first, int goal)
+{
+    if (!st->best_changed) return;
+    const int steps = st->best_steps;
+    const size_t off = (size_t)(st->best_ant - shard_first) * cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= steps; i += gridDim.x * blockDim.x) {
+        uint32_t id = i < steps ? path_ids[off + i] : (uint32_t)goal;
+        best_ids[i] = id;
+        if (i < steps) best_dirs[i] = path_dirs[off + i];
+        atomicOr(&onbest[id >> 5], 1u << (id & 31));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *best_n = steps + 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Deposit records (:198-215).  One CTA per eligible rank; record i of rank r goes to
+// rec_off[r] + i, so records are emitted in (rank, step) order and a STABLE sort by slot keeps
+// rank order inside every slot — the order the reference adds them in.
+//   value = (lambda - order)*Q/L_ant + float(onBest)*lambda*Q/L_best      (:210-211)
+// ------------------------------------------------------------------------------------------
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const uint32_t* __restrict__ rank_keys,
+                                                      const uint32_t* __restrict__ rank_vals, const uint32_t* __restrict__ rec_off,
+                                                      const uint32_t* __restrict__ path_ids, const uint8_t* __restrict__ path_dirs, int cap,
+                                                      int goal, const float* __restrict__ Ltab, const uint32_t* __restrict__ onbest,
+                                                      uint32_t* __restrict__ rec_keys, uint32_t* __restrict__ rec_vals, float* tau)
+{
+    const int r = blockIdx.x;
+    if (r >= st->n_eligible) return;
+    const int steps = (int)rank_keys[r];
+    const size_t ant = rank_vals[r];
+    const int order = r + 1;
+    const float lambda = st->lambda, Q = st->Q;
+    const float base = __fdiv_rn(__fmul_rn(__fsub_rn(lambda, (float)order), Q), Ltab[steps]);
+    const float elite = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, lambda), Q), st->best_L);
+    const float with_elite = __fadd_rn(base, elite), without = __fadd_rn(base, 0.0f);
+    const uint32_t off = rec_off[r];
+    const uint32_t* pid = path_ids + ant * cap;
+    const uint8_t* pdir = path_dirs + ant * cap;
+    for (int i = threadIdx.x; i < steps; i += blockDim.x) {
+        const uint32_t node = pid[i];
+        const uint32_t next = (i + 1 < steps) ? pid[i + 1] : (uint32_t)goal;
+        const bool onb = ((onbest[node >> 5] >> (node & 31)) & 1u) && ((onbest[next >> 5] >> (next & 31)) & 1u);
+        const float val = onb ? with_elite : without;
+        const uint32_t slot = node * 6u + pdir[i];
+        if (ATOMIC) atomicAdd(&tau[slot], val);
+        else { rec_keys[off + i] = slot; rec_vals[off + i] = __float_as_uint(val); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 split variants
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_evaporate(float4* __restrict__ tau4, size_t n4, float rho)
+{   // :268-272, 16 B per thread per trip, grid-stride
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = tau4[i];
+        v.x = __fmul_rn(v.x, rho); v.y = __fmul_rn(v.y, rho); v.z = __fmul_rn(v.z, rho); v.w = __fmul_rn(v.w, rho);
+        tau4[i] = v;
+    }
+}
+
+__global__ void k_deposit_apply(const IterState* st, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, float* tau)
+{
+    const int n = st->n_records;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t key = keys[i];
+        if (i > 0 && keys[i - 1] == key) continue;   // not the head of its slot run
+        float t = tau[key];
+        int j = i;
+        do { t = __fadd_rn(t, __uint_as_float(vals[j])); j++; } while (j < n && keys[j] == key);
+        tau[key] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 fused: evaporation + rank-ordered deposits in a single HBM pass.
+// Persistent CTAs stream the pheromone field in 16 KB tiles: TMA bulk load into a 4-stage
+// shared-memory ring (mbarrier completion), scale in place, apply the tile's (slot-sorted)
+// deposit runs in place, TMA bulk store back.  tile_off[t] .. tile_off[t+1] delimit tile t's
+// records (k_tile_offsets, binary search over the sorted slot keys).
+// ------------------------------------------------------------------------------------------
+__global__ void k_tile_offsets(const IterState* st, const uint32_t* __restrict__ keys, uint32_t* __restrict__ tile_off, unsigned ntiles)
+{
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    const int n = st->n_records;
+    const unsigned long long target = (unsigned long long)t * kUpdTile;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((unsigned long long)keys[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    tile_off[t] = (uint32_t)lo;
+}
+
+__global__ void __launch_bounds__(kUpdThreads) k_update_fused(float* tau, unsigned ntiles, float rho, const uint32_t* __restrict__ rec_keys,
+                                                               const uint32_t* __restrict__ rec_vals, const uint32_t* __restrict__ tile_off)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);                                  // [kUpdStages][kUpdTile]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + (size_t)kUpdStages * kUpdTile);   // [kUpdStages]
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kUpdStages; s++) tma::mbar_init(&full[s], 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    const unsigned first = blockIdx.x, stride = gridDim.x;
+    const unsigned cnt = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+    constexpr uint32_t kBytes = kUpdTile * sizeof(float);
+    if (tid == 0) {
+        for (unsigned i = 0; i < (unsigned)(kUpdStages - 1) && i < cnt; i++) {
+            tma::mbar_arrive_expect_tx(&full[i], kBytes);
+            tma::bulk_g2s(stage + (size_t)i * kUpdTile, tau + (size_t)(first + i * stride) * kUpdTile, kBytes, &full[i]);
+        }
+    }
+    for (unsigned i = 0; i < cnt; i++) {
+        const unsigned s = i % kUpdStages;
+        const unsigned t = first + i * stride;
+        float* buf = stage + (size_t)s * kUpdTile;
+        tma::mbar_wait(&full[s], (i / kUpdStages) & 1u);
+        float4* b4 = reinterpret_cast<float4*>(buf);
+#pragma unroll
+        for (int j = 0; j < kUpdTile / 4 / kUpdThreads; j++) {
+            float4 v = b4[j * kUpdThreads + tid];
+            v.x = __fmul_rn(v.x, rho); v.y = __fmul_rn(v.y, rho); v.z = __fmul_rn(v.z, rho); v.w = __fmul_rn(v.w, rho);
+            b4[j * kUpdThreads + tid] = v;
+        }
+        const uint32_t lo = tile_off[t], hi = tile_off[t + 1];
+        if (lo < hi) {   // block-uniform
+            __syncthreads();
+            const uint32_t tbase = t * (uint32_t)kUpdTile;
+            for (uint32_t r = lo + tid; r < hi; r += kUpdThreads) {
+                const uint32_t key = rec_keys[r];
+                if (r > lo && rec_keys[r - 1] == key) continue;
+                float x = buf[key - tbase];
+                uint32_t j = r;
+                do { x = __fadd_rn(x, __uint_as_float(rec_vals[j])); j++; } while (j < hi && rec_keys[j] == key);
+                buf[key - tbase] = x;
+            }
+        }
+        tma::fence_proxy_async();   // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) {
+            tma::bulk_s2g(tau + (size_t)t * kUpdTile, buf, kBytes);
+            tma::bulk_commit();
+            const unsigned nxt = i + kUpdStages - 1;
+            if (nxt < cnt) {
+                tma::bulk_wait_read<1>();   // the store of tile i-1 has drained stage (i-1)%S
+                const unsigned ns = nxt % kUpdStages;
+                tma::mbar_arrive_expect_tx(&full[ns], kBytes);
+                tma::bulk_g2s(stage + (size_t)ns * kUpdTile, tau + (size_t)(first + nxt * stride) * kUpdTile, kBytes, &full[ns]);
+            }
+        }
+    }
+    if (tid == 0) tma::bulk_wait<0>();
+}
+
+// reset() :307-315 and the initial field of initFromGridMap :391-401
+__global__ void k_tau_fill(float* tau, size_t n, float v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) tau[i] = v;
+}
+__global__ void k_tau_init(float* tau, int rx, int ry, int rz, unsigned long long N, float tau0)
+{   // out-of-bounds slots start at 0 (:396), in-bounds at tau0 (:401)
+    unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N) return;
+    const unsigned long long rxy = (unsigned long long)rx * ry;
+    int z = (int)(id / rxy);
+    unsigned r = (unsigned)(id % rxy);
+    int y = r / rx, x = r % rx;
+    float* t = tau + id * 6;
+    t[0] = z > 0 ? tau0 : 0.f; t[1] = y > 0 ? tau0 : 0.f; t[2] = x > 0 ? tau0 : 0.f;
+    t[3] = x + 1 < rx ? tau0 : 0.f; t[4] = y + 1 < ry ? tau0 : 0.f; t[5] = z + 1 < rz ? tau0 : 0.f;
+}
+
+}  // namespace wr
