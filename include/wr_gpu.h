@@ -126,6 +126,12 @@ int wr_acs_counters(wr_acs* a, uint64_t out[9]);
  * [0] walk [1] rank+best [2] deposit build+sort [3] update (evaporate+deposit) [4] whole iterations */
 int wr_acs_kernel_ms(wr_acs* a, float out[5]);
 int wr_acs_set_timing(wr_acs* a, int enabled);
+/* measurement hook: run ONE kernel of the update path `reps` times back to back on the handle's
+ * stream and report the average device time per launch (CUDA events).  which: 0 = fused TMA update
+ * (evaporation + the last iteration's deposit records), 1 = float4 evaporation pass alone,
+ * 2 = device-to-device copy of the pheromone field (in-run copy ceiling).  The field is
+ * multiplied by rho each time (which 0/1), so call it on a scratch search only. */
+int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch);
 /* use an existing CUDA stream (cudaStream_t as void*); default: a private non-blocking stream */
 int wr_acs_set_stream(wr_acs* a, void* cuda_stream);
 

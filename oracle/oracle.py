@@ -74,6 +74,9 @@ def lib():
         L.wro_acs_set_endpoints.argtypes = [vp, C.c_int64, C.c_int64]
         L.wro_acs_begin.argtypes = [vp, C.c_float]
         L.wro_acs_iterate.argtypes = [vp, C.c_int]
+        L.wro_acs_seq_seek.argtypes = [vp, C.c_uint64]
+        L.wro_acs_seq_tell.restype = C.c_uint64
+        L.wro_acs_seq_tell.argtypes = [vp]
         L.wro_acs_reset.argtypes = [vp]
         L.wro_acs_best.argtypes = [vp, vp, vp, C.c_int, vp]
         L.wro_acs_pheromone.argtypes = [vp, vp]
@@ -229,8 +232,11 @@ class Acs:
     def set_endpoints(self, s, e):
         return bool(lib().wro_acs_set_endpoints(self.h, s, e))
 
-    def begin(self, predict):
+    def begin(self, predict, seq_pos=0):
+        """seq_pos: position of the sequential stream (rng_mode SEQUENTIAL only); None = continue."""
+        keep = lib().wro_acs_seq_tell(self.h)
         lib().wro_acs_begin(self.h, predict)
+        lib().wro_acs_seq_seek(self.h, keep if seq_pos is None else seq_pos)
 
     def iterate(self, n):
         r = lib().wro_acs_iterate(self.h, n)

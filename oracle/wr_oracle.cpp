@@ -340,6 +340,10 @@ extern "C" void wro_acs_begin(wro_acs* a, float predict)
     a->best.L = WRO_INF_FLOAT; /* best.path is left as is, like the reference */
     a->predict = predict; a->iter = 0; a->seq_calls = 0;
 }
+/* position of the sequential (n-th call) stream: the genuine all-pairs driver (:472-499) never
+ * reseeds between pairs, so a pinning run seeks to the cumulative draw count before each pair */
+extern "C" void wro_acs_seq_seek(wro_acs* a, uint64_t pos) { a->seq_calls = pos; }
+extern "C" uint64_t wro_acs_seq_tell(const wro_acs* a) { return a->seq_calls; }
 
 /* :307-315 — every slot, including the out-of-bounds ones, becomes tau0 */
 extern "C" void wro_acs_reset(wro_acs* a)

@@ -68,6 +68,8 @@ int wro_acs_set_points(wro_acs* a, const float s[3], const float e[3], int64_t i
 int wro_acs_set_points_scan(wro_acs* a, const float s[3], const float e[3], int64_t ids[2]); /* literal full scan */
 int wro_acs_set_endpoints(wro_acs* a, int64_t start_id, int64_t goal_id);
 void wro_acs_begin(wro_acs* a, float predict_path_len);   /* :229-233 */
+void wro_acs_seq_seek(wro_acs* a, uint64_t pos);           /* sequential-stream position (pinning runs) */
+uint64_t wro_acs_seq_tell(const wro_acs* a);
 int wro_acs_iterate(wro_acs* a, int n);                    /* n passes of the loop body :237-299 */
 void wro_acs_reset(wro_acs* a);                            /* :307-315 */
 int wro_acs_best(const wro_acs* a, int64_t* ids, int* dirs, int cap, float* L); /* node count */

@@ -526,6 +526,42 @@ extern "C" int wr_acs_kernel_ms(wr_acs* a, float out[5])
     return WR_OK;
 }
 
+extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch)
+{
+    WR_REQUIRE(a && ms_per_launch && reps > 0 && which >= 0 && which <= 2, WR_ERR_INVALID, "wr_acs_bench_kernel: bad argument");
+    WR_REQUIRE(a->begun, WR_ERR_STATE, "wr_acs_bench_kernel: call wr_acs_begin first");
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    cudaEvent_t e0, e1;
+    WR_CUDA(cudaEventCreate(&e0));
+    WR_CUDA(cudaEventCreate(&e1));
+    float* scratch = nullptr;
+    if (which == 2) WR_CUDA(cudaMalloc(&scratch, a->n_slots_pad * sizeof(float)));
+    const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
+    const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
+    const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
+    const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * 2);
+    for (int r = -1; r < reps; r++) {   // one untimed warm-up launch
+        if (r == 0) WR_CUDA(cudaEventRecord(e0, s));
+        if (which == 0) {
+            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
+            k_update_fused<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
+        } else if (which == 1) {
+            k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
+        } else {
+            WR_CUDA(cudaMemcpyAsync(scratch, a->d_tau, a->n_slots_pad * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    WR_CUDA(cudaEventRecord(e1, s));
+    WR_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    WR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(scratch);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
 // ---- ant sharding (filled in with the multi-GPU step) ---------------------------------------
 extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks)
 {
