@@ -2,21 +2,24 @@
 """bench.py — ant-steps/s of the rank-based 3-D ACS search on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU code (oracle/_ref)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (oracle/_ref)
 
-Workload (config.workload "C2"): BASELINE.json configs[1] — the simplified_piece mesh voxelised on
-the GPU at a 256-long grid (precision 0.823812/235.5, wall 10) and embedded in 256^3 free space
-(SURVEY.md §8d), 4096 ants per GPU, K = 6, Philox seed 1, start/goal at opposite corners inset by 5
-cells.  One "step" = `--iters` ACS iterations (ant construction + ranking + fused pheromone update)
-of one search.  With N GPUs the colony is 4096*N ants sharded by ant index (weak scaling), one
-exchange per iteration.  The pheromone field (403 MB) is larger than L2 (126 MB), so every
-iteration streams it from HBM.
+Workload "C2" (BASELINE.json configs[1]): the simplified_piece mesh voxelised at a
+256-long grid (precision 0.823812/235.5, wall 10) and embedded in a 256^3 lattice whose node
+coordinates follow the reference's formula (model_grid_map.hpp:204-211) for a cubic bounding box;
+4096 ants per GPU, K = 6, Philox seed 1, start/goal at opposite corners inset by 5 cells, step cap
+8192.  One "step" = `--iters` ACS iterations (ant construction + ranking + pheromone update) of one
+search.  With N GPUs the colony is 4096*N ants sharded by ant index (weak scaling) with one exchange
+per iteration.  The pheromone field (403 MB) is larger than L2 (126 MB): every iteration streams it
+from HBM, so no L2 flush is needed between timed iterations.
 
-Prints ONE JSON line (see the contract in the task description): `value` is whole-job
-ant-steps/s with the grid already in HBM; `e2e` goes through the public API from HOST buffers
-(occupancy upload, handle creation, search, best-path download) every step.
+Prints ONE JSON line.  `value` = whole-job ant-steps/s with the grid already in HBM (CUDA events on
+the launching stream, max over ranks); `e2e` = the same metric through the public API from HOST
+buffers, every step: occupancy upload, handle creation, search, best-path download.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -35,7 +38,7 @@ SEED = 1
 PRECISION = 0.823812 / 235.5
 WALL = 10
 CUBE = 256
-PREDICT = 1.0   # unused with a fixed colony except for Q of the first iterations (ACSRank_3D.hpp:249)
+PREDICT = 1.0                # with a fixed colony only Q of the pre-arrival iterations depends on it (ACSRank_3D.hpp:249)
 WALK_BYTES_PER_STEP = 30     # 4*K tau + K/8 occupancy + 4 id + 1 dir, K = 6
 UPDATE_BYTES_PER_SLOT = 8    # 4 read + 4 write per directed slot per iteration
 
@@ -55,24 +58,29 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
         try:
-            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
-        while not self.stop_flag:
-            line = p.stdout.readline()
-            if not line:
-                break
+        for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
-        p.terminate()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in self.rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if len(r) > 1 and num(r[1]) is not None]
         reasons = set()
         for r in self.rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -82,92 +90,126 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def build_workload():
-    """Host copy of the C2 occupancy: GPU-voxelised natural grid embedded in CUBE^3 free space."""
+# ---------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------
+def axis_coords(rng, wall, mn, mx, precision):
+    """model_grid_map.hpp:204-205 in float32 (bit-identical to the C expression, see tests)."""
+    f = np.float32
+    out = np.zeros(rng, np.float32)
+    for i in range(rng):
+        if i < wall:
+            out[i] = f(mn) - f(f(wall - i) * f(precision))
+        elif i >= rng - wall:
+            out[i] = f(mx) + f(f(i - rng + wall) * f(precision))
+        else:
+            out[i] = f(mn) + f(f(i - wall) * f(precision))
+    return out
+
+
+def embed(free_zyx, gmin, gmax):
+    """Natural voxelisation -> CUBE^3 workload: cubic bounding box (the long axis' extent on all axes),
+    the reference's coordinate formula, the piece's occupancy centred, everything else free."""
+    rz, ry, rx = free_zyx.shape
+    assert max(rx, ry, rz) == CUBE, (rx, ry, rz)
+    f = np.float32
+    ext = max(f(gmax[k]) - f(gmin[k]) for k in range(3))
+    cmin = [f(gmin[k]) for k in range(3)]
+    cmax = [f(f(gmin[k]) + f(ext)) for k in range(3)]
+    axes = [axis_coords(CUBE, WALL, cmin[k], cmax[k], f(PRECISION)) for k in range(3)]
+    cube = np.ones((CUBE, CUBE, CUBE), np.uint8)
+    oz, oy, ox = (CUBE - rz) // 2, (CUBE - ry) // 2, (CUBE - rx) // 2
+    cube[oz:oz + rz, oy:oy + ry, ox:ox + rx] = free_zyx
+    nid = lambda x, y, z: (z * CUBE + y) * CUBE + x  # noqa: E731
+    start, goal = nid(5, 5, 5), nid(CUBE - 6, CUBE - 6, CUBE - 6)
+    flat = np.ascontiguousarray(cube.ravel())
+    assert flat[start] and flat[goal]
+    return dict(isfree=flat, xs=axes[0], ys=axes[1], zs=axes[2], start=start, goal=goal, natural=(rx, ry, rz),
+                cmin=[float(v) for v in cmin], cmax=[float(v) for v in cmax])
+
+
+def build_workload_gpu():
+    """Natural grid from the product's GPU voxeliser (K1)."""
     import welding_robot_b200 as wr
     tris = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))["simplified_piece"]
     g = wr.GridMap()
-    import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         g.creatGridMap(tris, PRECISION, WALL)
-    rx, ry, rz = g.rangeX, g.rangeY, g.rangeZ
-    assert max(rx, ry, rz) == CUBE, (rx, ry, rz)
-    free = g.isfree().reshape(rz, ry, rx)
-    xs, ys, zs = g.coords()
-    vox = g.stats()
-    p = np.float32(PRECISION)
-
-    def extend(c, n):
-        lo = (n - len(c)) // 2
-        hi = n - len(c) - lo
-        return np.concatenate([c[0] - p * np.arange(lo, 0, -1, dtype=np.float32), c, c[-1] + p * np.arange(1, hi + 1, dtype=np.float32)]).astype(np.float32), lo
-
-    X, ox = extend(xs, CUBE); Y, oy = extend(ys, CUBE); Z, oz = extend(zs, CUBE)
-    cube = np.ones((CUBE, CUBE, CUBE), np.uint8)
-    cube[oz:oz + rz, oy:oy + ry, ox:ox + rx] = free
-    nid = lambda x, y, z: (z * CUBE + y) * CUBE + x  # noqa: E731
-    start, goal = nid(5, 5, 5), nid(CUBE - 6, CUBE - 6, CUBE - 6)
-    assert cube.ravel()[start] and cube.ravel()[goal]
-    return dict(isfree=np.ascontiguousarray(cube.ravel()), xs=X, ys=Y, zs=Z, start=start, goal=goal, natural=(rx, ry, rz), vox=vox, ntri=len(tris))
+    free = g.isfree().reshape(g.rangeZ, g.rangeY, g.rangeX)
+    mn, mx = g.bbox()
+    wl = embed(free, mn, mx)
+    wl["vox"] = g.stats(); wl["ntri"] = len(tris)
+    return wl
 
 
+def build_workload_cpu():
+    """The same workload built on the CPU (reference arm): the oracle's box-restricted voxeliser gives
+    the natural grid (the reference's own O(T*N) loop would need ~140 s for it)."""
+    from oracle import oracle as O
+    tris = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))["simplified_piece"]
+    G = O.Grid.from_triangles(tris, PRECISION, WALL, O.VOX_AABB)
+    rx, ry, rz = G.dims
+    v = tris[:, 3:].reshape(-1, 3)
+    wl = embed(G.isfree().reshape(rz, ry, rx), v.min(0), v.max(0))
+    wl["ntri"] = len(tris)
+    return wl
+
+
+# ---------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import welding_robot_b200 as wr
     from welding_robot_b200 import _lib
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch with `python -m torch.distributed.run --nproc-per-node %d bench.py --gpus %d ...`" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     _lib.check(_lib.lib().wr_set_device(local))
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    wl = build_workload()
+    wl = build_workload_gpu()
     n_nodes = CUBE ** 3
     colony = ANTS_PER_GPU * world
 
-    def make_search():
+    def make_search(host_free):
         acs = wr.ACS_Rank(seed=SEED, fixed_colony=colony, step_cap=STEP_CAP, update_mode=args.update_mode)
-        acs.creatFromOccupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], PRECISION)
-        import contextlib, io
+        acs.creatFromOccupancy(host_free, wl["xs"], wl["ys"], wl["zs"], PRECISION)     # H2D: occupancy + coordinates
         with contextlib.redirect_stdout(io.StringIO()):
             acs.initFromGridMap()
         return acs
 
-    acs = make_search()
+    acs = make_search(wl["isfree"])
     stream = torch.cuda.current_stream()
     _lib.check(_lib.lib().wr_acs_set_stream(acs._a, stream.cuda_stream))
+    acs.setEndpoints(wl["start"], wl["goal"])
     if world > 1:
         from welding_robot_b200.dist import ShardedSearch
         driver = ShardedSearch(acs, rank, world)
+        driver.begin(PREDICT)
+        step = lambda: driver.iterate(args.iters)  # noqa: E731
     else:
-        driver = None
-    acs.setEndpoints(wl["start"], wl["goal"])
-    acs.begin(PREDICT) if driver is None else driver.begin(PREDICT)
-
-    def step():
-        if driver is None:
-            acs.iterate(args.iters)
-        else:
-            driver.iterate(args.iters)
+        acs.begin(PREDICT)
+        step = lambda: acs.iterate(args.iters)  # noqa: E731
 
     def barrier():
-        if world > 1:
-            import torch.distributed as dist
+        if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         step()
     barrier()
-    # ---- timed region: device-resident (value) ---------------------------------------------------
+    # ---- timed region, device resident -------------------------------------------------------------
     acs.setTiming(True)
     c0 = acs.counters()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.2)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -176,60 +218,61 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    sampler.stop()
     c1 = acs.counters()
     kms = acs.kernelMs()
     acs.setTiming(False)
-    if world > 1:
-        import torch.distributed as dist
+    local_steps = c1["ant_steps"] - c0["ant_steps"]
+    steps_done = local_steps
+    if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        s = torch.tensor([c1["ant_steps"] - c0["ant_steps"]], device="cuda", dtype=torch.int64)
+        s = torch.tensor([local_steps], device="cuda", dtype=torch.int64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         steps_done = int(s.item())
-    else:
-        steps_done = c1["ant_steps"] - c0["ant_steps"]
     iters_done = args.steps * args.iters
     value = steps_done / (ms * 1e-3)
 
-    # ---- end to end through the public API from HOST buffers ---------------------------------------
+    # ---- kernels timed alone (burst roofline of K3) ---------------------------------------------------
+    alone = {}
+    if world == 1:
+        for name, which in (("fused_tma", 0), ("evaporate_float4", 1), ("d2d_copy", 2)):
+            t_ms = acs.benchKernel(which, 20)
+            alone[name] = {"ms": t_ms, "GBps": UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (t_ms * 1e-3) / 1e9}
+
+    # ---- end to end through the public API from HOST buffers -------------------------------------------
     e2e = None
     if world == 1:
         pinned = torch.from_numpy(wl["isfree"]).pin_memory()
         host_free = pinned.numpy()
         e2e_steps = max(1, min(args.steps, 5))
-        tot_steps = 0
+        tot_steps, d2h = 0, 0
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        d2h = 0
         for _ in range(e2e_steps):
-            a2 = wr.ACS_Rank(seed=SEED, fixed_colony=colony, step_cap=STEP_CAP, update_mode=args.update_mode)
-            a2.creatFromOccupancy(host_free, wl["xs"], wl["ys"], wl["zs"], PRECISION)     # H2D: occupancy + coordinates
-            import contextlib, io
-            with contextlib.redirect_stdout(io.StringIO()):
-                a2.initFromGridMap()
+            a2 = make_search(host_free)
             a2.setEndpoints(wl["start"], wl["goal"])
             a2.begin(PREDICT)
             a2.iterate(args.iters)
             ids, dirs, L = a2.bestPath()                                                # D2H: the result
             tot_steps += a2.counters()["ant_steps"]
-            d2h = ids.nbytes // 2 + dirs.nbytes // 4 + 4 + 9 * 8
+            d2h = len(ids) * 4 + len(dirs) + 4 + 9 * 8
             del a2
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = {"value": tot_steps / dt, "unit": "ant-steps/s", "h2d_bytes_per_step": int(host_free.nbytes + 3 * CUBE * 4 + 16),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "what": "per step: occupancy upload -> wr_grid_create_from_occupancy -> wr_acs_create -> begin -> %d iterations -> wr_acs_best" % args.iters}
-    sampler.stop_flag = True
-
+               "what": "per step, from host buffers: wr_grid_create_from_occupancy (16.8 MB H2D) -> wr_acs_create -> wr_acs_begin -> "
+                       "%d x wr_acs_iterate -> wr_acs_best (D2H)" % args.iters}
     if rank != 0:
         return
     hbm, hbm_src = peaks()
     walk_ms = kms["walk"] / iters_done
     upd_ms = kms["update"] / iters_done
-    local_steps = (c1["ant_steps"] - c0["ant_steps"])
     walk_gbs = WALK_BYTES_PER_STEP * (local_steps / iters_done) / (walk_ms * 1e-3) / 1e9
     upd_gbs = UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (upd_ms * 1e-3) / 1e9
+    ants_done = max(1, c1["ants"] - c0["ants"])
     out = {
         "metric": "ant-steps/s", "value": value, "unit": "ant-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -238,82 +281,142 @@ def run_ours(args):
                    "grid": [CUBE, CUBE, CUBE], "natural_grid": list(wl["natural"]), "ants": colony, "iters_per_step": args.iters,
                    "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic"][args.update_mode],
                    "parallelism": "ants sharded x%d" % world,
-                   "l2_rule": "pheromone field 403 MB > 126 MB L2: every iteration streams it from HBM (no flush needed)"},
+                   "l2_rule": "inputs larger than L2: the 403 MB pheromone field is streamed from HBM every iteration"},
         "acs_iterations_per_s": iters_done / (ms * 1e-3),
-        "ant_steps": steps_done, "arrived": c1["arrived"] - c0["arrived"], "ants": c1["ants"] - c0["ants"],
-        "gpu_launches": None,
+        "ant_steps": steps_done, "arrived_local": c1["arrived"] - c0["arrived"], "ants_local": c1["ants"] - c0["ants"],
+        "mean_steps_per_ant": local_steps / ants_done,
+        "gpu_launches": launches_per_iteration(args.update_mode) * iters_done,
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
-        "roofline": {"kernel": "k_walk (K2 ant construction, dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
+        "roofline": {"kernel": "k_walk (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
                      "frac": walk_gbs / hbm, "traffic": None, "peak_source": hbm_src,
-                     "note": "30 B algorithmic per ant-step; latency-bound: %d dependent steps per ant" % (local_steps // max(1, c1["ants"] - c0["ants"]))},
-        "roofline_update": {"kernel": "k_update_fused (K3 evaporate+deposit, TMA)" if args.update_mode == 0 else "k_evaporate+deposit", "bound": "hbm",
-                            "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm, "traffic": None, "peak_source": hbm_src},
+                     "note": "30 B algorithmic per ant-step; a walk is a chain of dependent gathers, so with 4096 ants the kernel is "
+                             "latency-bound, not bandwidth-bound (see DESIGN.md)"},
+        "roofline_update": {"kernel": "k_update_fused (K3 evaporate+deposit, TMA)" if args.update_mode == 0 else "k_evaporate + k_deposit_apply (K3)",
+                            "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm, "traffic": None,
+                            "peak_source": hbm_src, "timed": "inside the iteration loop"},
+        "kernels_alone": alone,
         "voxelise": {"triangles": wl["ntri"], "grid": list(wl["natural"]), "kernel_ms": wl["vox"]["kernel_ms"], "tests": wl["vox"]["tests"]},
         "clocks": sampler.summary(),
     }
     if e2e:
         out["e2e"] = e2e
-    launches_per_iter = launches_per_iteration(acs, args.update_mode)
-    out["gpu_launches"] = launches_per_iter * iters_done
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline(wl, sample_ants=args.cpu_ants)
+        out["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(out))
 
 
-def launches_per_iteration(acs, update_mode):
-    """Kernels of OURS launched per ACS iteration (see welding_robot_b200/csrc/acs.cu)."""
+def launches_per_iteration(update_mode):
+    """Kernels of OURS launched per ACS iteration (welding_robot_b200/csrc/acs.cu)."""
     cap_bits = int(np.ceil(np.log2(STEP_CAP + 2)))
     slot_bits = int(np.ceil(np.log2(CUBE ** 3 * 6)))
-    sort = lambda bits: 3 * ((bits + 7) // 8)  # noqa: E731  hist+scan+scatter per 8-bit pass
+    sort = lambda bits: 3 * ((bits + 7) // 8)  # noqa: E731  hist + scan + scatter per 8-bit pass
     n = 1 + 3 + 1 + sort(cap_bits) + 1 + 2 + 1   # iter_begin, walk x2 + queue reset, rank keys, sort, rank finish, best x2, iter_end
     if update_mode == 2:
         return n + 2
-    return n + 1 + sort(slot_bits) + 2           # deposit gen, sort, (tile offsets + fused) or (evaporate + apply)
+    return n + 1 + sort(slot_bits) + 2           # deposit gen, sort, (tile offsets + fused) | (evaporate + apply)
 
 
-def reference_sample(wl, sample_ants, seed):
-    """One iteration of the UNMODIFIED reference (oracle/_ref) on the C2 grid with `sample_ants` ants.
-    The reference sizes its colony as int(0.35*predict/precision) (ACSRank_3D.hpp:247), so predict
-    is chosen to give exactly the sample size."""
+# ---------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle/_ref = UNMODIFIED reference headers), or the oracle port
+# ---------------------------------------------------------------------------------------------------
+def reference_worker(args):
+    """One process: `warmup + steps` first-iterations of computeSolution (ACSRank_3D.hpp:220-305) with a
+    colony of `cpu_ants` on the C2 grid.  Prints {"kind", "ant_steps": [...], "seconds": [...], "init_s"}."""
     from oracle import oracle as O
-    R = O.Ref()
-    # a 1-triangle mesh would not reproduce the grid: drive the reference on the SAME occupancy by
-    # voxelising a tiny mesh of the right extent and overwriting isFree (coordinates are its own).
-    raise NotImplementedError
-
-
-def cpu_baseline(wl, sample_ants):
-    """The CPU oracle (a port of the reference's arithmetic, single thread like the reference) on a
-    bounded sample of the same workload: ONE iteration of `sample_ants` of the 4096 ants on the
-    same 256^3 grid, same seed."""
-    from oracle import oracle as O
+    wl = build_workload_cpu()
+    seed = SEED + 1000 * args.worker
+    # the reference sizes its colony as int(0.35*predict/precision) while no path is known (:247)
+    predict = (args.cpu_ants + 0.5) * PRECISION / 0.35
     t0 = time.perf_counter()
-    G = O.Grid.from_occupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], PRECISION)
-    A = O.Acs(G, seed=SEED, fixed_colony=sample_ants, step_cap=STEP_CAP)
-    A.set_endpoints(wl["start"], wl["goal"])
-    A.begin(PREDICT)
-    t1 = time.perf_counter()
-    A.iterate(1)
-    t2 = time.perf_counter()
-    c = A.counters(); ph = A.phase_seconds()
-    return {"value": c["ant_steps"] / (t2 - t1), "unit": "ant-steps/s", "cores": 1, "kind": "port",
-            "sample": "1 iteration, %d of %d ants, full 256^3 grid (evaporation sweep included)" % (sample_ants, ANTS_PER_GPU),
-            "seconds": t2 - t1, "init_seconds": t1 - t0, "ant_steps": c["ant_steps"],
-            "phase_seconds": {k: float(v) for k, v in ph.items()},
-            "walk_only_ant_steps_per_s": c["ant_steps"] / max(ph["walk"], 1e-9),
-            "evaporate_GBps": UPDATE_BYTES_PER_SLOT * CUBE ** 3 * 6 / max(ph["evaporate"], 1e-9) / 1e9}
+    use_ref = O.have_ref() and not args.port
+    steps, secs = [], []
+    if use_ref:
+        R = O.Ref()
+        c0, c1 = wl["cmin"], wl["cmax"]
+        dummy = np.array([[0, 0, 1, c0[0], c0[1], c0[2], c1[0], c1[1], c1[2], c0[0], c1[1], c0[2]]], np.float32)
+        R.voxelize(dummy, PRECISION, WALL)      # same lattice: cubic box through creatGridMap's own formula
+        assert R.dims == (CUBE, CUBE, CUBE), R.dims
+        _, xs, ys, zs = R.grid()
+        assert np.array_equal(xs, wl["xs"]) and np.array_equal(ys, wl["ys"]) and np.array_equal(zs, wl["zs"])
+        R.set_free(wl["isfree"])
+        R.acs_init()
+        assert R.set_endpoints(wl["start"], wl["goal"])
+        init_s = time.perf_counter() - t0
+        for _ in range(args.warmup + args.steps):
+            t1 = time.perf_counter()
+            calls = R.compute(predict, 1, seed)    # every successful step draws once (ACSRank_3D.hpp:169)
+            secs.append(time.perf_counter() - t1); steps.append(int(calls))
+    else:
+        G = O.Grid.from_occupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], PRECISION)
+        A = O.Acs(G, seed=seed, rng_mode=O.RNG_SEQUENTIAL, sort_mode=O.SORT_STD)
+        A.set_endpoints(wl["start"], wl["goal"])
+        init_s = time.perf_counter() - t0
+        for _ in range(args.warmup + args.steps):
+            before = A.counters()["ant_steps"]
+            t1 = time.perf_counter()
+            A.begin(predict); A.iterate(1)
+            secs.append(time.perf_counter() - t1); steps.append(A.counters()["ant_steps"] - before)
+    print(json.dumps({"kind": "reference" if use_ref else "port", "ant_steps": steps[args.warmup:], "seconds": secs[args.warmup:], "init_s": init_s}))
+
+
+def run_reference_pool(args, steps, warmup, workers):
+    """`workers` concurrent single-thread processes (the reference has no threads: independent searches
+    are the only parallelism that keeps its arithmetic)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--worker-mode", "--steps", str(steps), "--warmup", str(warmup),
+           "--cpu-ants", str(args.cpu_ants)] + (["--port"] if args.port else [])
+    procs = [subprocess.Popen(cmd + ["--worker", str(i)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for i in range(workers)]
+    res = []
+    for p in procs:
+        out, err = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("reference worker failed:\n" + err[-2000:])
+        res.append(json.loads(out.strip().splitlines()[-1]))
+    tot = sum(sum(r["ant_steps"]) for r in res)
+    wall = max(sum(r["seconds"]) for r in res)
+    return res, tot, wall
+
+
+def host_workers(args):
+    cores = os.cpu_count() or 1
+    try:
+        with open("/proc/meminfo") as f:
+            avail_kb = next(int(l.split()[1]) for l in f if l.startswith("MemAvailable"))
+    except Exception:
+        avail_kb = 16 << 20
+    by_mem = max(1, int(avail_kb * 0.6 / (7 << 20)))    # ~6 GB per unmodified-reference process at 256^3
+    return max(1, min(cores, by_mem, args.max_workers))
+
+
+def cpu_baseline(args):
+    """Bounded sample for the default run: ONE process, 1 warm-up + 2 timed first-iterations."""
+    res, tot, wall = run_reference_pool(args, steps=2, warmup=1, workers=1)
+    return {"value": tot / wall, "unit": "ant-steps/s", "cores": 1, "kind": res[0]["kind"],
+            "sample": "2 iterations of computeSolution with %d of the %d ants on the same 256^3 grid (evaporation sweep of the whole field "
+                      "included), 1 process" % (args.cpu_ants, ANTS_PER_GPU),
+            "seconds": wall, "init_seconds": res[0]["init_s"], "ant_steps": tot}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from bench_reference import run as run_ref
-    print(json.dumps(run_ref(args, build_workload_cpu())))
-
-
-def build_workload_cpu():
-    raise NotImplementedError
+    steps, warmup = max(1, min(args.steps, 4)), min(args.warmup, 1)
+    workers = host_workers(args)
+    res, tot, wall = run_reference_pool(args, steps, warmup, workers)
+    value = tot / wall
+    print(json.dumps({
+        "impl": "reference", "metric": "ant-steps/s", "value": value, "unit": "ant-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic: same C2 grid as the GPU arm, built on the CPU",
+        "config": {"workload": "C2: ACSRank_3D, simplified_piece @256-long grid in 256^3, %d ants/GPU, K=6" % ANTS_PER_GPU,
+                   "grid": [CUBE, CUBE, CUBE], "sample_ants": args.cpu_ants, "processes": workers},
+        "cpu_baseline": {"value": value, "unit": "ant-steps/s", "cores": workers, "kind": res[0]["kind"],
+                         "sample": "%d timed first-iterations of computeSolution (ACSRank_3D.hpp:220-305) with %d-ant colonies on the 256^3 grid, "
+                                   "%d concurrent single-thread processes (independent searches), evaporation sweep included"
+                                   % (steps, args.cpu_ants, workers)},
+        "e2e": {"value": value, "unit": "ant-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
 
 
 def main():
@@ -324,13 +427,20 @@ def main():
     ap.add_argument("--iters", type=int, default=5, help="ACS iterations per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--update-mode", type=int, default=0)
-    ap.add_argument("--cpu-ants", type=int, default=1024)
+    ap.add_argument("--cpu-ants", type=int, default=1024, help="colony size of the CPU sample")
+    ap.add_argument("--max-workers", type=int, default=16)
+    ap.add_argument("--port", action="store_true", help="time the oracle port instead of oracle/_ref")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--worker-mode", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--worker", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
-        run_reference(args)
+        if args.worker_mode:
+            reference_worker(args)
+        else:
+            run_reference(args)
     else:
+        args.warmup = max(args.warmup, 3)
         run_ours(args)
 
 

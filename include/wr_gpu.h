@@ -136,19 +136,29 @@ int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch);
 int wr_acs_set_stream(wr_acs* a, void* cuda_stream);
 
 /* ---- ant sharding across ranks: one process per GPU ----------------------
- * With a shard set, wr_acs_walk() constructs only ants [first, first+count) of the global colony
- * (Philox is keyed by the GLOBAL ant index, so results do not depend on the rank count);
- * the host exchanges the packed results (torch.distributed / NCCL all_gather) and every rank
- * applies the identical global update with wr_acs_update_from_gathered(). */
-int wr_acs_set_shard(wr_acs* a, int rank, int nranks);
-int wr_acs_walk(wr_acs* a);                                  /* iter_begin + local ant construction */
-int wr_acs_local_steps_dev(wr_acs* a, int** dev_steps, int* first, int* count); /* device int32[count], -1 = dead */
-/* all ranks' steps, global ant order, as a DEVICE int32[colony] buffer -> global ranking */
+ * The pheromone field and the grid are replicated; rank r constructs ants
+ * [r*chunk, (r+1)*chunk) of the global colony, chunk = ceil(colony_max / nranks).  Philox is keyed
+ * by the GLOBAL ant index, so the result does not depend on the rank count.  One iteration is
+ *     wr_acs_walk -> all_gather(local steps) -> wr_acs_rank_global -> all_reduce(best candidate)
+ *     -> wr_acs_apply_best -> wr_acs_build_records -> all_reduce(record keys, record values)
+ *     -> wr_acs_finish_iteration
+ * with the collectives issued by the host on the handle's stream (NCCL through
+ * torch.distributed; see welding_robot_b200/dist.py).  Every all_reduce is an integer SUM over
+ * buffers in which exactly one rank holds a non-zero word per position, so the merged deposit
+ * list — and with it the pheromone field on every rank — is bit-identical to a 1-GPU run. */
+int wr_acs_set_shard(wr_acs* a, int rank, int nranks);       /* before wr_acs_begin */
+int wr_acs_walk(wr_acs* a);                                  /* iteration parameters (:247-249) + local ant construction */
+/* this rank's steps: DEVICE int32[*count] (*count = chunk; -1 = dead or beyond the colony); *first = global index of entry 0 */
+int wr_acs_local_steps_dev(wr_acs* a, int** dev_steps, int* first, int* count);
+/* all ranks' steps concatenated in rank order (DEVICE int32[nranks*chunk]) -> global ranking, best decision,
+ * deposit offsets; fills the best-candidate buffer (zeros unless this rank owns the new best ant) */
 int wr_acs_rank_global(wr_acs* a, const int* dev_all_steps);
-/* pack this rank's ants that are in the global top-w into a device buffer; *dev_buf, *bytes */
-int wr_acs_pack_top(wr_acs* a, void** dev_buf, size_t* bytes, size_t* max_bytes);
-/* gathered = concatenation over ranks of max_bytes-sized packs (device) */
-int wr_acs_update_from_gathered(wr_acs* a, const void* dev_gathered, int nranks, size_t stride_bytes);
+int wr_acs_best_candidate_dev(wr_acs* a, uint32_t** dev_words, size_t* nwords);   /* all_reduce(SUM, int32) this */
+int wr_acs_apply_best(wr_acs* a);                            /* install the (merged) new best path, if any */
+/* deposit records of this rank's ants at their global positions, zeros elsewhere; reads the record count back
+ * (the one host sync of a sharded iteration).  all_reduce(SUM, int32) keys[0..*n) and vals[0..*n). */
+int wr_acs_build_records(wr_acs* a, uint32_t** dev_keys, uint32_t** dev_vals, int* n);
+int wr_acs_finish_iteration(wr_acs* a);                      /* slot sort + pheromone update + iteration counter */
 
 /* ------------------------------------------------------------------------------------------
  * Seam ordering — replaces ACS_GTSP (core/ACS_GTSP.hpp), batched: B independent colonies on

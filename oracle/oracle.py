@@ -120,6 +120,7 @@ def ref():
         L.wrref_grid_set_free.argtypes = [vp, vp]
         L.wrref_acs_init.argtypes = [vp]
         L.wrref_acs_set_points.argtypes = [vp, vp, vp, vp]
+        L.wrref_acs_set_endpoints.argtypes = [vp, C.c_int64, C.c_int64]
         L.wrref_acs_compute.argtypes = [vp, C.c_float, C.c_int, C.c_uint64, vp]
         L.wrref_acs_best.argtypes = [vp, vp, vp, C.c_int, vp]
         L.wrref_acs_pheromone.argtypes = [vp, vp]
@@ -383,6 +384,9 @@ class Ref:
         ids = np.zeros(2, np.int64)
         ok = self.L.wrref_acs_set_points(self.h, _p(s), _p(e), _p(ids))
         return bool(ok), int(ids[0]), int(ids[1])
+
+    def set_endpoints(self, start_id, goal_id):
+        return bool(self.L.wrref_acs_set_endpoints(self.h, start_id, goal_id))
 
     def compute(self, predict, max_iter, seed):
         calls = C.c_uint64()

@@ -184,6 +184,17 @@ int wrref_acs_set_points(void* h, const float s[3], const float e[3], int64_t id
     return ok ? 1 : 0;
 }
 
+// choose the endpoints by node id (what setPoints would leave in start_node / end_node)
+int wrref_acs_set_endpoints(void* h, int64_t start_id, int64_t goal_id)
+{
+    ACS_Rank* a = (ACS_Rank*)h;
+    int rx = a->rangeX, ry = a->rangeY;
+    auto node = [&](int64_t id) { int z = id / ((int64_t)rx * ry); int r = id % ((int64_t)rx * ry); return &a->nodes[z][r / rx][r % rx]; };
+    a->start_node = node(start_id);
+    a->end_node = node(goal_id);
+    return (a->start_node->isFree && a->end_node->isFree) ? 1 : 0;
+}
+
 // ACSRank_3D.hpp:220-305 with max_iteration overridden and rand() = Philox SEQ stream.
 int wrref_acs_compute(void* h, float predict, int max_iter, uint64_t seed, uint64_t* rand_calls)
 {

@@ -1,0 +1,88 @@
+"""GPU, 2 ranks, NCCL: an ant-sharded search must equal the un-sharded search bit for bit
+(pheromone field, best path, ranks) on every rank — Philox is keyed by the global ant index and the
+deposit merge is order-preserving."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def worker(rank, world, port, q):
+    import contextlib
+    import io
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import welding_robot_b200 as wr
+        from welding_robot_b200 import _lib
+        from welding_robot_b200.dist import ShardedSearch
+        _lib.check(_lib.lib().wr_set_device(rank))
+        tris = np.load(os.path.join(GOLDEN, "meshes.npz"))["simplified_piece"]
+
+        def make():
+            a = wr.ACS_Rank(seed=21, fixed_colony=1001, step_cap=600)     # odd colony: ragged last chunk
+            with contextlib.redirect_stdout(io.StringIO()):
+                a.creatGridMap(tris, 0.012, 4)
+                a.initFromGridMap()
+            _lib.check(_lib.lib().wr_acs_set_stream(a._a, torch.cuda.current_stream().cuda_stream))
+            free = np.flatnonzero(a.isfree())
+            a.setEndpoints(int(free[11]), int(free[-11]))
+            return a
+
+        single = make(); single.begin(1.0); single.iterate(6)
+        sharded = make()
+        S = ShardedSearch(sharded, rank, world)
+        S.begin(1.0); S.iterate(6)
+        torch.cuda.synchronize()
+        t1, t2 = single.pheromone(), sharded.pheromone()
+        assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), "sharded pheromone field differs from the 1-GPU field"
+        b1, b2 = single.bestPath(), sharded.bestPath()
+        assert np.array_equal(b1[0], b2[0]) and np.array_equal(b1[1], b2[1]) and np.float32(b1[2]) == np.float32(b2[2])
+        chunk = (1001 + world - 1) // world
+        for k in range(rank * chunk, min((rank + 1) * chunk, 1001), 37):
+            i1, d1, L1, o1 = single.lastAnt(k); i2, d2, L2, o2 = sharded.lastAnt(k)
+            assert o1 == o2 and np.array_equal(i1, i2) and (L1 == L2 or (np.isinf(L1) and np.isinf(L2)))
+        c1, c2 = single.counters(), sharded.counters()
+        tot = torch.tensor([c2["ant_steps"], c2["ants"]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert int(tot[0]) == c1["ant_steps"] and int(tot[1]) == c1["ants"]
+        q.put((rank, "ok", S.bytes_exchanged))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_equals_single_gpu_world2():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in res:
+        assert status == "ok", "rank %d: %s" % (rank, info)

@@ -83,7 +83,10 @@ struct wr_acs {
     uint32_t* d_best_ids = nullptr;
     uint8_t* d_best_dirs = nullptr;
     // per-colony buffers (sized at begin)
-    int* d_ant_steps = nullptr;
+    int* d_ant_steps = nullptr;      // global colony order (ranking input)
+    int* d_local_steps = nullptr;    // this rank's chunk (== d_ant_steps when nranks == 1)
+    uint32_t* d_cand = nullptr;      // best-candidate exchange buffer (sharded)
+    size_t cand_words = 0;
     uint32_t* d_path_ids = nullptr;
     uint8_t* d_path_dirs = nullptr;
     uint32_t* d_overflow = nullptr;
@@ -106,6 +109,8 @@ static void free_colony_buffers(wr_acs* a)
 {
     cudaFree(a->d_ant_steps); cudaFree(a->d_path_ids); cudaFree(a->d_path_dirs); cudaFree(a->d_overflow);
     cudaFree(a->d_gkeys); cudaFree(a->d_gmasks); cudaFree(a->d_rec_off); cudaFree(a->d_order);
+    if (a->d_local_steps != a->d_ant_steps) cudaFree(a->d_local_steps);
+    cudaFree(a->d_cand); a->d_local_steps = nullptr; a->d_cand = nullptr;
     a->d_ant_steps = nullptr; a->d_path_ids = nullptr; a->d_path_dirs = nullptr; a->d_overflow = nullptr;
     a->d_gkeys = nullptr; a->d_gmasks = nullptr; a->d_rec_off = nullptr; a->d_order = nullptr;
     sort_plan_destroy(&a->sort_ants); sort_plan_destroy(&a->sort_recs);
@@ -123,7 +128,12 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     a->w_max = (int)(0.2 * (double)cm) + 1;
     const size_t rec_max = (size_t)a->w_max * cap;
     if (rec_max >= 0x7fffffffull) { set_error("colony %zu x step cap %zu needs too many deposit records; set step_cap", cm, cap); return WR_ERR_NOMEM; }
-    WR_CUDA(cudaMalloc(&a->d_ant_steps, cm * sizeof(int)));   // sized for the global colony: ranking reads all ranks' steps
+    WR_CUDA(cudaMalloc(&a->d_ant_steps, (chunk * a->nranks) * sizeof(int)));   // global colony: ranking reads all ranks' steps
+    if (a->nranks > 1) {
+        WR_CUDA(cudaMalloc(&a->d_local_steps, chunk * sizeof(int)));
+        a->cand_words = 2 * cap + 2;
+        WR_CUDA(cudaMalloc(&a->d_cand, a->cand_words * sizeof(uint32_t)));
+    } else a->d_local_steps = a->d_ant_steps;
     WR_CUDA(cudaMalloc(&a->d_path_ids, chunk * cap * sizeof(uint32_t)));
     WR_CUDA(cudaMalloc(&a->d_path_dirs, chunk * cap));
     WR_CUDA(cudaMalloc(&a->d_overflow, chunk * sizeof(uint32_t)));
@@ -317,7 +327,7 @@ static int launch_walk(wr_acs* a)
     w.seed_lo = (uint32_t)a->p.seed; w.seed_hi = (uint32_t)(a->p.seed >> 32);
     w.alpha = a->p.alpha; w.beta = a->p.beta; w.cap = a->cap;
     w.shard_first = a->rank * a->chunk; w.shard_chunk = a->chunk;
-    w.ant_steps = a->d_ant_steps + (a->nranks > 1 ? 0 : 0);
+    w.ant_steps = a->d_local_steps;
     w.path_ids = a->d_path_ids; w.path_dirs = a->d_path_dirs;
     w.table_log2 = a->table_log2; w.overflow_list = a->d_overflow;
     w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks;
@@ -334,43 +344,62 @@ static int launch_walk(wr_acs* a)
     return WR_OK;
 }
 
-static int launch_rank_and_update(wr_acs* a, const int* d_all_steps)
+static const uint32_t* rank_keys(const wr_acs* a) { return a->ants_in_b ? a->sort_ants.keys_b : a->sort_ants.keys_a; }
+static const uint32_t* rank_vals(const wr_acs* a) { return a->ants_in_b ? a->sort_ants.vals_b : a->sort_ants.vals_a; }
+
+// colony ranking (:273-274), best decision (:263-264), deposit eligibility and offsets (:200)
+static int launch_rank(wr_acs* a, const int* d_all_steps)
 {
     const int cm = std::max(a->colony_max, 1);
     cudaStream_t s = a->stream;
     k_rank_keys<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->cap, a->sort_ants.keys_a, a->sort_ants.vals_a);
     int st = sort_pairs(&a->sort_ants, a->dptr_colony(), a->rank_bits, s, &a->ants_in_b);
     if (st != WR_OK) return st;
-    const uint32_t* rk = a->ants_in_b ? a->sort_ants.keys_b : a->sort_ants.keys_a;
-    const uint32_t* rv = a->ants_in_b ? a->sort_ants.vals_b : a->sort_ants.vals_a;
-    k_rank_finish<<<1, 1024, 0, s>>>(a->d_state, rk, rv, a->cap, a->d_Ltab, a->d_rec_off, a->d_order);
+    k_rank_finish<<<1, 1024, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->cap, a->d_Ltab, a->d_rec_off, a->d_order);
     k_best_clear<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_onbest);
-    k_best_copy<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_path_ids, a->d_path_dirs, a->cap,
-                                  a->rank * a->chunk, (int)a->goal);
-    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    const int evap_blocks = kNumSMs * 8;
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+// deposit records of this rank's ants (:198-215), at their global (rank, step) positions
+static int launch_deposit_gen(wr_acs* a)
+{
+    cudaStream_t s = a->stream;
+    const int first = a->rank * a->chunk;
     if (a->p.update_mode == WR_UPDATE_ATOMIC) {
-        k_evaporate<<<evap_blocks, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
-        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-        k_deposit_gen<true><<<a->w_max, 128, 0, s>>>(a->d_state, rk, rv, a->d_rec_off, a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal,
-                                                     a->d_Ltab, a->d_onbest, nullptr, nullptr, a->d_tau);
+        k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
+        k_deposit_gen<true><<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_rec_off, a->d_path_ids, a->d_path_dirs, a->cap,
+                                                     first, a->chunk, (int)a->goal, a->d_Ltab, a->d_onbest, nullptr, nullptr, a->d_tau);
     } else {
-        k_deposit_gen<false><<<a->w_max, 128, 0, s>>>(a->d_state, rk, rv, a->d_rec_off, a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal,
-                                                      a->d_Ltab, a->d_onbest, a->sort_recs.keys_a, a->sort_recs.vals_a, nullptr);
-        st = sort_pairs(&a->sort_recs, a->dptr_nrec(), a->slot_bits, s, &a->recs_in_b);
-        if (st != WR_OK) return st;
-        const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
-        const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
+        k_deposit_gen<false><<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_rec_off, a->d_path_ids, a->d_path_dirs, a->cap,
+                                                      first, a->chunk, (int)a->goal, a->d_Ltab, a->d_onbest, a->sort_recs.keys_a,
+                                                      a->sort_recs.vals_a, nullptr);
+    }
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+// slot sort (stable: rank order survives inside a slot) + evaporation + deposits (:268-280)
+static int launch_update(wr_acs* a)
+{
+    cudaStream_t s = a->stream;
+    if (a->p.update_mode == WR_UPDATE_ATOMIC) {
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-        if (a->p.update_mode == WR_UPDATE_FUSED) {
-            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
-            const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
-            const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * 2);
-            k_update_fused<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
-        } else {
-            k_evaporate<<<evap_blocks, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
-            k_deposit_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, ck, cv, a->d_tau);
-        }
+        return WR_OK;   // evaporation + atomic deposits already issued by launch_deposit_gen
+    }
+    int st = sort_pairs(&a->sort_recs, a->dptr_nrec(), a->slot_bits, s, &a->recs_in_b);
+    if (st != WR_OK) return st;
+    const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
+    const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    if (a->p.update_mode == WR_UPDATE_FUSED) {
+        k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
+        const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
+        const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * 2);
+        k_update_fused<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
+    } else {
+        k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
+        k_deposit_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, ck, cv, a->d_tau);
     }
     WR_CUDA(cudaGetLastError());
     return WR_OK;
@@ -380,7 +409,7 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
 {
     WR_REQUIRE(a && n >= 0, WR_ERR_INVALID, "wr_acs_iterate: bad argument");
     WR_REQUIRE(a->begun, WR_ERR_STATE, "wr_acs_iterate: call wr_acs_begin first");
-    WR_REQUIRE(a->nranks == 1, WR_ERR_STATE, "wr_acs_iterate: sharded handles iterate through wr_acs_walk / wr_acs_update_from_gathered");
+    WR_REQUIRE(a->nranks == 1, WR_ERR_STATE, "wr_acs_iterate: a sharded handle iterates through wr_acs_walk ... wr_acs_finish_iteration");
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
     for (int it = 0; it < n; it++) {
@@ -389,11 +418,107 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
         int st = launch_walk(a);
         if (st != WR_OK) return st;
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-        st = launch_rank_and_update(a, a->d_ant_steps);
+        st = launch_rank(a, a->d_ant_steps);
+        if (st != WR_OK) return st;
+        k_best_copy<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_path_ids, a->d_path_dirs, a->cap,
+                                      0, (int)a->goal);
+        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+        st = launch_deposit_gen(a);
+        if (st != WR_OK) return st;
+        st = launch_update(a);
         if (st != WR_OK) return st;
         k_iter_end<<<1, 1, 0, s>>>(a->d_state);
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     }
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+// ---- ant sharding across ranks ------------------------------------------------------------------
+extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks)
+{
+    WR_REQUIRE(a && nranks >= 1 && rank >= 0 && rank < nranks, WR_ERR_INVALID, "wr_acs_set_shard: bad argument");
+    WR_REQUIRE(!a->begun || (a->rank == rank && a->nranks == nranks), WR_ERR_STATE, "wr_acs_set_shard: set the shard before wr_acs_begin");
+    WR_REQUIRE(nranks == 1 || a->p.update_mode != WR_UPDATE_ATOMIC, WR_ERR_INVALID, "wr_acs_set_shard: sharded colonies use the rank-ordered update modes");
+    a->rank = rank; a->nranks = nranks;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_walk(wr_acs* a)
+{
+    WR_REQUIRE(a && a->begun, WR_ERR_STATE, "wr_acs_walk: call wr_acs_begin first");
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0);
+    WR_CUDA(cudaMemsetAsync(a->d_local_steps, 0xFF, (size_t)a->chunk * sizeof(int), s));   // -1: beyond the colony
+    int st = launch_walk(a);
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    return st;
+}
+
+extern "C" int wr_acs_local_steps_dev(wr_acs* a, int** dev_steps, int* first, int* count)
+{
+    WR_REQUIRE(a && dev_steps && first && count && a->begun, WR_ERR_STATE, "wr_acs_local_steps_dev: call wr_acs_begin first");
+    *dev_steps = a->d_local_steps; *first = a->rank * a->chunk; *count = a->chunk;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_rank_global(wr_acs* a, const int* dev_all_steps)
+{
+    WR_REQUIRE(a && dev_all_steps && a->begun, WR_ERR_STATE, "wr_acs_rank_global: bad state");
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    WR_CUDA(cudaMemcpyAsync(a->d_ant_steps, dev_all_steps, (size_t)std::max(a->colony_max, 1) * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    int st = launch_rank(a, a->d_ant_steps);
+    if (st != WR_OK) return st;
+    WR_CUDA(cudaMemsetAsync(a->d_cand, 0, a->cand_words * sizeof(uint32_t), s));
+    k_best_candidate<<<8, 256, 0, s>>>(a->d_state, a->d_cand, a->d_path_ids, a->d_path_dirs, a->cap, a->rank * a->chunk, a->chunk, (int)a->goal);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+extern "C" int wr_acs_best_candidate_dev(wr_acs* a, uint32_t** dev_words, size_t* nwords)
+{
+    WR_REQUIRE(a && dev_words && nwords && a->begun, WR_ERR_STATE, "wr_acs_best_candidate_dev: bad state");
+    *dev_words = a->d_cand; *nwords = a->cand_words;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_apply_best(wr_acs* a)
+{
+    WR_REQUIRE(a && a->begun, WR_ERR_STATE, "wr_acs_apply_best: bad state");
+    cudaStream_t s = a->stream;
+    k_best_install<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_cand, a->cap);
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+extern "C" int wr_acs_build_records(wr_acs* a, uint32_t** dev_keys, uint32_t** dev_vals, int* n)
+{
+    WR_REQUIRE(a && dev_keys && dev_vals && n && a->begun, WR_ERR_STATE, "wr_acs_build_records: bad state");
+    cudaStream_t s = a->stream;
+    IterState st;
+    WR_CUDA(cudaMemcpyAsync(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost, s));
+    WR_CUDA(cudaStreamSynchronize(s));   // the one host sync of a sharded iteration: the record count sizes the all_reduce
+    *n = st.n_records;
+    if (st.n_records > 0) {
+        WR_CUDA(cudaMemsetAsync(a->sort_recs.keys_a, 0, (size_t)st.n_records * sizeof(uint32_t), s));
+        WR_CUDA(cudaMemsetAsync(a->sort_recs.vals_a, 0, (size_t)st.n_records * sizeof(uint32_t), s));
+    }
+    int rc = launch_deposit_gen(a);
+    *dev_keys = a->sort_recs.keys_a; *dev_vals = a->sort_recs.vals_a;
+    return rc;
+}
+
+extern "C" int wr_acs_finish_iteration(wr_acs* a)
+{
+    WR_REQUIRE(a && a->begun, WR_ERR_STATE, "wr_acs_finish_iteration: bad state");
+    int st = launch_update(a);
+    if (st != WR_OK) return st;
+    k_iter_end<<<1, 1, 0, a->stream>>>(a->d_state);
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), a->stream);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -562,16 +687,3 @@ extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per
     return WR_OK;
 }
 
-// ---- ant sharding (filled in with the multi-GPU step) ---------------------------------------
-extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks)
-{
-    WR_REQUIRE(a && nranks >= 1 && rank >= 0 && rank < nranks, WR_ERR_INVALID, "wr_acs_set_shard: bad argument");
-    WR_REQUIRE(!a->begun || (a->rank == rank && a->nranks == nranks), WR_ERR_STATE, "wr_acs_set_shard: set the shard before wr_acs_begin");
-    a->rank = rank; a->nranks = nranks;
-    return WR_OK;
-}
-extern "C" int wr_acs_walk(wr_acs*) { set_error("wr_acs_walk: not implemented yet"); return WR_ERR_STATE; }
-extern "C" int wr_acs_local_steps_dev(wr_acs*, int**, int*, int*) { set_error("not implemented yet"); return WR_ERR_STATE; }
-extern "C" int wr_acs_rank_global(wr_acs*, const int*) { set_error("not implemented yet"); return WR_ERR_STATE; }
-extern "C" int wr_acs_pack_top(wr_acs*, void**, size_t*, size_t*) { set_error("not implemented yet"); return WR_ERR_STATE; }
-extern "C" int wr_acs_update_from_gathered(wr_acs*, const void*, int, size_t) { set_error("not implemented yet"); return WR_ERR_STATE; }

@@ -370,6 +370,37 @@ __global__ void k_best_copy(const IterState* st, int* best_n, uint32_t* best_ids
     if (blockIdx.x == 0 && threadIdx.x == 0) *best_n = steps + 1;
 }
 
+// Sharded colonies: the rank that walked the new best ant publishes its trail in a buffer that is
+// zero everywhere else, so an integer all_reduce(SUM) hands every rank the same words.
+// Layout: [0] = 1 if filled, [1 .. cap+1] node ids (goal included), [cap+2 .. 2*cap+1] chosen slots.
+__global__ void k_best_candidate(const IterState* st, uint32_t* cand, const uint32_t* __restrict__ path_ids,
+                                 const uint8_t* __restrict__ path_dirs, int cap, int shard_first, int shard_chunk, int goal)
+{
+    if (!st->best_changed) return;
+    const int ant = st->best_ant;
+    if (ant < shard_first || ant >= shard_first + shard_chunk) return;
+    const int steps = st->best_steps;
+    const size_t off = (size_t)(ant - shard_first) * cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= steps; i += gridDim.x * blockDim.x) {
+        cand[1 + i] = i < steps ? path_ids[off + i] : (uint32_t)goal;
+        if (i < steps) cand[cap + 2 + i] = path_dirs[off + i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cand[0] = 1u;
+}
+__global__ void k_best_install(const IterState* st, int* best_n, uint32_t* best_ids, uint8_t* best_dirs, uint32_t* onbest,
+                               const uint32_t* __restrict__ cand, int cap)
+{
+    if (!st->best_changed) return;
+    const int steps = st->best_steps;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= steps; i += gridDim.x * blockDim.x) {
+        const uint32_t id = cand[1 + i];
+        best_ids[i] = id;
+        if (i < steps) best_dirs[i] = (uint8_t)cand[cap + 2 + i];
+        atomicOr(&onbest[id >> 5], 1u << (id & 31));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *best_n = steps + 1;
+}
+
 // ------------------------------------------------------------------------------------------
 // Deposit records (:198-215).  One CTA per eligible rank; record i of rank r goes to
 // rec_off[r] + i, so records are emitted in (rank, step) order and a STABLE sort by slot keeps
@@ -380,13 +411,16 @@ template <bool ATOMIC>
 __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const uint32_t* __restrict__ rank_keys,
                                                       const uint32_t* __restrict__ rank_vals, const uint32_t* __restrict__ rec_off,
                                                       const uint32_t* __restrict__ path_ids, const uint8_t* __restrict__ path_dirs, int cap,
+                                                      int shard_first, int shard_chunk,
                                                       int goal, const float* __restrict__ Ltab, const uint32_t* __restrict__ onbest,
                                                       uint32_t* __restrict__ rec_keys, uint32_t* __restrict__ rec_vals, float* tau)
 {
     const int r = blockIdx.x;
     if (r >= st->n_eligible) return;
     const int steps = (int)rank_keys[r];
-    const size_t ant = rank_vals[r];
+    const int ant_global = (int)rank_vals[r];
+    if (ant_global < shard_first || ant_global >= shard_first + shard_chunk) return;   // another rank holds this trail
+    const size_t ant = (size_t)(ant_global - shard_first);
     const int order = r + 1;
     const float lambda = st->lambda, Q = st->Q;
     const float base = __fdiv_rn(__fmul_rn(__fsub_rn(lambda, (float)order), Q), Ltab[steps]);
