@@ -458,3 +458,134 @@ class ACS_Rank(GridMap):
         except Exception:
             pass
         super().__del__()
+
+
+class ACS_GTSP:
+    """ACS_GTSP (core/ACS_GTSP.hpp:82-328): ant-colony ordering of the weld seams (a symmetric TSP
+    over the pair-length matrix), on the GPU.  `computeBatch` is the batched entry point the
+    reference lacks: B independent colonies on the same matrix, one CTA each."""
+
+    def __init__(self, seed=0):
+        self.seed = seed
+        self.city_num = 0
+        self.dis = None
+        self.cnt = 0
+        self._g = None
+        self._batch = 0
+        self.best_path = np.zeros((0, 2), np.int32)   # best.path: (r, s) per edge
+        self.best_L = float(0x3f3f3f3f)
+        self.g_path_x, self.g_path_y, self.g_path_z = [], [], []
+        self.init_flag = False
+
+    def readFromGraphFile(self, filename):
+        """ACS_GTSP.hpp:224-253: "<city_num> <cnt>" then the upper triangle, row by row."""
+        with open(filename, "r") as fp:
+            tok = fp.read().split()
+        n, cnt = int(tok[0]), int(tok[1])
+        vals = [float(t) for t in tok[2:2 + n * (n - 1) // 2]]
+        if len(vals) != n * (n - 1) // 2:
+            raise _lib.WrError(-7, "graph file holds %d of %d distances" % (len(vals), n * (n - 1) // 2))
+        dis = np.zeros((n, n), np.float64)
+        it = iter(vals)
+        for i in range(n):
+            for j in range(i + 1, n):
+                dis[i, j] = dis[j, i] = next(it)
+                print("distance: %f \r" % dis[i, j])
+        return self.setDistanceMatrix(dis, cnt)
+
+    def setDistanceMatrix(self, dis, cnt=None):
+        """In-memory variant of readFromGraphFile (the hand-off SURVEY.md §8f asks for)."""
+        dis = np.ascontiguousarray(dis, np.float64)
+        self.city_num = dis.shape[0]
+        self.dis = dis
+        self.cnt = self.city_num * (self.city_num - 1) // 2 if cnt is None else cnt
+        self._create(1)
+        self.init_flag = True
+        return True
+
+    def _create(self, batch, colony_first=0):
+        if self._g is not None:
+            lib().wr_gtsp_destroy(self._g)
+            self._g = None
+        h = C.c_void_p()
+        check(lib().wr_gtsp_create(ptr(self.dis), self.city_num, self.cnt, batch, colony_first, self.seed, C.byref(h)))
+        self._g, self._batch = h, batch
+        self.best_L = float(0x3f3f3f3f)
+
+    def tau0(self):
+        t = C.c_double()
+        check(lib().wr_gtsp_tau0(self._g, C.byref(t)))
+        return t.value
+
+    def iterate(self, n=1):
+        check(lib().wr_gtsp_iterate(self._g, n))
+
+    def best(self, colony=0):
+        n = C.c_int(); L = C.c_double()
+        tour = np.zeros(2 * self.city_num, np.int32)
+        check(lib().wr_gtsp_best(self._g, colony, ptr(tour), C.byref(n), C.byref(L)))
+        return tour[:2 * n.value].reshape(n.value, 2).copy(), L.value
+
+    def pheromone(self, colony=0):
+        out = np.zeros((self.city_num, self.city_num), np.float64)
+        check(lib().wr_gtsp_download_pheromone(self._g, colony, ptr(out)))
+        return out
+
+    def kernelMs(self):
+        out = np.zeros(3, np.float32)
+        check(lib().wr_gtsp_kernel_ms(self._g, ptr(out)))
+        return dict(info=float(out[0]), construct=float(out[1]), update=float(out[2]))
+
+    def computeSolution(self, max_iterations=None):
+        """ACS_GTSP.hpp:255-284: iterate until MAX_itera = N^2 or more than N iterations without
+        improvement."""
+        if not self.init_flag:
+            return False
+        last = float(0x3f3f3f3f)
+        bad_times = 0
+        max_it = self.city_num * self.city_num if max_iterations is None else max_iterations
+        for index_itera in range(max_it):
+            if bad_times > self.city_num:
+                break
+            self.iterate(1)
+            self.best_path, self.best_L = self.best(0)
+            print("iteration %d:Best so far = %.2f" % (index_itera, self.best_L))
+            if last > self.best_L:
+                last = self.best_L
+                bad_times = 0
+            else:
+                bad_times += 1
+        print("Best in all = %.2f" % self.best_L)
+        if len(self.best_path):
+            print("->".join(str(r + 1) for r, _ in self.best_path) + "->%d" % (self.best_path[-1][1] + 1))
+        return True
+
+    def computeBatch(self, batch, iterations, colony_first=0):
+        """B independent colonies (Philox streams colony_first .. colony_first+B-1), fixed iterations."""
+        self._create(batch, colony_first)
+        self.iterate(iterations)
+        return [self.best(b) for b in range(batch)]
+
+    def path_segment_nums(self):
+        return len(self.best_path) - 1
+
+    def read_segment(self, best_matrix, i):
+        """ACS_GTSP.hpp:303-312 (i starts from 1)."""
+        r, s = self.best_path[i - 1]
+        for node in best_matrix[r][s].getPath():
+            self.g_path_x.append(node.pt.x); self.g_path_y.append(node.pt.y); self.g_path_z.append(node.pt.z)
+
+    def read_all_segments(self, best_matrix):
+        """ACS_GTSP.hpp:286-298: the first N-1 edges of the best tour."""
+        for i in range(1, len(self.best_path)):
+            self.read_segment(best_matrix, i)
+
+    def plot_route_path(self, figureNumber=1):
+        pass
+
+    def __del__(self):
+        try:
+            if self._g is not None:
+                lib().wr_gtsp_destroy(self._g)
+        except Exception:
+            pass
