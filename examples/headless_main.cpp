@@ -1,0 +1,58 @@
+// Headless planning pipeline — the reference's "demo 3" (main.cpp:268-283, and its commented-out
+// headless twin :500-525) without CoppeliaSim, on the B200-native facade:
+//   STL -> voxel grid -> all-pairs ant-colony path search -> seam ordering -> stitched path.
+// Usage: headless_main <file.stl> [precision=0.005] [wall=10] [predict=0.5] [workdir=/tmp]
+// The reference's weld-point file is not shipped (.gitignore:43); six points on the free plane
+// x = min_x - 2*precision of the mesh box are synthesised.
+#include <stdlib.h>
+
+#include "ACSRank_3D.hpp"
+#include "read_STL.hpp"
+#include "ACS_GTSP.hpp"
+
+int main(int argc, char** argv)
+{
+    if (argc < 2) { fprintf(stderr, "usage: %s <file.stl> [precision] [wall] [predict] [workdir]\n", argv[0]); return 2; }
+    const float precision = argc > 2 ? atof(argv[2]) : 0.005f;
+    const int wall = argc > 3 ? atoi(argv[3]) : 10;
+    const float predict = argc > 4 ? atof(argv[4]) : 0.5f;
+    const std::string dir = argc > 5 ? argv[5] : "/tmp";
+    try {
+        STLReader model;
+        ACS_Rank SearchPath;
+        ACS_GTSP GlobalRoute;
+        model.readFile(argv[1]);
+        const std::vector<Triangles<float>> meshes = model.TriangleList();
+        SearchPath.creatGridMap(meshes, precision, wall, dir + "/grid_map.in");
+
+        float mn[3] = {meshes[0].vertex[0].x, meshes[0].vertex[0].y, meshes[0].vertex[0].z}, mx[3] = {mn[0], mn[1], mn[2]};
+        for (const auto& t : meshes)
+            for (int i = 0; i < 3; i++) {
+                const float v[3] = {t.vertex[i].x, t.vertex[i].y, t.vertex[i].z};
+                for (int k = 0; k < 3; k++) { mn[k] = v[k] < mn[k] ? v[k] : mn[k]; mx[k] = v[k] > mx[k] ? v[k] : mx[k]; }
+            }
+        const std::string points = dir + "/weld_points.in", graph = dir + "/graph.in";
+        FILE* fp = fopen(points.c_str(), "w");
+        if (!fp) { fprintf(stderr, "cannot write %s\n", points.c_str()); return 1; }
+        const float px = mn[0] - 2 * precision;
+        const float ys[3] = {mn[1] - 2 * precision, 0.5f * (mn[1] + mx[1]), mx[1] - 3 * precision};
+        const float zs[2] = {mn[2] - 2 * precision, mx[2] - 3 * precision};
+        fprintf(fp, "6\n");
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 2; b++) fprintf(fp, "%.6f %.6f %.6f\n", px, ys[a], zs[b]);
+        fclose(fp);
+
+        SearchPath.searchBestPathOfPoints(predict, points, graph);
+        GlobalRoute.readFromGraphFile(graph);
+        GlobalRoute.computeSolution();
+        GlobalRoute.read_all_segments(SearchPath.best_matrix);
+        uint64_t c[9];
+        SearchPath.counters(c);
+        printf("[headless] stitched path: %zu points over %d segments; last search: %llu ant-steps, %llu ants\n", GlobalRoute.g_path_x.size(),
+               GlobalRoute.path_segment_nums(), (unsigned long long)c[0], (unsigned long long)c[1]);
+    } catch (const wr::Error& e) {
+        fprintf(stderr, "[headless] %s (status %d)\n", e.what(), e.status);
+        return 1;
+    }
+    return 0;
+}
