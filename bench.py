@@ -237,7 +237,7 @@ def run_ours(args):
     # ---- kernels timed alone (burst roofline of K3) ---------------------------------------------------
     alone = {}
     if world == 1:
-        for name, which in (("fused_tma", 0), ("evaporate_float4", 1), ("d2d_copy", 2)):
+        for name, which in (("update_fused", 0), ("update_tma_ring", 3), ("evaporate_float4", 1), ("d2d_copy", 2)):
             t_ms = acs.benchKernel(which, 20)
             alone[name] = {"ms": t_ms, "GBps": UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (t_ms * 1e-3) / 1e9}
 

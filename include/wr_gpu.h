@@ -91,9 +91,10 @@ typedef struct {
 } wr_acs_params;
 
 enum {
-    WR_UPDATE_FUSED = 0,   /* one HBM pass: TMA tile in, evaporate + rank-ordered deposits, TMA tile out */
-    WR_UPDATE_SPLIT = 1,   /* float4 evaporation pass, then rank-ordered deposit pass (same bits) */
-    WR_UPDATE_ATOMIC = 2   /* evaporation pass + atomicAdd deposits (fast, order not reproducible) */
+    WR_UPDATE_FUSED = 0,     /* one HBM pass: tile streamed through registers, rank-ordered deposits applied while the tile is in L2 */
+    WR_UPDATE_SPLIT = 1,     /* float4 evaporation pass, then rank-ordered deposit pass (same bits) */
+    WR_UPDATE_ATOMIC = 2,    /* evaporation pass + atomicAdd deposits (fast, order not reproducible) */
+    WR_UPDATE_FUSED_TMA = 3  /* one HBM pass through a 4-stage TMA ring in shared memory (same bits; measurement variant) */
 };
 
 int wr_acs_default_params(wr_acs_params* p);                        /* literals of initFromGridMap :319-325 */
@@ -127,9 +128,10 @@ int wr_acs_counters(wr_acs* a, uint64_t out[9]);
 int wr_acs_kernel_ms(wr_acs* a, float out[5]);
 int wr_acs_set_timing(wr_acs* a, int enabled);
 /* measurement hook: run ONE kernel of the update path `reps` times back to back on the handle's
- * stream and report the average device time per launch (CUDA events).  which: 0 = fused TMA update
+ * stream and report the average device time per launch (CUDA events).  which: 0 = fused update
  * (evaporation + the last iteration's deposit records), 1 = float4 evaporation pass alone,
- * 2 = device-to-device copy of the pheromone field (in-run copy ceiling).  The field is
+ * 2 = device-to-device copy of the pheromone field (in-run copy ceiling), 3 = the all-TMA ring
+ * variant of the fused update (kept as a measurement point).  The field is
  * multiplied by rho each time (which 0/1), so call it on a scratch search only. */
 int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch);
 /* use an existing CUDA stream (cudaStream_t as void*); default: a private non-blocking stream */

@@ -14,7 +14,7 @@ WR_OK = 0
 STATUS = {0: "WR_OK", -1: "WR_ERR_INVALID", -2: "WR_ERR_CUDA", -3: "WR_ERR_NOMEM", -4: "WR_ERR_STATE",
           -5: "WR_ERR_NOTFOUND", -6: "WR_ERR_CAPACITY", -7: "WR_ERR_FORMAT"}
 WR_ERR_NOTFOUND = -5
-UPDATE_FUSED, UPDATE_SPLIT, UPDATE_ATOMIC = 0, 1, 2
+UPDATE_FUSED, UPDATE_SPLIT, UPDATE_ATOMIC, UPDATE_FUSED_TMA = 0, 1, 2, 3
 
 
 class WrError(RuntimeError):

@@ -441,7 +441,7 @@ class ACS_Rank(GridMap):
         return dict(walk=float(out[0]), rank=float(out[1]), deposit_build=float(out[2]), update=float(out[3]), total=float(out[4]))
 
     def benchKernel(self, which, reps=20):
-        """Average device ms of one update-path kernel run alone (0 fused TMA, 1 float4 evaporation, 2 D2D copy)."""
+        """Average device ms of one update-path kernel run alone (0 fused update, 1 float4 evaporation, 2 D2D copy, 3 all-TMA ring variant)."""
         ms = C.c_float()
         check(lib().wr_acs_bench_kernel(self._need(), which, reps, C.byref(ms)))
         return ms.value

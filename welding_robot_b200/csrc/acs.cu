@@ -199,7 +199,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     *out = nullptr;
     WR_REQUIRE(p->K == 6, WR_ERR_INVALID, "wr_acs_create: only K = 6 (the reference's neighbourhood) is implemented");
     WR_REQUIRE(p->alpha >= 0 && p->alpha < 64, WR_ERR_INVALID, "wr_acs_create: alpha out of range");
-    WR_REQUIRE(p->update_mode >= WR_UPDATE_FUSED && p->update_mode <= WR_UPDATE_ATOMIC, WR_ERR_INVALID, "wr_acs_create: bad update_mode");
+    WR_REQUIRE(p->update_mode >= WR_UPDATE_FUSED && p->update_mode <= WR_UPDATE_FUSED_TMA, WR_ERR_INVALID, "wr_acs_create: bad update_mode");
     WR_REQUIRE((unsigned long long)g->N * 6 < 0xFFFFFFFFull - kUpdTile, WR_ERR_INVALID, "wr_acs_create: grid too large for 32-bit slot ids");
     WR_REQUIRE(g->N >= 2, WR_ERR_INVALID, "wr_acs_create: grid too small");
     wr_acs* a = new wr_acs();
@@ -239,7 +239,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     WR_CUDA_A(cudaMalloc(&a->d_tile_off, ((size_t)a->ntiles + 2) * sizeof(uint32_t)));
     {
         size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
-        WR_CUDA_A(cudaFuncSetAttribute(k_update_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WR_CUDA_A(cudaFuncSetAttribute(k_update_tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         size_t ws = (((size_t)(g->rx + g->ry + g->rz) * 4 + 15) & ~(size_t)15) + ((size_t)kAntsPerCta << a->table_log2) * 12;
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         WR_CUDA_A(cudaFuncSetAttribute(k_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
@@ -394,9 +394,12 @@ static int launch_update(wr_acs* a)
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     if (a->p.update_mode == WR_UPDATE_FUSED) {
         k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
+        const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * kFusedCtasPerSm);
+        k_update_fused<<<blocks, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
+    } else if (a->p.update_mode == WR_UPDATE_FUSED_TMA) {
+        k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
         const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
-        const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * 2);
-        k_update_fused<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
+        k_update_tma_ring<<<std::min<unsigned>(a->ntiles, kNumSMs * 2), kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
     } else {
         k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
         k_deposit_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, ck, cv, a->d_tau);
@@ -653,7 +656,7 @@ extern "C" int wr_acs_kernel_ms(wr_acs* a, float out[5])
 
 extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch)
 {
-    WR_REQUIRE(a && ms_per_launch && reps > 0 && which >= 0 && which <= 2, WR_ERR_INVALID, "wr_acs_bench_kernel: bad argument");
+    WR_REQUIRE(a && ms_per_launch && reps > 0 && which >= 0 && which <= 3, WR_ERR_INVALID, "wr_acs_bench_kernel: bad argument");
     WR_REQUIRE(a->begun, WR_ERR_STATE, "wr_acs_bench_kernel: call wr_acs_begin first");
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
@@ -670,7 +673,11 @@ extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per
         if (r == 0) WR_CUDA(cudaEventRecord(e0, s));
         if (which == 0) {
             k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
-            k_update_fused<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
+            k_update_fused<<<std::min<unsigned>(a->ntiles, kNumSMs * kFusedCtasPerSm), kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv,
+                                                                                                              a->d_tile_off);
+        } else if (which == 3) {
+            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
+            k_update_tma_ring<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
         } else if (which == 1) {
             k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
         } else {

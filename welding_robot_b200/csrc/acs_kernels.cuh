@@ -441,6 +441,66 @@ __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// Rank-ordered deposit application.  Records [lo, hi) are sorted by slot and, inside a slot, by
+// rank (stable sort of records emitted in rank order); slot s lives at buf[s - base].  The float
+// additions of one slot form a dependent chain in the reference's order (tau*rho + d_1) + d_2 ...
+// Short runs are summed by the thread that owns the run head.  When the colony converges every
+// top-w ant deposits on the same few hundred slots (runs of ~0.2*colony records): those runs are
+// handed to the whole warp, which loads 32 records per request and lets the chain run on values
+// exchanged by shuffle, so the chain costs ~1 FADD per record instead of one L2 round trip.
+// Must be called by all threads of the CTA (NT = threads taking part, a multiple of 32).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void apply_runs(float* buf, uint32_t base, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                           uint32_t lo, uint32_t hi, uint32_t first, uint32_t stride)
+{
+    const int lane = threadIdx.x & 31;
+    for (uint32_t r0 = lo + first; r0 < hi; r0 += stride) {   // r0 is warp-uniform: all 32 lanes run the same trips
+        const uint32_t r = r0 + lane;
+        bool head = r < hi;
+        uint32_t key = 0;
+        if (head) { key = keys[r]; head = (r == lo) || keys[r - 1] != key; }
+        float x = 0.0f;
+        uint32_t j = r;
+        bool more = false;
+        if (head) {
+            x = buf[key - base];
+            do { x = __fadd_rn(x, __uint_as_float(vals[j])); j++; } while (j < hi && j < r + 8 && keys[j] == key);
+            more = j < hi && keys[j] == key;
+            if (!more) buf[key - base] = x;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, more);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t key0 = __shfl_sync(0xffffffffu, key, src);
+            uint32_t j0 = __shfl_sync(0xffffffffu, j, src);
+            float x0 = __shfl_sync(0xffffffffu, x, src);
+            // software pipeline: the loads of batch b+1 are in flight while the chain consumes batch b
+            uint32_t idx = j0 + lane;
+            bool valid = idx < hi && keys[idx] == key0;
+            float v = valid ? __uint_as_float(vals[idx]) : 0.0f;
+            while (true) {
+                const unsigned bm = __ballot_sync(0xffffffffu, valid);
+                const int cnt = bm == 0xffffffffu ? 32 : (__ffs(~bm) - 1);
+                const float vc = v;
+                if (cnt == 32) {   // warp-uniform
+                    idx += 32;
+                    valid = idx < hi && keys[idx] == key0;
+                    v = valid ? __uint_as_float(vals[idx]) : 0.0f;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const float t = __shfl_sync(0xffffffffu, vc, i);
+                    if (i < cnt) x0 = __fadd_rn(x0, t);
+                }
+                if (cnt < 32) break;
+            }
+            if (lane == src) buf[key0 - base] = x0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3 split variants
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_evaporate(float4* __restrict__ tau4, size_t n4, float rho)
@@ -452,25 +512,21 @@ __global__ void __launch_bounds__(256) k_evaporate(float4* __restrict__ tau4, si
     }
 }
 
-__global__ void k_deposit_apply(const IterState* st, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, float* tau)
+__global__ void __launch_bounds__(256) k_deposit_apply(const IterState* st, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, float* tau)
 {
-    const int n = st->n_records;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t key = keys[i];
-        if (i > 0 && keys[i - 1] == key) continue;   // not the head of its slot run
-        float t = tau[key];
-        int j = i;
-        do { t = __fadd_rn(t, __uint_as_float(vals[j])); j++; } while (j < n && keys[j] == key);
-        tau[key] = t;
-    }
+    const uint32_t n = (uint32_t)st->n_records;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    apply_runs(tau, 0u, keys, vals, 0u, n, warp * 32u, nwarps * 32u);
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 fused: evaporation + rank-ordered deposits in a single HBM pass.
-// Persistent CTAs stream the pheromone field in 16 KB tiles: TMA bulk load into a 4-stage
-// shared-memory ring (mbarrier completion), scale in place, apply the tile's (slot-sorted)
-// deposit runs in place, TMA bulk store back.  tile_off[t] .. tile_off[t+1] delimit tile t's
-// records (k_tile_offsets, binary search over the sorted slot keys).
+// K3 fused: evaporation + rank-ordered deposits in a single HBM pass over the pheromone field, in
+// 16 KB tiles.  tile_off[t] .. tile_off[t+1] delimit tile t's (slot-sorted) records
+// (k_tile_offsets, binary search).  Two variants:
+//   k_update_tma_ring  every tile goes through a 4-stage TMA ring in shared memory (first design;
+//                      kept as a measurement point: 63 % of the measured copy bandwidth);
+//   k_update_fused     the shipped kernel, below.
 // ------------------------------------------------------------------------------------------
 __global__ void k_tile_offsets(const IterState* st, const uint32_t* __restrict__ keys, uint32_t* __restrict__ tile_off, unsigned ntiles)
 {
@@ -486,8 +542,8 @@ __global__ void k_tile_offsets(const IterState* st, const uint32_t* __restrict__
     tile_off[t] = (uint32_t)lo;
 }
 
-__global__ void __launch_bounds__(kUpdThreads) k_update_fused(float* tau, unsigned ntiles, float rho, const uint32_t* __restrict__ rec_keys,
-                                                               const uint32_t* __restrict__ rec_vals, const uint32_t* __restrict__ tile_off)
+__global__ void __launch_bounds__(kUpdThreads) k_update_tma_ring(float* tau, unsigned ntiles, float rho, const uint32_t* __restrict__ rec_keys,
+                                                                  const uint32_t* __restrict__ rec_vals, const uint32_t* __restrict__ tile_off)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);                                  // [kUpdStages][kUpdTile]
@@ -498,8 +554,11 @@ __global__ void __launch_bounds__(kUpdThreads) k_update_fused(float* tau, unsign
         tma::fence_barrier_init();
     }
     __syncthreads();
-    const unsigned first = blockIdx.x, stride = gridDim.x;
-    const unsigned cnt = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+    // contiguous tile range per CTA: a path's hot tiles are a fixed stride apart (one z-plane = 96 tiles at
+    // 256^3), which a round-robin assignment folds onto a few CTAs
+    const unsigned per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const unsigned first = blockIdx.x * per, stride = 1;
+    const unsigned cnt = first < ntiles ? min(per, ntiles - first) : 0;
     constexpr uint32_t kBytes = kUpdTile * sizeof(float);
     if (tid == 0) {
         for (unsigned i = 0; i < (unsigned)(kUpdStages - 1) && i < cnt; i++) {
@@ -522,15 +581,7 @@ __global__ void __launch_bounds__(kUpdThreads) k_update_fused(float* tau, unsign
         const uint32_t lo = tile_off[t], hi = tile_off[t + 1];
         if (lo < hi) {   // block-uniform
             __syncthreads();
-            const uint32_t tbase = t * (uint32_t)kUpdTile;
-            for (uint32_t r = lo + tid; r < hi; r += kUpdThreads) {
-                const uint32_t key = rec_keys[r];
-                if (r > lo && rec_keys[r - 1] == key) continue;
-                float x = buf[key - tbase];
-                uint32_t j = r;
-                do { x = __fadd_rn(x, __uint_as_float(rec_vals[j])); j++; } while (j < hi && rec_keys[j] == key);
-                buf[key - tbase] = x;
-            }
+            apply_runs(buf, t * (uint32_t)kUpdTile, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads);
         }
         tma::fence_proxy_async();   // generic-proxy writes -> visible to the bulk store
         __syncthreads();
@@ -547,6 +598,48 @@ __global__ void __launch_bounds__(kUpdThreads) k_update_fused(float* tau, unsign
         }
     }
     if (tid == 0) tma::bulk_wait<0>();
+}
+
+// The shipped fused update.  A CTA owns a contiguous run of 16 KB tiles.  Every tile is streamed
+// register-to-register: 4 independent LDG.128 per thread, scale, STG.128 (the instruction mix that
+// reaches 95 % of the copy bandwidth in k_evaporate).  If the tile receives deposits (< 5 % of the
+// tiles), the CTA synchronises and applies the tile's rank-ordered deposit runs straight away with
+// read-modify-writes that hit the lines it has just written (still dirty in L2), so every slot still
+// costs one HBM read and one HBM write.  Tiles with deposits are processed first: their dependent
+// add chains are the long pole and the plain streaming of the rest of the grid hides them.
+// Measured against the all-TMA ring above in profiles/ (the ring pays a load round trip per
+// deposit tile; this variant does not stage anything).
+constexpr int kFusedCtasPerSm = 8;
+__global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(float* tau, unsigned ntiles, float rho,
+                                                                                const uint32_t* __restrict__ rec_keys,
+                                                                                const uint32_t* __restrict__ rec_vals,
+                                                                                const uint32_t* __restrict__ tile_off)
+{
+    const int tid = threadIdx.x;
+    const unsigned per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const unsigned first = blockIdx.x * per;
+    const unsigned cnt = first < ntiles ? min(per, ntiles - first) : 0;
+    constexpr int kVec = kUpdTile / 4 / kUpdThreads;   // float4 per thread per tile
+    for (int pass = 0; pass < 2; pass++) {
+        for (unsigned i = 0; i < cnt; i++) {
+            const unsigned t = first + i;
+            const uint32_t lo = tile_off[t], hi = tile_off[t + 1];
+            if ((lo == hi) != (pass == 1)) continue;   // block-uniform
+            float4* g4 = reinterpret_cast<float4*>(tau + (size_t)t * kUpdTile);
+            float4 v[kVec];
+#pragma unroll
+            for (int j = 0; j < kVec; j++) v[j] = g4[j * kUpdThreads + tid];
+#pragma unroll
+            for (int j = 0; j < kVec; j++) {
+                v[j].x = __fmul_rn(v[j].x, rho); v[j].y = __fmul_rn(v[j].y, rho); v[j].z = __fmul_rn(v[j].z, rho); v[j].w = __fmul_rn(v[j].w, rho);
+                g4[j * kUpdThreads + tid] = v[j];
+            }
+            if (pass == 0) {
+                __syncthreads();   // the scaled tile is visible to the whole CTA
+                apply_runs(tau, 0u, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads);
+            }
+        }
+    }
 }
 
 // reset() :307-315 and the initial field of initFromGridMap :391-401
