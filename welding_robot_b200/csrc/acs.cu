@@ -96,6 +96,8 @@ struct wr_acs {
     uint32_t* d_rec_off = nullptr;
     int* d_order = nullptr;
     uint32_t* d_tile_off = nullptr;
+    uint32_t* d_dep_list = nullptr;   // tiles that receive deposits this iteration
+    uint32_t* d_upd_q = nullptr;      // [0] deposit-tile queue [1] plain-chunk queue [2] deposit-tile count
     SortPlan sort_ants, sort_recs;
     bool ants_in_b = false, recs_in_b = false;
     size_t alloc_colony = 0;
@@ -184,7 +186,7 @@ extern "C" int wr_acs_destroy(wr_acs* a)
     if (a->stream) cudaStreamSynchronize(a->stream);
     free_colony_buffers(a);
     cudaFree(a->d_tau); cudaFree(a->d_state); cudaFree(a->d_onbest); cudaFree(a->d_Ltab);
-    cudaFree(a->d_best_n); cudaFree(a->d_best_ids); cudaFree(a->d_best_dirs); cudaFree(a->d_tile_off);
+    cudaFree(a->d_best_n); cudaFree(a->d_best_ids); cudaFree(a->d_best_dirs); cudaFree(a->d_tile_off); cudaFree(a->d_dep_list); cudaFree(a->d_upd_q);
     if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
     delete a;
     return WR_OK;
@@ -237,6 +239,8 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     WR_CUDA_A(cudaMalloc(&a->d_best_ids, ((size_t)a->cap + 2) * sizeof(uint32_t)));
     WR_CUDA_A(cudaMalloc(&a->d_best_dirs, (size_t)a->cap + 2));
     WR_CUDA_A(cudaMalloc(&a->d_tile_off, ((size_t)a->ntiles + 2) * sizeof(uint32_t)));
+    WR_CUDA_A(cudaMalloc(&a->d_dep_list, ((size_t)a->ntiles + 2) * sizeof(uint32_t)));
+    WR_CUDA_A(cudaMalloc(&a->d_upd_q, 4 * sizeof(uint32_t)));
     {
         size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
         WR_CUDA_A(cudaFuncSetAttribute(k_update_tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -379,6 +383,17 @@ static int launch_deposit_gen(wr_acs* a)
     return WR_OK;
 }
 
+// K3, shipped variant: tile offsets + list of deposit tiles, then the fused single-pass update
+static int launch_fused(wr_acs* a, const uint32_t* ck, const uint32_t* cv)
+{
+    cudaStream_t s = a->stream;
+    WR_CUDA(cudaMemsetAsync(a->d_upd_q, 0, 4 * sizeof(uint32_t), s));
+    k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles, a->d_dep_list, a->d_upd_q + 2);
+    k_update_fused<<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
 // slot sort (stable: rank order survives inside a slot) + evaporation + deposits (:268-280)
 static int launch_update(wr_acs* a)
 {
@@ -393,11 +408,10 @@ static int launch_update(wr_acs* a)
     const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     if (a->p.update_mode == WR_UPDATE_FUSED) {
-        k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
-        const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * kFusedCtasPerSm);
-        k_update_fused<<<blocks, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
+        int rc = launch_fused(a, ck, cv);
+        if (rc != WR_OK) return rc;
     } else if (a->p.update_mode == WR_UPDATE_FUSED_TMA) {
-        k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
+        k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
         const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
         k_update_tma_ring<<<std::min<unsigned>(a->ntiles, kNumSMs * 2), kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
     } else {
@@ -672,11 +686,10 @@ extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per
     for (int r = -1; r < reps; r++) {   // one untimed warm-up launch
         if (r == 0) WR_CUDA(cudaEventRecord(e0, s));
         if (which == 0) {
-            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
-            k_update_fused<<<std::min<unsigned>(a->ntiles, kNumSMs * kFusedCtasPerSm), kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv,
-                                                                                                              a->d_tile_off);
+            int rc = launch_fused(a, ck, cv);
+            if (rc != WR_OK) return rc;
         } else if (which == 3) {
-            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles);
+            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
             k_update_tma_ring<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
         } else if (which == 1) {
             k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);

@@ -475,25 +475,55 @@ __device__ __forceinline__ void apply_runs(float* buf, uint32_t base, const uint
             const uint32_t key0 = __shfl_sync(0xffffffffu, key, src);
             uint32_t j0 = __shfl_sync(0xffffffffu, j, src);
             float x0 = __shfl_sync(0xffffffffu, x, src);
-            // software pipeline: the loads of batch b+1 are in flight while the chain consumes batch b
-            uint32_t idx = j0 + lane;
-            bool valid = idx < hi && keys[idx] == key0;
-            float v = valid ? __uint_as_float(vals[idx]) : 0.0f;
+            // The chain only needs the values in order; their loads do not depend on it.  A round fetches
+            // kRound*32 records (kRound independent coalesced requests per array) and the next round is in
+            // flight while the chain consumes the current one: one memory round trip per 256 records even
+            // when the streaming part of the kernel keeps HBM saturated (loaded latency of microseconds).
+            constexpr int kRound = 8;
+            float v[kRound];
+            unsigned ok = 0;   // bit b: this lane's record of batch b belongs to the run
+#pragma unroll
+            for (int q = 0; q < kRound; q++) {
+                const uint32_t idx = j0 + q * 32 + lane;
+                const bool valid = idx < hi && keys[idx] == key0;
+                v[q] = valid ? __uint_as_float(vals[idx]) : 0.0f;
+                ok |= (valid ? 1u : 0u) << q;
+            }
             while (true) {
-                const unsigned bm = __ballot_sync(0xffffffffu, valid);
-                const int cnt = bm == 0xffffffffu ? 32 : (__ffs(~bm) - 1);
-                const float vc = v;
-                if (cnt == 32) {   // warp-uniform
-                    idx += 32;
-                    valid = idx < hi && keys[idx] == key0;
-                    v = valid ? __uint_as_float(vals[idx]) : 0.0f;
+                int cnt = 0;
+                bool open = true;
+#pragma unroll
+                for (int q = 0; q < kRound; q++) {
+                    const unsigned bm = __ballot_sync(0xffffffffu, (ok >> q) & 1u);
+                    const int c = bm == 0xffffffffu ? 32 : (__ffs(~bm) - 1);
+                    if (open) cnt += c;
+                    open = open && c == 32;
+                }
+                float vc[kRound];
+#pragma unroll
+                for (int q = 0; q < kRound; q++) vc[q] = v[q];
+                if (open) {   // warp-uniform: the run continues past this round
+                    j0 += kRound * 32;
+                    ok = 0;
+#pragma unroll
+                    for (int q = 0; q < kRound; q++) {
+                        const uint32_t idx = j0 + q * 32 + lane;
+                        const bool valid = idx < hi && keys[idx] == key0;
+                        v[q] = valid ? __uint_as_float(vals[idx]) : 0.0f;
+                        ok |= (valid ? 1u : 0u) << q;
+                    }
                 }
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const float t = __shfl_sync(0xffffffffu, vc, i);
-                    if (i < cnt) x0 = __fadd_rn(x0, t);
+                for (int q = 0; q < kRound; q++) {
+                    if (q * 32 < cnt) {   // warp-uniform
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const float t = __shfl_sync(0xffffffffu, vc[q], i);
+                            if (q * 32 + i < cnt) x0 = __fadd_rn(x0, t);
+                        }
+                    }
                 }
-                if (cnt < 32) break;
+                if (!open) break;
             }
             if (lane == src) buf[key0 - base] = x0;
         }
@@ -528,18 +558,25 @@ __global__ void __launch_bounds__(256) k_deposit_apply(const IterState* st, cons
 //                      kept as a measurement point: 63 % of the measured copy bandwidth);
 //   k_update_fused     the shipped kernel, below.
 // ------------------------------------------------------------------------------------------
-__global__ void k_tile_offsets(const IterState* st, const uint32_t* __restrict__ keys, uint32_t* __restrict__ tile_off, unsigned ntiles)
+__device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys, int n, unsigned long long target)
 {
-    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > ntiles) return;
-    const int n = st->n_records;
-    const unsigned long long target = (unsigned long long)t * kUpdTile;
     int lo = 0, hi = n;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if ((unsigned long long)keys[mid] < target) lo = mid + 1; else hi = mid;
     }
+    return lo;
+}
+// tile_off[t] = first record of tile t (t = 0 .. ntiles); optionally the list of tiles that receive deposits
+__global__ void k_tile_offsets(const IterState* st, const uint32_t* __restrict__ keys, uint32_t* __restrict__ tile_off, unsigned ntiles,
+                               uint32_t* __restrict__ dep_list, uint32_t* dep_n)
+{
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    const int n = st->n_records;
+    const int lo = lower_bound_key(keys, n, (unsigned long long)t * kUpdTile);
     tile_off[t] = (uint32_t)lo;
+    if (dep_list && t < ntiles && lo < n && (unsigned long long)keys[lo] < (unsigned long long)(t + 1) * kUpdTile) dep_list[atomicAdd(dep_n, 1u)] = t;
 }
 
 __global__ void __launch_bounds__(kUpdThreads) k_update_tma_ring(float* tau, unsigned ntiles, float rho, const uint32_t* __restrict__ rec_keys,
@@ -609,36 +646,59 @@ __global__ void __launch_bounds__(kUpdThreads) k_update_tma_ring(float* tau, uns
 // add chains are the long pole and the plain streaming of the rest of the grid hides them.
 // Measured against the all-TMA ring above in profiles/ (the ring pays a load round trip per
 // deposit tile; this variant does not stage anything).
-constexpr int kFusedCtasPerSm = 8;
+constexpr int kFusedCtasPerSm = 5;   // 48 registers per thread (the warp-cooperative chain) -> 5 x 256 threads per SM
+constexpr int kFusedChunk = 8;       // plain tiles per queue grab (128 KB)
+
+__device__ __forceinline__ void stream_tile(float* tau, unsigned t, float rho, int tid)
+{
+    constexpr int kVec = kUpdTile / 4 / kUpdThreads;   // float4 per thread per tile
+    float4* g4 = reinterpret_cast<float4*>(tau + (size_t)t * kUpdTile);
+    float4 v[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; j++) v[j] = g4[j * kUpdThreads + tid];
+#pragma unroll
+    for (int j = 0; j < kVec; j++) {
+        v[j].x = __fmul_rn(v[j].x, rho); v[j].y = __fmul_rn(v[j].y, rho); v[j].z = __fmul_rn(v[j].z, rho); v[j].w = __fmul_rn(v[j].w, rho);
+        g4[j * kUpdThreads + tid] = v[j];
+    }
+}
+
+// q[0]: queue of deposit tiles, q[1]: queue of plain-tile chunks, q[2]: number of deposit tiles (all zeroed
+// before k_tile_offsets).  Work is handed out dynamically: a CTA that sits on a long deposit chain simply
+// takes fewer tiles, so the chain is hidden behind the other CTAs' streaming instead of extending the kernel.
 __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(float* tau, unsigned ntiles, float rho,
                                                                                 const uint32_t* __restrict__ rec_keys,
                                                                                 const uint32_t* __restrict__ rec_vals,
-                                                                                const uint32_t* __restrict__ tile_off)
+                                                                                const uint32_t* __restrict__ tile_off,
+                                                                                const uint32_t* __restrict__ dep_list, uint32_t* q)
 {
+    __shared__ unsigned s_next;
+    __shared__ uint32_t s_off[kFusedChunk + 1];
     const int tid = threadIdx.x;
-    const unsigned per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const unsigned first = blockIdx.x * per;
-    const unsigned cnt = first < ntiles ? min(per, ntiles - first) : 0;
-    constexpr int kVec = kUpdTile / 4 / kUpdThreads;   // float4 per thread per tile
-    for (int pass = 0; pass < 2; pass++) {
-        for (unsigned i = 0; i < cnt; i++) {
-            const unsigned t = first + i;
-            const uint32_t lo = tile_off[t], hi = tile_off[t + 1];
-            if ((lo == hi) != (pass == 1)) continue;   // block-uniform
-            float4* g4 = reinterpret_cast<float4*>(tau + (size_t)t * kUpdTile);
-            float4 v[kVec];
-#pragma unroll
-            for (int j = 0; j < kVec; j++) v[j] = g4[j * kUpdThreads + tid];
-#pragma unroll
-            for (int j = 0; j < kVec; j++) {
-                v[j].x = __fmul_rn(v[j].x, rho); v[j].y = __fmul_rn(v[j].y, rho); v[j].z = __fmul_rn(v[j].z, rho); v[j].w = __fmul_rn(v[j].w, rho);
-                g4[j * kUpdThreads + tid] = v[j];
-            }
-            if (pass == 0) {
-                __syncthreads();   // the scaled tile is visible to the whole CTA
-                apply_runs(tau, 0u, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads);
-            }
-        }
+    const unsigned dep_n = q[2];
+    while (true) {   // ---- tiles that receive deposits, first ----
+        if (tid == 0) s_next = atomicAdd(&q[0], 1u);
+        __syncthreads();
+        const unsigned i = s_next;
+        __syncthreads();
+        if (i >= dep_n) break;
+        const unsigned t = dep_list[i];
+        const uint32_t lo = tile_off[t], hi = tile_off[t + 1];
+        stream_tile(tau, t, rho, tid);
+        __syncthreads();   // the scaled tile is visible to the whole CTA
+        apply_runs(tau, 0u, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads);
+    }
+    while (true) {   // ---- everything else: pure streaming ----
+        if (tid == 0) s_next = atomicAdd(&q[1], (unsigned)kFusedChunk);
+        __syncthreads();
+        const unsigned c0 = s_next;
+        if (c0 < ntiles && tid <= kFusedChunk) s_off[tid] = tile_off[min(c0 + tid, ntiles)];
+        __syncthreads();
+        if (c0 >= ntiles) break;
+        const unsigned c1 = min(c0 + kFusedChunk, ntiles);
+        for (unsigned t = c0; t < c1; t++)
+            if (s_off[t - c0] == s_off[t - c0 + 1]) stream_tile(tau, t, rho, tid);
+        __syncthreads();   // s_off / s_next are reused by the next grab
     }
 }
 
