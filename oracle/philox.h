@@ -53,4 +53,16 @@ static inline uint32_t wr_rand31(uint64_t seed, uint32_t a, uint32_t b, uint32_t
     return out[0] >> 1;
 }
 
+/* The 3-D search's keyed stream: one Philox block serves 4 consecutive steps of an ant —
+ * draw(iteration, ant, step) = word (step & 3) of Philox(counter = (iteration, ant, step >> 2, stream)) >> 1.
+ * Still a pure function of (seed; iteration, ant, step); the GPU evaluates a block once per 4 steps. */
+static inline uint32_t wr_rand31_step(uint64_t seed, uint32_t iteration, uint32_t ant, uint32_t step, uint32_t stream)
+{
+    uint32_t ctr[4] = {iteration, ant, step >> 2, stream};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t out[4];
+    wr_philox4x32_10(ctr, key, out);
+    return out[step & 3] >> 1;
+}
+
 #endif

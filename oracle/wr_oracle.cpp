@@ -358,7 +358,7 @@ static inline uint32_t draw31(wro_acs* a, uint32_t iter, uint32_t ant, uint32_t 
         uint64_t n = a->seq_calls++;
         return wr_rand31(a->p.seed, (uint32_t)n, (uint32_t)(n >> 32), 0, WR_STREAM_SEQ);
     }
-    return wr_rand31(a->p.seed, iter, ant, step, WR_STREAM_ACS3D);
+    return wr_rand31_step(a->p.seed, iter, ant, step, WR_STREAM_ACS3D);
 }
 
 /* One construction step — :134-193.  Returns 1: moved and not at the goal, 0: stop.

@@ -244,7 +244,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     {
         size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
         WR_CUDA_A(cudaFuncSetAttribute(k_update_tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        size_t ws = (((size_t)(g->rx + g->ry + g->rz) * 4 + 15) & ~(size_t)15) + ((size_t)kAntsPerCta << a->table_log2) * 12;
+        size_t ws = (((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15) + ((size_t)kAntsPerCta << a->table_log2) * 12;
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         WR_CUDA_A(cudaFuncSetAttribute(k_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
     }
@@ -335,7 +335,7 @@ static int launch_walk(wr_acs* a)
     w.path_ids = a->d_path_ids; w.path_dirs = a->d_path_dirs;
     w.table_log2 = a->table_log2; w.overflow_list = a->d_overflow;
     w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks;
-    const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz) * 4 + 15) & ~(size_t)15;
+    const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15;   // + guard elements
     const size_t smem1 = coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem1 + 1024)));
     const int blocks1 = std::max(1, std::min((a->chunk + kAntsPerCta - 1) / kAntsPerCta, kNumSMs * std::min(per_sm, 16)));

@@ -88,14 +88,22 @@ __global__ void k_iter_end(IterState* st)
 __global__ void k_queue_reset(IterState* st) { st->queue = 0; }
 
 // ------------------------------------------------------------------------------------------
-// K2: one ant per 8-lane group, 4 ants per warp, 16 per CTA; persistent groups pull ants from a
-// device-side queue.  Lane k < 6 owns neighbour slot k: it loads tau[cur][k] (the six lanes of a
-// group read 24 contiguous bytes: one coalesced request), probes the visited set for its
-// neighbour and evaluates tau^alpha * (1 + beta*cos).  The roulette needs the reference's exact
-// summation order (ascending for `total`, descending for `prob_sum`), so the six scores are
-// exchanged with shuffles and every lane re-adds them sequentially — 11 dependent FADDs, cheap
-// next to the pheromone gather.  The Philox draw for (iteration, ant, step) does not depend on
-// the loads and overlaps them.
+// K2: one ant per 8-lane group, 4 ants per warp, 16 per CTA; persistent warps pull 4 ants at a time
+// from a device-side queue and step them in LOCKSTEP, so every warp collective runs with the full
+// mask (one SHFL / VOTE instruction each; sub-warp masks held in registers make the compiler emit a
+// MATCH/REDUX/WARPSYNC sequence per collective — measured 421 instructions per warp-step, see
+// profiles/).  A step is straight-line predicated code: an ant that has arrived or died just idles
+// until its three warp mates are done.
+//
+// Lane k < 6 owns neighbour slot k: it loads tau[cur][k] (the six lanes of a group read 24
+// contiguous bytes: one coalesced request), probes the visited set for its neighbour and evaluates
+// tau^alpha * (1 + beta*cos).  The roulette needs the reference's exact summation order (ascending
+// for `total`, descending for `prob_sum`), so the six scores are exchanged with width-8 shuffles and
+// every lane re-adds them sequentially — two chains of 6 dependent FADDs, cheap next to the
+// pheromone gather.  Non-candidates carry info = +0, which is the identity of the chain.
+// The walk of one ant is a chain of dependent steps, so with a few thousand ants the kernel is
+// bound by the latency of one step, not by bandwidth: everything in the step is about a short
+// critical path (one Philox call per 4 steps, |d| instead of sqrt(d*d), unconditional first probe).
 //
 // Visited set ("tabu", std::set at :70): an open-addressed hash of 4x4x4-node tiles, 64-bit
 // occupancy mask per tile, in shared memory.  A lattice walk re-visits the same few tiles, so a
@@ -103,20 +111,27 @@ __global__ void k_queue_reset(IterState* st) { st->queue = 0; }
 // re-run from scratch by pass 2 (GLOBAL = true) with a table in HBM sized for the step cap —
 // exact, because its draws are a pure function of (iteration, ant, step).
 // ------------------------------------------------------------------------------------------
+__device__ __noinline__ float slow_norm1(float d) { return __fsqrt_rn(__fmul_rn(d, d)); }
+
 template <bool GLOBAL>
 __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* xs = reinterpret_cast<float*>(smem_raw);
-    float* ys = xs + a.rx;
-    float* zs = ys + a.ry;
-    const int ncoord = a.rx + a.ry + a.rz;
-    for (int i = threadIdx.x; i < ncoord; i += kWalkThreads) xs[i] = a.coords[i];
+    // coordinate tables with one guard element on each side (out-of-bounds neighbour lanes read them)
+    float* xs = reinterpret_cast<float*>(smem_raw) + 1;
+    float* ys = xs + a.rx + 2;
+    float* zs = ys + a.ry + 2;
+    const int ncoord = a.rx + a.ry + a.rz + 6;
+    for (int i = threadIdx.x; i < ncoord; i += kWalkThreads) reinterpret_cast<float*>(smem_raw)[i] = 0.0f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.rx; i += kWalkThreads) xs[i] = a.coords[i];
+    for (int i = threadIdx.x; i < a.ry; i += kWalkThreads) ys[i] = a.coords[a.rx + i];
+    for (int i = threadIdx.x; i < a.rz; i += kWalkThreads) zs[i] = a.coords[a.rx + a.ry + i];
     __syncthreads();
 
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int gbase = lane & 24;
-    const unsigned gmask = 0xFFu << gbase;
     const int k = lane & 7;
     const int g = threadIdx.x >> 3;
     const int E = 1 << a.table_log2;
@@ -139,29 +154,35 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
     const int TX = (rx + 3) >> 2, TY = (ry + 3) >> 2;
     const int dxk = (k == 3) - (k == 2), dyk = (k == 4) - (k == 1), dzk = (k == 5) - (k == 0);
     const int stride_k = dxk + dyk * rx + dzk * rxy;
+    const int axis_k = (k == 2 || k == 3) ? 0 : ((k == 1 || k == 4) ? 1 : 2);   // which component of b is non-zero
 
     const int sz = a.start / rxy, sy = (a.start % rxy) / rx, sx = a.start % rx;
     const int gz = a.goal / rxy, gy = (a.goal % rxy) / rx, gx = a.goal % rx;
     const float gxc = xs[gx], gyc = ys[gy], gzc = zs[gz];
+    const bool alpha1 = a.alpha == 1;
+    const float beta = a.beta;
 
     IterState* st = a.st;
     const int colony = st->colony;
     const uint32_t iter = (uint32_t)st->iter;
     int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
     if (GLOBAL) local_n = (int)st->overflow_n;
+    const int limit = (E >> 2) * 3;
 
     unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
 
     while (true) {
-        unsigned q = 0;
-        if (k == 0) q = atomicAdd(&st->queue, 1u);
-        q = __shfl_sync(gmask, q, gbase);
-        if (q >= (unsigned)local_n) break;
-        const int ant_local = GLOBAL ? (int)a.overflow_list[q] : (int)q;
+        unsigned q0 = 0;
+        if (lane == 0) q0 = atomicAdd(&st->queue, 4u);
+        q0 = __shfl_sync(FULL, q0, 0);
+        if (q0 >= (unsigned)local_n) break;                       // warp-uniform
+        const unsigned q = q0 + (unsigned)(lane >> 3);
+        const bool has = q < (unsigned)local_n;
+        const int ant_local = has ? (GLOBAL ? (int)a.overflow_list[q] : (int)q) : 0;
         const uint32_t ant_global = (uint32_t)(a.shard_first + ant_local);
 
         for (int i = k; i < E; i += kGroup) keys[i] = kEmptyKey;
-        __syncwarp(gmask);
+        __syncwarp();
         int cur = a.start, x = sx, y = sy, z = sz, steps = 0, ntiles = 1;
         if (k == 0) {   // addStartNode :81-86
             uint32_t tile = (uint32_t)(((z >> 2) * TY + (y >> 2)) * TX + (x >> 2));
@@ -169,100 +190,104 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             unsigned slot = (tile * 2654435761u) >> hshift;
             keys[slot] = tile; masks[slot] = 1ull << bit;
         }
-        __syncwarp(gmask);
+        __syncwarp();
 
-        int result;  // >=0 steps (arrived), -1 dead, -2 pending
+        bool live = has;
+        int result = -1;   // >= 0: steps of an ant that arrived, -1: dead, -2: pending (table overflow -> pass 2)
         uint32_t* pid = a.path_ids + (size_t)ant_local * a.cap;
         uint8_t* pdir = a.path_dirs + (size_t)ant_local * a.cap;
-        while (true) {
-            if (steps >= a.cap) { result = -1; c_cap++; break; }
-            // ---- issue the loads of this step --------------------------------------------
+        uint32_t rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0;
+
+        while (__any_sync(FULL, live)) {
+            // ---- step cap (a deviation the oracle mirrors; the reference is unbounded) ------------
+            if (live && steps >= a.cap) { live = false; c_cap++; }
+            // ---- the loads of this step ---------------------------------------------------------
             const unsigned open = a.open6[cur];
             const float tau_k = (k < 6) ? __ldg(a.tau + (size_t)cur * 6 + k) : 0.0f;
-            // ---- Philox draw, rnd = (float)rand()/(float)RAND_MAX (:169) ------------------
-            const uint32_t r31 = rand31(a.seed_lo, a.seed_hi, iter, ant_global, (uint32_t)steps, kStreamAcs3D);
-            const float u = __fdiv_rn(__int2float_rn((int)r31), 2147483648.0f);
-            // ---- neighbour k: bounds+free (open mask), tabu probe ------------------------
+            // ---- Philox: one call yields the draws of 4 consecutive steps (live ants of a warp are in
+            //      lockstep, so the branch is warp-uniform) ------------------------------------------
+            if (live && (steps & 3) == 0) philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
+            const uint32_t rsel = (steps & 2) ? ((steps & 1) ? rw3 : rw2) : ((steps & 1) ? rw1 : rw0);
+            const float u = __fdiv_rn(__int2float_rn((int)(rsel >> 1)), 2147483648.0f);   // (float)rand()/(float)RAND_MAX (:169)
+            // ---- neighbour k: bounds+free (open mask), tabu probe -------------------------------
             const int nx = x + dxk, ny = y + dyk, nz = z + dzk;
             const int nid = cur + stride_k;
             const bool open_k = (k < 6) && ((open >> k) & 1u);
-            bool found = false;
-            unsigned slot = 0, bit = 0;
-            uint32_t tile = 0;
-            bool vis = false;
-            if (open_k) {
-                tile = (uint32_t)(((nz >> 2) * TY + (ny >> 2)) * TX + (nx >> 2));
-                bit = ((nz & 3) << 4) | ((ny & 3) << 2) | (nx & 3);
-                slot = (tile * 2654435761u) >> hshift;
-                while (true) {
-                    uint32_t kk = keys[slot];
-                    if (kk == tile) { found = true; break; }
-                    if (kk == kEmptyKey) break;
-                    slot = (slot + 1) & (E - 1);
-                }
-                vis = found && ((masks[slot] >> bit) & 1ull);
+            const uint32_t tile = (uint32_t)(((nz >> 2) * TY + (ny >> 2)) * TX + (nx >> 2));
+            const unsigned bit = ((nz & 3) << 4) | ((ny & 3) << 2) | (nx & 3);
+            unsigned slot = (tile * 2654435761u) >> hshift;
+            uint32_t kk = keys[slot];
+            unsigned long long mm = masks[slot];
+            while (open_k && kk != tile && kk != kEmptyKey) {   // collisions are rare at load <= 3/4
+                slot = (slot + 1) & (E - 1);
+                kk = keys[slot]; mm = masks[slot];
             }
-            const bool cand = open_k && !vis;
-            // ---- info = tau^alpha * (1 + beta*cos)  (:151-154) ---------------------------
-            float info = 0.0f;
-            if (cand) {
-                const float cx = xs[x], cy = ys[y], cz = zs[z];
-                const float ax = __fsub_rn(gxc, cx), ay = __fsub_rn(gyc, cy), az = __fsub_rn(gzc, cz);
-                const float bx = __fsub_rn(xs[nx], cx), by = __fsub_rn(ys[ny], cy), bz = __fsub_rn(zs[nz], cz);
-                const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
-                const float nb = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz)));
-                const float dot = __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
-                const float cosv = __fdiv_rn(dot, __fmul_rn(na, nb));
-                info = __fmul_rn(pow_int(tau_k, a.alpha), __fadd_rn(1.0f, __fmul_rn(a.beta, cosv)));
-            }
-            const unsigned cb = (__ballot_sync(gmask, cand) >> gbase) & 0x3Fu;
-            if (cb == 0) { result = -1; c_nocand++; break; }   // :162-166
-            // ---- roulette in the reference's order (:155, :172-181) ----------------------
-            float v[6];
-#pragma unroll
-            for (int j = 0; j < 6; j++) v[j] = __shfl_sync(gmask, info, gbase + j);
-            float total = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 6; j++) if ((cb >> j) & 1u) total = __fadd_rn(total, v[j]);
+            const bool found = kk == tile;
+            const bool cand = live && open_k && !(found && ((mm >> bit) & 1ull));
+            // ---- info = tau^alpha * (1 + beta*cos)  (:151-154) ----------------------------------
+            // vector_b has a single non-zero component d, so dot(a,b) = a_c*d and |b| = sqrt(d*d) = |d|
+            // exactly (the zero terms add exactly; sqrt(RN(d*d)) == |d| in binary floating point unless
+            // d*d leaves the normal range, which takes the slow path).
+            const float cx = xs[x], cy = ys[y], cz = zs[z];
+            const float ax = __fsub_rn(gxc, cx), ay = __fsub_rn(gyc, cy), az = __fsub_rn(gzc, cz);
+            const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+            const float ac = axis_k == 0 ? ax : (axis_k == 1 ? ay : az);
+            const float cc = axis_k == 0 ? cx : (axis_k == 1 ? cy : cz);
+            const float nc = axis_k == 0 ? xs[nx] : (axis_k == 1 ? ys[ny] : zs[nz]);
+            const float d = __fsub_rn(nc, cc);
+            float nb = fabsf(d);
+            if (!(nb >= 1e-18f && nb <= 1e18f) && nb != 0.0f) nb = slow_norm1(d);
+            const float cosv = __fdiv_rn(__fmul_rn(ac, d), __fmul_rn(na, nb));
+            const float tpow = alpha1 ? tau_k : pow_int(tau_k, a.alpha);
+            const float info = cand ? __fmul_rn(tpow, __fadd_rn(1.0f, __fmul_rn(beta, cosv))) : 0.0f;
+            const unsigned cb = (__ballot_sync(FULL, cand) >> gbase) & 0x3Fu;
+            // ---- roulette in the reference's order (:155, :172-181) ------------------------------
+            const float v0 = __shfl_sync(FULL, info, 0, 8), v1 = __shfl_sync(FULL, info, 1, 8), v2 = __shfl_sync(FULL, info, 2, 8);
+            const float v3 = __shfl_sync(FULL, info, 3, 8), v4 = __shfl_sync(FULL, info, 4, 8), v5 = __shfl_sync(FULL, info, 5, 8);
+            const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, v0), v1), v2), v3), v4), v5);
             const float rnd = __fmul_rn(u, total);
-            float ps = 0.0f, mine = 0.0f;
-#pragma unroll
-            for (int j = 5; j >= 0; j--) {
-                if ((cb >> j) & 1u) ps = __fadd_rn(ps, v[j]);
-                if (j == k) mine = ps;
-            }
+            const float p5 = __fadd_rn(0.0f, v5), p4 = __fadd_rn(p5, v4), p3 = __fadd_rn(p4, v3), p2 = __fadd_rn(p3, v2);
+            const float p1 = __fadd_rn(p2, v1), p0 = __fadd_rn(p1, v0);
+            const float mine = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : (k == 3 ? p3 : (k == 4 ? p4 : p5))));
             const bool pick = cand && (mine >= rnd);
-            const unsigned pb = (__ballot_sync(gmask, pick) >> gbase) & 0x3Fu;
-            if (pb == 0) { result = -1; c_fall++; break; }     // NaN / rounding fall-through (:191-192)
-            const int c = 31 - __clz(pb);                      // first hit scanning 5 -> 0
-            // ---- addNextNode (:73-79) ----------------------------------------------------
-            if (k == 0) { pid[steps] = (uint32_t)cur; pdir[steps] = (uint8_t)c; }
-            if (k == c) {
-                if (found) masks[slot] |= 1ull << bit;
+            const unsigned pb = (__ballot_sync(FULL, pick) >> gbase) & 0x3Fu;
+            const int c = (31 - __clz((int)(pb | 1u)));            // first hit scanning 5 -> 0 (pb == 0 handled below)
+            // ---- outcome -------------------------------------------------------------------------
+            const bool stepok = live && pb != 0;
+            c_nocand += (live && cb == 0) ? 1 : 0;                // :162-166
+            c_fall += (live && cb != 0 && pb == 0) ? 1 : 0;       // NaN / rounding fall-through (:191-192)
+            // addNextNode (:73-79)
+            if (stepok && k == 0) { pid[steps] = (uint32_t)cur; pdir[steps] = (uint8_t)c; }
+            if (stepok && k == c) {
+                if (found) masks[slot] = mm | (1ull << bit);
                 else { keys[slot] = tile; masks[slot] = 1ull << bit; }
             }
-            const int src = gbase + c;
-            cur = __shfl_sync(gmask, nid, src);
-            x = __shfl_sync(gmask, nx, src); y = __shfl_sync(gmask, ny, src); z = __shfl_sync(gmask, nz, src);
-            const int newtile = __shfl_sync(gmask, found ? 0 : 1, src);
-            ntiles += newtile;
-            steps++;
-            __syncwarp(gmask);
-            if (cur == a.goal) { result = steps; c_arrived++; break; }   // :182-186
-            if (!GLOBAL && newtile && ntiles > (E >> 2) * 3) { result = -2; break; }
+            const int nid_c = __shfl_sync(FULL, nid, c, 8);
+            const int nx_c = __shfl_sync(FULL, nx, c, 8), ny_c = __shfl_sync(FULL, ny, c, 8), nz_c = __shfl_sync(FULL, nz, c, 8);
+            const int newtile = __shfl_sync(FULL, found ? 0 : 1, c, 8);
+            if (stepok) { cur = nid_c; x = nx_c; y = ny_c; z = nz_c; steps++; ntiles += newtile; }
+            const bool arrived = stepok && cur == a.goal;          // :182-186
+            const bool over = !GLOBAL && stepok && !arrived && newtile && ntiles > limit;
+            if (arrived) result = steps;
+            if (over) result = -2;
+            c_arrived += arrived ? 1 : 0;
+            live = stepok && !arrived && !over;
+            __syncwarp();
         }
-        if (result == -2) {
-            if (k == 0) {
-                unsigned o = atomicAdd(&st->overflow_n, 1u);
-                a.overflow_list[o] = (uint32_t)ant_local;
-                a.ant_steps[ant_local] = -2;
+        if (has) {
+            if (result == -2) {
+                if (k == 0) {
+                    unsigned o = atomicAdd(&st->overflow_n, 1u);
+                    a.overflow_list[o] = (uint32_t)ant_local;
+                    a.ant_steps[ant_local] = -2;
+                }
+                c_over++;
+            } else {
+                if (k == 0) a.ant_steps[ant_local] = result;
+                c_steps += (unsigned long long)steps; c_ants++;
             }
-            c_over++;
-        } else {
-            if (k == 0) a.ant_steps[ant_local] = result;
-            c_steps += (unsigned long long)steps; c_ants++;
         }
-        __syncwarp(gmask);
+        __syncwarp();
     }
     if (k == 0) {
         if (c_steps) atomicAdd(&st->cnt[0], c_steps);

@@ -63,6 +63,26 @@ __host__ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t 
     return c0;
 }
 
+// all four output words (the 3-D search uses word (step & 3) of the block keyed by step >> 2)
+__host__ __device__ __forceinline__ void philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                                 uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
+        uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+#else
+        uint64_t p0 = (uint64_t)kPhiloxM0 * c0, p1 = (uint64_t)kPhiloxM1 * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += kPhiloxW0; k1 += kPhiloxW1;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
 // rand() stand-in: 31-bit draw (RAND_MAX = 2^31-1), see oracle/philox.h.
 __host__ __device__ __forceinline__ uint32_t rand31(uint32_t seed_lo, uint32_t seed_hi, uint32_t a, uint32_t b, uint32_t c,
                                                     uint32_t stream)
