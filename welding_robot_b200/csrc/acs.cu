@@ -4,6 +4,7 @@
 // device (IterState), so wr_acs_iterate(n) never synchronises with the host.
 #include <stdarg.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <utility>
@@ -68,6 +69,7 @@ struct wr_acs {
     unsigned ntiles = 0;
     int cap = 0, rank_bits = 0, slot_bits = 0;
     int table_log2 = 9, gtable_log2 = 0;
+    bool walk_thread = false;  // thread-per-ant walk kernel (measurement variant); default: the 8-lane-group kernel
     int64_t start = -1, goal = -1;
     bool begun = false;
     int colony_max = 0, w_max = 0;
@@ -145,7 +147,7 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     // pass-2 visited tables in HBM: every tile an ant can touch fits (tiles <= steps+1 <= cap+1)
     a->gtable_log2 = ceil_log2((unsigned long long)cap + 3);
     a->walk2_blocks = (int)std::min<size_t>((chunk + kAntsPerCta - 1) / kAntsPerCta, 32);
-    const size_t gslots = (size_t)a->walk2_blocks * kAntsPerCta << a->gtable_log2;
+    const size_t gslots = (size_t)a->walk2_blocks * kWalkTAnts << a->gtable_log2;   // 32 tables per pass-2 CTA (thread-per-ant kernel)
     WR_CUDA(cudaMalloc(&a->d_gkeys, gslots * sizeof(uint32_t)));
     WR_CUDA(cudaMalloc(&a->d_gmasks, gslots * sizeof(unsigned long long)));
     int st = sort_plan_create(&a->sort_ants, cm);
@@ -247,6 +249,9 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
         size_t ws = (((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15) + ((size_t)kAntsPerCta << a->table_log2) * 12;
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         WR_CUDA_A(cudaFuncSetAttribute(k_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        size_t wt = (((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15) + ((size_t)kWalkTAnts << a->table_log2) * 12;
+        a->walk_thread = getenv("WR_WALK_THREAD") != nullptr && wt <= 227 * 1024;   // measurement variant, see DESIGN.md
+        if (a->walk_thread) WR_CUDA_A(cudaFuncSetAttribute(k_walk_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wt));
     }
     WR_CUDA_A(cudaStreamSynchronize(a->stream));
 #undef WR_CUDA_A
@@ -339,11 +344,21 @@ static int launch_walk(wr_acs* a)
     const size_t smem1 = coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem1 + 1024)));
     const int blocks1 = std::max(1, std::min((a->chunk + kAntsPerCta - 1) / kAntsPerCta, kNumSMs * std::min(per_sm, 16)));
-    k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-    // pass 2: ants whose shared-memory table overflowed (usually none: the kernel exits at once)
-    k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
-    w.table_log2 = a->gtable_log2;
-    k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
+    if (a->walk_thread) {
+        const size_t smemt = coord_bytes + ((size_t)kWalkTAnts << a->table_log2) * 12;
+        const int per_sm_t = std::max(1, (int)((227 * 1024) / (smemt + 1024)));
+        const int blocks_t = std::max(1, std::min((a->chunk + kWalkTAnts - 1) / kWalkTAnts, kNumSMs * per_sm_t));
+        k_walk_t<false><<<blocks_t, 32, smemt, a->stream>>>(w);
+        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
+        w.table_log2 = a->gtable_log2;
+        k_walk_t<true><<<a->walk2_blocks, 32, coord_bytes, a->stream>>>(w);
+    } else {
+        k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+        // pass 2: ants whose shared-memory table overflowed (usually none: the kernel exits at once)
+        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
+        w.table_log2 = a->gtable_log2;
+        k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
+    }
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }

@@ -155,10 +155,13 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
     const int dxk = (k == 3) - (k == 2), dyk = (k == 4) - (k == 1), dzk = (k == 5) - (k == 0);
     const int stride_k = dxk + dyk * rx + dzk * rxy;
     const int axis_k = (k == 2 || k == 3) ? 0 : ((k == 1 || k == 4) ? 1 : 2);   // which component of b is non-zero
+    const int dk = dxk + dyk + dzk;                                          // +-1 along that axis (0 for the idle lanes)
+    const int kk6 = k < 6 ? k : 5;                                           // idle lanes re-read slot 5 (same sector)
 
     const int sz = a.start / rxy, sy = (a.start % rxy) / rx, sx = a.start % rx;
     const int gz = a.goal / rxy, gy = (a.goal % rxy) / rx, gx = a.goal % rx;
     const float gxc = xs[gx], gyc = ys[gy], gzc = zs[gz];
+    const float* axis_tab = axis_k == 0 ? xs : (axis_k == 1 ? ys : zs);
     const bool alpha1 = a.alpha == 1;
     const float beta = a.beta;
 
@@ -194,24 +197,28 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
 
         bool live = has;
         int result = -1;   // >= 0: steps of an ant that arrived, -1: dead, -2: pending (table overflow -> pass 2)
+        int reason = 0;    // why a dead ant died: 1 no candidate, 2 roulette fall-through, 3 step cap
         uint32_t* pid = a.path_ids + (size_t)ant_local * a.cap;
         uint8_t* pdir = a.path_dirs + (size_t)ant_local * a.cap;
         uint32_t rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0;
+        int pos = axis_k == 0 ? x : (axis_k == 1 ? y : z);        // the ant's index along this lane's axis
 
         while (__any_sync(FULL, live)) {
             // ---- step cap (a deviation the oracle mirrors; the reference is unbounded) ------------
-            if (live && steps >= a.cap) { live = false; c_cap++; }
+            const bool capped = live && steps >= a.cap;
+            reason = capped ? 3 : reason;
+            live = live && !capped;
             // ---- the loads of this step ---------------------------------------------------------
             const unsigned open = a.open6[cur];
-            const float tau_k = (k < 6) ? __ldg(a.tau + (size_t)cur * 6 + k) : 0.0f;
-            // ---- Philox: one call yields the draws of 4 consecutive steps (live ants of a warp are in
-            //      lockstep, so the branch is warp-uniform) ------------------------------------------
+            const float tau_k = __ldg(a.tau + (size_t)cur * 6 + kk6);
+            // ---- Philox: one call yields the draws of 4 consecutive steps (the live ants of a warp are
+            //      in lockstep, so the branch is warp-uniform) ---------------------------------------
             if (live && (steps & 3) == 0) philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
             const uint32_t rsel = (steps & 2) ? ((steps & 1) ? rw3 : rw2) : ((steps & 1) ? rw1 : rw0);
-            const float u = __fdiv_rn(__int2float_rn((int)(rsel >> 1)), 2147483648.0f);   // (float)rand()/(float)RAND_MAX (:169)
+            // (float)rand()/(float)RAND_MAX (:169): (float)RAND_MAX is 2^31, so the division is an exact scaling
+            const float u = __fmul_rn(__int2float_rn((int)(rsel >> 1)), 4.656612873077392578125e-10f);
             // ---- neighbour k: bounds+free (open mask), tabu probe -------------------------------
             const int nx = x + dxk, ny = y + dyk, nz = z + dzk;
-            const int nid = cur + stride_k;
             const bool open_k = (k < 6) && ((open >> k) & 1u);
             const uint32_t tile = (uint32_t)(((nz >> 2) * TY + (ny >> 2)) * TX + (nx >> 2));
             const unsigned bit = ((nz & 3) << 4) | ((ny & 3) << 2) | (nx & 3);
@@ -229,11 +236,11 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             // exactly (the zero terms add exactly; sqrt(RN(d*d)) == |d| in binary floating point unless
             // d*d leaves the normal range, which takes the slow path).
             const float cx = xs[x], cy = ys[y], cz = zs[z];
+            const float nc = axis_tab[pos + dk];
             const float ax = __fsub_rn(gxc, cx), ay = __fsub_rn(gyc, cy), az = __fsub_rn(gzc, cz);
             const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
             const float ac = axis_k == 0 ? ax : (axis_k == 1 ? ay : az);
             const float cc = axis_k == 0 ? cx : (axis_k == 1 ? cy : cz);
-            const float nc = axis_k == 0 ? xs[nx] : (axis_k == 1 ? ys[ny] : zs[nz]);
             const float d = __fsub_rn(nc, cc);
             float nb = fabsf(d);
             if (!(nb >= 1e-18f && nb <= 1e18f) && nb != 0.0f) nb = slow_norm1(d);
@@ -246,33 +253,39 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             const float v3 = __shfl_sync(FULL, info, 3, 8), v4 = __shfl_sync(FULL, info, 4, 8), v5 = __shfl_sync(FULL, info, 5, 8);
             const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, v0), v1), v2), v3), v4), v5);
             const float rnd = __fmul_rn(u, total);
-            const float p5 = __fadd_rn(0.0f, v5), p4 = __fadd_rn(p5, v4), p3 = __fadd_rn(p4, v3), p2 = __fadd_rn(p3, v2);
-            const float p1 = __fadd_rn(p2, v1), p0 = __fadd_rn(p1, v0);
-            const float mine = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : (k == 3 ? p3 : (k == 4 ? p4 : p5))));
+            // this lane's prob_sum: v5 + v4 + ... + v_k, then zeros (the identity), so one chain serves all lanes
+            const float mine = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, v5), k <= 4 ? v4 : 0.0f), k <= 3 ? v3 : 0.0f),
+                                                              k <= 2 ? v2 : 0.0f), k <= 1 ? v1 : 0.0f), k <= 0 ? v0 : 0.0f);
             const bool pick = cand && (mine >= rnd);
             const unsigned pb = (__ballot_sync(FULL, pick) >> gbase) & 0x3Fu;
             const int c = (31 - __clz((int)(pb | 1u)));            // first hit scanning 5 -> 0 (pb == 0 handled below)
             // ---- outcome -------------------------------------------------------------------------
             const bool stepok = live && pb != 0;
-            c_nocand += (live && cb == 0) ? 1 : 0;                // :162-166
-            c_fall += (live && cb != 0 && pb == 0) ? 1 : 0;       // NaN / rounding fall-through (:191-192)
+            reason = (live && !stepok) ? (cb == 0 ? 1 : 2) : reason;   // :162-166 / fall-through :191-192
             // addNextNode (:73-79)
             if (stepok && k == 0) { pid[steps] = (uint32_t)cur; pdir[steps] = (uint8_t)c; }
-            if (stepok && k == c) {
-                if (found) masks[slot] = mm | (1ull << bit);
-                else { keys[slot] = tile; masks[slot] = 1ull << bit; }
+            if (stepok && k == c) { keys[slot] = tile; masks[slot] = found ? (mm | (1ull << bit)) : (1ull << bit); }
+            const unsigned fb = (__ballot_sync(FULL, found) >> gbase) & 0x3Fu;
+            const int newtile = stepok ? (int)(((fb >> c) & 1u) ^ 1u) : 0;
+            const int mdx = (c == 3) - (c == 2), mdy = (c == 4) - (c == 1), mdz = (c == 5) - (c == 0);
+            if (stepok) {
+                x += mdx; y += mdy; z += mdz;
+                cur += mdx + mdy * rx + mdz * rxy;
+                pos += axis_k == 0 ? mdx : (axis_k == 1 ? mdy : mdz);
+                steps++;
+                ntiles += newtile;
             }
-            const int nid_c = __shfl_sync(FULL, nid, c, 8);
-            const int nx_c = __shfl_sync(FULL, nx, c, 8), ny_c = __shfl_sync(FULL, ny, c, 8), nz_c = __shfl_sync(FULL, nz, c, 8);
-            const int newtile = __shfl_sync(FULL, found ? 0 : 1, c, 8);
-            if (stepok) { cur = nid_c; x = nx_c; y = ny_c; z = nz_c; steps++; ntiles += newtile; }
             const bool arrived = stepok && cur == a.goal;          // :182-186
             const bool over = !GLOBAL && stepok && !arrived && newtile && ntiles > limit;
-            if (arrived) result = steps;
-            if (over) result = -2;
-            c_arrived += arrived ? 1 : 0;
+            result = arrived ? steps : (over ? -2 : result);
             live = stepok && !arrived && !over;
             __syncwarp();
+        }
+        if (has && result != -2) {
+            c_arrived += result >= 0 ? 1 : 0;
+            c_nocand += (result < 0 && reason == 1) ? 1 : 0;
+            c_fall += (result < 0 && reason == 2) ? 1 : 0;
+            c_cap += (result < 0 && reason == 3) ? 1 : 0;
         }
         if (has) {
             if (result == -2) {
@@ -297,6 +310,207 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
         if (c_fall) atomicAdd(&st->cnt[4], c_fall);
         if (c_cap) atomicAdd(&st->cnt[5], c_cap);
         if (c_over) atomicAdd(&st->cnt[8], c_over);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2, thread-per-ant variant.  One ant per THREAD, one warp per CTA, 32 visited tables in shared
+// memory interleaved by lane (table[slot][lane]: conflict-free).  No cross-lane traffic at all: the
+// six neighbours are evaluated by the owning thread, fully unrolled, which gives the scheduler six
+// independent dependency chains to interleave (the 8-lane kernel above spends ~300 instructions per
+// step for FOUR ants, mostly serial; this one spends about as many for THIRTY-TWO).
+// ------------------------------------------------------------------------------------------
+constexpr int kWalkTAnts = 32;
+
+template <bool GLOBAL>
+__global__ void __launch_bounds__(32) k_walk_t(WalkArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw) + 1;
+    float* ys = xs + a.rx + 2;
+    float* zs = ys + a.ry + 2;
+    const int ncoord = a.rx + a.ry + a.rz + 6;
+    const int lane = threadIdx.x;
+    for (int i = lane; i < ncoord; i += 32) reinterpret_cast<float*>(smem_raw)[i] = 0.0f;
+    __syncwarp();
+    for (int i = lane; i < a.rx; i += 32) xs[i] = a.coords[i];
+    for (int i = lane; i < a.ry; i += 32) ys[i] = a.coords[a.rx + i];
+    for (int i = lane; i < a.rz; i += 32) zs[i] = a.coords[a.rx + a.ry + i];
+    __syncwarp();
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const int E = 1 << a.table_log2;
+    const int hshift = 32 - a.table_log2;
+    unsigned long long* masks;   // [E][32]
+    uint32_t* keys;              // [E][32]
+    if (GLOBAL) {
+        keys = a.gkeys + (size_t)blockIdx.x * kWalkTAnts * E;
+        masks = a.gmasks + (size_t)blockIdx.x * kWalkTAnts * E;
+    } else {
+        masks = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)ncoord * 4 + 15) & ~(size_t)15));
+        keys = reinterpret_cast<uint32_t*>(masks + (size_t)kWalkTAnts * E);
+    }
+    keys += lane; masks += lane;   // this thread's column
+
+    const int rx = a.rx, ry = a.ry;
+    const int rxy = rx * ry;
+    const int TX = (rx + 3) >> 2, TY = (ry + 3) >> 2;
+    const int sz = a.start / rxy, sy = (a.start % rxy) / rx, sx = a.start % rx;
+    const int gz = a.goal / rxy, gy = (a.goal % rxy) / rx, gx = a.goal % rx;
+    const float gxc = xs[gx], gyc = ys[gy], gzc = zs[gz];
+    const bool alpha1 = a.alpha == 1;
+    const float beta = a.beta;
+
+    IterState* st = a.st;
+    const int colony = st->colony;
+    const uint32_t iter = (uint32_t)st->iter;
+    int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
+    if (GLOBAL) local_n = (int)st->overflow_n;
+    const int limit = (E >> 2) * 3;
+
+    unsigned c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
+
+    while (true) {
+        unsigned q0 = 0;
+        if (lane == 0) q0 = atomicAdd(&st->queue, (unsigned)kWalkTAnts);
+        q0 = __shfl_sync(FULL, q0, 0);
+        if (q0 >= (unsigned)local_n) break;
+        const unsigned q = q0 + (unsigned)lane;
+        const bool has = q < (unsigned)local_n;
+        const int ant_local = has ? (GLOBAL ? (int)a.overflow_list[q] : (int)q) : 0;
+        const uint32_t ant_global = (uint32_t)(a.shard_first + ant_local);
+
+        for (int i = 0; i < E; i++) keys[i * 32] = kEmptyKey;
+        int cur = a.start, x = sx, y = sy, z = sz, steps = 0, ntiles = 1;
+        {   // addStartNode :81-86
+            const uint32_t tile = (uint32_t)(((z >> 2) * TY + (y >> 2)) * TX + (x >> 2));
+            const unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
+            const unsigned slot = (tile * 2654435761u) >> hshift;
+            keys[slot * 32] = tile; masks[slot * 32] = 1ull << bit;
+        }
+        bool live = has;
+        int result = -1, reason = 0;
+        uint32_t* pid = a.path_ids + (size_t)ant_local * a.cap;
+        uint8_t* pdir = a.path_dirs + (size_t)ant_local * a.cap;
+        uint32_t rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0;
+
+        while (__any_sync(FULL, live)) {
+            const bool capped = live && steps >= a.cap;
+            reason = capped ? 3 : reason;
+            live = live && !capped;
+            // ---- loads ---------------------------------------------------------------------------
+            const unsigned open = a.open6[cur];
+            const float2* tp = reinterpret_cast<const float2*>(a.tau + (size_t)cur * 6);
+            const float2 t01 = __ldg(tp), t23 = __ldg(tp + 1), t45 = __ldg(tp + 2);
+            if (live && (steps & 3) == 0) philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
+            const uint32_t rsel = (steps & 2) ? ((steps & 1) ? rw3 : rw2) : ((steps & 1) ? rw1 : rw0);
+            const float u = __fmul_rn(__int2float_rn((int)(rsel >> 1)), 4.656612873077392578125e-10f);
+            // ---- geometry shared by the six neighbours -------------------------------------------
+            const float cx = xs[x], cy = ys[y], cz = zs[z];
+            const float ax = __fsub_rn(gxc, cx), ay = __fsub_rn(gyc, cy), az = __fsub_rn(gzc, cz);
+            const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+            const float tauk[6] = {t01.x, t01.y, t23.x, t23.y, t45.x, t45.y};
+            float info[6];
+            unsigned slotk[6];
+            unsigned long long mmk[6];
+            uint32_t tilek[6];
+            unsigned bitk[6];
+            unsigned foundm = 0, candm = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int dx = (k == 3) - (k == 2), dy = (k == 4) - (k == 1), dz = (k == 5) - (k == 0);
+                const int nx = x + dx, ny = y + dy, nz = z + dz;
+                const bool open_k = (open >> k) & 1u;
+                const uint32_t tile = (uint32_t)(((nz >> 2) * TY + (ny >> 2)) * TX + (nx >> 2));
+                const unsigned bit = ((nz & 3) << 4) | ((ny & 3) << 2) | (nx & 3);
+                unsigned slot = (tile * 2654435761u) >> hshift;
+                uint32_t kk = keys[slot * 32];
+                unsigned long long mm = masks[slot * 32];
+                while (open_k && kk != tile && kk != kEmptyKey) {
+                    slot = (slot + 1) & (E - 1);
+                    kk = keys[slot * 32]; mm = masks[slot * 32];
+                }
+                const bool found = kk == tile;
+                const bool cand = live && open_k && !(found && ((mm >> bit) & 1ull));
+                const float ac = dx ? ax : (dy ? ay : az);
+                const float cc = dx ? cx : (dy ? cy : cz);
+                const float nc = dx ? xs[nx] : (dy ? ys[ny] : zs[nz]);
+                const float d = __fsub_rn(nc, cc);
+                float nb = fabsf(d);
+                if (!(nb >= 1e-18f && nb <= 1e18f) && nb != 0.0f) nb = slow_norm1(d);
+                const float cosv = __fdiv_rn(__fmul_rn(ac, d), __fmul_rn(na, nb));
+                const float tpow = alpha1 ? tauk[k] : pow_int(tauk[k], a.alpha);
+                info[k] = cand ? __fmul_rn(tpow, __fadd_rn(1.0f, __fmul_rn(beta, cosv))) : 0.0f;
+                slotk[k] = slot; mmk[k] = mm; tilek[k] = tile; bitk[k] = bit;
+                foundm |= (found ? 1u : 0u) << k;
+                candm |= (cand ? 1u : 0u) << k;
+            }
+            // ---- roulette (:155, :168-181) -------------------------------------------------------
+            const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, info[0]), info[1]), info[2]), info[3]), info[4]), info[5]);
+            const float rnd = __fmul_rn(u, total);
+            float ps = 0.0f;
+            int c = -1;
+#pragma unroll
+            for (int k = 5; k >= 0; k--) {
+                ps = __fadd_rn(ps, info[k]);
+                if (c < 0 && ((candm >> k) & 1u) && ps >= rnd) c = k;
+            }
+            const bool stepok = live && c >= 0;
+            reason = (live && !stepok) ? (candm == 0 ? 1 : 2) : reason;
+            const int cs = c < 0 ? 0 : c;
+            // ---- addNextNode (:73-79) ------------------------------------------------------------
+            unsigned slot_c = slotk[0]; unsigned long long mm_c = mmk[0]; uint32_t tile_c = tilek[0]; unsigned bit_c = bitk[0];
+#pragma unroll
+            for (int k = 1; k < 6; k++) if (cs == k) { slot_c = slotk[k]; mm_c = mmk[k]; tile_c = tilek[k]; bit_c = bitk[k]; }
+            const bool found_c = (foundm >> cs) & 1u;
+            if (stepok) {
+                pid[steps] = (uint32_t)cur; pdir[steps] = (uint8_t)cs;
+                keys[slot_c * 32] = tile_c;
+                masks[slot_c * 32] = found_c ? (mm_c | (1ull << bit_c)) : (1ull << bit_c);
+                const int mdx = (cs == 3) - (cs == 2), mdy = (cs == 4) - (cs == 1), mdz = (cs == 5) - (cs == 0);
+                x += mdx; y += mdy; z += mdz;
+                cur += mdx + mdy * rx + mdz * rxy;
+                steps++;
+                ntiles += found_c ? 0 : 1;
+            }
+            const bool arrived = stepok && cur == a.goal;
+            const bool over = !GLOBAL && stepok && !arrived && !found_c && ntiles > limit;
+            result = arrived ? steps : (over ? -2 : result);
+            live = stepok && !arrived && !over;
+        }
+        if (has) {
+            if (result == -2) {
+                unsigned o = atomicAdd(&st->overflow_n, 1u);
+                a.overflow_list[o] = (uint32_t)ant_local;
+                a.ant_steps[ant_local] = -2;
+                c_over++;
+            } else {
+                a.ant_steps[ant_local] = result;
+                c_steps += (unsigned)steps; c_ants++;
+                c_arrived += result >= 0 ? 1 : 0;
+                c_nocand += (result < 0 && reason == 1) ? 1 : 0;
+                c_fall += (result < 0 && reason == 2) ? 1 : 0;
+                c_cap += (result < 0 && reason == 3) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+    }
+    // warp-reduce the counters, one atomic per counter per warp
+    unsigned long long cs64 = c_steps;
+    for (int o = 16; o; o >>= 1) {
+        cs64 += __shfl_xor_sync(FULL, cs64, o);
+        c_ants += __shfl_xor_sync(FULL, c_ants, o); c_arrived += __shfl_xor_sync(FULL, c_arrived, o);
+        c_nocand += __shfl_xor_sync(FULL, c_nocand, o); c_fall += __shfl_xor_sync(FULL, c_fall, o);
+        c_cap += __shfl_xor_sync(FULL, c_cap, o); c_over += __shfl_xor_sync(FULL, c_over, o);
+    }
+    if (lane == 0) {
+        if (cs64) atomicAdd(&st->cnt[0], cs64);
+        if (c_ants) atomicAdd(&st->cnt[1], (unsigned long long)c_ants);
+        if (c_arrived) atomicAdd(&st->cnt[2], (unsigned long long)c_arrived);
+        if (c_nocand) atomicAdd(&st->cnt[3], (unsigned long long)c_nocand);
+        if (c_fall) atomicAdd(&st->cnt[4], (unsigned long long)c_fall);
+        if (c_cap) atomicAdd(&st->cnt[5], (unsigned long long)c_cap);
+        if (c_over) atomicAdd(&st->cnt[8], (unsigned long long)c_over);
     }
 }
 
