@@ -279,7 +279,7 @@ def run_ours(args):
         "data": "synthetic: reference mesh fixture voxelised on the GPU, embedded in 256^3 free space; synthetic start/goal",
         "config": {"workload": "C2: ACSRank_3D, simplified_piece @256-long grid in 256^3, %d ants/GPU, K=6" % ANTS_PER_GPU,
                    "grid": [CUBE, CUBE, CUBE], "natural_grid": list(wl["natural"]), "ants": colony, "iters_per_step": args.iters,
-                   "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic"][args.update_mode],
+                   "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic", "fused_tma"][args.update_mode],
                    "parallelism": "ants sharded x%d" % world,
                    "l2_rule": "inputs larger than L2: the 403 MB pheromone field is streamed from HBM every iteration"},
         "acs_iterations_per_s": iters_done / (ms * 1e-3),
@@ -291,7 +291,8 @@ def run_ours(args):
                      "frac": walk_gbs / hbm, "traffic": None, "peak_source": hbm_src,
                      "note": "30 B algorithmic per ant-step; a walk is a chain of dependent gathers, so with 4096 ants the kernel is "
                              "latency-bound, not bandwidth-bound (see DESIGN.md)"},
-        "roofline_update": {"kernel": "k_update_fused (K3 evaporate+deposit, TMA)" if args.update_mode == 0 else "k_evaporate + k_deposit_apply (K3)",
+        "roofline_update": {"kernel": ["k_update_fused (K3: evaporation + rank-ordered deposits, one HBM pass)", "k_evaporate + k_deposit_apply (K3 split)",
+                                       "k_evaporate + atomic deposits (K3 atomic)", "k_update_tma_ring (K3 through a TMA ring)"][args.update_mode],
                             "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm, "traffic": None,
                             "peak_source": hbm_src, "timed": "inside the iteration loop"},
         "kernels_alone": alone,
