@@ -268,6 +268,12 @@ def run_ours(args):
     if rank != 0:
         return
     hbm, hbm_src = peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram__bytes_read+write per launch from the committed ncu --set full captures
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj.items() if isinstance(v, dict)}
     walk_ms = kms["walk"] / iters_done
     upd_ms = kms["update"] / iters_done
     walk_gbs = WALK_BYTES_PER_STEP * (local_steps / iters_done) / (walk_ms * 1e-3) / 1e9
@@ -288,12 +294,15 @@ def run_ours(args):
         "gpu_launches": launches_per_iteration(args.update_mode) * iters_done,
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
         "roofline": {"kernel": "k_walk (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
-                     "frac": walk_gbs / hbm, "traffic": None, "peak_source": hbm_src,
+                     "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk"), "peak_source": hbm_src,
+                     "algorithmic_bytes_per_launch": WALK_BYTES_PER_STEP * (local_steps / iters_done),
                      "note": "30 B algorithmic per ant-step; a walk is a chain of dependent gathers, so with 4096 ants the kernel is "
                              "latency-bound, not bandwidth-bound (see DESIGN.md)"},
         "roofline_update": {"kernel": ["k_update_fused (K3: evaporation + rank-ordered deposits, one HBM pass)", "k_evaporate + k_deposit_apply (K3 split)",
                                        "k_evaporate + atomic deposits (K3 atomic)", "k_update_tma_ring (K3 through a TMA ring)"][args.update_mode],
-                            "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm, "traffic": None,
+                            "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm,
+                            "traffic": traffic.get("k_update_fused") if args.update_mode == 0 else None,
+                            "algorithmic_bytes_per_launch": UPDATE_BYTES_PER_SLOT * n_nodes * 6,
                             "peak_source": hbm_src, "timed": "inside the iteration loop"},
         "kernels_alone": alone,
         "voxelise": {"triangles": wl["ntri"], "grid": list(wl["natural"]), "kernel_ms": wl["vox"]["kernel_ms"], "tests": wl["vox"]["tests"]},
