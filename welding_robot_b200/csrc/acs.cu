@@ -26,6 +26,28 @@ void set_error(const char* fmt, ...)
     g_err = buf;
 }
 
+cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t s)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, s);
+}
+void pool_free(void* p, cudaStream_t s)
+{
+    if (p) cudaFreeAsync(p, s);
+}
+
 static int ceil_log2(unsigned long long v)
 {
     int b = 0;
@@ -111,13 +133,14 @@ struct wr_acs {
 
 static void free_colony_buffers(wr_acs* a)
 {
-    cudaFree(a->d_ant_steps); cudaFree(a->d_path_ids); cudaFree(a->d_path_dirs); cudaFree(a->d_overflow);
-    cudaFree(a->d_gkeys); cudaFree(a->d_gmasks); cudaFree(a->d_rec_off); cudaFree(a->d_order);
-    if (a->d_local_steps != a->d_ant_steps) cudaFree(a->d_local_steps);
-    cudaFree(a->d_cand); a->d_local_steps = nullptr; a->d_cand = nullptr;
+    cudaStream_t s = a->stream;
+    pool_free(a->d_ant_steps, s); pool_free(a->d_path_ids, s); pool_free(a->d_path_dirs, s); pool_free(a->d_overflow, s);
+    pool_free(a->d_gkeys, s); pool_free(a->d_gmasks, s); pool_free(a->d_rec_off, s); pool_free(a->d_order, s);
+    if (a->d_local_steps != a->d_ant_steps) pool_free(a->d_local_steps, s);
+    pool_free(a->d_cand, s); a->d_local_steps = nullptr; a->d_cand = nullptr;
     a->d_ant_steps = nullptr; a->d_path_ids = nullptr; a->d_path_dirs = nullptr; a->d_overflow = nullptr;
     a->d_gkeys = nullptr; a->d_gmasks = nullptr; a->d_rec_off = nullptr; a->d_order = nullptr;
-    sort_plan_destroy(&a->sort_ants); sort_plan_destroy(&a->sort_recs);
+    sort_plan_destroy(&a->sort_ants, s); sort_plan_destroy(&a->sort_recs, s);
     a->alloc_colony = 0;
 }
 
@@ -132,27 +155,27 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     a->w_max = (int)(0.2 * (double)cm) + 1;
     const size_t rec_max = (size_t)a->w_max * cap;
     if (rec_max >= 0x7fffffffull) { set_error("colony %zu x step cap %zu needs too many deposit records; set step_cap", cm, cap); return WR_ERR_NOMEM; }
-    WR_CUDA(cudaMalloc(&a->d_ant_steps, (chunk * a->nranks) * sizeof(int)));   // global colony: ranking reads all ranks' steps
+    WR_CUDA(dmalloc(&a->d_ant_steps, (chunk * a->nranks) * sizeof(int), a->stream));   // global colony: ranking reads all ranks' steps
     if (a->nranks > 1) {
-        WR_CUDA(cudaMalloc(&a->d_local_steps, chunk * sizeof(int)));
+        WR_CUDA(dmalloc(&a->d_local_steps, chunk * sizeof(int), a->stream));
         a->cand_words = 2 * cap + 2;
-        WR_CUDA(cudaMalloc(&a->d_cand, a->cand_words * sizeof(uint32_t)));
+        WR_CUDA(dmalloc(&a->d_cand, a->cand_words * sizeof(uint32_t), a->stream));
     } else a->d_local_steps = a->d_ant_steps;
-    WR_CUDA(cudaMalloc(&a->d_path_ids, chunk * cap * sizeof(uint32_t)));
-    WR_CUDA(cudaMalloc(&a->d_path_dirs, chunk * cap));
-    WR_CUDA(cudaMalloc(&a->d_overflow, chunk * sizeof(uint32_t)));
-    WR_CUDA(cudaMalloc(&a->d_rec_off, cm * sizeof(uint32_t)));
-    WR_CUDA(cudaMalloc(&a->d_order, cm * sizeof(int)));
+    WR_CUDA(dmalloc(&a->d_path_ids, chunk * cap * sizeof(uint32_t), a->stream));
+    WR_CUDA(dmalloc(&a->d_path_dirs, chunk * cap, a->stream));
+    WR_CUDA(dmalloc(&a->d_overflow, chunk * sizeof(uint32_t), a->stream));
+    WR_CUDA(dmalloc(&a->d_rec_off, cm * sizeof(uint32_t), a->stream));
+    WR_CUDA(dmalloc(&a->d_order, cm * sizeof(int), a->stream));
     WR_CUDA(cudaMemsetAsync(a->d_order, 0, cm * sizeof(int), a->stream));
     // pass-2 visited tables in HBM: every tile an ant can touch fits (tiles <= steps+1 <= cap+1)
     a->gtable_log2 = ceil_log2((unsigned long long)cap + 3);
     a->walk2_blocks = (int)std::min<size_t>((chunk + kAntsPerCta - 1) / kAntsPerCta, 32);
     const size_t gslots = (size_t)a->walk2_blocks * kWalkTAnts << a->gtable_log2;   // 32 tables per pass-2 CTA (thread-per-ant kernel)
-    WR_CUDA(cudaMalloc(&a->d_gkeys, gslots * sizeof(uint32_t)));
-    WR_CUDA(cudaMalloc(&a->d_gmasks, gslots * sizeof(unsigned long long)));
-    int st = sort_plan_create(&a->sort_ants, cm);
+    WR_CUDA(dmalloc(&a->d_gkeys, gslots * sizeof(uint32_t), a->stream));
+    WR_CUDA(dmalloc(&a->d_gmasks, gslots * sizeof(unsigned long long), a->stream));
+    int st = sort_plan_create(&a->sort_ants, cm, a->stream);
     if (st != WR_OK) return st;
-    st = sort_plan_create(&a->sort_recs, rec_max);
+    st = sort_plan_create(&a->sort_recs, rec_max, a->stream);
     if (st != WR_OK) return st;
     a->alloc_colony = cm;
     return WR_OK;
@@ -187,8 +210,11 @@ extern "C" int wr_acs_destroy(wr_acs* a)
     if (!a) return WR_OK;
     if (a->stream) cudaStreamSynchronize(a->stream);
     free_colony_buffers(a);
-    cudaFree(a->d_tau); cudaFree(a->d_state); cudaFree(a->d_onbest); cudaFree(a->d_Ltab);
-    cudaFree(a->d_best_n); cudaFree(a->d_best_ids); cudaFree(a->d_best_dirs); cudaFree(a->d_tile_off); cudaFree(a->d_dep_list); cudaFree(a->d_upd_q);
+    cudaStream_t s = a->stream;
+    pool_free(a->d_tau, s); pool_free(a->d_state, s); pool_free(a->d_onbest, s); pool_free(a->d_Ltab, s);
+    pool_free(a->d_best_n, s); pool_free(a->d_best_ids, s); pool_free(a->d_best_dirs, s); pool_free(a->d_tile_off, s); pool_free(a->d_dep_list, s);
+    pool_free(a->d_upd_q, s);
+    if (a->stream) cudaStreamSynchronize(a->stream);
     if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
     delete a;
     return WR_OK;
@@ -222,27 +248,27 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     a->own_stream = true;
     int st = grid_ensure_open6(g, a->stream);
     if (st != WR_OK) { wr_acs_destroy(a); return st; }
-    WR_CUDA_A(cudaMalloc(&a->d_tau, a->n_slots_pad * sizeof(float)));
+    WR_CUDA_A(dmalloc(&a->d_tau, a->n_slots_pad * sizeof(float), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_tau, 0, a->n_slots_pad * sizeof(float), a->stream));
     k_tau_init<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, p->tau0);
     WR_CUDA_A(cudaGetLastError());
-    WR_CUDA_A(cudaMalloc(&a->d_state, sizeof(IterState)));
+    WR_CUDA_A(dmalloc(&a->d_state, sizeof(IterState), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_state, 0, sizeof(IterState), a->stream));
     k_begin<<<1, 1, 0, a->stream>>>(a->d_state, 0.0f);
-    WR_CUDA_A(cudaMalloc(&a->d_onbest, (a->N / 32 + 2) * sizeof(uint32_t)));
+    WR_CUDA_A(dmalloc(&a->d_onbest, (a->N / 32 + 2) * sizeof(uint32_t), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_onbest, 0, (a->N / 32 + 2) * sizeof(uint32_t), a->stream));
     // L after s steps: precision added s times in float (Agent::addNextNode :78)
     a->h_Ltab.resize((size_t)a->cap + 2);
     { float L = 0; a->h_Ltab[0] = 0; for (int s = 1; s <= a->cap + 1; s++) { L += g->precision; a->h_Ltab[s] = L; } }
-    WR_CUDA_A(cudaMalloc(&a->d_Ltab, a->h_Ltab.size() * sizeof(float)));
+    WR_CUDA_A(dmalloc(&a->d_Ltab, a->h_Ltab.size() * sizeof(float), a->stream));
     WR_CUDA_A(cudaMemcpyAsync(a->d_Ltab, a->h_Ltab.data(), a->h_Ltab.size() * sizeof(float), cudaMemcpyHostToDevice, a->stream));
-    WR_CUDA_A(cudaMalloc(&a->d_best_n, sizeof(int)));
+    WR_CUDA_A(dmalloc(&a->d_best_n, sizeof(int), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_best_n, 0, sizeof(int), a->stream));
-    WR_CUDA_A(cudaMalloc(&a->d_best_ids, ((size_t)a->cap + 2) * sizeof(uint32_t)));
-    WR_CUDA_A(cudaMalloc(&a->d_best_dirs, (size_t)a->cap + 2));
-    WR_CUDA_A(cudaMalloc(&a->d_tile_off, ((size_t)a->ntiles + 2) * sizeof(uint32_t)));
-    WR_CUDA_A(cudaMalloc(&a->d_dep_list, ((size_t)a->ntiles + 2) * sizeof(uint32_t)));
-    WR_CUDA_A(cudaMalloc(&a->d_upd_q, 4 * sizeof(uint32_t)));
+    WR_CUDA_A(dmalloc(&a->d_best_ids, ((size_t)a->cap + 2) * sizeof(uint32_t), a->stream));
+    WR_CUDA_A(dmalloc(&a->d_best_dirs, (size_t)a->cap + 2, a->stream));
+    WR_CUDA_A(dmalloc(&a->d_tile_off, ((size_t)a->ntiles + 2) * sizeof(uint32_t), a->stream));
+    WR_CUDA_A(dmalloc(&a->d_dep_list, ((size_t)a->ntiles + 2) * sizeof(uint32_t), a->stream));
+    WR_CUDA_A(dmalloc(&a->d_upd_q, 4 * sizeof(uint32_t), a->stream));
     {
         size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
         WR_CUDA_A(cudaFuncSetAttribute(k_update_tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -693,7 +719,7 @@ extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per
     WR_CUDA(cudaEventCreate(&e0));
     WR_CUDA(cudaEventCreate(&e1));
     float* scratch = nullptr;
-    if (which == 2) WR_CUDA(cudaMalloc(&scratch, a->n_slots_pad * sizeof(float)));
+    if (which == 2) WR_CUDA(dmalloc(&scratch, a->n_slots_pad * sizeof(float), s));
     const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
     const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
     const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
@@ -717,7 +743,7 @@ extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per
     float ms = 0;
     WR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *ms_per_launch = ms / reps;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(scratch);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); pool_free(scratch, s);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }

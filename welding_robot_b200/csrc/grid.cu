@@ -211,12 +211,20 @@ __global__ void k_open6(const uint32_t* __restrict__ bits, uint8_t* __restrict__
     open6[id] = (uint8_t)m;
 }
 
-__global__ void k_pack_isfree(const uint8_t* __restrict__ isfree, uint32_t* __restrict__ bits, unsigned long long N)
+__global__ void k_pack_isfree(const uint8_t* __restrict__ isfree, uint32_t* __restrict__ bits, unsigned long long N, unsigned long long* occupied)
 {
+    __shared__ unsigned cta_occ;
+    if (threadIdx.x == 0) cta_occ = 0;
+    __syncthreads();
     unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool occ = id < N && isfree[id] == 0;
     unsigned m = __ballot_sync(0xffffffffu, occ);
-    if ((threadIdx.x & 31) == 0 && id < N) bits[id >> 5] = m;
+    if ((threadIdx.x & 31) == 0) {
+        if (id < N) bits[id >> 5] = m;
+        if (m) atomicAdd(&cta_occ, (unsigned)__popc(m));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && cta_occ) atomicAdd(occupied, (unsigned long long)cta_occ);
 }
 __global__ void k_unpack_isfree(const uint32_t* __restrict__ bits, uint8_t* __restrict__ isfree, unsigned long long N)
 {
@@ -236,13 +244,13 @@ static int grid_alloc_common(wr_grid* g)
     g->N = (size_t)g->rx * g->ry * g->rz;
     g->nwords = (g->N + 31) / 32;
     size_t nc = (size_t)g->rx + g->ry + g->rz;
-    WR_CUDA(cudaMalloc(&g->d_coords, nc * sizeof(float)));
+    WR_CUDA(dmalloc(&g->d_coords, nc * sizeof(float), 0));
     std::vector<float> c(nc);
     std::copy(g->h_xs.begin(), g->h_xs.end(), c.begin());
     std::copy(g->h_ys.begin(), g->h_ys.end(), c.begin() + g->rx);
     std::copy(g->h_zs.begin(), g->h_zs.end(), c.begin() + g->rx + g->ry);
     WR_CUDA(cudaMemcpy(g->d_coords, c.data(), nc * sizeof(float), cudaMemcpyHostToDevice));
-    WR_CUDA(cudaMalloc(&g->d_bits, (g->nwords + 4) * sizeof(uint32_t)));
+    WR_CUDA(dmalloc(&g->d_bits, (g->nwords + 4) * sizeof(uint32_t), 0));
     WR_CUDA(cudaMemset(g->d_bits, 0, (g->nwords + 4) * sizeof(uint32_t)));
     return WR_OK;
 }
@@ -250,7 +258,7 @@ static int grid_alloc_common(wr_grid* g)
 int grid_ensure_open6(wr_grid* g, cudaStream_t s)
 {
     if (g->d_open6) return WR_OK;
-    WR_CUDA(cudaMalloc(&g->d_open6, g->N));
+    WR_CUDA(dmalloc(&g->d_open6, g->N, s));
     unsigned blocks = (unsigned)((g->N + 255) / 256);
     k_open6<<<blocks, 256, 0, s>>>(g->d_bits, g->d_open6, g->rx, g->ry, g->rz, g->N);
     WR_CUDA(cudaGetLastError());
@@ -332,11 +340,11 @@ extern "C" int wr_grid_create_from_triangles(const float* t12, int ntri, float p
     float* d_soa = nullptr;
     unsigned long long* d_cnt = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    auto fail = [&](int code) { cudaFree(d_soa); cudaFree(d_cnt); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); wr_grid_destroy(g); return code; };
+    auto fail = [&](int code) { pool_free(d_soa, 0); pool_free(d_cnt, 0); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); wr_grid_destroy(g); return code; };
 #define WR_CUDA_F(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); return fail(WR_ERR_CUDA); } } while (0)
-    WR_CUDA_F(cudaMalloc(&d_soa, soa.size() * sizeof(float)));
+    WR_CUDA_F(dmalloc(&d_soa, soa.size() * sizeof(float), 0));
     WR_CUDA_F(cudaMemcpy(d_soa, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice));
-    WR_CUDA_F(cudaMalloc(&d_cnt, 2 * sizeof(unsigned long long)));
+    WR_CUDA_F(dmalloc(&d_cnt, 2 * sizeof(unsigned long long), 0));
     WR_CUDA_F(cudaMemset(d_cnt, 0, 2 * sizeof(unsigned long long)));
     VoxArgs a;
     a.soa = d_soa; a.Tpad = Tpad; a.nchunks = Tpad / kVoxChunk; a.rx = g->rx; a.ry = g->ry; a.rz = g->rz; a.N = g->N;
@@ -358,7 +366,7 @@ extern "C" int wr_grid_create_from_triangles(const float* t12, int ntri, float p
     WR_CUDA_F(cudaMemcpy(h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost));
 #undef WR_CUDA_F
     g->occupied = h_cnt[0]; g->tests = h_cnt[1];
-    cudaFree(d_soa); cudaFree(d_cnt); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    pool_free(d_soa, 0); pool_free(d_cnt, 0); cudaEventDestroy(e0); cudaEventDestroy(e1);
     *out = g;
     return WR_OK;
 }
@@ -375,18 +383,20 @@ extern "C" int wr_grid_create_from_occupancy(const uint8_t* isfree, int rx, int 
     int st = grid_alloc_common(g);
     if (st != WR_OK) { wr_grid_destroy(g); return st; }
     uint8_t* d_free = nullptr;
-    cudaError_t e = cudaMalloc(&d_free, g->N);
-    if (e == cudaSuccess) e = cudaMemcpy(d_free, isfree, g->N, cudaMemcpyHostToDevice);
+    unsigned long long* d_occ = nullptr;
+    unsigned long long occ = 0;
+    cudaError_t e = dmalloc(&d_free, g->N, 0);
+    if (e == cudaSuccess) e = dmalloc(&d_occ, sizeof(unsigned long long), 0);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_occ, 0, sizeof(unsigned long long), 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_free, isfree, g->N, cudaMemcpyHostToDevice, 0);
     if (e == cudaSuccess) {
         unsigned blocks = (unsigned)((g->N + 255) / 256);
-        k_pack_isfree<<<blocks, 256>>>(d_free, g->d_bits, g->N);
+        k_pack_isfree<<<blocks, 256>>>(d_free, g->d_bits, g->N, d_occ);
         e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(&occ, d_occ, sizeof occ, cudaMemcpyDeviceToHost);   // also orders the upload before the caller reuses `isfree`
     }
-    cudaFree(d_free);
+    pool_free(d_free, 0); pool_free(d_occ, 0);
     if (e != cudaSuccess) { set_error("occupancy upload failed: %s", cudaGetErrorString(e)); wr_grid_destroy(g); return WR_ERR_CUDA; }
-    uint64_t occ = 0;
-    for (size_t i = 0; i < g->N; i++) occ += isfree[i] == 0;
     g->occupied = occ;
     *out = g;
     return WR_OK;
@@ -395,7 +405,7 @@ extern "C" int wr_grid_create_from_occupancy(const uint8_t* isfree, int rx, int 
 extern "C" int wr_grid_destroy(wr_grid* g)
 {
     if (!g) return WR_OK;
-    cudaFree(g->d_coords); cudaFree(g->d_bits); cudaFree(g->d_open6);
+    pool_free(g->d_coords, 0); pool_free(g->d_bits, 0); pool_free(g->d_open6, 0);
     delete g;
     return WR_OK;
 }
@@ -438,11 +448,11 @@ extern "C" int wr_grid_download_isfree(const wr_grid* g, uint8_t* isfree, size_t
     WR_REQUIRE(g && isfree, WR_ERR_INVALID, "wr_grid_download_isfree: null");
     WR_REQUIRE(n >= g->N, WR_ERR_CAPACITY, "wr_grid_download_isfree: buffer too small");
     uint8_t* d = nullptr;
-    WR_CUDA(cudaMalloc(&d, g->N));
+    WR_CUDA(dmalloc(&d, g->N, 0));
     k_unpack_isfree<<<(unsigned)((g->N + 255) / 256), 256>>>(g->d_bits, d, g->N);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(isfree, d, g->N, cudaMemcpyDeviceToHost);
-    cudaFree(d);
+    pool_free(d, 0);
     if (e != cudaSuccess) { set_error("wr_grid_download_isfree: %s", cudaGetErrorString(e)); return WR_ERR_CUDA; }
     return WR_OK;
 }

@@ -116,22 +116,22 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
     }
 }
 
-int sort_plan_create(SortPlan* p, size_t max_n)
+int sort_plan_create(SortPlan* p, size_t max_n, cudaStream_t s)
 {
     if (max_n < 1) max_n = 1;
     p->max_n = max_n;
     p->max_tiles = (int)((max_n + kTile - 1) / kTile);
-    WR_CUDA(cudaMalloc(&p->keys_a, max_n * sizeof(uint32_t)));
-    WR_CUDA(cudaMalloc(&p->keys_b, max_n * sizeof(uint32_t)));
-    WR_CUDA(cudaMalloc(&p->vals_a, max_n * sizeof(uint32_t)));
-    WR_CUDA(cudaMalloc(&p->vals_b, max_n * sizeof(uint32_t)));
-    WR_CUDA(cudaMalloc(&p->hist, ((size_t)256 * p->max_tiles + 256) * sizeof(uint32_t)));   // + 256 digit totals
+    WR_CUDA(dmalloc(&p->keys_a, max_n * sizeof(uint32_t), s));
+    WR_CUDA(dmalloc(&p->keys_b, max_n * sizeof(uint32_t), s));
+    WR_CUDA(dmalloc(&p->vals_a, max_n * sizeof(uint32_t), s));
+    WR_CUDA(dmalloc(&p->vals_b, max_n * sizeof(uint32_t), s));
+    WR_CUDA(dmalloc(&p->hist, ((size_t)256 * p->max_tiles + 256) * sizeof(uint32_t), s));   // + 256 digit totals
     return WR_OK;
 }
 
-void sort_plan_destroy(SortPlan* p)
+void sort_plan_destroy(SortPlan* p, cudaStream_t s)
 {
-    cudaFree(p->keys_a); cudaFree(p->keys_b); cudaFree(p->vals_a); cudaFree(p->vals_b); cudaFree(p->hist);
+    pool_free(p->keys_a, s); pool_free(p->keys_b, s); pool_free(p->vals_a, s); pool_free(p->vals_b, s); pool_free(p->hist, s);
     *p = SortPlan();
 }
 

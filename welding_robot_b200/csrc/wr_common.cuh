@@ -38,6 +38,13 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Stream-ordered device memory from the device's default pool with the release threshold lifted, so
+// that creating and destroying handles in a loop (one search per request) re-uses HBM instead of
+// going back to the driver: a 403 MB pheromone field costs microseconds to obtain, not milliseconds.
+cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t s);
+void pool_free(void* p, cudaStream_t s);
+template <class T> inline cudaError_t dmalloc(T** p, size_t bytes, cudaStream_t s) { return pool_malloc(reinterpret_cast<void**>(p), bytes, s); }
+
 // ---- Philox4x32-10 (Salmon et al. SC'11), same stream layout as the CPU oracle ------------
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;

@@ -33,8 +33,8 @@ struct SortPlan {
     size_t max_n = 0;
     int max_tiles = 0;
 };
-int sort_plan_create(SortPlan* p, size_t max_n);
-void sort_plan_destroy(SortPlan* p);
+int sort_plan_create(SortPlan* p, size_t max_n, cudaStream_t s);
+void sort_plan_destroy(SortPlan* p, cudaStream_t s);
 // Sorts keys_a/vals_a (first *d_n entries) by the low `key_bits` bits; result lands in
 // keys_a/vals_a again when the pass count is even, else in keys_b/vals_b: returns which.
 int sort_pairs(SortPlan* p, const int* d_n, int key_bits, cudaStream_t s, bool* result_in_b);
