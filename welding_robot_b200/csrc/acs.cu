@@ -91,7 +91,6 @@ struct wr_acs {
     unsigned ntiles = 0;
     int cap = 0, rank_bits = 0, slot_bits = 0;
     int table_log2 = 9, gtable_log2 = 0;
-    bool walk_thread = false;  // thread-per-ant walk kernel (measurement variant); default: the 8-lane-group kernel
     int64_t start = -1, goal = -1;
     bool begun = false;
     int colony_max = 0, w_max = 0;
@@ -114,8 +113,9 @@ struct wr_acs {
     uint32_t* d_path_ids = nullptr;
     uint8_t* d_path_dirs = nullptr;
     uint32_t* d_overflow = nullptr;
-    uint32_t* d_gkeys = nullptr;
+    uint32_t* d_gkeys = nullptr;      // HBM visited tables for overflowed ants, one per local ant
     unsigned long long* d_gmasks = nullptr;
+    int4* d_resume = nullptr;
     int walk2_blocks = 0;
     uint32_t* d_rec_off = nullptr;
     int* d_order = nullptr;
@@ -135,7 +135,7 @@ static void free_colony_buffers(wr_acs* a)
 {
     cudaStream_t s = a->stream;
     pool_free(a->d_ant_steps, s); pool_free(a->d_path_ids, s); pool_free(a->d_path_dirs, s); pool_free(a->d_overflow, s);
-    pool_free(a->d_gkeys, s); pool_free(a->d_gmasks, s); pool_free(a->d_rec_off, s); pool_free(a->d_order, s);
+    pool_free(a->d_gkeys, s); pool_free(a->d_gmasks, s); pool_free(a->d_resume, s); a->d_resume = nullptr; pool_free(a->d_rec_off, s); pool_free(a->d_order, s);
     if (a->d_local_steps != a->d_ant_steps) pool_free(a->d_local_steps, s);
     pool_free(a->d_cand, s); a->d_local_steps = nullptr; a->d_cand = nullptr;
     a->d_ant_steps = nullptr; a->d_path_ids = nullptr; a->d_path_dirs = nullptr; a->d_overflow = nullptr;
@@ -167,12 +167,15 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     WR_CUDA(dmalloc(&a->d_rec_off, cm * sizeof(uint32_t), a->stream));
     WR_CUDA(dmalloc(&a->d_order, cm * sizeof(int), a->stream));
     WR_CUDA(cudaMemsetAsync(a->d_order, 0, cm * sizeof(int), a->stream));
-    // pass-2 visited tables in HBM: every tile an ant can touch fits (tiles <= steps+1 <= cap+1)
+    // HBM visited tables for ants whose shared-memory table fills up: every tile an ant can touch fits
+    // (tiles <= steps+1 <= cap+1), one table per local ant so that any number of them can overflow
     a->gtable_log2 = ceil_log2((unsigned long long)cap + 3);
-    a->walk2_blocks = (int)std::min<size_t>((chunk + kAntsPerCta - 1) / kAntsPerCta, 32);
-    const size_t gslots = (size_t)a->walk2_blocks * kWalkTAnts << a->gtable_log2;   // 32 tables per pass-2 CTA (thread-per-ant kernel)
+    a->walk2_blocks = (int)std::min<size_t>((chunk + kAntsPerCta - 1) / kAntsPerCta, (size_t)kNumSMs * 4);
+    const size_t gslots = chunk << a->gtable_log2;
+    if (gslots * 12 > ((size_t)48 << 30)) { set_error("colony %zu x step cap %zu needs %zu GB of overflow tables; set a smaller step_cap", cm, cap, (gslots * 12) >> 30); return WR_ERR_NOMEM; }
     WR_CUDA(dmalloc(&a->d_gkeys, gslots * sizeof(uint32_t), a->stream));
     WR_CUDA(dmalloc(&a->d_gmasks, gslots * sizeof(unsigned long long), a->stream));
+    WR_CUDA(dmalloc(&a->d_resume, chunk * sizeof(int4), a->stream));
     int st = sort_plan_create(&a->sort_ants, cm, a->stream);
     if (st != WR_OK) return st;
     st = sort_plan_create(&a->sort_recs, rec_max, a->stream);
@@ -275,9 +278,6 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
         size_t ws = (((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15) + ((size_t)kAntsPerCta << a->table_log2) * 12;
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         WR_CUDA_A(cudaFuncSetAttribute(k_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
-        size_t wt = (((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15) + ((size_t)kWalkTAnts << a->table_log2) * 12;
-        a->walk_thread = getenv("WR_WALK_THREAD") != nullptr && wt <= 227 * 1024;   // measurement variant, see DESIGN.md
-        if (a->walk_thread) WR_CUDA_A(cudaFuncSetAttribute(k_walk_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wt));
     }
     WR_CUDA_A(cudaStreamSynchronize(a->stream));
 #undef WR_CUDA_A
@@ -365,26 +365,16 @@ static int launch_walk(wr_acs* a)
     w.ant_steps = a->d_local_steps;
     w.path_ids = a->d_path_ids; w.path_dirs = a->d_path_dirs;
     w.table_log2 = a->table_log2; w.overflow_list = a->d_overflow;
-    w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks;
+    w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks; w.gtable_log2 = a->gtable_log2; w.resume = a->d_resume;
     const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15;   // + guard elements
     const size_t smem1 = coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem1 + 1024)));
     const int blocks1 = std::max(1, std::min((a->chunk + kAntsPerCta - 1) / kAntsPerCta, kNumSMs * std::min(per_sm, 16)));
-    if (a->walk_thread) {
-        const size_t smemt = coord_bytes + ((size_t)kWalkTAnts << a->table_log2) * 12;
-        const int per_sm_t = std::max(1, (int)((227 * 1024) / (smemt + 1024)));
-        const int blocks_t = std::max(1, std::min((a->chunk + kWalkTAnts - 1) / kWalkTAnts, kNumSMs * per_sm_t));
-        k_walk_t<false><<<blocks_t, 32, smemt, a->stream>>>(w);
-        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
-        w.table_log2 = a->gtable_log2;
-        k_walk_t<true><<<a->walk2_blocks, 32, coord_bytes, a->stream>>>(w);
-    } else {
-        k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-        // pass 2: ants whose shared-memory table overflowed (usually none: the kernel exits at once)
-        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
-        w.table_log2 = a->gtable_log2;
-        k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
-    }
+    k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+    // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
+    k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
+    w.table_log2 = a->gtable_log2;
+    k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }

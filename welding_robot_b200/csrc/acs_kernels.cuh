@@ -40,8 +40,10 @@ struct WalkArgs {
     uint8_t* path_dirs;      // [chunk][cap]   slot chosen at step i
     int table_log2;          // shared-memory (pass 1) or global (pass 2) visited-tile table size
     uint32_t* overflow_list; // [chunk]
-    uint32_t* gkeys;         // pass 2: [groups][1<<table_log2]
+    uint32_t* gkeys;         // HBM visited tables, one per overflowed ant: [chunk][1 << gtable_log2]
     unsigned long long* gmasks;
+    int gtable_log2;
+    int4* resume;            // [chunk] state of an overflowed ant: {cur, steps, ntiles, -}
 };
 
 __device__ __forceinline__ float pow_int(float x, int y)
@@ -107,9 +109,11 @@ __global__ void k_queue_reset(IterState* st) { st->queue = 0; }
 //
 // Visited set ("tabu", std::set at :70): an open-addressed hash of 4x4x4-node tiles, 64-bit
 // occupancy mask per tile, in shared memory.  A lattice walk re-visits the same few tiles, so a
-// 512-slot table (6 KB) holds walks of thousands of steps.  An ant that fills its table to 3/4 is
-// re-run from scratch by pass 2 (GLOBAL = true) with a table in HBM sized for the step cap —
-// exact, because its draws are a pure function of (iteration, ant, step).
+// 512-slot table (6 KB) holds walks of thousands of steps.  An ant that fills its table to 3/4
+// moves its visited set to a table in HBM sized for the step cap (parallel CAS inserts), parks its
+// state, and is RESUMED by pass 2 (GLOBAL = true) from the step it stopped at — exact, because its
+// draws are a pure function of (iteration, ant, step).  Keeping the two table kinds in two launches
+// lets the common path keep shared-memory addressing (a run-time switch costs 8-13 % per step).
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ float slow_norm1(float d) { return __fsqrt_rn(__fmul_rn(d, d)); }
 
@@ -140,9 +144,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
     unsigned long long* masks;
     uint32_t* keys;
     if (GLOBAL) {
-        size_t slot = (size_t)blockIdx.x * kAntsPerCta + g;
-        keys = a.gkeys + slot * E;
-        masks = a.gmasks + slot * E;
+        keys = a.gkeys; masks = a.gmasks;   // re-pointed per ant below
     } else {
         unsigned long long* mbase = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)ncoord * 4 + 15) & ~(size_t)15));
         masks = mbase + (size_t)g * E;
@@ -184,14 +186,26 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
         const int ant_local = has ? (GLOBAL ? (int)a.overflow_list[q] : (int)q) : 0;
         const uint32_t ant_global = (uint32_t)(a.shard_first + ant_local);
 
-        for (int i = k; i < E; i += kGroup) keys[i] = kEmptyKey;
-        __syncwarp();
         int cur = a.start, x = sx, y = sy, z = sz, steps = 0, ntiles = 1;
-        if (k == 0) {   // addStartNode :81-86
-            uint32_t tile = (uint32_t)(((z >> 2) * TY + (y >> 2)) * TX + (x >> 2));
-            unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
-            unsigned slot = (tile * 2654435761u) >> hshift;
-            keys[slot] = tile; masks[slot] = 1ull << bit;
+        uint32_t rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0;
+        if (GLOBAL) {   // resume a parked ant: its visited set already lives in HBM table q
+            keys = a.gkeys + (size_t)(has ? q : 0) * E;
+            masks = a.gmasks + (size_t)(has ? q : 0) * E;
+            if (has) {
+                const int4 r = a.resume[q];
+                cur = r.x; steps = r.y; ntiles = r.z;
+                z = cur / rxy; y = (cur % rxy) / rx; x = cur % rx;
+                philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
+            }
+        } else {
+            for (int i = k; i < E; i += kGroup) keys[i] = kEmptyKey;
+            __syncwarp();
+            if (k == 0) {   // addStartNode :81-86
+                uint32_t tile = (uint32_t)(((z >> 2) * TY + (y >> 2)) * TX + (x >> 2));
+                unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
+                unsigned slot = (tile * 2654435761u) >> hshift;
+                keys[slot] = tile; masks[slot] = 1ull << bit;
+            }
         }
         __syncwarp();
 
@@ -200,7 +214,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
         int reason = 0;    // why a dead ant died: 1 no candidate, 2 roulette fall-through, 3 step cap
         uint32_t* pid = a.path_ids + (size_t)ant_local * a.cap;
         uint8_t* pdir = a.path_dirs + (size_t)ant_local * a.cap;
-        uint32_t rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0;
         int pos = axis_k == 0 ? x : (axis_k == 1 ? y : z);        // the ant's index along this lane's axis
 
         while (__any_sync(FULL, live)) {
@@ -280,6 +293,31 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             result = arrived ? steps : (over ? -2 : result);
             live = stepok && !arrived && !over;
             __syncwarp();
+            if (!GLOBAL && __any_sync(FULL, over)) {   // rare: an ant of this warp filled its shared-memory table to 3/4
+                int o = 0;
+                if (over && k == 0) o = (int)atomicAdd(&st->overflow_n, 1u);
+                o = __shfl_sync(FULL, o, 0, 8);
+                const int Eg = 1 << a.gtable_log2, gsh = 32 - a.gtable_log2;
+                uint32_t* nkeys = a.gkeys + (size_t)(over ? o : 0) * Eg;
+                unsigned long long* nmasks = a.gmasks + (size_t)(over ? o : 0) * Eg;
+                if (over) for (int i = k; i < Eg; i += kGroup) nkeys[i] = kEmptyKey;
+                __syncwarp();
+                if (over) {
+                    for (int i = k; i < E; i += kGroup) {
+                        const uint32_t t = keys[i];
+                        if (t == kEmptyKey) continue;
+                        unsigned sl = (t * 2654435761u) >> gsh;
+                        while (atomicCAS(&nkeys[sl], kEmptyKey, t) != kEmptyKey) sl = (sl + 1) & (Eg - 1);
+                        nmasks[sl] = masks[i];
+                    }
+                    if (k == 0) {
+                        a.resume[o] = make_int4(cur, steps, ntiles, 0);
+                        a.overflow_list[o] = (uint32_t)ant_local;
+                        a.ant_steps[ant_local] = -2;
+                    }
+                }
+                __syncwarp();
+            }
         }
         if (has && result != -2) {
             c_arrived += result >= 0 ? 1 : 0;
@@ -289,12 +327,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
         }
         if (has) {
             if (result == -2) {
-                if (k == 0) {
-                    unsigned o = atomicAdd(&st->overflow_n, 1u);
-                    a.overflow_list[o] = (uint32_t)ant_local;
-                    a.ant_steps[ant_local] = -2;
-                }
-                c_over++;
+                c_over++;   // parked for pass 2 (its steps are counted there)
             } else {
                 if (k == 0) a.ant_steps[ant_local] = result;
                 c_steps += (unsigned long long)steps; c_ants++;
@@ -310,207 +343,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
         if (c_fall) atomicAdd(&st->cnt[4], c_fall);
         if (c_cap) atomicAdd(&st->cnt[5], c_cap);
         if (c_over) atomicAdd(&st->cnt[8], c_over);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K2, thread-per-ant variant.  One ant per THREAD, one warp per CTA, 32 visited tables in shared
-// memory interleaved by lane (table[slot][lane]: conflict-free).  No cross-lane traffic at all: the
-// six neighbours are evaluated by the owning thread, fully unrolled, which gives the scheduler six
-// independent dependency chains to interleave (the 8-lane kernel above spends ~300 instructions per
-// step for FOUR ants, mostly serial; this one spends about as many for THIRTY-TWO).
-// ------------------------------------------------------------------------------------------
-constexpr int kWalkTAnts = 32;
-
-template <bool GLOBAL>
-__global__ void __launch_bounds__(32) k_walk_t(WalkArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* xs = reinterpret_cast<float*>(smem_raw) + 1;
-    float* ys = xs + a.rx + 2;
-    float* zs = ys + a.ry + 2;
-    const int ncoord = a.rx + a.ry + a.rz + 6;
-    const int lane = threadIdx.x;
-    for (int i = lane; i < ncoord; i += 32) reinterpret_cast<float*>(smem_raw)[i] = 0.0f;
-    __syncwarp();
-    for (int i = lane; i < a.rx; i += 32) xs[i] = a.coords[i];
-    for (int i = lane; i < a.ry; i += 32) ys[i] = a.coords[a.rx + i];
-    for (int i = lane; i < a.rz; i += 32) zs[i] = a.coords[a.rx + a.ry + i];
-    __syncwarp();
-
-    constexpr unsigned FULL = 0xffffffffu;
-    const int E = 1 << a.table_log2;
-    const int hshift = 32 - a.table_log2;
-    unsigned long long* masks;   // [E][32]
-    uint32_t* keys;              // [E][32]
-    if (GLOBAL) {
-        keys = a.gkeys + (size_t)blockIdx.x * kWalkTAnts * E;
-        masks = a.gmasks + (size_t)blockIdx.x * kWalkTAnts * E;
-    } else {
-        masks = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)ncoord * 4 + 15) & ~(size_t)15));
-        keys = reinterpret_cast<uint32_t*>(masks + (size_t)kWalkTAnts * E);
-    }
-    keys += lane; masks += lane;   // this thread's column
-
-    const int rx = a.rx, ry = a.ry;
-    const int rxy = rx * ry;
-    const int TX = (rx + 3) >> 2, TY = (ry + 3) >> 2;
-    const int sz = a.start / rxy, sy = (a.start % rxy) / rx, sx = a.start % rx;
-    const int gz = a.goal / rxy, gy = (a.goal % rxy) / rx, gx = a.goal % rx;
-    const float gxc = xs[gx], gyc = ys[gy], gzc = zs[gz];
-    const bool alpha1 = a.alpha == 1;
-    const float beta = a.beta;
-
-    IterState* st = a.st;
-    const int colony = st->colony;
-    const uint32_t iter = (uint32_t)st->iter;
-    int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
-    if (GLOBAL) local_n = (int)st->overflow_n;
-    const int limit = (E >> 2) * 3;
-
-    unsigned c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
-
-    while (true) {
-        unsigned q0 = 0;
-        if (lane == 0) q0 = atomicAdd(&st->queue, (unsigned)kWalkTAnts);
-        q0 = __shfl_sync(FULL, q0, 0);
-        if (q0 >= (unsigned)local_n) break;
-        const unsigned q = q0 + (unsigned)lane;
-        const bool has = q < (unsigned)local_n;
-        const int ant_local = has ? (GLOBAL ? (int)a.overflow_list[q] : (int)q) : 0;
-        const uint32_t ant_global = (uint32_t)(a.shard_first + ant_local);
-
-        for (int i = 0; i < E; i++) keys[i * 32] = kEmptyKey;
-        int cur = a.start, x = sx, y = sy, z = sz, steps = 0, ntiles = 1;
-        {   // addStartNode :81-86
-            const uint32_t tile = (uint32_t)(((z >> 2) * TY + (y >> 2)) * TX + (x >> 2));
-            const unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
-            const unsigned slot = (tile * 2654435761u) >> hshift;
-            keys[slot * 32] = tile; masks[slot * 32] = 1ull << bit;
-        }
-        bool live = has;
-        int result = -1, reason = 0;
-        uint32_t* pid = a.path_ids + (size_t)ant_local * a.cap;
-        uint8_t* pdir = a.path_dirs + (size_t)ant_local * a.cap;
-        uint32_t rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0;
-
-        while (__any_sync(FULL, live)) {
-            const bool capped = live && steps >= a.cap;
-            reason = capped ? 3 : reason;
-            live = live && !capped;
-            // ---- loads ---------------------------------------------------------------------------
-            const unsigned open = a.open6[cur];
-            const float2* tp = reinterpret_cast<const float2*>(a.tau + (size_t)cur * 6);
-            const float2 t01 = __ldg(tp), t23 = __ldg(tp + 1), t45 = __ldg(tp + 2);
-            if (live && (steps & 3) == 0) philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
-            const uint32_t rsel = (steps & 2) ? ((steps & 1) ? rw3 : rw2) : ((steps & 1) ? rw1 : rw0);
-            const float u = __fmul_rn(__int2float_rn((int)(rsel >> 1)), 4.656612873077392578125e-10f);
-            // ---- geometry shared by the six neighbours -------------------------------------------
-            const float cx = xs[x], cy = ys[y], cz = zs[z];
-            const float ax = __fsub_rn(gxc, cx), ay = __fsub_rn(gyc, cy), az = __fsub_rn(gzc, cz);
-            const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
-            const float tauk[6] = {t01.x, t01.y, t23.x, t23.y, t45.x, t45.y};
-            float info[6];
-            unsigned slotk[6];
-            unsigned long long mmk[6];
-            uint32_t tilek[6];
-            unsigned bitk[6];
-            unsigned foundm = 0, candm = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                const int dx = (k == 3) - (k == 2), dy = (k == 4) - (k == 1), dz = (k == 5) - (k == 0);
-                const int nx = x + dx, ny = y + dy, nz = z + dz;
-                const bool open_k = (open >> k) & 1u;
-                const uint32_t tile = (uint32_t)(((nz >> 2) * TY + (ny >> 2)) * TX + (nx >> 2));
-                const unsigned bit = ((nz & 3) << 4) | ((ny & 3) << 2) | (nx & 3);
-                unsigned slot = (tile * 2654435761u) >> hshift;
-                uint32_t kk = keys[slot * 32];
-                unsigned long long mm = masks[slot * 32];
-                while (open_k && kk != tile && kk != kEmptyKey) {
-                    slot = (slot + 1) & (E - 1);
-                    kk = keys[slot * 32]; mm = masks[slot * 32];
-                }
-                const bool found = kk == tile;
-                const bool cand = live && open_k && !(found && ((mm >> bit) & 1ull));
-                const float ac = dx ? ax : (dy ? ay : az);
-                const float cc = dx ? cx : (dy ? cy : cz);
-                const float nc = dx ? xs[nx] : (dy ? ys[ny] : zs[nz]);
-                const float d = __fsub_rn(nc, cc);
-                float nb = fabsf(d);
-                if (!(nb >= 1e-18f && nb <= 1e18f) && nb != 0.0f) nb = slow_norm1(d);
-                const float cosv = __fdiv_rn(__fmul_rn(ac, d), __fmul_rn(na, nb));
-                const float tpow = alpha1 ? tauk[k] : pow_int(tauk[k], a.alpha);
-                info[k] = cand ? __fmul_rn(tpow, __fadd_rn(1.0f, __fmul_rn(beta, cosv))) : 0.0f;
-                slotk[k] = slot; mmk[k] = mm; tilek[k] = tile; bitk[k] = bit;
-                foundm |= (found ? 1u : 0u) << k;
-                candm |= (cand ? 1u : 0u) << k;
-            }
-            // ---- roulette (:155, :168-181) -------------------------------------------------------
-            const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, info[0]), info[1]), info[2]), info[3]), info[4]), info[5]);
-            const float rnd = __fmul_rn(u, total);
-            float ps = 0.0f;
-            int c = -1;
-#pragma unroll
-            for (int k = 5; k >= 0; k--) {
-                ps = __fadd_rn(ps, info[k]);
-                if (c < 0 && ((candm >> k) & 1u) && ps >= rnd) c = k;
-            }
-            const bool stepok = live && c >= 0;
-            reason = (live && !stepok) ? (candm == 0 ? 1 : 2) : reason;
-            const int cs = c < 0 ? 0 : c;
-            // ---- addNextNode (:73-79) ------------------------------------------------------------
-            unsigned slot_c = slotk[0]; unsigned long long mm_c = mmk[0]; uint32_t tile_c = tilek[0]; unsigned bit_c = bitk[0];
-#pragma unroll
-            for (int k = 1; k < 6; k++) if (cs == k) { slot_c = slotk[k]; mm_c = mmk[k]; tile_c = tilek[k]; bit_c = bitk[k]; }
-            const bool found_c = (foundm >> cs) & 1u;
-            if (stepok) {
-                pid[steps] = (uint32_t)cur; pdir[steps] = (uint8_t)cs;
-                keys[slot_c * 32] = tile_c;
-                masks[slot_c * 32] = found_c ? (mm_c | (1ull << bit_c)) : (1ull << bit_c);
-                const int mdx = (cs == 3) - (cs == 2), mdy = (cs == 4) - (cs == 1), mdz = (cs == 5) - (cs == 0);
-                x += mdx; y += mdy; z += mdz;
-                cur += mdx + mdy * rx + mdz * rxy;
-                steps++;
-                ntiles += found_c ? 0 : 1;
-            }
-            const bool arrived = stepok && cur == a.goal;
-            const bool over = !GLOBAL && stepok && !arrived && !found_c && ntiles > limit;
-            result = arrived ? steps : (over ? -2 : result);
-            live = stepok && !arrived && !over;
-        }
-        if (has) {
-            if (result == -2) {
-                unsigned o = atomicAdd(&st->overflow_n, 1u);
-                a.overflow_list[o] = (uint32_t)ant_local;
-                a.ant_steps[ant_local] = -2;
-                c_over++;
-            } else {
-                a.ant_steps[ant_local] = result;
-                c_steps += (unsigned)steps; c_ants++;
-                c_arrived += result >= 0 ? 1 : 0;
-                c_nocand += (result < 0 && reason == 1) ? 1 : 0;
-                c_fall += (result < 0 && reason == 2) ? 1 : 0;
-                c_cap += (result < 0 && reason == 3) ? 1 : 0;
-            }
-        }
-        __syncwarp();
-    }
-    // warp-reduce the counters, one atomic per counter per warp
-    unsigned long long cs64 = c_steps;
-    for (int o = 16; o; o >>= 1) {
-        cs64 += __shfl_xor_sync(FULL, cs64, o);
-        c_ants += __shfl_xor_sync(FULL, c_ants, o); c_arrived += __shfl_xor_sync(FULL, c_arrived, o);
-        c_nocand += __shfl_xor_sync(FULL, c_nocand, o); c_fall += __shfl_xor_sync(FULL, c_fall, o);
-        c_cap += __shfl_xor_sync(FULL, c_cap, o); c_over += __shfl_xor_sync(FULL, c_over, o);
-    }
-    if (lane == 0) {
-        if (cs64) atomicAdd(&st->cnt[0], cs64);
-        if (c_ants) atomicAdd(&st->cnt[1], (unsigned long long)c_ants);
-        if (c_arrived) atomicAdd(&st->cnt[2], (unsigned long long)c_arrived);
-        if (c_nocand) atomicAdd(&st->cnt[3], (unsigned long long)c_nocand);
-        if (c_fall) atomicAdd(&st->cnt[4], (unsigned long long)c_fall);
-        if (c_cap) atomicAdd(&st->cnt[5], (unsigned long long)c_cap);
-        if (c_over) atomicAdd(&st->cnt[8], (unsigned long long)c_over);
     }
 }
 
