@@ -202,3 +202,55 @@ def test_path_properties_full_size(wr, meshes):
     assert checked > 5
     ids, dirs, L = g.bestPath()
     assert ids[0] == s and ids[-1] == e and len(ids) == len(dirs) + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# larger grids (BASELINE configs[2] / configs[4] shapes)
+# ---------------------------------------------------------------------------------------------
+def test_voxel_grid_512_long_matches_oracle(wr, oracle, meshes):
+    """C3: origin_piece.stl (29 888 triangles) at a 512-long grid (~20 M nodes).  The reference's
+    O(T*N) loop cannot run at this size (4e15 tests); the oracle's box-restricted form of the same
+    predicate can."""
+    precision = 0.823812 / 491.5
+    G = oracle.Grid.from_triangles(meshes["origin_piece"], precision, 10, oracle.VOX_AABB)
+    g = gpu_grid(wr, meshes["origin_piece"], precision, 10)
+    assert (g.rangeX, g.rangeY, g.rangeZ) == G.dims and max(G.dims) == 512
+    assert np.array_equal(g.isfree(), G.isfree())
+    st = g.stats()
+    assert st["tests"] == G.tests() and st["occupied"] == int((G.isfree() == 0).sum())
+
+
+def synthetic_boxes(n, nboxes, seed):
+    """C5-style obstacle grid: union of axis-aligned boxes, 10-cell free wall, coordinates = indices."""
+    rng = np.random.default_rng(seed)
+    occ = np.zeros((n, n, n), bool)
+    for _ in range(nboxes):
+        e = rng.integers(4, 49, 3)
+        c = [int(rng.integers(10, n - 10 - int(e[k]))) for k in range(3)]
+        occ[c[2]:c[2] + e[2], c[1]:c[1] + e[1], c[0]:c[0] + e[0]] = True
+    return (~occ).astype(np.uint8).ravel()
+
+
+def test_synthetic_512_cubed_query(wr, oracle):
+    """C5 shape: one start/goal query on a synthetic 512^3 obstacle grid (3.2 GB pheromone field),
+    256 ants, against the oracle for two iterations — every ant, best path and the whole field."""
+    n = 512
+    free = synthetic_boxes(n, 1500, 4)
+    axis = np.arange(n, dtype=np.float32)
+    ids = np.flatnonzero(free)
+    rng = np.random.default_rng(5)
+    s = int(ids[rng.integers(0, len(ids))])
+    sz, sy, sx = s // (n * n), (s // n) % n, s % n
+    cand = ids[(np.abs(ids // (n * n) - sz) + np.abs((ids // n) % n - sy) + np.abs(ids % n - sx)) == 96]
+    e = int(cand[rng.integers(0, len(cand))])
+    G = oracle.Grid.from_occupancy(free, axis, axis, axis, 1.0)
+    A = oracle.Acs(G, seed=5, fixed_colony=256, step_cap=2048)
+    g = wr.ACS_Rank(seed=5, fixed_colony=256, step_cap=2048)
+    g.creatFromOccupancy(free, axis, axis, axis, 1.0)
+    g.initFromGridMap()
+    A.set_endpoints(s, e); g.setEndpoints(s, e)
+    A.begin(100.0); g.begin(100.0)
+    for _ in range(2):
+        A.iterate(1); g.iterate(1)
+        compare_iteration(A, g)
+    assert g.counters()["arrived"] > 0
