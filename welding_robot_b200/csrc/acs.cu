@@ -98,6 +98,8 @@ struct wr_acs {
     int rank = 0, nranks = 1, chunk = 0;
 
     float* d_tau = nullptr;
+    float* d_heur = nullptr;          // [N][6] heuristic factor for the current goal
+    int64_t heur_goal = -1;           // goal it was computed for
     IterState* d_state = nullptr;
     uint32_t* d_onbest = nullptr;
     float* d_Ltab = nullptr;
@@ -214,7 +216,7 @@ extern "C" int wr_acs_destroy(wr_acs* a)
     if (a->stream) cudaStreamSynchronize(a->stream);
     free_colony_buffers(a);
     cudaStream_t s = a->stream;
-    pool_free(a->d_tau, s); pool_free(a->d_state, s); pool_free(a->d_onbest, s); pool_free(a->d_Ltab, s);
+    pool_free(a->d_tau, s); pool_free(a->d_heur, s); pool_free(a->d_state, s); pool_free(a->d_onbest, s); pool_free(a->d_Ltab, s);
     pool_free(a->d_best_n, s); pool_free(a->d_best_ids, s); pool_free(a->d_best_dirs, s); pool_free(a->d_tile_off, s); pool_free(a->d_dep_list, s);
     pool_free(a->d_upd_q, s);
     if (a->stream) cudaStreamSynchronize(a->stream);
@@ -344,6 +346,12 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     int st = alloc_colony_buffers(a, cm);
     if (st != WR_OK) return st;
     a->colony_max = cm;
+    if (!a->d_heur) WR_CUDA(dmalloc(&a->d_heur, a->n_slots_pad * sizeof(float), a->stream));
+    if (a->heur_goal != a->goal) {   // selectNext's geometric factor, tabulated once per goal
+        k_heuristic<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_heur, a->g->d_coords, a->g->rx, a->g->ry, a->g->rz, a->N, (int)a->goal,
+                                                                            a->p.beta);
+        a->heur_goal = a->goal;
+    }
     k_begin<<<1, 1, 0, a->stream>>>(a->d_state, predict);
     WR_CUDA(cudaGetLastError());
     a->begun = true;
@@ -356,7 +364,7 @@ static int launch_walk(wr_acs* a)
 {
     const wr_grid* g = a->g;
     WalkArgs w;
-    w.st = a->d_state; w.tau = a->d_tau; w.open6 = g->d_open6; w.coords = g->d_coords;
+    w.st = a->d_state; w.tau = a->d_tau; w.heur = a->d_heur; w.open6 = g->d_open6; w.coords = g->d_coords;
     w.rx = g->rx; w.ry = g->ry; w.rz = g->rz;
     w.start = (int)a->start; w.goal = (int)a->goal;
     w.seed_lo = (uint32_t)a->p.seed; w.seed_hi = (uint32_t)(a->p.seed >> 32);

@@ -26,6 +26,7 @@ constexpr int kUpdThreads = 256;
 struct WalkArgs {
     IterState* st;
     const float* tau;        // [N][6] node-major ("edge-major": a node's 6 directed slots are contiguous)
+    const float* heur;       // [N][6]  1 + beta*cos(theta) per directed slot for the current goal (k_heuristic)
     const uint8_t* open6;    // [N]
     const float* coords;     // xs | ys | zs
     int rx, ry, rz;
@@ -90,6 +91,51 @@ __global__ void k_iter_end(IterState* st)
 __global__ void k_queue_reset(IterState* st) { st->queue = 0; }
 
 // ------------------------------------------------------------------------------------------
+// Heuristic table for the current goal: heur[node][k] = 1 + beta*cos(theta), theta between (goal - node) and
+// (neighbour_k - node) — selectNext :151-154, evaluated once per (node, slot) instead of once per ant-step.
+// vector_b has a single non-zero component d, so dot(a,b) = a_c*d and |b| = sqrt(d*d) = |d| exactly (the zero
+// terms add exactly; sqrt(RN(d*d)) == |d| in binary floating point unless d*d leaves the normal range, which
+// takes the slow path).  NaN on duplicate-coordinate planes (d = 0 -> 0/0) is produced here and propagates
+// through the roulette exactly like in the reference.
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ float slow_norm1(float d) { return __fsqrt_rn(__fmul_rn(d, d)); }
+
+__global__ void __launch_bounds__(256) k_heuristic(float* __restrict__ heur, const float* __restrict__ coords, int rx, int ry, int rz,
+                                                    unsigned long long N, int goal, float beta)
+{
+    const unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N) return;
+    const float* xs = coords;
+    const float* ys = xs + rx;
+    const float* zs = ys + ry;
+    const unsigned long long rxy = (unsigned long long)rx * ry;
+    const int z = (int)(id / rxy), y = (int)((id % rxy) / rx), x = (int)(id % rx);
+    const int gz = (int)(goal / rxy), gy = (int)((goal % rxy) / rx), gx = (int)(goal % rx);
+    const float cx = xs[x], cy = ys[y], cz = zs[z];
+    const float ax = __fsub_rn(xs[gx], cx), ay = __fsub_rn(ys[gy], cy), az = __fsub_rn(zs[gz], cz);
+    const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+    float h[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int dx = (k == 3) - (k == 2), dy = (k == 4) - (k == 1), dz = (k == 5) - (k == 0);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        const bool inb = nx >= 0 && nx < rx && ny >= 0 && ny < ry && nz >= 0 && nz < rz;
+        float v = 0.0f;   // out-of-bounds slots are never candidates
+        if (inb) {
+            const float ac = dx ? ax : (dy ? ay : az);
+            const float d = dx ? __fsub_rn(xs[nx], cx) : (dy ? __fsub_rn(ys[ny], cy) : __fsub_rn(zs[nz], cz));
+            float nb = fabsf(d);
+            if (!(nb >= 1e-18f && nb <= 1e18f) && nb != 0.0f) nb = slow_norm1(d);
+            const float cosv = __fdiv_rn(__fmul_rn(ac, d), __fmul_rn(na, nb));
+            v = __fadd_rn(1.0f, __fmul_rn(beta, cosv));
+        }
+        h[k] = v;
+    }
+    float2* o = reinterpret_cast<float2*>(heur + id * 6);
+    o[0] = make_float2(h[0], h[1]); o[1] = make_float2(h[2], h[3]); o[2] = make_float2(h[4], h[5]);
+}
+
+// ------------------------------------------------------------------------------------------
 // K2: one ant per 8-lane group, 4 ants per warp, 16 per CTA; persistent warps pull 4 ants at a time
 // from a device-side queue and step them in LOCKSTEP, so every warp collective runs with the full
 // mask (one SHFL / VOTE instruction each; sub-warp masks held in registers make the compiler emit a
@@ -115,8 +161,6 @@ __global__ void k_queue_reset(IterState* st) { st->queue = 0; }
 // draws are a pure function of (iteration, ant, step).  Keeping the two table kinds in two launches
 // lets the common path keep shared-memory addressing (a run-time switch costs 8-13 % per step).
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ float slow_norm1(float d) { return __fsqrt_rn(__fmul_rn(d, d)); }
-
 template <bool GLOBAL>
 __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
 {
@@ -224,6 +268,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             // ---- the loads of this step ---------------------------------------------------------
             const unsigned open = a.open6[cur];
             const float tau_k = __ldg(a.tau + (size_t)cur * 6 + kk6);
+            const float heur_k = __ldg(a.heur + (size_t)cur * 6 + kk6);
             // ---- Philox: one call yields the draws of 4 consecutive steps (the live ants of a warp are
             //      in lockstep, so the branch is warp-uniform) ---------------------------------------
             if (live && (steps & 3) == 0) philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
@@ -245,21 +290,11 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             const bool found = kk == tile;
             const bool cand = live && open_k && !(found && ((mm >> bit) & 1ull));
             // ---- info = tau^alpha * (1 + beta*cos)  (:151-154) ----------------------------------
-            // vector_b has a single non-zero component d, so dot(a,b) = a_c*d and |b| = sqrt(d*d) = |d|
-            // exactly (the zero terms add exactly; sqrt(RN(d*d)) == |d| in binary floating point unless
-            // d*d leaves the normal range, which takes the slow path).
-            const float cx = xs[x], cy = ys[y], cz = zs[z];
-            const float nc = axis_tab[pos + dk];
-            const float ax = __fsub_rn(gxc, cx), ay = __fsub_rn(gyc, cy), az = __fsub_rn(gzc, cz);
-            const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
-            const float ac = axis_k == 0 ? ax : (axis_k == 1 ? ay : az);
-            const float cc = axis_k == 0 ? cx : (axis_k == 1 ? cy : cz);
-            const float d = __fsub_rn(nc, cc);
-            float nb = fabsf(d);
-            if (!(nb >= 1e-18f && nb <= 1e18f) && nb != 0.0f) nb = slow_norm1(d);
-            const float cosv = __fdiv_rn(__fmul_rn(ac, d), __fmul_rn(na, nb));
+            // the geometric factor depends only on (node, slot, goal): k_heuristic tabulated it with the reference's
+            // operations when the endpoints were set, so a step gathers it next to the pheromone (same 24-byte row
+            // pattern) instead of redoing three coordinate look-ups, a square root and a division
             const float tpow = alpha1 ? tau_k : pow_int(tau_k, a.alpha);
-            const float info = cand ? __fmul_rn(tpow, __fadd_rn(1.0f, __fmul_rn(beta, cosv))) : 0.0f;
+            const float info = cand ? __fmul_rn(tpow, heur_k) : 0.0f;
             const unsigned cb = (__ballot_sync(FULL, cand) >> gbase) & 0x3Fu;
             // ---- roulette in the reference's order (:155, :172-181) ------------------------------
             const float v0 = __shfl_sync(FULL, info, 0, 8), v1 = __shfl_sync(FULL, info, 1, 8), v2 = __shfl_sync(FULL, info, 2, 8);
