@@ -265,6 +265,9 @@ def run_ours(args):
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "what": "per step, from host buffers: wr_grid_create_from_occupancy (16.8 MB H2D) -> wr_acs_create -> wr_acs_begin -> "
                        "%d x wr_acs_iterate -> wr_acs_best (D2H)" % args.iters}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     hbm, hbm_src = peaks()

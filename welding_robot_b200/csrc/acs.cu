@@ -251,8 +251,6 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     WR_CUDA_A(cudaGetDevice(&a->device));
     WR_CUDA_A(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
     a->own_stream = true;
-    int st = grid_ensure_open6(g, a->stream);
-    if (st != WR_OK) { wr_acs_destroy(a); return st; }
     WR_CUDA_A(dmalloc(&a->d_tau, a->n_slots_pad * sizeof(float), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_tau, 0, a->n_slots_pad * sizeof(float), a->stream));
     k_tau_init<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, p->tau0);
@@ -348,7 +346,7 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     a->colony_max = cm;
     if (!a->d_heur) WR_CUDA(dmalloc(&a->d_heur, a->n_slots_pad * sizeof(float), a->stream));
     if (a->heur_goal != a->goal) {   // selectNext's geometric factor, tabulated once per goal
-        k_heuristic<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_heur, a->g->d_coords, a->g->rx, a->g->ry, a->g->rz, a->N, (int)a->goal,
+        k_heuristic<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_heur, a->g->d_coords, a->g->d_bits, a->g->rx, a->g->ry, a->g->rz, a->N, (int)a->goal,
                                                                             a->p.beta);
         a->heur_goal = a->goal;
     }
@@ -364,7 +362,7 @@ static int launch_walk(wr_acs* a)
 {
     const wr_grid* g = a->g;
     WalkArgs w;
-    w.st = a->d_state; w.tau = a->d_tau; w.heur = a->d_heur; w.open6 = g->d_open6; w.coords = g->d_coords;
+    w.st = a->d_state; w.tau = a->d_tau; w.heur = a->d_heur; w.coords = g->d_coords;
     w.rx = g->rx; w.ry = g->ry; w.rz = g->rz;
     w.start = (int)a->start; w.goal = (int)a->goal;
     w.seed_lo = (uint32_t)a->p.seed; w.seed_hi = (uint32_t)(a->p.seed >> 32);

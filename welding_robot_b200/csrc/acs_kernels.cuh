@@ -27,7 +27,6 @@ struct WalkArgs {
     IterState* st;
     const float* tau;        // [N][6] node-major ("edge-major": a node's 6 directed slots are contiguous)
     const float* heur;       // [N][6]  1 + beta*cos(theta) per directed slot for the current goal (k_heuristic)
-    const uint8_t* open6;    // [N]
     const float* coords;     // xs | ys | zs
     int rx, ry, rz;
     int start, goal;
@@ -96,12 +95,15 @@ __global__ void k_queue_reset(IterState* st) { st->queue = 0; }
 // vector_b has a single non-zero component d, so dot(a,b) = a_c*d and |b| = sqrt(d*d) = |d| exactly (the zero
 // terms add exactly; sqrt(RN(d*d)) == |d| in binary floating point unless d*d leaves the normal range, which
 // takes the slow path).  NaN on duplicate-coordinate planes (d = 0 -> 0/0) is produced here and propagates
-// through the roulette exactly like in the reference.
+// through the roulette exactly like in the reference.  A slot whose neighbour is out of
+// bounds or occupied gets the sentinel -1, so the walk needs no separate open-neighbour mask.
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ float slow_norm1(float d) { return __fsqrt_rn(__fmul_rn(d, d)); }
 
-__global__ void __launch_bounds__(256) k_heuristic(float* __restrict__ heur, const float* __restrict__ coords, int rx, int ry, int rz,
-                                                    unsigned long long N, int goal, float beta)
+constexpr float kClosedSlot = -1.0f;   // heur value of a slot whose neighbour is out of bounds or occupied (a real factor is >= 1 - beta or NaN)
+
+__global__ void __launch_bounds__(256) k_heuristic(float* __restrict__ heur, const float* __restrict__ coords, const uint32_t* __restrict__ occ_bits,
+                                                    int rx, int ry, int rz, unsigned long long N, int goal, float beta)
 {
     const unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= N) return;
@@ -120,8 +122,11 @@ __global__ void __launch_bounds__(256) k_heuristic(float* __restrict__ heur, con
         const int dx = (k == 3) - (k == 2), dy = (k == 4) - (k == 1), dz = (k == 5) - (k == 0);
         const int nx = x + dx, ny = y + dy, nz = z + dz;
         const bool inb = nx >= 0 && nx < rx && ny >= 0 && ny < ry && nz >= 0 && nz < rz;
-        float v = 0.0f;   // out-of-bounds slots are never candidates
-        if (inb) {
+        const unsigned long long nid = id + dx + (long long)dy * rx + (long long)dz * (long long)rxy;
+        // the neighbour must exist (:391-393) and be free (:148); the open mask is folded into the table
+        const bool open = inb && !((occ_bits[nid >> 5] >> (nid & 31)) & 1u);
+        float v = kClosedSlot;
+        if (open) {
             const float ac = dx ? ax : (dy ? ay : az);
             const float d = dx ? __fsub_rn(xs[nx], cx) : (dy ? __fsub_rn(ys[ny], cy) : __fsub_rn(zs[nz], cz));
             float nb = fabsf(d);
@@ -165,16 +170,14 @@ template <bool GLOBAL>
 __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // coordinate tables with one guard element on each side (out-of-bounds neighbour lanes read them)
-    float* xs = reinterpret_cast<float*>(smem_raw) + 1;
-    float* ys = xs + a.rx + 2;
-    float* zs = ys + a.ry + 2;
-    const int ncoord = a.rx + a.ry + a.rz + 6;
-    for (int i = threadIdx.x; i < ncoord; i += kWalkThreads) reinterpret_cast<float*>(smem_raw)[i] = 0.0f;
-    __syncthreads();
-    for (int i = threadIdx.x; i < a.rx; i += kWalkThreads) xs[i] = a.coords[i];
-    for (int i = threadIdx.x; i < a.ry; i += kWalkThreads) ys[i] = a.coords[a.rx + i];
-    for (int i = threadIdx.x; i < a.rz; i += kWalkThreads) zs[i] = a.coords[a.rx + a.ry + i];
+    // move table: slot c -> {node-id stride, dx, dy, dz} (one LDS.128 per step instead of a dozen compares)
+    int4* move_lut = reinterpret_cast<int4*>(smem_raw);
+    const int ncoord = a.rx + a.ry + a.rz + 6;   // the visited tables start behind this (reserved) region
+    if (threadIdx.x < 8) {
+        const int c = threadIdx.x;
+        const int dx = (c == 3) - (c == 2), dy = (c == 4) - (c == 1), dz = (c == 5) - (c == 0);
+        move_lut[c] = make_int4(dx + dy * a.rx + dz * a.rx * a.ry, dx, dy, dz);
+    }
     __syncthreads();
 
     constexpr unsigned FULL = 0xffffffffu;
@@ -206,8 +209,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
 
     const int sz = a.start / rxy, sy = (a.start % rxy) / rx, sx = a.start % rx;
     const int gz = a.goal / rxy, gy = (a.goal % rxy) / rx, gx = a.goal % rx;
-    const float gxc = xs[gx], gyc = ys[gy], gzc = zs[gz];
-    const float* axis_tab = axis_k == 0 ? xs : (axis_k == 1 ? ys : zs);
     const bool alpha1 = a.alpha == 1;
     const float beta = a.beta;
 
@@ -258,7 +259,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
         int reason = 0;    // why a dead ant died: 1 no candidate, 2 roulette fall-through, 3 step cap
         uint32_t* pid = a.path_ids + (size_t)ant_local * a.cap;
         uint8_t* pdir = a.path_dirs + (size_t)ant_local * a.cap;
-        int pos = axis_k == 0 ? x : (axis_k == 1 ? y : z);        // the ant's index along this lane's axis
 
         while (__any_sync(FULL, live)) {
             // ---- step cap (a deviation the oracle mirrors; the reference is unbounded) ------------
@@ -266,7 +266,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             reason = capped ? 3 : reason;
             live = live && !capped;
             // ---- the loads of this step ---------------------------------------------------------
-            const unsigned open = a.open6[cur];
             const float tau_k = __ldg(a.tau + (size_t)cur * 6 + kk6);
             const float heur_k = __ldg(a.heur + (size_t)cur * 6 + kk6);
             // ---- Philox: one call yields the draws of 4 consecutive steps (the live ants of a warp are
@@ -277,7 +276,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             const float u = __fmul_rn(__int2float_rn((int)(rsel >> 1)), 4.656612873077392578125e-10f);
             // ---- neighbour k: bounds+free (open mask), tabu probe -------------------------------
             const int nx = x + dxk, ny = y + dyk, nz = z + dzk;
-            const bool open_k = (k < 6) && ((open >> k) & 1u);
+            const bool open_k = (k < 6) && heur_k != kClosedSlot;   // NaN (duplicate plane) stays open, as in the reference
             const uint32_t tile = (uint32_t)(((nz >> 2) * TY + (ny >> 2)) * TX + (nx >> 2));
             const unsigned bit = ((nz & 3) << 4) | ((ny & 3) << 2) | (nx & 3);
             unsigned slot = (tile * 2654435761u) >> hshift;
@@ -315,11 +314,9 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             if (stepok && k == c) { keys[slot] = tile; masks[slot] = found ? (mm | (1ull << bit)) : (1ull << bit); }
             const unsigned fb = (__ballot_sync(FULL, found) >> gbase) & 0x3Fu;
             const int newtile = stepok ? (int)(((fb >> c) & 1u) ^ 1u) : 0;
-            const int mdx = (c == 3) - (c == 2), mdy = (c == 4) - (c == 1), mdz = (c == 5) - (c == 0);
+            const int4 mv = move_lut[c];
             if (stepok) {
-                x += mdx; y += mdy; z += mdz;
-                cur += mdx + mdy * rx + mdz * rxy;
-                pos += axis_k == 0 ? mdx : (axis_k == 1 ? mdy : mdz);
+                cur += mv.x; x += mv.y; y += mv.z; z += mv.w;
                 steps++;
                 ntiles += newtile;
             }
