@@ -16,7 +16,7 @@
 
 namespace wr {
 
-constexpr int kTile = 2048;          // items per warp
+constexpr int kTile = 512;           // items per warp: short tiles = many warps, the passes are latency-bound per warp
 constexpr int kSortWarps = 4;        // warps per CTA
 constexpr int kSortThreads = kSortWarps * 32;
 
@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __re
     __syncwarp();
     if (tile < ntiles) {
         const int lo = tile * kTile, hi = min(lo + kTile, n);
+#pragma unroll 4
         for (int i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & 255u], 1u);
         __syncwarp();
         for (int d = lane; d < 256; d += 32) hist[(size_t)d * ntiles + tile] = cnt[w][d];
@@ -99,11 +100,14 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
     __syncwarp();
     const int lo = tile * kTile, hi = min(lo + kTile, n);
     const unsigned lt = (1u << lane) - 1;
+    // the chunk after the current one is already in flight while the current one is ranked and scattered
+    uint32_t nk = 0, nv = 0;
+    if (lo + lane < hi) { nk = keys_in[lo + lane]; nv = vals_in[lo + lane]; }
     for (int i0 = lo; i0 < hi; i0 += 32) {
         const int i = i0 + lane;
         const bool act = i < hi;
-        uint32_t k = 0, v = 0;
-        if (act) { k = keys_in[i]; v = vals_in[i]; }
+        const uint32_t k = nk, v = nv;
+        if (i + 32 < hi) { nk = keys_in[i + 32]; nv = vals_in[i + 32]; }
         const unsigned d = act ? ((k >> shift) & 255u) : 256u;  // inactive lanes form their own group
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         if (act) {
