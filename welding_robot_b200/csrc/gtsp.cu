@@ -16,8 +16,11 @@
 // cities in shared memory during the single streaming pass, and the second scan re-adds only the
 // 16 cities of the interval that contains the threshold, starting from the exact check-pointed
 // partial sum — the same additions in the same order, 1/16 of the traffic.
-// Per colony-iteration the matrix (N^2 doubles, 512 KB at N = 256) is streamed N times from L2.
+// Per colony-iteration the matrix (N^2 doubles, 512 KB at N = 256) is streamed N times from L2/HBM: that
+// stream (134 GB per iteration of 1024 colonies) is what bounds the kernel — measured 34.7k colony-iterations/s
+// = 4.6 TB/s of matrix rows at N = 256, B = 1024 (the resident colonies' matrices exceed L2, so most of it is HBM).
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -27,11 +30,14 @@
 namespace wr {
 
 constexpr int kGtspRows = 8;     // rows per TMA chunk
+constexpr int kGtspMaxStages = 4; // TMA ring depth is a template parameter of the kernel (2..4)
 constexpr int kGtspIv = 16;      // check-point interval (cities)
 constexpr double kGtspInf = 1061109567.0;   // INF 0x3f3f3f3f (ACS_GTSP.hpp:19), ACS_Tour::clean :29-34
 
 struct GtspArgs {
     int n, npad;                 // cities; row stride of every matrix (multiple of 2 doubles = 16 B)
+    int stages;                  // TMA ring depth
+    size_t mat_stride;           // doubles between consecutive colonies' matrices
     int iterations, iter0;
     int colony_first;
     uint32_t seed_lo, seed_hi;
@@ -54,6 +60,7 @@ __device__ __forceinline__ unsigned long long gtimer()
     return t;
 }
 
+template <int kGtspStages>
 __global__ void k_gtsp_iterate(GtspArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -64,29 +71,36 @@ __global__ void k_gtsp_iterate(GtspArgs a)
     const int nck = (n + kGtspIv - 1) / kGtspIv;
     const int nwords = (n + 31) / 32;
     // shared layout
-    double* rows = reinterpret_cast<double*>(smem_raw);                       // [2][kGtspRows][npad]
-    double* ckpt = rows + 2 * kGtspRows * npad;                               // [nck][nthreads]
+    double* rows = reinterpret_cast<double*>(smem_raw);                       // [kGtspStages][kGtspRows][npad]
+    double* ckpt = rows + kGtspStages * kGtspRows * npad;                               // [nck][nthreads]
     uint32_t* vis = reinterpret_cast<uint32_t*>(ckpt + (size_t)nck * nthreads);   // [nwords][nthreads]  bit set = visited
     double* redL = reinterpret_cast<double*>(vis + (size_t)nwords * nthreads);    // [32]
     int* redK = reinterpret_cast<int*>(redL + 32);                            // [32]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(redK + 32);                   // [2]
-    int* bcast = reinterpret_cast<int*>(bar + 2);                             // [4]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(redK + 32);                   // [kGtspStages]
+    int* bcast = reinterpret_cast<int*>(bar + kGtspMaxStages);                // [4]
 
     const size_t mat = (size_t)n * npad;
     const int colony = blockIdx.x;
-    double* ph = a.ph + (size_t)colony * mat;
-    double* info = a.info + (size_t)colony * mat;
+    double* ph = a.ph + (size_t)colony * a.mat_stride;
+    double* info = a.info + (size_t)colony * a.mat_stride;
     uint16_t* tours = a.tours + (size_t)colony * n * n;
     const uint32_t stream = kStreamGtsp + (uint32_t)(a.colony_first + colony);
 
     if (k == 0) {
-        tma::mbar_init(&bar[0], 1);
-        tma::mbar_init(&bar[1], 1);
+        for (int s = 0; s < kGtspStages; s++) tma::mbar_init(&bar[s], 1);
         tma::fence_barrier_init();
     }
     __syncthreads();
-    unsigned phase_bits = 0;   // parity of the next wait on bar[0] (bit 0) / bar[1] (bit 1)
+    unsigned phase_bits = 0;   // bit s: parity of the next wait on bar[s]
+    unsigned consumed = 0, issued = 0;   // chunks waited for / requested so far (ring positions persist across iterations)
     const int nchunks = (n + kGtspRows - 1) / kGtspRows;
+    const int total = n * nchunks;       // chunks per iteration: every step streams the whole matrix once
+    auto issue = [&](int j) {            // thread 0: request chunk j of this iteration into ring slot issued % S
+        const int c0 = (j % nchunks) * kGtspRows, nr = min(kGtspRows, n - c0);
+        const unsigned st = issued % kGtspStages;
+        tma::mbar_arrive_expect_tx(&bar[st], (uint32_t)(nr * npad * sizeof(double)));
+        tma::bulk_g2s(rows + (size_t)st * kGtspRows * npad, info + (size_t)c0 * npad, (uint32_t)(nr * npad * sizeof(double)), &bar[st]);
+    };
     unsigned long long t_info = 0, t_cons = 0, t_upd = 0;
 
     for (int it = 0; it < a.iterations; it++) {
@@ -102,34 +116,41 @@ __global__ void k_gtsp_iterate(GtspArgs a)
         __syncthreads();
         unsigned long long t1 = gtimer();
         // ---- construct_solution(): n steps, every ant moves once per step (:146-159) ------------
+        int it_issued = 0;
+        for (; it_issued < kGtspStages - 1 && it_issued < total; it_issued++, issued++) if (k == 0) issue(it_issued);
         for (int step = 0; step < n; step++) {
             double sum = 0.0;
-            if (k == 0) {
-                const int rows0 = min(kGtspRows, n);
-                tma::mbar_arrive_expect_tx(&bar[0], (uint32_t)(rows0 * npad * sizeof(double)));
-                tma::bulk_g2s(rows, info, (uint32_t)(rows0 * npad * sizeof(double)), &bar[0]);
-            }
             for (int ch = 0; ch < nchunks; ch++) {
-                const int b = ch & 1;
-                if (k == 0 && ch + 1 < nchunks) {   // buffer b^1 was released by the barrier that ended chunk ch-1
-                    const int c0 = (ch + 1) * kGtspRows, nr = min(kGtspRows, n - c0);
-                    tma::mbar_arrive_expect_tx(&bar[b ^ 1], (uint32_t)(nr * npad * sizeof(double)));
-                    tma::bulk_g2s(rows + (size_t)(b ^ 1) * kGtspRows * npad, info + (size_t)c0 * npad, (uint32_t)(nr * npad * sizeof(double)), &bar[b ^ 1]);
-                }
+                // ring slot (consumed-1) % S was released by the barrier that ended the previous chunk: refill it
+                // (this runs ahead across step boundaries: `info` does not change within an iteration)
+                if (it_issued < total) { if (k == 0) issue(it_issued); it_issued++; issued++; }
+                const unsigned b = consumed % kGtspStages;
                 tma::mbar_wait(&bar[b], (phase_bits >> b) & 1u);
                 phase_bits ^= 1u << b;
+                consumed++;
                 if (ant && left > 0) {
-                    const double* rb = rows + (size_t)b * kGtspRows * npad;
+                    // column r of the staged rows: info[c][r] == info[r][c]
+                    const double* col = rows + (int)b * (kGtspRows * npad) + r;
                     const int c0 = ch * kGtspRows, nr = min(kGtspRows, n - c0);
-                    const uint32_t vw = vis[(c0 >> 5) * nthreads + k];   // kGtspRows divides 32: one word per chunk
+                    // kGtspRows divides 32 and c0 is a multiple of it: the chunk's visited bits are one byte
+                    const uint32_t vb = vis[(c0 >> 5) * nthreads + k] >> (c0 & 31);
+                    if (nr == kGtspRows) {
+                        // all eight loads first (unconditional), then the dependent chain; a visited city contributes
+                        // +0.0, which is the identity of the (non-negative) running sum, so no load sits under a predicate
+                        double x[kGtspRows];
 #pragma unroll
-                    for (int j = 0; j < kGtspRows; j++) {
-                        if (j < nr) {
-                            const int c = c0 + j;
-                            if (!((vw >> (c & 31)) & 1u)) sum = __dadd_rn(sum, rb[(size_t)j * npad + r]);   // info[c][r] == info[r][c]
-                            if ((c & (kGtspIv - 1)) == kGtspIv - 1 || c == n - 1) ckpt[(c / kGtspIv) * nthreads + k] = sum;
+                        for (int j = 0; j < kGtspRows; j++) x[j] = col[j * npad];
+#pragma unroll
+                        for (int j = 0; j < kGtspRows; j++) sum = __dadd_rn(sum, ((vb >> j) & 1u) ? 0.0 : x[j]);
+                    } else {
+                        for (int j = 0; j < nr; j++) {
+                            const double x = col[j * npad];
+                            if (!((vb >> j) & 1u)) sum = __dadd_rn(sum, x);
                         }
                     }
+                    // check-point after cities 16i+15 and after the last city (warp-uniform condition)
+                    const int cend = c0 + nr;
+                    if ((cend & (kGtspIv - 1)) == 0 || cend == n) ckpt[((cend - 1) / kGtspIv) * nthreads + k] = sum;
                 }
                 __syncthreads();
             }
@@ -143,12 +164,24 @@ __global__ void k_gtsp_iterate(GtspArgs a)
                 for (int j = 0; j < nck; j++) if (ckpt[j * nthreads + k] >= rnd) { iv = j; break; }
                 if (iv >= 0) {
                     double s = iv > 0 ? ckpt[(iv - 1) * nthreads + k] : 0.0;
-                    const int c0 = iv * kGtspIv, c1 = min(c0 + kGtspIv, n);
-                    const uint32_t vw = vis[(c0 >> 5) * nthreads + k];
-                    for (int c = c0; c < c1; c++) {
-                        if ((vw >> (c & 31)) & 1u) continue;
-                        s = __dadd_rn(s, info[(size_t)c * npad + r]);
-                        if (s >= rnd) { next = c; break; }
+                    const int c0 = iv * kGtspIv;
+                    const uint32_t vb = vis[(c0 >> 5) * nthreads + k] >> (c0 & 31);   // kGtspIv divides 32
+                    // the 16 candidates of the interval are fetched together (independent L2 gathers), then re-added
+                    // in city order from the exact check-pointed partial sum
+                    double xv[kGtspIv];
+#pragma unroll
+                    for (int j = 0; j < kGtspIv; j++) {
+                        const int c = c0 + j;
+                        xv[j] = (c < n && !((vb >> j) & 1u)) ? info[(size_t)c * npad + r] : 0.0;
+                    }
+                    bool hit = false;
+#pragma unroll
+                    for (int j = 0; j < kGtspIv; j++) {
+                        const int c = c0 + j;
+                        if (c < n && !((vb >> j) & 1u)) {
+                            s = __dadd_rn(s, xv[j]);
+                            if (!hit && s >= rnd) { next = c; hit = true; }
+                        }
                     }
                 }
             }
@@ -233,6 +266,8 @@ struct wr_gtsp {
     float ms_total = 0;
     size_t smem = 0;
     int threads = 0;
+    int stages = 6;
+    size_t mat_stride = 0;
 };
 
 template <class T> static T host_power(T x, int y)
@@ -274,13 +309,17 @@ extern "C" int wr_gtsp_create(const double* dis, int n, int cnt, int batch, int 
             hh[(size_t)i * npad + j] = host_power(1 / (d + 1e-8), 6);  // herustic :211, beta = 6 :191, power() :117-118
         }
     const size_t mat = (size_t)n * npad;
+    // TMA ring depth 3 (two CTAs per SM at N = 256) measured best: 2 -> 33.0k, 3 -> 34.7k, 4 -> 31.9k, 6 -> 21.3k colony-iterations/s
+    // at N = 256 x 1024 colonies (per-CTA latency wants more CTAs per SM, L2 capacity wants fewer resident matrices)
+    g->stages = 3;
+    g->mat_stride = mat;
 #define WR_CUDA_G(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); wr_gtsp_destroy(g); return WR_ERR_CUDA; } } while (0)
     WR_CUDA_G(cudaGetDevice(&g->device));
     WR_CUDA_G(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     WR_CUDA_G(cudaMalloc(&g->d_dis, mat * sizeof(double)));
     WR_CUDA_G(cudaMalloc(&g->d_h6, mat * sizeof(double)));
-    WR_CUDA_G(cudaMalloc(&g->d_ph, mat * batch * sizeof(double)));
-    WR_CUDA_G(cudaMalloc(&g->d_info, mat * batch * sizeof(double)));
+    WR_CUDA_G(cudaMalloc(&g->d_ph, g->mat_stride * batch * sizeof(double)));
+    WR_CUDA_G(cudaMalloc(&g->d_info, g->mat_stride * batch * sizeof(double)));
     WR_CUDA_G(cudaMalloc(&g->d_tours, (size_t)n * n * batch * sizeof(uint16_t)));
     WR_CUDA_G(cudaMalloc(&g->d_best_tour, (size_t)n * batch * sizeof(uint16_t)));
     WR_CUDA_G(cudaMalloc(&g->d_best_start, batch * sizeof(int)));
@@ -290,7 +329,7 @@ extern "C" int wr_gtsp_create(const double* dis, int n, int cnt, int batch, int 
     WR_CUDA_G(cudaMemcpy(g->d_dis, hd.data(), mat * sizeof(double), cudaMemcpyHostToDevice));
     WR_CUDA_G(cudaMemcpy(g->d_h6, hh.data(), mat * sizeof(double), cudaMemcpyHostToDevice));
     {
-        std::vector<double> p0(mat * batch, g->tau0);                  // pheromone[i][j] = pheromone_0 (:209)
+        std::vector<double> p0(g->mat_stride * batch, g->tau0);        // pheromone[i][j] = pheromone_0 (:209)
         WR_CUDA_G(cudaMemcpy(g->d_ph, p0.data(), p0.size() * sizeof(double), cudaMemcpyHostToDevice));
         std::vector<double> bl(batch, kGtspInf);                       // best.clean() (:214)
         WR_CUDA_G(cudaMemcpy(g->d_best_L, bl.data(), batch * sizeof(double), cudaMemcpyHostToDevice));
@@ -299,10 +338,12 @@ extern "C" int wr_gtsp_create(const double* dis, int n, int cnt, int batch, int 
     }
     g->threads = (n + 31) / 32 * 32;
     const int nck = (n + kGtspIv - 1) / kGtspIv, nwords = (n + 31) / 32;
-    g->smem = (size_t)2 * kGtspRows * npad * sizeof(double) + (size_t)nck * g->threads * sizeof(double) + (size_t)nwords * g->threads * sizeof(uint32_t) +
-              32 * sizeof(double) + 32 * sizeof(int) + 2 * sizeof(uint64_t) + 4 * sizeof(int);
+    g->smem = (size_t)g->stages * kGtspRows * npad * sizeof(double) + (size_t)nck * g->threads * sizeof(double) +
+              (size_t)nwords * g->threads * sizeof(uint32_t) + 32 * sizeof(double) + 32 * sizeof(int) + kGtspMaxStages * sizeof(uint64_t) + 4 * sizeof(int);
     if (g->smem > 227 * 1024) { set_error("wr_gtsp_create: %d cities need %zu B of shared memory", n, g->smem); wr_gtsp_destroy(g); return WR_ERR_INVALID; }
-    WR_CUDA_G(cudaFuncSetAttribute(k_gtsp_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
+    WR_CUDA_G(cudaFuncSetAttribute(k_gtsp_iterate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
+    WR_CUDA_G(cudaFuncSetAttribute(k_gtsp_iterate<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
+    WR_CUDA_G(cudaFuncSetAttribute(k_gtsp_iterate<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
 #undef WR_CUDA_G
     *out = g;
     return WR_OK;
@@ -315,7 +356,7 @@ extern "C" int wr_gtsp_iterate(wr_gtsp* g, int iterations)
     if (iterations == 0) return WR_OK;
     WR_CUDA(cudaSetDevice(g->device));
     GtspArgs a;
-    a.n = g->n; a.npad = g->npad; a.iterations = iterations; a.iter0 = g->iter; a.colony_first = g->colony_first;
+    a.n = g->n; a.npad = g->npad; a.stages = g->stages; a.mat_stride = g->mat_stride; a.iterations = iterations; a.iter0 = g->iter; a.colony_first = g->colony_first;
     a.seed_lo = (uint32_t)g->seed; a.seed_hi = (uint32_t)(g->seed >> 32);
     a.evap = 1 - 0.1;   // (1 - alpha), alpha = 0.1 (:189)
     a.dis = g->d_dis; a.h6 = g->d_h6; a.ph = g->d_ph; a.info = g->d_info; a.tours = g->d_tours; a.best_tour = g->d_best_tour;
@@ -324,7 +365,9 @@ extern "C" int wr_gtsp_iterate(wr_gtsp* g, int iterations)
     WR_CUDA(cudaEventCreate(&e0));
     WR_CUDA(cudaEventCreate(&e1));
     WR_CUDA(cudaEventRecord(e0, g->stream));
-    k_gtsp_iterate<<<g->batch, g->threads, g->smem, g->stream>>>(a);
+    if (g->stages == 2) k_gtsp_iterate<2><<<g->batch, g->threads, g->smem, g->stream>>>(a);
+    else if (g->stages == 3) k_gtsp_iterate<3><<<g->batch, g->threads, g->smem, g->stream>>>(a);
+    else k_gtsp_iterate<4><<<g->batch, g->threads, g->smem, g->stream>>>(a);
     WR_CUDA(cudaGetLastError());
     WR_CUDA(cudaEventRecord(e1, g->stream));
     WR_CUDA(cudaEventSynchronize(e1));
@@ -365,7 +408,7 @@ extern "C" int wr_gtsp_download_pheromone(wr_gtsp* g, int colony, double* out)
 {
     WR_REQUIRE(g && out && colony >= 0 && colony < g->batch, WR_ERR_INVALID, "wr_gtsp_download_pheromone: bad argument");
     WR_CUDA(cudaStreamSynchronize(g->stream));
-    WR_CUDA(cudaMemcpy2D(out, (size_t)g->n * sizeof(double), g->d_ph + (size_t)colony * g->n * g->npad, (size_t)g->npad * sizeof(double),
+    WR_CUDA(cudaMemcpy2D(out, (size_t)g->n * sizeof(double), g->d_ph + (size_t)colony * g->mat_stride, (size_t)g->npad * sizeof(double),
                          (size_t)g->n * sizeof(double), g->n, cudaMemcpyDeviceToHost));
     return WR_OK;
 }
