@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "acs_kernels.cuh"
+#include "walk2.cuh"
 #include "wr_internal.cuh"
 
 namespace wr {
@@ -186,6 +187,29 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     return WR_OK;
 }
 
+// walk kernel generation: 2 (default) = k_walk2, 1 = k_walk (also taken when an axis exceeds the packed-coordinate range)
+static int walk_version(const wr_grid* g)
+{
+    static const int env = [] { const char* e = getenv("WR_WALK_V"); return e ? atoi(e) : 2; }();
+    return (env == 1 || g->rx > 1024 || g->ry > 1024 || g->rz > 1024) ? 1 : 2;
+}
+static int walk_prefetch()
+{
+    static const int env = [] { const char* e = getenv("WR_WALK_PREFETCH"); return e ? atoi(e) : 2; }();
+    return env;
+}
+static int walk_warm()
+{
+    static const int env = [] { const char* e = getenv("WR_WALK_WARM"); return e ? atoi(e) : 1; }();
+    return env;
+}
+static size_t walk_smem(const wr_acs* a)
+{
+    if (walk_version(a->g) == 2) return 192 + ((size_t)kAntsPerCta << a->table_log2) * sizeof(unsigned long long);
+    const size_t coord_bytes = ((size_t)(a->g->rx + a->g->ry + a->g->rz + 6) * 4 + 15) & ~(size_t)15;
+    return coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
+}
+
 extern "C" const char* wr_last_error(void) { return g_err.c_str(); }
 extern "C" int wr_version(void) { return 100; }
 extern "C" int wr_device_count(int* count)
@@ -275,9 +299,14 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     {
         size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
         WR_CUDA_A(cudaFuncSetAttribute(k_update_tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        size_t ws = (((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15) + ((size_t)kAntsPerCta << a->table_log2) * 12;
+        const size_t ws = walk_smem(a);
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         WR_CUDA_A(cudaFuncSetAttribute(k_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
     }
     WR_CUDA_A(cudaStreamSynchronize(a->stream));
 #undef WR_CUDA_A
@@ -358,6 +387,27 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     return WR_OK;
 }
 
+template <bool GLOBAL>
+static void launch_walk2(const WalkArgs& w, bool alpha1, int prefetch, int blocks, size_t smem, cudaStream_t s)
+{
+    if (alpha1) {
+        if (prefetch == 1) k_walk2<GLOBAL, true, 1><<<blocks, kWalkThreads, smem, s>>>(w);
+        else if (prefetch == 2) k_walk2<GLOBAL, true, 2><<<blocks, kWalkThreads, smem, s>>>(w);
+        else if (prefetch == 3) k_walk2<GLOBAL, true, 3><<<blocks, kWalkThreads, smem, s>>>(w);
+        else k_walk2<GLOBAL, true, 0><<<blocks, kWalkThreads, smem, s>>>(w);
+    } else {
+        k_walk2<GLOBAL, false, 0><<<blocks, kWalkThreads, smem, s>>>(w);
+    }
+}
+
+// before k_iter_begin: pull the rows under last iteration's deposits into L2 (see k_path_warm)
+static void launch_warm(wr_acs* a)
+{
+    if (!walk_warm() || walk_version(a->g) != 2 || a->p.update_mode == WR_UPDATE_ATOMIC) return;
+    const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
+    k_path_warm<<<kNumSMs, 256, 0, a->stream>>>(a->d_state, ck, a->d_tau, a->d_heur);
+}
+
 static int launch_walk(wr_acs* a)
 {
     const wr_grid* g = a->g;
@@ -371,16 +421,25 @@ static int launch_walk(wr_acs* a)
     w.ant_steps = a->d_local_steps;
     w.path_ids = a->d_path_ids; w.path_dirs = a->d_path_dirs;
     w.table_log2 = a->table_log2; w.overflow_list = a->d_overflow;
-    w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks; w.gtable_log2 = a->gtable_log2; w.resume = a->d_resume;
-    const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15;   // + guard elements
-    const size_t smem1 = coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
+    w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks; w.gtab = a->d_gmasks; w.gtable_log2 = a->gtable_log2; w.resume = a->d_resume;
+    const int ver = walk_version(g);
+    const size_t smem1 = walk_smem(a);
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem1 + 1024)));
     const int blocks1 = std::max(1, std::min((a->chunk + kAntsPerCta - 1) / kAntsPerCta, kNumSMs * std::min(per_sm, 16)));
-    k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-    // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
-    k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
-    w.table_log2 = a->gtable_log2;
-    k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
+    if (ver == 2) {
+        const bool alpha1 = a->p.alpha == 1;
+        launch_walk2<false>(w, alpha1, walk_prefetch(), blocks1, smem1, a->stream);
+        // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
+        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
+        w.table_log2 = a->gtable_log2;
+        launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, 192, a->stream);
+    } else {
+        const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15;   // + guard elements
+        k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
+        w.table_log2 = a->gtable_log2;
+        k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
+    }
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -468,6 +527,7 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
     cudaStream_t s = a->stream;
     for (int it = 0; it < n; it++) {
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+        launch_warm(a);
         k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0);
         int st = launch_walk(a);
         if (st != WR_OK) return st;
@@ -504,6 +564,7 @@ extern "C" int wr_acs_walk(wr_acs* a)
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    launch_warm(a);
     k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0);
     WR_CUDA(cudaMemsetAsync(a->d_local_steps, 0xFF, (size_t)a->chunk * sizeof(int), s));   // -1: beyond the colony
     int st = launch_walk(a);

@@ -42,6 +42,7 @@ struct WalkArgs {
     uint32_t* overflow_list; // [chunk]
     uint32_t* gkeys;         // HBM visited tables, one per overflowed ant: [chunk][1 << gtable_log2]
     unsigned long long* gmasks;
+    unsigned long long* gtab;   // k_walk2: HBM visited tables of 64-bit entries (aliases gmasks)
     int gtable_log2;
     int4* resume;            // [chunk] state of an overflowed ant: {cur, steps, ntiles, -}
 };

@@ -1,0 +1,321 @@
+// K2, second generation of the ant-construction kernel (selectNext ACSRank_3D.hpp:134-193 + the ant loop :252-265).
+// Same parallelisation as k_walk (one ant per 8-lane group, 4 ants per warp in lockstep, persistent warps on a
+// device queue) and bit-identical results; what changed is the length of the per-step instruction stream, which is
+// what bounds a colony of a few thousand ants (profiles/: ~300 warp-instructions per step at ~6 cycles each):
+//   * node coordinates live in ONE packed register  P = z<<20 | y<<10 | x  (a move is one add; needs dims <= 1024,
+//     larger grids take k_walk);
+//   * the visited set is an open-addressed table of 64-bit entries  (1<<31 | tile key) << 32 | 32-bit mask  over
+//     4x4x2-node tiles: one LDS.64 per probe, one STS.64 per insert, key = P & ~lowbits (one LOP3);
+//   * the chosen lane does everything that belongs to the move in one branch: visited insert, trail append
+//     (addNextNode :73-79), tile count; the table-full flag travels through shared memory instead of a vote;
+//   * parking an ant whose table filled up (-> pass 2 with a table in HBM) happens after the lockstep loop;
+//   * the uniform draws of four steps are converted to float once per Philox call; alpha == 1 (the reference's
+//     literal, :319) is a template parameter; the step cap is checked off the critical path.
+#pragma once
+#include "acs_kernels.cuh"
+
+namespace wr {
+
+constexpr uint32_t kPackLow = 0x00100C03u;                    // x bits 0-1, y bits 10-11, z bit 20: position inside a 4x4x2 tile
+constexpr uint32_t kPackKey = 0x3FFFFFFFu & ~kPackLow;        // the tile
+constexpr uint32_t kPackMul = 0x00101010u;                    // gathers the five position bits at 20..24 (no carries: partial products are disjoint)
+constexpr uint32_t kKeyTag = 0x80000000u;                     // a stored key is never 0 (0 = empty entry)
+
+__device__ __forceinline__ uint32_t pack_xyz(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 10) | ((uint32_t)z << 20); }
+__device__ __forceinline__ uint32_t tile_hash(uint32_t key, int hshift) { return (key * 2654435761u) >> hshift; }
+
+// visited-table access: 32-bit shared-window addresses for the on-chip tables (a generic pointer makes the compiler
+// re-derive the shared window base inside the step loop), plain global pointers for the HBM tables of pass 2
+template <bool GLOBAL> struct TabRef {
+    unsigned long long* gp;
+    uint32_t sa;
+    __device__ __forceinline__ unsigned long long load(unsigned slot) const
+    {
+        if (GLOBAL) return gp[slot];
+        unsigned long long v;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(sa + slot * 8u) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void store(unsigned slot, unsigned long long v) const
+    {
+        if (GLOBAL) { gp[slot] = v; return; }
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(sa + slot * 8u), "l"(v) : "memory");
+    }
+};
+
+// L2 warm-up for the walk.  The fused update has just streamed the whole pheromone field through L2, so the rows the
+// colony is about to read are back in HBM — and a converging colony advances in lockstep over a small family of paths,
+// so every step would wait for somebody's DRAM miss.  Where the colony will walk is known: the slot-sorted deposit
+// records of the previous iteration name every node the top-ranked ants crossed.  Pull the tau and heuristic rows of
+// those nodes (each distinct node once) into L2 before the ants start: a few hundred KB, microseconds.
+// Must run BEFORE k_iter_begin (which clears n_records).
+__global__ void __launch_bounds__(256) k_path_warm(const IterState* st, const uint32_t* __restrict__ rec_keys, const float* tau, const float* heur)
+{
+    const int n = st->n_records;
+    uint32_t acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t node = rec_keys[i] / 6u;
+        if (i > 0 && rec_keys[i - 1] / 6u == node) continue;
+        const uint32_t* pt = reinterpret_cast<const uint32_t*>(tau) + (size_t)node * 6;
+        const uint32_t* ph = reinterpret_cast<const uint32_t*>(heur) + (size_t)node * 6;
+        // a 24-byte row touches one or two 32-byte sectors: its first and last word cover it
+        acc ^= __ldcg(pt) ^ __ldcg(pt + 5) ^ __ldcg(ph) ^ __ldcg(ph + 5);
+    }
+    if (acc == 0x9E3779B9u && n < 0) const_cast<IterState*>(st)->cnt[8] = 0;   // keeps the loads alive; never true
+}
+
+template <bool GLOBAL, bool ALPHA1, int PREFETCH>
+__global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int2* move_lut = reinterpret_cast<int2*>(smem_raw);                        // [8]  slot c -> {node-id stride, packed-coordinate delta}
+    uint32_t* ntiles_s = reinterpret_cast<uint32_t*>(smem_raw + 64);            // [16] tiles in the ant's table
+    volatile uint32_t* flag_s = reinterpret_cast<volatile uint32_t*>(smem_raw + 128);   // [16] table reached 3/4 -> park after this step
+    unsigned long long* tab_s = reinterpret_cast<unsigned long long*>(smem_raw + 192);  // [16][E]
+    if (threadIdx.x < 8) {
+        const int c = threadIdx.x;
+        const int dx = (c == 3) - (c == 2), dy = (c == 4) - (c == 1), dz = (c == 5) - (c == 0);
+        move_lut[c] = make_int2(dx + dy * a.rx + dz * a.rx * a.ry, dx + dy * 1024 + dz * 1048576);
+    }
+    __syncthreads();
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane & 24;
+    const int k = lane & 7;
+    const int g = threadIdx.x >> 3;
+    const int E = 1 << a.table_log2;
+    const int hshift = 32 - a.table_log2;
+    uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(move_lut);
+    TabRef<GLOBAL> tab;
+    tab.gp = a.gtab;
+    tab.sa = (uint32_t)__cvta_generic_to_shared(tab_s + (size_t)g * E);
+    uint32_t flag_sa = (uint32_t)__cvta_generic_to_shared(smem_raw + 128 + 4 * g);
+    // opaque to the optimiser: otherwise it re-derives the shared-window base (S2UR + ULEA) inside the step loop
+    asm volatile("" : "+r"(lut_sa), "+r"(tab.sa), "+r"(flag_sa));
+
+    const int rx = a.rx, rxy = a.rx * a.ry;
+    const int dxk = (k == 3) - (k == 2), dyk = (k == 4) - (k == 1), dzk = (k == 5) - (k == 0);
+    const uint32_t dPk = (uint32_t)(dxk + dyk * 1024 + dzk * 1048576);
+    const int kk6 = k < 6 ? k : 5;                                             // idle lanes re-read slot 5 (same sector)
+    const float* tau_k = a.tau + kk6;
+    const float* heur_k_base = a.heur + kk6;
+    const long long stride_k = (long long)(dxk + dyk * rx + dzk * rxy);
+    const long long last_node = (long long)rxy * a.rz - 1;
+    // lane masks of the descending prefix chain: lane k adds v_j only for j >= k
+    uint32_t m4 = k <= 4 ? ~0u : 0u, m3 = k <= 3 ? ~0u : 0u, m2 = k <= 2 ? ~0u : 0u, m1 = k <= 1 ? ~0u : 0u, m0 = k <= 0 ? ~0u : 0u;
+    asm volatile("" : "+r"(m4), "+r"(m3), "+r"(m2), "+r"(m1), "+r"(m0));   // keep them as register masks (one LOP3 each) instead of re-derived predicates
+
+    const uint32_t Pstart = pack_xyz(a.start % rx, (a.start % rxy) / rx, a.start / rxy);
+
+    IterState* st = a.st;
+    const int colony = st->colony;
+    const uint32_t iter = (uint32_t)st->iter;
+    int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
+    if (GLOBAL) local_n = (int)st->overflow_n;
+    const uint32_t limit = (uint32_t)((E >> 2) * 3);
+    const int cap = a.cap, goal = a.goal;
+
+    unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
+    uint32_t sink = 0, pre0 = 0, pre1 = 0, pre2 = 0, pre3 = 0;
+
+    while (true) {
+        unsigned q0 = 0;
+        if (lane == 0) q0 = atomicAdd(&st->queue, 4u);
+        q0 = __shfl_sync(FULL, q0, 0);
+        if (q0 >= (unsigned)local_n) break;                                    // warp-uniform
+        const unsigned q = q0 + (unsigned)(lane >> 3);
+        const bool has = q < (unsigned)local_n;
+        const int ant_local = has ? (GLOBAL ? (int)a.overflow_list[q] : (int)q) : 0;
+        const uint32_t ant_global = (uint32_t)(a.shard_first + ant_local);
+
+        int cur = a.start, steps = 0;
+        uint32_t P = Pstart;
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+        auto draw4 = [&](uint32_t block) {
+            uint32_t w0, w1, w2, w3;
+            philox4(iter, ant_global, block, kStreamAcs3D, a.seed_lo, a.seed_hi, w0, w1, w2, w3);
+            // (float)rand()/(float)RAND_MAX (:169): (float)RAND_MAX is 2^31, so the division is an exact scaling
+            u0 = __fmul_rn(__int2float_rn((int)(w0 >> 1)), 4.656612873077392578125e-10f);
+            u1 = __fmul_rn(__int2float_rn((int)(w1 >> 1)), 4.656612873077392578125e-10f);
+            u2 = __fmul_rn(__int2float_rn((int)(w2 >> 1)), 4.656612873077392578125e-10f);
+            u3 = __fmul_rn(__int2float_rn((int)(w3 >> 1)), 4.656612873077392578125e-10f);
+        };
+        if (GLOBAL) {   // resume a parked ant: its visited set already lives in HBM table q
+            tab.gp = a.gtab + (size_t)(has ? q : 0) * E;
+            if (has) {
+                const int4 r = a.resume[q];
+                cur = r.x; steps = r.y;
+                P = pack_xyz(cur % rx, (cur % rxy) / rx, cur / rxy);
+                draw4((uint32_t)steps >> 2);
+            }
+        } else {
+            for (int i = k; i < E; i += kGroup) tab.store(i, 0ull);
+            if (k == 0) { ntiles_s[g] = 1u; flag_s[g] = 0u; }
+            __syncwarp();
+            if (k == 0) {   // addStartNode :81-86
+                const uint32_t key = (P & kPackKey) | kKeyTag;
+                const uint32_t bit = (((P & kPackLow) * kPackMul) >> 20) & 31u;
+                tab.store(tile_hash(key, hshift), ((unsigned long long)key << 32) | (unsigned long long)(1u << bit));
+            }
+        }
+        __syncwarp();
+
+        bool live = has;
+        int result = -1;   // >= 0: steps of an ant that arrived, -1: dead, -2: parked (table 3/4 full -> pass 2)
+        int reason = 0;    // why a dead ant died: 1 no candidate, 2 roulette fall-through, 3 step cap
+        if (live && steps >= cap) { live = false; reason = 3; }
+        uint32_t* pid = a.path_ids + (size_t)ant_local * cap;
+        uint8_t* pdir = a.path_dirs + (size_t)ant_local * cap;
+
+        while (__any_sync(FULL, live)) {
+            // ---- the loads of this step ---------------------------------------------------------
+            const float tau_v = __ldg(tau_k + (size_t)cur * 6);
+            const float heur_v = __ldg(heur_k_base + (size_t)cur * 6);
+            if (PREFETCH) {   // the row of neighbour k is the next step's row if k wins: pull both arrays' lines towards the SM now
+                long long nb = (long long)cur + stride_k;
+                nb = nb < 0 ? 0 : (nb > last_node ? last_node : nb);
+                const float* pt = a.tau + nb * 6;
+                const float* ph = a.heur + nb * 6;
+                if (PREFETCH == 1) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pt));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ph));
+                } else if (PREFETCH == 3) {
+                    // real loads, one step ahead: a 24-byte row touches one or two 32-byte sectors, so its first and last word
+                    // cover it.  ptxas drops loads whose result is dead, so the words are folded into `sink` one step later
+                    // (by then they have landed) and `sink` reaches a store that never executes.
+                    sink ^= pre0 ^ pre1;
+                    sink ^= pre2 ^ pre3;
+                    pre0 = __ldg(reinterpret_cast<const uint32_t*>(pt));
+                    pre1 = __ldg(reinterpret_cast<const uint32_t*>(pt) + 5);
+                    pre2 = __ldg(reinterpret_cast<const uint32_t*>(ph));
+                    pre3 = __ldg(reinterpret_cast<const uint32_t*>(ph) + 5);
+                } else {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pt));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ph));
+                }
+            }
+            uint32_t flag = 0;
+            if (!GLOBAL) asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(flag) : "r"(flag_sa) : "memory");
+            // ---- Philox: one call yields the draws of 4 consecutive steps (live ants of a warp are in lockstep) ----
+            if (live && (steps & 3) == 0) draw4((uint32_t)steps >> 2);
+            const float u = (steps & 2) ? ((steps & 1) ? u3 : u2) : ((steps & 1) ? u1 : u0);
+            // ---- neighbour k: open (in bounds + free, folded into the heuristic table), tabu probe ------------------
+            const uint32_t Pk = P + dPk;
+            const uint32_t key = (Pk & kPackKey) | kKeyTag;
+            const uint32_t bitm = 1u << ((((Pk & kPackLow) * kPackMul) >> 20) & 31u);
+            const bool open_k = (k < 6) && heur_v != kClosedSlot;   // NaN (duplicate plane) stays open, as in the reference
+            unsigned slot = tile_hash(key, hshift);
+            unsigned long long e = tab.load(slot);
+            while (open_k && (uint32_t)(e >> 32) != key && (uint32_t)(e >> 32) != 0u) {   // collisions are rare at load <= 3/4
+                slot = (slot + 1) & (E - 1);
+                e = tab.load(slot);
+            }
+            const bool found = (uint32_t)(e >> 32) == key;
+            const uint32_t emask = found ? (uint32_t)e : 0u;
+            const bool cand = live && open_k && !(emask & bitm);
+            // ---- info = tau^alpha * (1 + beta*cos)  (:151-154; the factor is tabulated by k_heuristic) --------------
+            const float tpow = ALPHA1 ? tau_v : pow_int(tau_v, a.alpha);
+            const float info = cand ? __fmul_rn(tpow, heur_v) : 0.0f;
+            // ---- roulette in the reference's order (:155, :172-181) ------------------------------
+            const unsigned cb = (__ballot_sync(FULL, cand) >> gbase) & 0x3Fu;
+            const float v0 = __shfl_sync(FULL, info, 0, 8), v1 = __shfl_sync(FULL, info, 1, 8), v2 = __shfl_sync(FULL, info, 2, 8);
+            const float v3 = __shfl_sync(FULL, info, 3, 8), v4 = __shfl_sync(FULL, info, 4, 8), v5 = __shfl_sync(FULL, info, 5, 8);
+            const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, v0), v1), v2), v3), v4), v5);
+            const float rnd = __fmul_rn(u, total);
+            // this lane's prob_sum: v5 + v4 + ... + v_k, then +0 (the identity: every v is >= +0 or NaN), so one chain serves all lanes
+            float mine = __fadd_rn(0.0f, v5);
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v4) & m4));
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v3) & m3));
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v2) & m2));
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v1) & m1));
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v0) & m0));
+            const bool pick = cand && (mine >= rnd);
+            const unsigned pb = (__ballot_sync(FULL, pick) >> gbase) & 0x3Fu;
+            const int c = 31 - __clz((int)(pb | 1u));                  // first hit scanning 5 -> 0 (pb == 0 handled below)
+            // ---- outcome -------------------------------------------------------------------------
+            const bool stepok = live && pb != 0;
+            if (live && !stepok) reason = cb == 0 ? 1 : 2;              // :162-166 / fall-through :191-192
+            if (stepok && k == c) {   // the winning lane performs the move's side effects: tabu insert + addNextNode (:73-79)
+                tab.store(slot, ((unsigned long long)key << 32) | (unsigned long long)(emask | bitm));
+                pid[steps] = (uint32_t)cur;
+                pdir[steps] = (uint8_t)c;
+                if (!GLOBAL && !found) {   // tile count lives next to the flag: [flag_sa - 64]
+                    uint32_t n;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n) : "r"(flag_sa - 64u) : "memory");
+                    n++;
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_sa - 64u), "r"(n) : "memory");
+                    if (n > limit) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(flag_sa), "r"(1u) : "memory");
+                }
+            }
+            int2 mv;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(mv.x), "=r"(mv.y) : "r"(lut_sa + (uint32_t)c * 8u) : "memory");
+            if (stepok) { cur += mv.x; P += (uint32_t)mv.y; steps++; }
+            const bool arrived = stepok && cur == goal;              // :182-186
+            const bool over = !GLOBAL && stepok && !arrived && flag != 0u;
+            const bool capped = stepok && !arrived && !over && steps >= cap;   // a deviation the oracle mirrors; the reference is unbounded
+            result = arrived ? steps : (over ? -2 : result);
+            reason = capped ? 3 : reason;
+            live = stepok && !arrived && !over && !capped;
+            __syncwarp();
+        }
+        // ---- park the ants whose shared-memory table filled up: move the visited set to an HBM table sized for the step
+        //      cap and record where to resume; pass 2 (GLOBAL) continues them from the very step they stopped at ---------
+        if (!GLOBAL) {
+            const bool parked = has && result == -2;
+            const unsigned pm = __ballot_sync(FULL, parked && k == 0);
+            if (pm) {   // warp-uniform, rare
+                int o = 0;
+                if (parked && k == 0) o = (int)atomicAdd(&st->overflow_n, 1u);
+                o = __shfl_sync(FULL, o, 0, 8);
+                const int Eg = 1 << a.gtable_log2, gsh = 32 - a.gtable_log2;
+                for (unsigned rest = pm; rest; rest &= rest - 1) {   // zero each parked ant's HBM table with the whole warp
+                    const int src = __ffs(rest) - 1;
+                    const int oo = __shfl_sync(FULL, o, src);
+                    uint4* z = reinterpret_cast<uint4*>(a.gtab + (size_t)oo * Eg);
+                    for (int i = lane; i < Eg / 2; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                __syncwarp();
+                if (parked) {
+                    unsigned long long* ntab = a.gtab + (size_t)o * Eg;
+                    for (int i = k; i < E; i += kGroup) {
+                        const unsigned long long t = tab.load(i);
+                        if (t == 0ull) continue;
+                        unsigned sl = tile_hash((uint32_t)(t >> 32), gsh);
+                        while (atomicCAS(&ntab[sl], 0ull, t) != 0ull) sl = (sl + 1) & (Eg - 1);
+                    }
+                    if (k == 0) {
+                        a.resume[o] = make_int4(cur, steps, 0, 0);
+                        a.overflow_list[o] = (uint32_t)ant_local;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (has) {
+            if (result == -2) {
+                c_over++;   // its steps are counted by pass 2
+            } else {
+                c_arrived += result >= 0 ? 1 : 0;
+                c_nocand += (result < 0 && reason == 1) ? 1 : 0;
+                c_fall += (result < 0 && reason == 2) ? 1 : 0;
+                c_cap += (result < 0 && reason == 3) ? 1 : 0;
+                c_steps += (unsigned long long)steps; c_ants++;
+            }
+            if (k == 0) a.ant_steps[ant_local] = result;
+        }
+        __syncwarp();
+    }
+    if (PREFETCH == 3 && (sink ^ pre0 ^ pre1 ^ pre2 ^ pre3) == 0x9E3779B9u && a.cap < 0) st->cnt[8] = 0;   // keeps the look-ahead loads alive; never true
+    if (k == 0) {
+        if (c_steps) atomicAdd(&st->cnt[0], c_steps);
+        if (c_ants) atomicAdd(&st->cnt[1], c_ants);
+        if (c_arrived) atomicAdd(&st->cnt[2], c_arrived);
+        if (c_nocand) atomicAdd(&st->cnt[3], c_nocand);
+        if (c_fall) atomicAdd(&st->cnt[4], c_fall);
+        if (c_cap) atomicAdd(&st->cnt[5], c_cap);
+        if (c_over) atomicAdd(&st->cnt[8], c_over);
+    }
+}
+
+}  // namespace wr
