@@ -247,18 +247,24 @@ def run_ours(args):
         pinned = torch.from_numpy(wl["isfree"]).pin_memory()
         host_free = pinned.numpy()
         e2e_steps = max(1, min(args.steps, 5))
-        tot_steps, d2h = 0, 0
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        def e2e_step():
             a2 = make_search(host_free)
             a2.setEndpoints(wl["start"], wl["goal"])
             a2.begin(PREDICT)
             a2.iterate(args.iters)
             ids, dirs, L = a2.bestPath()                                                # D2H: the result
-            tot_steps += a2.counters()["ant_steps"]
-            d2h = len(ids) * 4 + len(dirs) + 4 + 9 * 8
+            n = a2.counters()["ant_steps"]
             del a2
+            return n, len(ids) * 4 + len(dirs) + 4 + 9 * 8
+
+        for _ in range(2):          # untimed: the first searches grow the stream-ordered memory pool by a second handle's worth
+            e2e_step()
+        tot_steps, d2h = 0, 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            n, d2h = e2e_step()
+            tot_steps += n
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = {"value": tot_steps / dt, "unit": "ant-steps/s", "h2d_bytes_per_step": int(host_free.nbytes + 3 * CUBE * 4 + 16),
@@ -322,8 +328,8 @@ def launches_per_iteration(update_mode):
     """Kernels of OURS launched per ACS iteration (welding_robot_b200/csrc/acs.cu)."""
     cap_bits = int(np.ceil(np.log2(STEP_CAP + 2)))
     slot_bits = int(np.ceil(np.log2(CUBE ** 3 * 6)))
-    sort = lambda bits: 3 * ((bits + 7) // 8)  # noqa: E731  hist + scan + scatter per 8-bit pass
-    n = 1 + 3 + 1 + sort(cap_bits) + 1 + 2 + 1   # iter_begin, walk x2 + queue reset, rank keys, sort, rank finish, best x2, iter_end
+    sort = lambda bits: 3 * ((bits + 9) // 10)  # noqa: E731  hist + scan + scatter per pass of <= 10-bit digits (radix_sort.cu)
+    n = 1 + 1 + 3 + 1 + sort(cap_bits) + 1 + 2 + 1   # L2 warm-up, iter_begin, walk x2 + queue reset, rank keys, sort, rank finish, best x2, iter_end
     if update_mode == 2:
         return n + 2
     return n + 1 + sort(slot_bits) + 2           # deposit gen, sort, (tile offsets + fused) | (evaporate + apply)

@@ -10,7 +10,7 @@ import bench  # noqa: E402
 import welding_robot_b200 as wr  # noqa: E402
 
 wl = bench.build_workload_gpu()
-for rep in range(3):
+for rep in range(8):
     t = [time.perf_counter()]
     a = wr.ACS_Rank(seed=1, fixed_colony=4096, step_cap=8192)
     a.creatFromOccupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], bench.PRECISION); t.append(time.perf_counter())

@@ -8,10 +8,11 @@
 //   * ordering deposit records by pheromone slot while keeping rank order inside a slot, so
 //     that the float additions of update_pheromone (:209-211) happen in the reference's order.
 //
-// 8-bit digits.  One warp owns one tile of kTile consecutive items: pass A counts digits per
-// tile, pass B scans each digit's row of the (digit, tile) matrix, pass C adds the digit bases,
-// re-reads the tile in order and scatters with warp-match ranking, which keeps equal digits in
-// input order (stable).
+// Digits of up to kMaxDigitBits bits, chosen per sort so that the key width splits into the fewest
+// equal passes (27-bit slot ids of a 256^3 grid: 3 x 9 instead of 4 x 8; 14-bit step counts: 2 x 7).
+// One warp owns one tile of kTile consecutive items: pass A counts digits per tile, pass B scans
+// each digit's row of the (digit, tile) matrix, pass C adds the digit bases, re-reads the tile in
+// order and scatters with warp-match ranking, which keeps equal digits in input order (stable).
 #include "wr_internal.cuh"
 
 namespace wr {
@@ -19,24 +20,27 @@ namespace wr {
 constexpr int kTile = 512;           // items per warp: short tiles = many warps, the passes are latency-bound per warp
 constexpr int kSortWarps = 4;        // warps per CTA
 constexpr int kSortThreads = kSortWarps * 32;
+constexpr int kMaxDigitBits = 10;
+constexpr int kMaxDigits = 1 << kMaxDigitBits;
 
-__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, const int* __restrict__ d_n, int shift,
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, const int* __restrict__ d_n, int shift, int bits,
                                                              uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t cnt[kSortWarps][256];
+    __shared__ uint32_t cnt[kSortWarps][kMaxDigits];
+    const int nd = 1 << bits;
+    const uint32_t dmask = (uint32_t)nd - 1u;
     const int n = *d_n;
     const int ntiles = (n + kTile - 1) / kTile;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * kSortWarps + w;
-    for (int d = lane; d < 256; d += 32) cnt[w][d] = 0;
+    if (tile >= ntiles) return;
+    for (int d = lane; d < nd; d += 32) cnt[w][d] = 0;
     __syncwarp();
-    if (tile < ntiles) {
-        const int lo = tile * kTile, hi = min(lo + kTile, n);
+    const int lo = tile * kTile, hi = min(lo + kTile, n);
 #pragma unroll 4
-        for (int i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & 255u], 1u);
-        __syncwarp();
-        for (int d = lane; d < 256; d += 32) hist[(size_t)d * ntiles + tile] = cnt[w][d];
-    }
+    for (int i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & dmask], 1u);
+    __syncwarp();
+    for (int d = lane; d < nd; d += 32) hist[(size_t)d * ntiles + tile] = cnt[w][d];
 }
 
 // Row scans: CTA d turns hist[d][0..ntiles) into exclusive prefixes (in place) and publishes the row total.
@@ -71,32 +75,44 @@ __global__ void __launch_bounds__(128) k_sort_scan_rows(uint32_t* __restrict__ h
 
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                                const int* __restrict__ d_n, int shift, const uint32_t* __restrict__ hist,
+                                                                const int* __restrict__ d_n, int shift, int bits, const uint32_t* __restrict__ hist,
                                                                 const uint32_t* __restrict__ totals)
 {
-    __shared__ uint32_t base[kSortWarps][256];
-    __shared__ uint32_t digit_base[256];
+    __shared__ uint32_t base[kSortWarps][kMaxDigits];
+    __shared__ uint32_t digit_base[kMaxDigits];
     __shared__ uint32_t wsum[kSortWarps];
+    const int nd = 1 << bits;
+    const uint32_t dmask = (uint32_t)nd - 1u;
     const int n = *d_n;
     const int ntiles = (n + kTile - 1) / kTile;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x * kSortWarps >= ntiles) return;   // whole CTA idle
-    {   // exclusive scan of the 256 digit totals (2 per thread)
-        const uint32_t t0 = totals[2 * threadIdx.x], t1 = totals[2 * threadIdx.x + 1];
-        uint32_t incl = t0 + t1;
+    {   // exclusive scan of the digit totals: thread t owns digits [t*per, (t+1)*per)
+        const int per = (nd + kSortThreads - 1) / kSortThreads;   // <= 8
+        uint32_t loc[kMaxDigits / kSortThreads];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxDigits / kSortThreads; j++) {
+            const int d = threadIdx.x * per + j;
+            loc[j] = (j < per && d < nd) ? totals[d] : 0u;
+            sum += loc[j];
+        }
+        uint32_t incl = sum;
         for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
         if (lane == 31) wsum[w] = incl;
         __syncthreads();
-        uint32_t before = 0;
-        for (int j = 0; j < w; j++) before += wsum[j];
-        const uint32_t ex = before + incl - (t0 + t1);
-        digit_base[2 * threadIdx.x] = ex;
-        digit_base[2 * threadIdx.x + 1] = ex + t0;
+        uint32_t run = incl - sum;
+        for (int j = 0; j < w; j++) run += wsum[j];
+#pragma unroll
+        for (int j = 0; j < kMaxDigits / kSortThreads; j++) {
+            const int d = threadIdx.x * per + j;
+            if (j < per && d < nd) { digit_base[d] = run; run += loc[j]; }
+        }
         __syncthreads();
     }
     const int tile = blockIdx.x * kSortWarps + w;
     if (tile >= ntiles) return;
-    for (int d = lane; d < 256; d += 32) base[w][d] = digit_base[d] + hist[(size_t)d * ntiles + tile];
+    for (int d = lane; d < nd; d += 32) base[w][d] = digit_base[d] + hist[(size_t)d * ntiles + tile];
     __syncwarp();
     const int lo = tile * kTile, hi = min(lo + kTile, n);
     const unsigned lt = (1u << lane) - 1;
@@ -108,7 +124,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
         const bool act = i < hi;
         const uint32_t k = nk, v = nv;
         if (i + 32 < hi) { nk = keys_in[i + 32]; nv = vals_in[i + 32]; }
-        const unsigned d = act ? ((k >> shift) & 255u) : 256u;  // inactive lanes form their own group
+        const unsigned d = act ? ((k >> shift) & dmask) : (unsigned)nd;  // inactive lanes form their own group
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         if (act) {
             const uint32_t pos = base[w][d] + __popc(peers & lt);
@@ -129,7 +145,7 @@ int sort_plan_create(SortPlan* p, size_t max_n, cudaStream_t s)
     WR_CUDA(dmalloc(&p->keys_b, max_n * sizeof(uint32_t), s));
     WR_CUDA(dmalloc(&p->vals_a, max_n * sizeof(uint32_t), s));
     WR_CUDA(dmalloc(&p->vals_b, max_n * sizeof(uint32_t), s));
-    WR_CUDA(dmalloc(&p->hist, ((size_t)256 * p->max_tiles + 256) * sizeof(uint32_t), s));   // + 256 digit totals
+    WR_CUDA(dmalloc(&p->hist, ((size_t)kMaxDigits * p->max_tiles + kMaxDigits) * sizeof(uint32_t), s));   // + the digit totals
     return WR_OK;
 }
 
@@ -141,14 +157,16 @@ void sort_plan_destroy(SortPlan* p, cudaStream_t s)
 
 int sort_pairs(SortPlan* p, const int* d_n, int key_bits, cudaStream_t s, bool* result_in_b)
 {
-    const int passes = (key_bits + 7) / 8;
+    if (key_bits < 1) key_bits = 1;
+    const int passes = (key_bits + kMaxDigitBits - 1) / kMaxDigitBits;
+    const int bits = (key_bits + passes - 1) / passes;   // fewest passes, then the narrowest digit that covers the key
     const int blocks = (p->max_tiles + kSortWarps - 1) / kSortWarps;
     uint32_t *ki = p->keys_a, *vi = p->vals_a, *ko = p->keys_b, *vo = p->vals_b;
+    uint32_t* totals = p->hist + (size_t)kMaxDigits * p->max_tiles;
     for (int pass = 0; pass < passes; pass++) {
-        k_sort_hist<<<blocks, kSortThreads, 0, s>>>(ki, d_n, pass * 8, p->hist);
-        uint32_t* totals = p->hist + (size_t)256 * p->max_tiles;
-        k_sort_scan_rows<<<256, 128, 0, s>>>(p->hist, totals, d_n);
-        k_sort_scatter<<<blocks, kSortThreads, 0, s>>>(ki, vi, ko, vo, d_n, pass * 8, p->hist, totals);
+        k_sort_hist<<<blocks, kSortThreads, 0, s>>>(ki, d_n, pass * bits, bits, p->hist);
+        k_sort_scan_rows<<<1 << bits, 128, 0, s>>>(p->hist, totals, d_n);
+        k_sort_scatter<<<blocks, kSortThreads, 0, s>>>(ki, vi, ko, vo, d_n, pass * bits, bits, p->hist, totals);
         std::swap(ki, ko); std::swap(vi, vo);
     }
     WR_CUDA(cudaGetLastError());
