@@ -173,7 +173,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = build_workload_gpu()
     n_nodes = CUBE ** 3
-    colony = ANTS_PER_GPU * world
+    colony = args.ants * world
 
     def make_search(host_free):
         acs = wr.ACS_Rank(seed=SEED, fixed_colony=colony, step_cap=STEP_CAP, update_mode=args.update_mode)
@@ -292,7 +292,7 @@ def run_ours(args):
         "metric": "ant-steps/s", "value": value, "unit": "ant-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic: reference mesh fixture voxelised on the GPU, embedded in 256^3 free space; synthetic start/goal",
-        "config": {"workload": "C2: ACSRank_3D, simplified_piece @256-long grid in 256^3, %d ants/GPU, K=6" % ANTS_PER_GPU,
+        "config": {"workload": "C2: ACSRank_3D, simplified_piece @256-long grid in 256^3, %d ants/GPU, K=6" % args.ants,
                    "grid": [CUBE, CUBE, CUBE], "natural_grid": list(wl["natural"]), "ants": colony, "iters_per_step": args.iters,
                    "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic", "fused_tma"][args.update_mode],
                    "parallelism": "ants sharded x%d" % world,
@@ -444,6 +444,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--iters", type=int, default=5, help="ACS iterations per step")
+    ap.add_argument("--ants", type=int, default=ANTS_PER_GPU, help="ants per GPU (default: the C2 colony; other values are exploration runs)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--update-mode", type=int, default=0)
     ap.add_argument("--cpu-ants", type=int, default=1024, help="colony size of the CPU sample")

@@ -22,12 +22,14 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <deque>
 #include <fstream>
 #include <iostream>
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../wr_gpu.h"
@@ -395,23 +397,41 @@ public:
         for (int i = 0; i < point_num; i++) best_matrix[i] = new Agent<float>[point_num];
         initFromGridMap();
         checkRoutePoints();
+        // the pair loop of :472-499 runs on the device (wr_acs_search_pairs): snap every point once, search all pairs
+        // up to the first one the reference would reject, read everything back once
+        std::vector<float> xyz(3 * (size_t)point_num + 3);
+        for (int i = 0; i < point_num; i++) { xyz[3 * i] = route_points[i].x; xyz[3 * i + 1] = route_points[i].y; xyz[3 * i + 2] = route_points[i].z; }
+        std::vector<int64_t> node(point_num + 1, -1);
+        wr::check(wr_acs_snap_points(acs_, xyz.data(), point_num, node.data()));
+        std::vector<std::pair<int, int>> pairs;
+        for (int i = 0; i < point_num; i++) for (int j = i + 1; j < point_num; j++) pairs.push_back(std::make_pair(i, j));
+        size_t good = 0;
+        while (good < pairs.size() && node[pairs[good].first] >= 0 && node[pairs[good].second] >= 0) good++;
         std::vector<float> lens;
-        for (int i = 0; i < point_num; i++) {
-            for (int j = i + 1; j < point_num; j++) {
-                if (setPoints(route_points[i], route_points[j])) {
-                    computeSolution(predict_path_len);
-                    reset();
-                    best_matrix[i][j] = best_;
-                    best_matrix[j][i] = best_;
-                    printf("[ACS 3D] <Point (%.3f, %.3f, %.3f) : Point (%.3f, %.3f, %.3f)> Path length: %.3f\r\n", route_points[i].x,
-                           route_points[i].y, route_points[i].z, route_points[j].x, route_points[j].y, route_points[j].z, best_.L);
-                    lens.push_back(best_.L);
-                } else {
-                    printf("[ACS 3D] Wrong point : (%.3f, %.3f, %.3f) or (%.3f, %.3f, %.3f), program will exit immediately \r\n",
-                           route_points[i].x, route_points[i].y, route_points[i].z, route_points[j].x, route_points[j].y, route_points[j].z);
-                    return;
-                }
+        if (good > 0) {
+            int dims[3]; wr::check(wr_grid_dims(grid_, dims));
+            const size_t nn = (size_t)dims[0] * dims[1] * dims[2];
+            const int cap = (params.step_cap > 0 ? params.step_cap : (int)std::min<size_t>(nn - 1, 65532)) + 1;
+            std::vector<int64_t> s_ids(good), g_ids(good), ids(good * (size_t)cap);
+            std::vector<int> cnt(good), dirs(good * (size_t)cap);
+            lens.resize(good);
+            for (size_t q = 0; q < good; q++) { s_ids[q] = node[pairs[q].first]; g_ids[q] = node[pairs[q].second]; }
+            wr::check(wr_acs_search_pairs(acs_, s_ids.data(), g_ids.data(), (int)good, predict_path_len, max_iteration, lens.data(), cnt.data(),
+                                          ids.data(), dirs.data(), cap));
+            for (size_t q = 0; q < good; q++) {
+                const int i = pairs[q].first, j = pairs[q].second;
+                make_agent(best_, ids.data() + q * cap, dirs.data() + q * cap, cnt[q], lens[q]);
+                best_matrix[i][j] = best_;
+                best_matrix[j][i] = best_;
+                printf("[ACS 3D] <Point (%.3f, %.3f, %.3f) : Point (%.3f, %.3f, %.3f)> Path length: %.3f\r\n", route_points[i].x,
+                       route_points[i].y, route_points[i].z, route_points[j].x, route_points[j].y, route_points[j].z, best_.L);
             }
+        }
+        if (good < pairs.size()) {
+            const int i = pairs[good].first, j = pairs[good].second;
+            printf("[ACS 3D] Wrong point : (%.3f, %.3f, %.3f) or (%.3f, %.3f, %.3f), program will exit immediately \r\n",
+                   route_points[i].x, route_points[i].y, route_points[i].z, route_points[j].x, route_points[j].y, route_points[j].z);
+            return;
         }
         if (output_file != "") {
             FILE* fp = fopen(output_file.c_str(), "w");
@@ -453,6 +473,18 @@ private:
         delete[] best_matrix;
         best_matrix = NULL;
     }
+    void make_agent(Agent<float>& out, const int64_t* ids, const int* dirs, int n, float L)
+    {
+        std::vector<ACS_Node<float>*> p;
+        for (int i = 0; i < n; i++) {
+            pool_.emplace_back();
+            ACS_Node<float>& nd = pool_.back();
+            nd.id = (unsigned long)ids[i]; nd.isFree = true; nd.pt = node_point(nd.id);
+            p.push_back(&nd);
+        }
+        std::vector<int> d(dirs, dirs + (n > 0 ? n - 1 : 0));
+        out.assign(p, d, L);
+    }
     void fetch_best(Agent<float>& out)
     {
         need();
@@ -461,15 +493,7 @@ private:
         std::vector<int64_t> ids(n > 0 ? n : 1);
         std::vector<int> dirs(n > 0 ? n : 1);
         if (n > 0) wr::check(wr_acs_best(acs_, ids.data(), dirs.data(), n, &n, &L));
-        std::vector<ACS_Node<float>*> p;
-        for (int i = 0; i < n; i++) {
-            pool_.emplace_back();
-            ACS_Node<float>& nd = pool_.back();
-            nd.id = (unsigned long)ids[i]; nd.isFree = true; nd.pt = node_point(nd.id);
-            p.push_back(&nd);
-        }
-        dirs.resize(n > 0 ? n - 1 : 0);
-        out.assign(p, dirs, L);
+        make_agent(out, ids.data(), dirs.data(), n, L);
     }
 };
 

@@ -104,6 +104,16 @@ int wr_acs_destroy(wr_acs* a);
  * 1.2*precision on every axis.  ids[0]/ids[1] = start/goal node id (-1 if none). */
 int wr_acs_set_points(wr_acs* a, const float start[3], const float goal[3], int64_t ids[2]);
 int wr_acs_set_endpoints(wr_acs* a, int64_t start_id, int64_t goal_id);
+/* setPoints' full-grid scan (:545-562) as a kernel, for any number of points at once: ids[i] = the node point i
+ * (3 floats each) snaps to, -1 if none.  checkRoutePoints (:511-535) = this call over route_points. */
+int wr_acs_snap_points(wr_acs* a, const float* pts_xyz, int npoints, int64_t* ids);
+/* The all-pairs loop of searchBestPathOfPoints (:472-499) on the device: for every pair, wr_acs_begin(predict) +
+ * n_iterations iterations + reset(), enqueued back to back with no host synchronisation; one read-back at the end.
+ * L[p] = best.L (+inf: no path), path_nodes[p] = node count of the best path (0: none); row p of path_ids / path_dirs
+ * (path_cap entries per row; both may be NULL with path_cap 0) gets min(path_nodes[p], path_cap) ids and one slot
+ * index less.  Independent queries (BASELINE config 5) shard by giving every rank its own pairs. */
+int wr_acs_search_pairs(wr_acs* a, const int64_t* start_ids, const int64_t* goal_ids, int npairs, float predict_path_len,
+                        int n_iterations, float* L, int* path_nodes, int64_t* path_ids, int* path_dirs, int path_cap);
 /* computeSolution :220-305 = wr_acs_begin(predict) + wr_acs_iterate(max_iteration) */
 int wr_acs_begin(wr_acs* a, float predict_path_len);                /* :229-233 */
 int wr_acs_iterate(wr_acs* a, int n_iterations);                    /* loop body :237-299, n times; asynchronous */

@@ -254,3 +254,54 @@ def test_synthetic_512_cubed_query(wr, oracle):
         A.iterate(1); g.iterate(1)
         compare_iteration(A, g)
     assert g.counters()["arrived"] > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# all-pairs driver on the device
+# ---------------------------------------------------------------------------------------------
+def test_snap_points_kernel_matches_host_scan_and_oracle(wr, oracle, meshes):
+    """setPoints' full-grid scan (ACSRank_3D.hpp:545-562) as a kernel == the host scan == the oracle's scan, for points
+    on nodes, between nodes, on the duplicate-coordinate plane, inside the solid and outside the grid."""
+    A, g = make_pair(wr, oracle, meshes["cubic"], 0.005, 10, seed=1)
+    rng = np.random.default_rng(11)
+    xs, ys, zs = g.coords()
+    pts = [tuple(p) for p in C1_POINTS] + list(C1_NAN_PAIR)
+    for _ in range(200):
+        pts.append((np.float32(rng.uniform(xs[0] - 0.01, xs[-1] + 0.01)), np.float32(rng.uniform(ys[0] - 0.01, ys[-1] + 0.01)),
+                    np.float32(rng.uniform(zs[0] - 0.01, zs[-1] + 0.01))))
+    ids = g.snapPoints(pts)
+    hits = 0
+    for p, i in zip(pts, ids):
+        ok = g.setPoints(p, p)
+        assert (g._start_id if ok else -1) == int(i)
+        ok_o, s, _ = A.set_points(p, p)
+        assert (s if ok_o else -1) == int(i)
+        hits += int(i) >= 0
+    assert 20 < hits < len(pts)
+
+
+def test_search_pairs_equals_pair_by_pair_loop(wr, oracle, meshes):
+    """wr_acs_search_pairs (no host synchronisation between pairs) == begin/iterate/best/reset pair by pair, bit for bit,
+    including the pair whose ants all die (NaN plane) and the pheromone field left behind."""
+    A, g = make_pair(wr, oracle, meshes["cubic"], 0.005, 10, seed=0x5EED)
+    pts = [C1_POINTS[0], C1_POINTS[3], C1_POINTS[5], C1_NAN_PAIR[0], C1_NAN_PAIR[1]]
+    node = g.snapPoints(pts)
+    assert (node >= 0).all()
+    pairs = [(0, 1), (1, 2), (3, 4), (0, 2)]
+    loop = []
+    for i, j in pairs:
+        g.setEndpoints(int(node[i]), int(node[j]))
+        g.begin(0.5); g.iterate(30)
+        loop.append(g.bestPath())
+        g.reset()
+    tau_loop = g.pheromone()
+    res = g.searchPairs([node[i] for i, _ in pairs], [node[j] for _, j in pairs], 0.5, iterations=30)
+    for (ids, dirs, L), (ids2, dirs2, L2) in zip(loop, res):
+        assert np.array_equal(ids, ids2) and np.array_equal(dirs, dirs2)
+        assert np.float32(L) == np.float32(L2) or (np.isinf(L) and np.isinf(L2))
+    assert np.isinf(res[2][2]) and len(res[2][0]) == 0 and np.isfinite(res[0][2])
+    assert np.array_equal(tau_loop.view(np.uint32), g.pheromone().view(np.uint32))
+    # and the oracle agrees on the first pair
+    A.set_endpoints(int(node[0]), int(node[1])); A.begin(0.5); A.iterate(30)
+    ids, dirs, L = A.best()
+    assert np.array_equal(ids, res[0][0]) and np.float32(L) == np.float32(res[0][2])

@@ -320,6 +320,33 @@ class ACS_Rank(GridMap):
         check(lib().wr_acs_set_endpoints(self._need(), start_id, goal_id))
         self._start_id, self._goal_id = int(start_id), int(goal_id)
 
+    def snapPoints(self, points):
+        """setPoints' scan (ACSRank_3D.hpp:545-562) for many points in one kernel -> int64 node ids (-1: no free node)."""
+        pts = np.ascontiguousarray(np.array([list(p) for p in points], np.float32).reshape(-1, 3))
+        ids = np.full(len(pts), -1, np.int64)
+        check(lib().wr_acs_snap_points(self._need(), ptr(pts), len(pts), ptr(ids)))
+        return ids
+
+    def stepCap(self):
+        return self.params.step_cap if self.params.step_cap > 0 else min(self.size_of_map() - 1, 65532)
+
+    def searchPairs(self, start_ids, goal_ids, predict_path_len, iterations=None, with_paths=True):
+        """The all-pairs loop (ACSRank_3D.hpp:472-499) on the device: per pair computeSolution + reset(), no host
+        synchronisation between pairs.  -> list of (ids, dirs, L) per pair (ids/dirs empty when no path)."""
+        s = np.ascontiguousarray(start_ids, np.int64); g = np.ascontiguousarray(goal_ids, np.int64)
+        n = len(s)
+        it = self.max_iteration if iterations is None else iterations
+        cap = self.stepCap() + 1 if with_paths else 0
+        L = np.zeros(max(n, 1), np.float32); cnt = np.zeros(max(n, 1), np.int32)
+        ids = np.zeros((max(n, 1), max(cap, 1)), np.int64); dirs = np.zeros((max(n, 1), max(cap, 1)), np.int32)
+        check(lib().wr_acs_search_pairs(self._need(), ptr(s), ptr(g), n, predict_path_len, it, ptr(L), ptr(cnt),
+                                        ptr(ids) if cap else None, ptr(dirs) if cap else None, cap))
+        out = []
+        for p in range(n):
+            k = int(cnt[p]) if cap else 0
+            out.append((ids[p, :k].copy(), dirs[p, :max(k - 1, 0)].copy(), float(L[p])))
+        return out
+
     def checkRoutePoints(self):
         """ACSRank_3D.hpp:511-535."""
         for p in self.route_points:
@@ -377,23 +404,26 @@ class ACS_Rank(GridMap):
         self.best_matrix = [[Agent(self) for _ in range(point_num)] for _ in range(point_num)]
         self.initFromGridMap()
         self.checkRoutePoints()
+        # the pair loop of :472-499 runs on the device (wr_acs_search_pairs): snap every point once, search all pairs up
+        # to the first one the reference would reject, read everything back once
+        node = self.snapPoints(self.route_points) if point_num else np.zeros(0, np.int64)
+        pairs = [(i, j) for i in range(point_num) for j in range(i + 1, point_num)]
+        bad = next((q for q, (i, j) in enumerate(pairs) if node[i] < 0 or node[j] < 0), len(pairs))
+        res = self.searchPairs([node[i] for i, _ in pairs[:bad]], [node[j] for _, j in pairs[:bad]], predict_path_len) if bad else []
         lengths = []
-        for i in range(point_num):
-            for j in range(i + 1, point_num):
-                pi, pj = self.route_points[i], self.route_points[j]
-                if self.setPoints(pi, pj):
-                    self.computeSolution(predict_path_len)
-                    self.reset()
-                    best = self.getSolution()
-                    self.best_matrix[i][j] = best
-                    self.best_matrix[j][i] = best
-                    print("[ACS 3D] <Point (%.3f, %.3f, %.3f) : Point (%.3f, %.3f, %.3f)> Path length: %.3f\r" %
-                          (pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, best.L))
-                    lengths.append(best.L)
-                else:
-                    print("[ACS 3D] Wrong point : (%.3f, %.3f, %.3f) or (%.3f, %.3f, %.3f), program will exit immediately \r" %
-                          (pi.x, pi.y, pi.z, pj.x, pj.y, pj.z))
-                    return
+        for (i, j), (ids, dirs, L) in zip(pairs[:bad], res):
+            pi, pj = self.route_points[i], self.route_points[j]
+            best = Agent(self, ids, dirs, L)
+            self.best_matrix[i][j] = best
+            self.best_matrix[j][i] = best
+            print("[ACS 3D] <Point (%.3f, %.3f, %.3f) : Point (%.3f, %.3f, %.3f)> Path length: %.3f\r" %
+                  (pi.x, pi.y, pi.z, pj.x, pj.y, pj.z, best.L))
+            lengths.append(best.L)
+        if bad < len(pairs):
+            pi, pj = self.route_points[pairs[bad][0]], self.route_points[pairs[bad][1]]
+            print("[ACS 3D] Wrong point : (%.3f, %.3f, %.3f) or (%.3f, %.3f, %.3f), program will exit immediately \r" %
+                  (pi.x, pi.y, pi.z, pj.x, pj.y, pj.z))
+            return
         if output_file:
             # the reference rewrites the header in place with "%d %d\r" (:500-501), which clobbers the
             # first distance once point_num >= 10; the header is written whole here.

@@ -355,6 +355,28 @@ extern "C" int wr_acs_set_points(wr_acs* a, const float s[3], const float e[3], 
     return WR_OK;
 }
 
+// setPoints' scan as a kernel: no host mirror of the occupancy bits, any number of points per call
+extern "C" int wr_acs_snap_points(wr_acs* a, const float* pts_xyz, int npoints, int64_t* ids)
+{
+    WR_REQUIRE(a && pts_xyz && ids && npoints >= 0, WR_ERR_INVALID, "wr_acs_snap_points: bad argument");
+    if (npoints == 0) return WR_OK;
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    float* d_pts = nullptr;
+    long long* d_ids = nullptr;
+    WR_CUDA(dmalloc(&d_pts, (size_t)npoints * 3 * sizeof(float), s));
+    WR_CUDA(dmalloc(&d_ids, (size_t)npoints * sizeof(long long), s));
+    WR_CUDA(cudaMemcpyAsync(d_pts, pts_xyz, (size_t)npoints * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    const float t = 1.2 * a->g->precision;   // double product rounded to float, as `float t = 1.2*precision`
+    k_snap_points<<<npoints, 128, 0, s>>>(d_pts, npoints, a->g->d_coords, a->g->rx, a->g->ry, a->g->rz, t, a->g->d_bits, d_ids);
+    std::vector<long long> h(npoints);
+    WR_CUDA(cudaMemcpyAsync(h.data(), d_ids, (size_t)npoints * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    WR_CUDA(cudaStreamSynchronize(s));
+    pool_free(d_pts, s); pool_free(d_ids, s);
+    for (int i = 0; i < npoints; i++) ids[i] = h[i];
+    return WR_OK;
+}
+
 extern "C" int wr_acs_set_endpoints(wr_acs* a, int64_t s, int64_t e)
 {
     WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_set_endpoints: null");
@@ -546,6 +568,60 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
     }
     WR_CUDA(cudaGetLastError());
     return WR_OK;
+}
+
+// searchBestPathOfPoints' loop (:472-499) on the device: every pair is a full computeSolution (begin + n iterations)
+// followed by reset(), enqueued back to back with NO host synchronisation in between; the results stay in HBM until
+// the single read-back at the end.
+extern "C" int wr_acs_search_pairs(wr_acs* a, const int64_t* start_ids, const int64_t* goal_ids, int npairs, float predict, int n_iterations,
+                                   float* L, int* path_nodes, int64_t* path_ids, int* path_dirs, int path_cap)
+{
+    WR_REQUIRE(a && start_ids && goal_ids && L && path_nodes && npairs >= 0 && n_iterations >= 0, WR_ERR_INVALID, "wr_acs_search_pairs: bad argument");
+    WR_REQUIRE(a->nranks == 1, WR_ERR_STATE, "wr_acs_search_pairs: independent searches are sharded by giving each rank its own pairs");
+    WR_REQUIRE(path_cap >= 0 && (path_cap == 0 || (path_ids && path_dirs)), WR_ERR_INVALID, "wr_acs_search_pairs: path buffers missing");
+    for (int p = 0; p < npairs; p++) {
+        if (start_ids[p] < 0 || goal_ids[p] < 0) { set_error("wr_acs_search_pairs: pair %d has an endpoint that did not snap to a free node", p); return WR_ERR_NOTFOUND; }
+        WR_REQUIRE((size_t)start_ids[p] < a->N && (size_t)goal_ids[p] < a->N, WR_ERR_INVALID, "wr_acs_search_pairs: id out of range");
+    }
+    if (npairs == 0) return WR_OK;
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    const int cap_out = std::min(path_cap, a->cap + 1);
+    const int cap_dev = std::max(cap_out, 1);
+    float* d_L = nullptr; int* d_n = nullptr; uint32_t* d_ids = nullptr; uint8_t* d_dirs = nullptr;
+    WR_CUDA(dmalloc(&d_L, (size_t)npairs * sizeof(float), s));
+    WR_CUDA(dmalloc(&d_n, (size_t)npairs * sizeof(int), s));
+    WR_CUDA(dmalloc(&d_ids, (size_t)npairs * cap_dev * sizeof(uint32_t), s));
+    WR_CUDA(dmalloc(&d_dirs, (size_t)npairs * cap_dev, s));
+    int rc = WR_OK;
+    for (int p = 0; p < npairs && rc == WR_OK; p++) {
+        a->start = start_ids[p]; a->goal = goal_ids[p];
+        rc = wr_acs_begin(a, predict);
+        if (rc == WR_OK) rc = wr_acs_iterate(a, n_iterations);
+        if (rc != WR_OK) break;
+        k_save_result<<<4, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, p, cap_out, d_L, d_n, d_ids, d_dirs);
+        rc = wr_acs_reset(a);
+    }
+    if (rc == WR_OK) {
+        std::vector<uint32_t> h_ids((size_t)npairs * cap_dev);
+        std::vector<uint8_t> h_dirs((size_t)npairs * cap_dev);
+        WR_CUDA(cudaMemcpyAsync(L, d_L, (size_t)npairs * sizeof(float), cudaMemcpyDeviceToHost, s));
+        WR_CUDA(cudaMemcpyAsync(path_nodes, d_n, (size_t)npairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (cap_out > 0) {
+            WR_CUDA(cudaMemcpyAsync(h_ids.data(), d_ids, h_ids.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            WR_CUDA(cudaMemcpyAsync(h_dirs.data(), d_dirs, h_dirs.size(), cudaMemcpyDeviceToHost, s));
+        }
+        WR_CUDA(cudaStreamSynchronize(s));
+        for (int p = 0; p < npairs && cap_out > 0; p++) {
+            const int n = std::min(path_nodes[p], cap_out);
+            for (int i = 0; i < n; i++) path_ids[(size_t)p * path_cap + i] = h_ids[(size_t)p * cap_dev + i];
+            for (int i = 0; i + 1 < n; i++) path_dirs[(size_t)p * path_cap + i] = h_dirs[(size_t)p * cap_dev + i];
+        }
+    } else {
+        cudaStreamSynchronize(s);
+    }
+    pool_free(d_L, s); pool_free(d_n, s); pool_free(d_ids, s); pool_free(d_dirs, s);
+    return rc;
 }
 
 // ---- ant sharding across ranks ------------------------------------------------------------------

@@ -806,6 +806,62 @@ __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(f
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// setPoints (:537-565) on the device.  The reference scans every node and keeps the LAST one (z,y,x
+// order = largest id) that is free and within 1.2*precision of the point on every axis.  The per-axis
+// test is separable, so the match set is a product of three tiny index lists; one CTA per point
+// collects them and takes the largest free id.  ids[p] = -1 when nothing matches.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_snap_points(const float* __restrict__ pts, int npts, const float* __restrict__ coords, int rx, int ry, int rz,
+                                                      float t, const uint32_t* __restrict__ occ_bits, long long* __restrict__ ids)
+{
+    constexpr int kMax = 16;   // matches per axis: spacing = precision, window 2.4*precision -> 2-3 (a few more on duplicate planes)
+    __shared__ int list[3][kMax];
+    __shared__ int cnt[3];
+    __shared__ long long best;
+    const int p = blockIdx.x;
+    if (p >= npts) return;
+    if (threadIdx.x < 3) cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) best = -1;
+    __syncthreads();
+    const int n[3] = {rx, ry, rz};
+    const float* axis[3] = {coords, coords + rx, coords + rx + ry};
+    for (int a = 0; a < 3; a++) {
+        const float q = pts[3 * p + a];
+        for (int i = threadIdx.x; i < n[a]; i += blockDim.x) {
+            const float d = __fsub_rn(q, axis[a][i]);
+            const float ad = d > 0.0f ? d : -d;   // my_abs
+            if (ad < t) { const int k = atomicAdd(&cnt[a], 1); if (k < kMax) list[a][k] = i; }
+        }
+    }
+    __syncthreads();
+    const int cx = min(cnt[0], kMax), cy = min(cnt[1], kMax), cz = min(cnt[2], kMax);
+    const int total = cx * cy * cz;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int x = list[0][i % cx], y = list[1][(i / cx) % cy], z = list[2][i / (cx * cy)];
+        const long long id = ((long long)z * ry + y) * rx + x;
+        if (!((occ_bits[id >> 5] >> (id & 31)) & 1u)) atomicMax(&best, id);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ids[p] = best;
+}
+
+// all-pairs driver: keep the finished search's best (getSolution :506-509) in slot `pair` of the result arrays
+__global__ void k_save_result(const IterState* st, const int* __restrict__ best_n, const uint32_t* __restrict__ best_ids,
+                              const uint8_t* __restrict__ best_dirs, int pair, int path_cap, float* __restrict__ res_L, int* __restrict__ res_n,
+                              uint32_t* __restrict__ res_ids, uint8_t* __restrict__ res_dirs)
+{
+    const bool found = st->best_steps != INT_MAX;
+    const int n = found ? *best_n : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { res_L[pair] = st->best_L; res_n[pair] = n; }
+    uint32_t* oi = res_ids + (size_t)pair * path_cap;
+    uint8_t* od = res_dirs + (size_t)pair * path_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < path_cap; i += gridDim.x * blockDim.x) {
+        oi[i] = best_ids[i];
+        if (i + 1 < n) od[i] = best_dirs[i];
+    }
+}
+
 // reset() :307-315 and the initial field of initFromGridMap :391-401
 __global__ void k_tau_fill(float* tau, size_t n, float v)
 {
