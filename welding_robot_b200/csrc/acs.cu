@@ -97,6 +97,15 @@ struct wr_acs {
     int colony_max = 0, w_max = 0;
     // shard (multi-rank)
     int rank = 0, nranks = 1, chunk = 0;
+    // owner-computes deposits (sharded): this rank's list of final slot values, pulled by the peers over NVLink.
+    // Plain cudaMalloc (IPC-exportable), double-buffered by iteration parity.
+    uint32_t* d_export[2] = {nullptr, nullptr};
+    size_t export_words = 0;
+    const uint32_t** d_peer_tab[2] = {nullptr, nullptr};   // device arrays of nranks pointers (own buffer included)
+    std::vector<void*> ipc_opened;
+    bool peers_set = false;
+    int* d_nq = nullptr;              // records in this rank's slot slice
+    unsigned slice_parity = 0;
 
     float* d_tau = nullptr;
     float* d_heur = nullptr;          // [N][6] heuristic factor for the current goal
@@ -144,6 +153,14 @@ static void free_colony_buffers(wr_acs* a)
     a->d_ant_steps = nullptr; a->d_path_ids = nullptr; a->d_path_dirs = nullptr; a->d_overflow = nullptr;
     a->d_gkeys = nullptr; a->d_gmasks = nullptr; a->d_rec_off = nullptr; a->d_order = nullptr;
     sort_plan_destroy(&a->sort_ants, s); sort_plan_destroy(&a->sort_recs, s);
+    for (void* p : a->ipc_opened) cudaIpcCloseMemHandle(p);
+    a->ipc_opened.clear();
+    for (int b = 0; b < 2; b++) {
+        if (a->d_export[b]) { cudaStreamSynchronize(s); cudaFree(a->d_export[b]); a->d_export[b] = nullptr; }
+        pool_free(a->d_peer_tab[b], s); a->d_peer_tab[b] = nullptr;
+    }
+    pool_free(a->d_nq, s); a->d_nq = nullptr;
+    a->peers_set = false; a->export_words = 0;
     a->alloc_colony = 0;
 }
 
@@ -163,6 +180,13 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
         WR_CUDA(dmalloc(&a->d_local_steps, chunk * sizeof(int), a->stream));
         a->cand_words = 2 * cap + 2;
         WR_CUDA(dmalloc(&a->d_cand, a->cand_words * sizeof(uint32_t), a->stream));
+        a->export_words = 4 + 2 * rec_max;
+        for (int b = 0; b < 2; b++) {
+            WR_CUDA(cudaMalloc(&a->d_export[b], a->export_words * sizeof(uint32_t)));
+            WR_CUDA(cudaMemsetAsync(a->d_export[b], 0, 4 * sizeof(uint32_t), a->stream));
+            WR_CUDA(dmalloc(&a->d_peer_tab[b], (size_t)a->nranks * sizeof(uint32_t*), a->stream));
+        }
+        WR_CUDA(dmalloc(&a->d_nq, sizeof(int), a->stream));
     } else a->d_local_steps = a->d_ant_steps;
     WR_CUDA(dmalloc(&a->d_path_ids, chunk * cap * sizeof(uint32_t), a->stream));
     WR_CUDA(dmalloc(&a->d_path_dirs, chunk * cap, a->stream));
@@ -426,6 +450,7 @@ static void launch_walk2(const WalkArgs& w, bool alpha1, int prefetch, int block
 static void launch_warm(wr_acs* a)
 {
     if (!walk_warm() || walk_version(a->g) != 2 || a->p.update_mode == WR_UPDATE_ATOMIC) return;
+    if (a->nranks > 1 && a->peers_set) return;   // owner-computes: k_pull_finals has just touched the rows under the deposits
     const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
     k_path_warm<<<kNumSMs, 256, 0, a->stream>>>(a->d_state, ck, a->d_tau, a->d_heur);
 }
@@ -502,12 +527,14 @@ static int launch_deposit_gen(wr_acs* a)
 }
 
 // K3, shipped variant: tile offsets + list of deposit tiles, then the fused single-pass update
-static int launch_fused(wr_acs* a, const uint32_t* ck, const uint32_t* cv)
+// K3, shipped variant: tile offsets + list of deposit tiles, then the fused single-pass update
+static int launch_fused(wr_acs* a, const uint32_t* ck, const uint32_t* cv, const int* d_n = nullptr, uint32_t* fin = nullptr)
 {
     cudaStream_t s = a->stream;
     WR_CUDA(cudaMemsetAsync(a->d_upd_q, 0, 4 * sizeof(uint32_t), s));
-    k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles, a->d_dep_list, a->d_upd_q + 2);
-    k_update_fused<<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q);
+    k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(d_n ? d_n : a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, a->d_dep_list, a->d_upd_q + 2);
+    if (fin) k_update_fused<true><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, fin);
+    else k_update_fused<false><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, nullptr);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -529,7 +556,7 @@ static int launch_update(wr_acs* a)
         int rc = launch_fused(a, ck, cv);
         if (rc != WR_OK) return rc;
     } else if (a->p.update_mode == WR_UPDATE_FUSED_TMA) {
-        k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
+        k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
         const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
         k_update_tma_ring<<<std::min<unsigned>(a->ntiles, kNumSMs * 2), kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
     } else {
@@ -714,6 +741,96 @@ extern "C" int wr_acs_finish_iteration(wr_acs* a)
     return WR_OK;
 }
 
+// ---- owner-computes deposits: peer buffers -------------------------------------------------------------------------
+extern "C" int wr_acs_peer_export(wr_acs* a, void* ipc_handles, void** raw_pointers)
+{
+    WR_REQUIRE(a && a->begun && a->nranks > 1 && a->d_export[0], WR_ERR_STATE, "wr_acs_peer_export: sharded handle after wr_acs_begin only");
+    for (int b = 0; b < 2; b++) {
+        if (ipc_handles) WR_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handles) + b, a->d_export[b]));
+        if (raw_pointers) raw_pointers[b] = a->d_export[b];
+    }
+    return WR_OK;
+}
+
+static int install_peers(wr_acs* a, const std::vector<const uint32_t*> (&tab)[2])
+{
+    for (int b = 0; b < 2; b++)
+        WR_CUDA(cudaMemcpyAsync(a->d_peer_tab[b], tab[b].data(), (size_t)a->nranks * sizeof(uint32_t*), cudaMemcpyHostToDevice, a->stream));
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    a->peers_set = true;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_peer_import(wr_acs* a, const void* all_ipc_handles)
+{
+    WR_REQUIRE(a && all_ipc_handles && a->begun && a->nranks > 1 && a->d_export[0], WR_ERR_STATE, "wr_acs_peer_import: sharded handle after wr_acs_begin only");
+    WR_CUDA(cudaSetDevice(a->device));
+    const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all_ipc_handles);
+    std::vector<const uint32_t*> tab[2];
+    for (int b = 0; b < 2; b++) tab[b].resize(a->nranks);
+    for (int r = 0; r < a->nranks; r++)
+        for (int b = 0; b < 2; b++) {
+            if (r == a->rank) { tab[b][r] = a->d_export[b]; continue; }
+            void* p = nullptr;
+            WR_CUDA(cudaIpcOpenMemHandle(&p, h[2 * r + b], cudaIpcMemLazyEnablePeerAccess));
+            a->ipc_opened.push_back(p);
+            tab[b][r] = static_cast<const uint32_t*>(p);
+        }
+    return install_peers(a, tab);
+}
+
+extern "C" int wr_acs_peer_set_pointers(wr_acs* a, void* const* all_raw_pointers)
+{
+    WR_REQUIRE(a && all_raw_pointers && a->begun && a->nranks > 1 && a->d_export[0], WR_ERR_STATE, "wr_acs_peer_set_pointers: sharded handle after wr_acs_begin only");
+    std::vector<const uint32_t*> tab[2];
+    for (int b = 0; b < 2; b++) {
+        tab[b].resize(a->nranks);
+        for (int r = 0; r < a->nranks; r++) tab[b][r] = r == a->rank ? a->d_export[b] : static_cast<const uint32_t*>(all_raw_pointers[2 * r + b]);
+    }
+    return install_peers(a, tab);
+}
+
+// Owner-computes finish: this rank keeps only the records of ITS slot slice (stable partition of the merged list),
+// sorts them, evaporates the whole field and applies its slice's deposits, listing the final values for the peers.
+extern "C" int wr_acs_finish_iteration_sliced(wr_acs* a)
+{
+    WR_REQUIRE(a && a->begun && a->nranks > 1, WR_ERR_STATE, "wr_acs_finish_iteration_sliced: sharded handle only");
+    WR_REQUIRE(a->peers_set, WR_ERR_STATE, "wr_acs_finish_iteration_sliced: exchange the peer buffers first (wr_acs_peer_export / _import)");
+    WR_REQUIRE(a->p.update_mode == WR_UPDATE_FUSED, WR_ERR_STATE, "wr_acs_finish_iteration_sliced: needs update_mode WR_UPDATE_FUSED");
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    const unsigned t_lo = (unsigned)(((unsigned long long)a->ntiles * a->rank) / a->nranks);
+    const unsigned t_hi = (unsigned)(((unsigned long long)a->ntiles * (a->rank + 1)) / a->nranks);
+    int st = sort_partition(&a->sort_recs, a->dptr_nrec(), t_lo * (uint32_t)kUpdTile, (t_hi - t_lo) * (uint32_t)kUpdTile, s, a->d_nq);
+    if (st != WR_OK) return st;
+    st = sort_pairs(&a->sort_recs, a->d_nq, a->slot_bits, s, &a->recs_in_b, true);
+    if (st != WR_OK) return st;
+    const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
+    const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    a->slice_parity ^= 1u;
+    uint32_t* fin = a->d_export[a->slice_parity];
+    WR_CUDA(cudaMemsetAsync(fin, 0, 4 * sizeof(uint32_t), s));
+    st = launch_fused(a, ck, cv, a->d_nq, fin);
+    if (st != WR_OK) return st;
+    k_iter_end<<<1, 1, 0, s>>>(a->d_state);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+// After a barrier across ranks (every rank has finished wr_acs_finish_iteration_sliced): overwrite the slots the
+// other ranks own with their final values, read straight from their HBM.
+extern "C" int wr_acs_pull_finals(wr_acs* a)
+{
+    WR_REQUIRE(a && a->begun && a->nranks > 1 && a->peers_set, WR_ERR_STATE, "wr_acs_pull_finals: bad state");
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(a->d_tau, walk_warm() ? a->d_heur : nullptr, a->d_peer_tab[a->slice_parity], a->nranks, a->rank);
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
 extern "C" int wr_acs_sync(wr_acs* a)
 {
     WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_sync: null");
@@ -863,7 +980,7 @@ extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per
             int rc = launch_fused(a, ck, cv);
             if (rc != WR_OK) return rc;
         } else if (which == 3) {
-            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->d_state, ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
+            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
             k_update_tma_ring<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
         } else if (which == 1) {
             k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);

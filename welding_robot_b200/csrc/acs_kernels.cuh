@@ -554,8 +554,11 @@ __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const 
 // exchanged by shuffle, so the chain costs ~1 FADD per record instead of one L2 round trip.
 // Must be called by all threads of the CTA (NT = threads taking part, a multiple of 32).
 // ------------------------------------------------------------------------------------------
+// EMIT (sharded colonies, owner-computes): every finished run also appends (slot, final value) to `fin` — the list the
+// other ranks pull over NVLink instead of redoing this rank's chains (fin[0] = count, records from word 4).
+template <bool EMIT = false>
 __device__ __forceinline__ void apply_runs(float* buf, uint32_t base, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                           uint32_t lo, uint32_t hi, uint32_t first, uint32_t stride)
+                                           uint32_t lo, uint32_t hi, uint32_t first, uint32_t stride, uint32_t* fin = nullptr)
 {
     const int lane = threadIdx.x & 31;
     for (uint32_t r0 = lo + first; r0 < hi; r0 += stride) {   // r0 is warp-uniform: all 32 lanes run the same trips
@@ -571,6 +574,16 @@ __device__ __forceinline__ void apply_runs(float* buf, uint32_t base, const uint
             do { x = __fadd_rn(x, __uint_as_float(vals[j])); j++; } while (j < hi && j < r + 8 && keys[j] == key);
             more = j < hi && keys[j] == key;
             if (!more) buf[key - base] = x;
+        }
+        if (EMIT) {   // warp-aggregated append: one atomic per warp trip
+            const bool done = head && !more;
+            const unsigned fm = __ballot_sync(0xffffffffu, done);
+            if (fm) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(fin, (uint32_t)__popc(fm));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (done) reinterpret_cast<uint2*>(fin + 4)[at + __popc(fm & ((1u << lane) - 1u))] = make_uint2(key, __float_as_uint(x));
+            }
         }
         unsigned m = __ballot_sync(0xffffffffu, more);
         while (m) {
@@ -629,7 +642,10 @@ __device__ __forceinline__ void apply_runs(float* buf, uint32_t base, const uint
                 }
                 if (!open) break;
             }
-            if (lane == src) buf[key0 - base] = x0;
+            if (lane == src) {
+                buf[key0 - base] = x0;
+                if (EMIT) reinterpret_cast<uint2*>(fin + 4)[atomicAdd(fin, 1u)] = make_uint2(key0, __float_as_uint(x0));
+            }
         }
     }
 }
@@ -672,12 +688,12 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys
     return lo;
 }
 // tile_off[t] = first record of tile t (t = 0 .. ntiles); optionally the list of tiles that receive deposits
-__global__ void k_tile_offsets(const IterState* st, const uint32_t* __restrict__ keys, uint32_t* __restrict__ tile_off, unsigned ntiles,
+__global__ void k_tile_offsets(const int* __restrict__ d_n, const uint32_t* __restrict__ keys, uint32_t* __restrict__ tile_off, unsigned ntiles,
                                uint32_t* __restrict__ dep_list, uint32_t* dep_n)
 {
     unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntiles) return;
-    const int n = st->n_records;
+    const int n = *d_n;
     const int lo = lower_bound_key(keys, n, (unsigned long long)t * kUpdTile);
     tile_off[t] = (uint32_t)lo;
     if (dep_list && t < ntiles && lo < n && (unsigned long long)keys[lo] < (unsigned long long)(t + 1) * kUpdTile) dep_list[atomicAdd(dep_n, 1u)] = t;
@@ -770,11 +786,12 @@ __device__ __forceinline__ void stream_tile(float* tau, unsigned t, float rho, i
 // q[0]: queue of deposit tiles, q[1]: queue of plain-tile chunks, q[2]: number of deposit tiles (all zeroed
 // before k_tile_offsets).  Work is handed out dynamically: a CTA that sits on a long deposit chain simply
 // takes fewer tiles, so the chain is hidden behind the other CTAs' streaming instead of extending the kernel.
+template <bool EMIT>
 __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(float* tau, unsigned ntiles, float rho,
                                                                                 const uint32_t* __restrict__ rec_keys,
                                                                                 const uint32_t* __restrict__ rec_vals,
                                                                                 const uint32_t* __restrict__ tile_off,
-                                                                                const uint32_t* __restrict__ dep_list, uint32_t* q)
+                                                                                const uint32_t* __restrict__ dep_list, uint32_t* q, uint32_t* fin)
 {
     __shared__ unsigned s_next;
     __shared__ uint32_t s_off[kFusedChunk + 1];
@@ -790,7 +807,7 @@ __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(f
         const uint32_t lo = tile_off[t], hi = tile_off[t + 1];
         stream_tile(tau, t, rho, tid);
         __syncthreads();   // the scaled tile is visible to the whole CTA
-        apply_runs(tau, 0u, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads);
+        apply_runs<EMIT>(tau, 0u, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads, fin);
     }
     while (true) {   // ---- everything else: pure streaming ----
         if (tid == 0) s_next = atomicAdd(&q[1], (unsigned)kFusedChunk);
@@ -860,6 +877,28 @@ __global__ void k_save_result(const IterState* st, const int* __restrict__ best_
         oi[i] = best_ids[i];
         if (i + 1 < n) od[i] = best_dirs[i];
     }
+}
+
+// Sharded colonies, owner-computes: rank r applied the deposits of its slot slice and listed the final values
+// (k_update_fused<true>); every other rank pulls that list straight out of r's HBM over NVLink (peer pointers) and
+// overwrites its own, so far only evaporated, copy.  bufs[p]: word 0 = count, records (slot, value bits) from word 4.
+// The same pass is the next walk's L2 warm-up (cf. k_path_warm): the slots that just received deposits are where the
+// colony walks next, so the tau lines are left dirty in L2 by the writes and the heuristic rows are touched here.
+__global__ void __launch_bounds__(256) k_pull_finals(float* tau, const float* __restrict__ heur, const uint32_t* const* __restrict__ bufs, int npeers, int me)
+{
+    uint32_t acc = 0;
+    for (int p = 0; p < npeers; p++) {
+        const uint32_t* buf = bufs[p];
+        const uint32_t cnt = __ldcg(buf);
+        const uint2* rec = reinterpret_cast<const uint2*>(buf + 4);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+            const uint2 r = __ldcg(rec + i);
+            if (p != me) tau[r.x] = __uint_as_float(r.y);
+            else acc ^= __ldcg(reinterpret_cast<const uint32_t*>(tau) + r.x);
+            if (heur) acc ^= __ldcg(reinterpret_cast<const uint32_t*>(heur) + r.x);
+        }
+    }
+    if (acc == 0x9E3779B9u && npeers < 0) tau[0] = 0.0f;   // keeps the warm-up loads alive; never true
 }
 
 // reset() :307-315 and the initial field of initFromGridMap :391-401

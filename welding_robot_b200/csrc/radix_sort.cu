@@ -23,8 +23,15 @@ constexpr int kSortThreads = kSortWarps * 32;
 constexpr int kMaxDigitBits = 10;
 constexpr int kMaxDigits = 1 << kMaxDigitBits;
 
+// digit of a key: bits [shift, shift+bits) — or, in PARTITION mode (span > 0), 0 for keys in [lo, lo+span) and 1 for the
+// rest: one stable pass that moves a rank's slot slice to the front of the list (sharded colonies, acs.cu)
+__device__ __forceinline__ unsigned digit_of(uint32_t key, int shift, uint32_t dmask, uint32_t lo, uint32_t span)
+{
+    return span ? ((key - lo) < span ? 0u : 1u) : ((key >> shift) & dmask);
+}
+
 __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, const int* __restrict__ d_n, int shift, int bits,
-                                                             uint32_t* __restrict__ hist)
+                                                             uint32_t* __restrict__ hist, uint32_t lo, uint32_t span)
 {
     __shared__ uint32_t cnt[kSortWarps][kMaxDigits];
     const int nd = 1 << bits;
@@ -36,9 +43,9 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __re
     if (tile >= ntiles) return;
     for (int d = lane; d < nd; d += 32) cnt[w][d] = 0;
     __syncwarp();
-    const int lo = tile * kTile, hi = min(lo + kTile, n);
+    const int t_lo = tile * kTile, t_hi = min(t_lo + kTile, n);
 #pragma unroll 4
-    for (int i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & dmask], 1u);
+    for (int i = t_lo + lane; i < t_hi; i += 32) atomicAdd(&cnt[w][digit_of(keys[i], shift, dmask, lo, span)], 1u);
     __syncwarp();
     for (int d = lane; d < nd; d += 32) hist[(size_t)d * ntiles + tile] = cnt[w][d];
 }
@@ -76,7 +83,7 @@ __global__ void __launch_bounds__(128) k_sort_scan_rows(uint32_t* __restrict__ h
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                 const int* __restrict__ d_n, int shift, int bits, const uint32_t* __restrict__ hist,
-                                                                const uint32_t* __restrict__ totals)
+                                                                const uint32_t* __restrict__ totals, uint32_t part_lo, uint32_t part_span)
 {
     __shared__ uint32_t base[kSortWarps][kMaxDigits];
     __shared__ uint32_t digit_base[kMaxDigits];
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
         const bool act = i < hi;
         const uint32_t k = nk, v = nv;
         if (i + 32 < hi) { nk = keys_in[i + 32]; nv = vals_in[i + 32]; }
-        const unsigned d = act ? ((k >> shift) & dmask) : (unsigned)nd;  // inactive lanes form their own group
+        const unsigned d = act ? digit_of(k, shift, dmask, part_lo, part_span) : (unsigned)nd;  // inactive lanes form their own group
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         if (act) {
             const uint32_t pos = base[w][d] + __popc(peers & lt);
@@ -155,22 +162,39 @@ void sort_plan_destroy(SortPlan* p, cudaStream_t s)
     *p = SortPlan();
 }
 
-int sort_pairs(SortPlan* p, const int* d_n, int key_bits, cudaStream_t s, bool* result_in_b)
+int sort_pairs(SortPlan* p, const int* d_n, int key_bits, cudaStream_t s, bool* result_in_b, bool input_in_b)
 {
     if (key_bits < 1) key_bits = 1;
     const int passes = (key_bits + kMaxDigitBits - 1) / kMaxDigitBits;
     const int bits = (key_bits + passes - 1) / passes;   // fewest passes, then the narrowest digit that covers the key
     const int blocks = (p->max_tiles + kSortWarps - 1) / kSortWarps;
     uint32_t *ki = p->keys_a, *vi = p->vals_a, *ko = p->keys_b, *vo = p->vals_b;
+    if (input_in_b) { std::swap(ki, ko); std::swap(vi, vo); }
     uint32_t* totals = p->hist + (size_t)kMaxDigits * p->max_tiles;
     for (int pass = 0; pass < passes; pass++) {
-        k_sort_hist<<<blocks, kSortThreads, 0, s>>>(ki, d_n, pass * bits, bits, p->hist);
+        k_sort_hist<<<blocks, kSortThreads, 0, s>>>(ki, d_n, pass * bits, bits, p->hist, 0u, 0u);
         k_sort_scan_rows<<<1 << bits, 128, 0, s>>>(p->hist, totals, d_n);
-        k_sort_scatter<<<blocks, kSortThreads, 0, s>>>(ki, vi, ko, vo, d_n, pass * bits, bits, p->hist, totals);
+        k_sort_scatter<<<blocks, kSortThreads, 0, s>>>(ki, vi, ko, vo, d_n, pass * bits, bits, p->hist, totals, 0u, 0u);
         std::swap(ki, ko); std::swap(vi, vo);
     }
     WR_CUDA(cudaGetLastError());
-    *result_in_b = (passes & 1) != 0;
+    *result_in_b = ((passes & 1) != 0) != input_in_b;
+    return WR_OK;
+}
+
+__global__ void k_copy_count(const uint32_t* __restrict__ src, int* __restrict__ dst) { *dst = (int)*src; }
+
+// Stable partition of keys_a/vals_a: pairs with key in [lo, lo+span) first (count -> *d_count_out), the rest behind them.
+// Result in keys_b/vals_b.
+int sort_partition(SortPlan* p, const int* d_n, uint32_t lo, uint32_t span, cudaStream_t s, int* d_count_out)
+{
+    const int blocks = (p->max_tiles + kSortWarps - 1) / kSortWarps;
+    uint32_t* totals = p->hist + (size_t)kMaxDigits * p->max_tiles;
+    k_sort_hist<<<blocks, kSortThreads, 0, s>>>(p->keys_a, d_n, 0, 1, p->hist, lo, span);
+    k_sort_scan_rows<<<2, 128, 0, s>>>(p->hist, totals, d_n);
+    k_sort_scatter<<<blocks, kSortThreads, 0, s>>>(p->keys_a, p->vals_a, p->keys_b, p->vals_b, d_n, 0, 1, p->hist, totals, lo, span);
+    k_copy_count<<<1, 1, 0, s>>>(totals, d_count_out);
+    WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
 

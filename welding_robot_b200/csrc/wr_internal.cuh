@@ -37,5 +37,7 @@ int sort_plan_create(SortPlan* p, size_t max_n, cudaStream_t s);
 void sort_plan_destroy(SortPlan* p, cudaStream_t s);
 // Sorts keys_a/vals_a (first *d_n entries) by the low `key_bits` bits; result lands in
 // keys_a/vals_a again when the pass count is even, else in keys_b/vals_b: returns which.
-int sort_pairs(SortPlan* p, const int* d_n, int key_bits, cudaStream_t s, bool* result_in_b);
+int sort_pairs(SortPlan* p, const int* d_n, int key_bits, cudaStream_t s, bool* result_in_b, bool input_in_b = false);
+// stable partition: pairs with key in [lo, lo+span) to the front (their count -> *d_count_out); input keys_a/vals_a, result in keys_b/vals_b
+int sort_partition(SortPlan* p, const int* d_n, uint32_t lo, uint32_t span, cudaStream_t s, int* d_count_out);
 }  // namespace wr

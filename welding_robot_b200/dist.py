@@ -12,7 +12,12 @@ ant index).  Per iteration:
      holds non-zero words)                                               wr_acs_apply_best
   5. deposit records of the local ants at their GLOBAL (rank, step) positions, zeros elsewhere,
      all_reduce(SUM, int32) of keys and values                           wr_acs_build_records
-  6. slot sort + fused evaporation/deposit (K3), identical on every rank  wr_acs_finish_iteration
+  6. owner-computes update (default): the slot space is cut into one tile-aligned slice per rank; every rank
+     keeps the merged records of ITS slice (stable partition), sorts and applies them while evaporating the
+     whole field, and lists the final value of every slot it touched       wr_acs_finish_iteration_sliced
+  7. barrier, then every rank pulls the peers' lists straight out of their HBM over NVLink (kernel-side peer
+     loads through CUDA IPC pointers, no host-sized collective)             wr_acs_pull_finals
+     (`sliced=False`: step 6 = slot sort + fused update of ALL records on every rank, wr_acs_finish_iteration)
 
 Every reduced position has exactly one non-zero contributor, so integer SUM is a merge, the merged
 deposit list equals the single-GPU list and the pheromone field stays bit-identical on all ranks and
@@ -81,19 +86,53 @@ class GpuBackend:
     def finish_iteration(self):
         check(lib().wr_acs_finish_iteration(self.h))
 
+    # ---- owner-computes deposits ----------------------------------------------------------------------
+    def export_handles(self):
+        """-> (128 bytes of CUDA IPC handles, [2 raw device pointers]) of this rank's two final-value lists."""
+        h = (C.c_ubyte * 128)(); raw = (C.c_void_p * 2)()
+        check(lib().wr_acs_peer_export(self.h, h, raw))
+        return bytes(h), [raw[0], raw[1]]
+
+    def peer_setup(self, world, group=None):
+        """Exchange the IPC handles of the final-value lists (once per begin)."""
+        mine, _ = self.export_handles()
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.device)
+        allh = torch.empty(128 * world, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, t, group=group)
+        buf = allh.cpu().numpy().tobytes()
+        check(lib().wr_acs_peer_import(self.h, buf))
+
+    def set_peer_pointers(self, all_raw):
+        arr = (C.c_void_p * len(all_raw))(*all_raw)
+        check(lib().wr_acs_peer_set_pointers(self.h, arr))
+
+    def finish_iteration_sliced(self):
+        check(lib().wr_acs_finish_iteration_sliced(self.h))
+
+    def pull_finals(self):
+        check(lib().wr_acs_pull_finals(self.h))
+
 
 class ShardedSearch:
-    """Drives one ant-sharded search.  `backend` defaults to the GPU backend of `acs`."""
+    """Drives one ant-sharded search.  `backend` defaults to the GPU backend of `acs`.
+    sliced: owner-computes update (steps 6-7 above); None = on when the backend supports it (WR_SHARD_SLICED=0 disables)."""
 
-    def __init__(self, acs, rank, world, group=None, backend=None):
+    def __init__(self, acs, rank, world, group=None, backend=None, sliced=None):
+        import os
         self.rank, self.world, self.group = rank, world, group
         self.backend = backend if backend is not None else GpuBackend(acs)
         self.backend.set_shard(rank, world)
+        if sliced is None:
+            sliced = world > 1 and hasattr(self.backend, "finish_iteration_sliced") and os.environ.get("WR_SHARD_SLICED", "1") != "0"
+        self.sliced = bool(sliced) and world > 1
         self._all = None
+        self._bar = None
         self.bytes_exchanged = 0
 
     def begin(self, predict_path_len):
         self.backend.begin(predict_path_len)
+        if self.sliced:
+            self.backend.peer_setup(self.world, self.group)
 
     def iterate(self, n=1):
         b = self.backend
@@ -101,6 +140,7 @@ class ShardedSearch:
             local = b.walk()                                   # int32[chunk], -1 = dead / beyond the colony
             if self._all is None or self._all.numel() != local.numel() * self.world:
                 self._all = torch.empty(local.numel() * self.world, dtype=local.dtype, device=local.device)
+                self._bar = torch.zeros(1, dtype=torch.int32, device=local.device)
             dist.all_gather_into_tensor(self._all, local, group=self.group)
             cand = b.rank_global(self._all)                    # zeros unless this rank owns the new best ant
             dist.all_reduce(cand, op=dist.ReduceOp.SUM, group=self.group)
@@ -109,5 +149,51 @@ class ShardedSearch:
             if keys.numel():
                 dist.all_reduce(keys, op=dist.ReduceOp.SUM, group=self.group)
                 dist.all_reduce(vals, op=dist.ReduceOp.SUM, group=self.group)
-            b.finish_iteration()
-            self.bytes_exchanged += 4 * (self._all.numel() + cand.numel() + 2 * keys.numel())
+            if self.sliced:
+                b.finish_iteration_sliced()
+                dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.group)   # barrier: every rank's list is complete
+                b.pull_finals()
+            else:
+                b.finish_iteration()
+            self.bytes_exchanged += 4 * (self._all.numel() + cand.numel() + 2 * keys.numel() + 1)
+
+
+class LocalShards:
+    """The same protocol for `world` shards of one colony that live in ONE process on ONE GPU (tests, debugging): the
+    collectives become tensor operations on the shared stream, the peer buffers plain device pointers."""
+
+    def __init__(self, searches):
+        self.world = len(searches)
+        self.backends = [GpuBackend(a) for a in searches]
+        stream = torch.cuda.current_stream().cuda_stream
+        for r, b in enumerate(self.backends):
+            check(lib().wr_acs_set_stream(b.h, C.c_void_p(stream)))
+            b.set_shard(r, self.world)
+
+    def begin(self, predict_path_len):
+        raws = []
+        for b in self.backends:
+            b.begin(predict_path_len)
+            raws += b.export_handles()[1]
+        for b in self.backends:
+            b.set_peer_pointers(raws)
+
+    def iterate(self, n=1):
+        bs = self.backends
+        for _ in range(n):
+            allsteps = torch.cat([b.walk() for b in bs])
+            cands = [b.rank_global(allsteps) for b in bs]
+            tot = torch.stack(cands).sum(0, dtype=torch.int32)
+            for b, c in zip(bs, cands):
+                c.copy_(tot)
+                b.apply_best()
+            recs = [b.build_records() for b in bs]
+            if recs[0][0].numel():
+                ks = torch.stack([k for k, _ in recs]).sum(0, dtype=torch.int32)
+                vs = torch.stack([v for _, v in recs]).sum(0, dtype=torch.int32)
+                for k, v in recs:
+                    k.copy_(ks); v.copy_(vs)
+            for b in bs:
+                b.finish_iteration_sliced()
+            for b in bs:
+                b.pull_finals()
