@@ -171,21 +171,27 @@ int wr_acs_apply_best(wr_acs* a);                            /* install the (mer
  * (the one host sync of a sharded iteration).  all_reduce(SUM, int32) keys[0..*n) and vals[0..*n). */
 int wr_acs_build_records(wr_acs* a, uint32_t** dev_keys, uint32_t** dev_vals, int* n);
 int wr_acs_finish_iteration(wr_acs* a);                      /* slot sort + pheromone update + iteration counter */
-/* Owner-computes variant of the last step (default of welding_robot_b200/dist.py on NVLink-connected GPUs): the slot
- * space is cut into nranks tile-aligned slices; rank r keeps only the merged records of ITS slice (one stable
- * partition pass), sorts and applies them — 1/nranks of the sort and of the dependent add chains — while evaporating
- * the whole field, and lists the final value of every slot it touched in a buffer the peers can read.  After a
- * barrier (any collective on the stream) every rank pulls the peers' lists straight out of their HBM over NVLink
- * (kernel-side peer loads, no host-sized collective) and overwrites those slots.  Same bits as wr_acs_finish_iteration.
- *     once after wr_acs_begin:  wr_acs_peer_export -> all_gather(handles) -> wr_acs_peer_import
- *     per iteration:            ... wr_acs_build_records -> all_reduce -> wr_acs_finish_iteration_sliced -> barrier
- *                               -> wr_acs_pull_finals
- * ipc_handles: 2 x 64 bytes (cudaIpcMemHandle_t of the two parity buffers); all_ipc_handles: nranks x 2 x 64 bytes in
- * rank order.  raw_pointers / wr_acs_peer_set_pointers: the same for handles that live in ONE process (tests). */
-int wr_acs_peer_export(wr_acs* a, void* ipc_handles, void** raw_pointers);
+/* ---- the same over NVLink peer memory (default of welding_robot_b200/dist.py; needs P2P between the GPUs) ------------
+ * Everything a peer reads lives in one slab per rank (ant trails and the list of final slot values, double-buffered by
+ * iteration parity), exported once with ONE CUDA IPC handle.  An iteration is then
+ *     wr_acs_walk -> all_gather(local steps) -> wr_acs_finish_iteration_peer(all_steps, sliced)
+ *     [sliced: -> barrier (any collective) -> wr_acs_pull_finals]
+ * with a single small collective and no host synchronisation: every rank ranks the colony, reads the new best trail
+ * and the trails of ALL eligible ants straight out of their owners' HBM (kernel-side peer loads) and generates the
+ * deposit records itself, in global (rank, step) order.
+ *   sliced = 0: replicated update — slot sort + fused update of all records on every rank;
+ *   sliced = 1: owner-computes update — the slot space is cut into nranks tile-aligned slices; rank r keeps (one stable
+ *               partition pass), sorts and applies only the records of ITS slice — 1/nranks of the sort and of the
+ *               dependent add chains — while evaporating the whole field, and lists the final value of every slot it
+ *               touched; after the barrier wr_acs_pull_finals reads the peers' lists and overwrites those slots.
+ * Both give the bits of the 1-GPU run.
+ *   once after wr_acs_begin:  wr_acs_peer_export -> all_gather(handles) -> wr_acs_peer_import
+ * ipc_handle: 64 bytes (cudaIpcMemHandle_t); all_ipc_handles: nranks x 64 bytes in rank order.  raw_pointer /
+ * wr_acs_peer_set_pointers: the same for handles that live in ONE process (tests). */
+int wr_acs_peer_export(wr_acs* a, void* ipc_handle, void** raw_pointer);
 int wr_acs_peer_import(wr_acs* a, const void* all_ipc_handles);
 int wr_acs_peer_set_pointers(wr_acs* a, void* const* all_raw_pointers);
-int wr_acs_finish_iteration_sliced(wr_acs* a);
+int wr_acs_finish_iteration_peer(wr_acs* a, const int* dev_all_steps, int sliced);
 int wr_acs_pull_finals(wr_acs* a);
 
 /* ------------------------------------------------------------------------------------------

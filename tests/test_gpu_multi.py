@@ -45,23 +45,29 @@ def worker(rank, world, port, q):
             return a
 
         single = make(); single.begin(1.0); single.iterate(6)
-        sharded = make()
-        S = ShardedSearch(sharded, rank, world)
-        S.begin(1.0); S.iterate(6)
-        torch.cuda.synchronize()
-        t1, t2 = single.pheromone(), sharded.pheromone()
-        assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), "sharded pheromone field differs from the 1-GPU field"
-        b1, b2 = single.bestPath(), sharded.bestPath()
-        assert np.array_equal(b1[0], b2[0]) and np.array_equal(b1[1], b2[1]) and np.float32(b1[2]) == np.float32(b2[2])
+        t1, b1, c1 = single.pheromone(), single.bestPath(), single.counters()
         chunk = (1001 + world - 1) // world
-        for k in range(rank * chunk, min((rank + 1) * chunk, 1001), 37):
-            i1, d1, L1, o1 = single.lastAnt(k); i2, d2, L2, o2 = sharded.lastAnt(k)
-            assert o1 == o2 and np.array_equal(i1, i2) and (L1 == L2 or (np.isinf(L1) and np.isinf(L2)))
-        c1, c2 = single.counters(), sharded.counters()
-        tot = torch.tensor([c2["ant_steps"], c2["ants"]], device="cuda", dtype=torch.int64)
-        dist.all_reduce(tot)
-        assert int(tot[0]) == c1["ant_steps"] and int(tot[1]) == c1["ants"]
-        q.put((rank, "ok", S.bytes_exchanged))
+        # NVLink peer-memory protocol with the owner-computes and with the replicated update, and the NCCL-only protocol
+        for peer, sliced in ((True, True), (True, False), (False, False)):
+            sharded = make()
+            S = ShardedSearch(sharded, rank, world, peer=peer, sliced=sliced)
+            assert (S.peer, S.sliced) == (peer, sliced)
+            S.begin(1.0); S.iterate(6)
+            torch.cuda.synchronize()
+            t2 = sharded.pheromone()
+            assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), "sharded pheromone field differs from the 1-GPU field (%s, %s)" % (peer, sliced)
+            b2 = sharded.bestPath()
+            assert np.array_equal(b1[0], b2[0]) and np.array_equal(b1[1], b2[1]) and np.float32(b1[2]) == np.float32(b2[2])
+            for k in range(rank * chunk, min((rank + 1) * chunk, 1001), 37):
+                i1, d1, L1, o1 = single.lastAnt(k); i2, d2, L2, o2 = sharded.lastAnt(k)
+                assert o1 == o2 and np.array_equal(i1, i2) and (L1 == L2 or (np.isinf(L1) and np.isinf(L2)))
+            c2 = sharded.counters()
+            tot = torch.tensor([c2["ant_steps"], c2["ants"]], device="cuda", dtype=torch.int64)
+            dist.all_reduce(tot)
+            assert int(tot[0]) == c1["ant_steps"] and int(tot[1]) == c1["ants"]
+            dist.barrier()
+            del S, sharded
+        q.put((rank, "ok", 0))
     except Exception:  # noqa: BLE001
         import traceback
         q.put((rank, "fail", traceback.format_exc()))

@@ -1,5 +1,6 @@
-"""GPU, one device: the owner-computes update of a sharded colony (slot slices, final-value lists pulled through peer
-pointers — welding_robot_b200/dist.py steps 6-7) with all shards living in ONE process, against the un-sharded search.
+"""GPU, one device: the peer-memory protocol of a sharded colony (trails read through peer pointers, replicated or
+owner-computes update with final-value lists — welding_robot_b200/dist.py) with all shards living in ONE process,
+against the un-sharded search.
 Covers the device side of the multi-GPU protocol on a 1-GPU box; tests/test_gpu_multi.py runs it over NCCL + CUDA IPC."""
 import contextlib
 import io
@@ -13,8 +14,8 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,colony", [(2, 1001), (3, 640)])
-def test_owner_computes_shards_equal_unsharded(world, colony):
+@pytest.mark.parametrize("world,colony,sliced", [(2, 1001, True), (3, 640, True), (2, 333, False)])
+def test_peer_protocol_shards_equal_unsharded(world, colony, sliced):
     import torch
     import welding_robot_b200 as wr
     from welding_robot_b200 import _lib
@@ -33,7 +34,7 @@ def test_owner_computes_shards_equal_unsharded(world, colony):
 
     single = make(); single.begin(1.0)
     shards = [make() for _ in range(world)]
-    S = LocalShards(shards); S.begin(1.0)
+    S = LocalShards(shards, sliced=sliced); S.begin(1.0)
     for its in (1, 1, 6):
         single.iterate(its); S.iterate(its)
         torch.cuda.synchronize()

@@ -39,7 +39,7 @@ wr_acs_iterate wr_acs_sync wr_acs_reset wr_acs_best wr_acs_download_pheromone wr
 wr_acs_last_colony wr_acs_last_ant wr_acs_counters wr_acs_kernel_ms wr_acs_set_timing wr_acs_bench_kernel wr_acs_set_stream
 wr_acs_set_shard wr_acs_walk wr_acs_local_steps_dev wr_acs_rank_global wr_acs_best_candidate_dev wr_acs_apply_best
 wr_acs_build_records wr_acs_finish_iteration wr_acs_peer_export wr_acs_peer_import wr_acs_peer_set_pointers
-wr_acs_finish_iteration_sliced wr_acs_pull_finals
+wr_acs_finish_iteration_peer wr_acs_pull_finals
 wr_gtsp_create wr_gtsp_destroy wr_gtsp_iterate wr_gtsp_sync wr_gtsp_best wr_gtsp_download_pheromone wr_gtsp_tau0
 wr_gtsp_kernel_ms""".split()
 
@@ -83,7 +83,7 @@ def lib():
         "wr_acs_walk": [vp], "wr_acs_local_steps_dev": [vp, vp, vp, vp], "wr_acs_rank_global": [vp, vp],
         "wr_acs_best_candidate_dev": [vp, vp, vp], "wr_acs_apply_best": [vp], "wr_acs_build_records": [vp, vp, vp, vp],
         "wr_acs_finish_iteration": [vp], "wr_acs_peer_export": [vp, vp, vp], "wr_acs_peer_import": [vp, vp],
-        "wr_acs_peer_set_pointers": [vp, vp], "wr_acs_finish_iteration_sliced": [vp], "wr_acs_pull_finals": [vp],
+        "wr_acs_peer_set_pointers": [vp, vp], "wr_acs_finish_iteration_peer": [vp, vp, i32], "wr_acs_pull_finals": [vp],
         "wr_gtsp_create": [vp, i32, i32, i32, i32, u64, vp], "wr_gtsp_destroy": [vp], "wr_gtsp_iterate": [vp, i32],
         "wr_gtsp_sync": [vp], "wr_gtsp_best": [vp, i32, vp, vp, vp], "wr_gtsp_download_pheromone": [vp, i32, vp],
         "wr_gtsp_tau0": [vp, vp], "wr_gtsp_kernel_ms": [vp, vp],

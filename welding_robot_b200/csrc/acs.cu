@@ -97,15 +97,17 @@ struct wr_acs {
     int colony_max = 0, w_max = 0;
     // shard (multi-rank)
     int rank = 0, nranks = 1, chunk = 0;
-    // owner-computes deposits (sharded): this rank's list of final slot values, pulled by the peers over NVLink.
-    // Plain cudaMalloc (IPC-exportable), double-buffered by iteration parity.
-    uint32_t* d_export[2] = {nullptr, nullptr};
-    size_t export_words = 0;
-    const uint32_t** d_peer_tab[2] = {nullptr, nullptr};   // device arrays of nranks pointers (own buffer included)
+    // Sharded colonies on NVLink: everything a peer reads lives in ONE cudaMalloc'd slab (IPC-exportable with a single
+    // handle, same layout on every rank): the ant trails and the list of final slot values of the owner-computes
+    // update, each double-buffered by iteration parity.   [ids0 | ids1 | dirs0 | dirs1 | fin0 | fin1]
+    unsigned char* d_slab = nullptr;
+    size_t slab_bytes = 0, off_ids[2] = {0, 0}, off_dirs[2] = {0, 0}, off_fin[2] = {0, 0};
+    const void** d_tabs = nullptr;    // device: [kind 0 ids,1 dirs,2 fin][parity][rank] -> pointer into rank's slab
     std::vector<void*> ipc_opened;
     bool peers_set = false;
     int* d_nq = nullptr;              // records in this rank's slot slice
-    unsigned slice_parity = 0;
+    unsigned parity = 0;              // flips at every wr_acs_walk of a sharded handle
+    bool warm_by_pull = false;        // the last iteration ended with k_pull_finals (which doubles as the L2 warm-up)
 
     float* d_tau = nullptr;
     float* d_heur = nullptr;          // [N][6] heuristic factor for the current goal
@@ -139,6 +141,8 @@ struct wr_acs {
     size_t alloc_colony = 0;
     PhaseTimer timer;
 
+    const void** tab(int kind, unsigned par) const { return d_tabs + ((size_t)kind * 2 + par) * nranks; }
+    uint32_t* fin_buf(unsigned par) const { return reinterpret_cast<uint32_t*>(d_slab + off_fin[par]); }
     const int* dptr_colony() const { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + offsetof(IterState, colony)); }
     const int* dptr_nrec() const { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + offsetof(IterState, n_records)); }
 };
@@ -146,7 +150,8 @@ struct wr_acs {
 static void free_colony_buffers(wr_acs* a)
 {
     cudaStream_t s = a->stream;
-    pool_free(a->d_ant_steps, s); pool_free(a->d_path_ids, s); pool_free(a->d_path_dirs, s); pool_free(a->d_overflow, s);
+    pool_free(a->d_ant_steps, s); pool_free(a->d_overflow, s);
+    if (!a->d_slab) { pool_free(a->d_path_ids, s); pool_free(a->d_path_dirs, s); }
     pool_free(a->d_gkeys, s); pool_free(a->d_gmasks, s); pool_free(a->d_resume, s); a->d_resume = nullptr; pool_free(a->d_rec_off, s); pool_free(a->d_order, s);
     if (a->d_local_steps != a->d_ant_steps) pool_free(a->d_local_steps, s);
     pool_free(a->d_cand, s); a->d_local_steps = nullptr; a->d_cand = nullptr;
@@ -155,12 +160,13 @@ static void free_colony_buffers(wr_acs* a)
     sort_plan_destroy(&a->sort_ants, s); sort_plan_destroy(&a->sort_recs, s);
     for (void* p : a->ipc_opened) cudaIpcCloseMemHandle(p);
     a->ipc_opened.clear();
-    for (int b = 0; b < 2; b++) {
-        if (a->d_export[b]) { cudaStreamSynchronize(s); cudaFree(a->d_export[b]); a->d_export[b] = nullptr; }
-        pool_free(a->d_peer_tab[b], s); a->d_peer_tab[b] = nullptr;
+    if (a->d_slab) {
+        cudaStreamSynchronize(s); cudaFree(a->d_slab); a->d_slab = nullptr;
+        a->d_path_ids = nullptr; a->d_path_dirs = nullptr;   // they pointed into the slab
     }
+    pool_free(a->d_tabs, s); a->d_tabs = nullptr;
     pool_free(a->d_nq, s); a->d_nq = nullptr;
-    a->peers_set = false; a->export_words = 0;
+    a->peers_set = false; a->slab_bytes = 0;
     a->alloc_colony = 0;
 }
 
@@ -180,16 +186,24 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
         WR_CUDA(dmalloc(&a->d_local_steps, chunk * sizeof(int), a->stream));
         a->cand_words = 2 * cap + 2;
         WR_CUDA(dmalloc(&a->d_cand, a->cand_words * sizeof(uint32_t), a->stream));
-        a->export_words = 4 + 2 * rec_max;
-        for (int b = 0; b < 2; b++) {
-            WR_CUDA(cudaMalloc(&a->d_export[b], a->export_words * sizeof(uint32_t)));
-            WR_CUDA(cudaMemsetAsync(a->d_export[b], 0, 4 * sizeof(uint32_t), a->stream));
-            WR_CUDA(dmalloc(&a->d_peer_tab[b], (size_t)a->nranks * sizeof(uint32_t*), a->stream));
-        }
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t o = 0;
+        for (int b = 0; b < 2; b++) { a->off_ids[b] = o; o += up(chunk * cap * sizeof(uint32_t)); }
+        for (int b = 0; b < 2; b++) { a->off_dirs[b] = o; o += up(chunk * cap); }
+        for (int b = 0; b < 2; b++) { a->off_fin[b] = o; o += up((4 + 2 * rec_max) * sizeof(uint32_t)); }
+        a->slab_bytes = o;
+        WR_CUDA(cudaMalloc(&a->d_slab, a->slab_bytes));
+        for (int b = 0; b < 2; b++) WR_CUDA(cudaMemsetAsync(a->d_slab + a->off_fin[b], 0, 4 * sizeof(uint32_t), a->stream));
+        WR_CUDA(dmalloc(&a->d_tabs, (size_t)6 * a->nranks * sizeof(void*), a->stream));
         WR_CUDA(dmalloc(&a->d_nq, sizeof(int), a->stream));
+        a->parity = 0;
+        a->d_path_ids = reinterpret_cast<uint32_t*>(a->d_slab + a->off_ids[0]);
+        a->d_path_dirs = a->d_slab + a->off_dirs[0];
     } else a->d_local_steps = a->d_ant_steps;
-    WR_CUDA(dmalloc(&a->d_path_ids, chunk * cap * sizeof(uint32_t), a->stream));
-    WR_CUDA(dmalloc(&a->d_path_dirs, chunk * cap, a->stream));
+    if (a->nranks == 1) {
+        WR_CUDA(dmalloc(&a->d_path_ids, chunk * cap * sizeof(uint32_t), a->stream));
+        WR_CUDA(dmalloc(&a->d_path_dirs, chunk * cap, a->stream));
+    }
     WR_CUDA(dmalloc(&a->d_overflow, chunk * sizeof(uint32_t), a->stream));
     WR_CUDA(dmalloc(&a->d_rec_off, cm * sizeof(uint32_t), a->stream));
     WR_CUDA(dmalloc(&a->d_order, cm * sizeof(int), a->stream));
@@ -450,7 +464,7 @@ static void launch_walk2(const WalkArgs& w, bool alpha1, int prefetch, int block
 static void launch_warm(wr_acs* a)
 {
     if (!walk_warm() || walk_version(a->g) != 2 || a->p.update_mode == WR_UPDATE_ATOMIC) return;
-    if (a->nranks > 1 && a->peers_set) return;   // owner-computes: k_pull_finals has just touched the rows under the deposits
+    if (a->warm_by_pull) return;   // owner-computes update: k_pull_finals has just touched the rows under the deposits
     const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
     k_path_warm<<<kNumSMs, 256, 0, a->stream>>>(a->d_state, ck, a->d_tau, a->d_heur);
 }
@@ -667,6 +681,11 @@ extern "C" int wr_acs_walk(wr_acs* a)
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    if (a->d_slab) {   // trails are double-buffered: a peer may still be reading the previous iteration's
+        a->parity ^= 1u;
+        a->d_path_ids = reinterpret_cast<uint32_t*>(a->d_slab + a->off_ids[a->parity]);
+        a->d_path_dirs = a->d_slab + a->off_dirs[a->parity];
+    }
     launch_warm(a);
     k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0);
     WR_CUDA(cudaMemsetAsync(a->d_local_steps, 0xFF, (size_t)a->chunk * sizeof(int), s));   // -1: beyond the colony
@@ -741,21 +760,25 @@ extern "C" int wr_acs_finish_iteration(wr_acs* a)
     return WR_OK;
 }
 
-// ---- owner-computes deposits: peer buffers -------------------------------------------------------------------------
-extern "C" int wr_acs_peer_export(wr_acs* a, void* ipc_handles, void** raw_pointers)
+// ---- sharded colonies over NVLink peer memory -------------------------------------------------------------------------
+extern "C" int wr_acs_peer_export(wr_acs* a, void* ipc_handle, void** raw_pointer)
 {
-    WR_REQUIRE(a && a->begun && a->nranks > 1 && a->d_export[0], WR_ERR_STATE, "wr_acs_peer_export: sharded handle after wr_acs_begin only");
-    for (int b = 0; b < 2; b++) {
-        if (ipc_handles) WR_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handles) + b, a->d_export[b]));
-        if (raw_pointers) raw_pointers[b] = a->d_export[b];
-    }
+    WR_REQUIRE(a && a->begun && a->nranks > 1 && a->d_slab, WR_ERR_STATE, "wr_acs_peer_export: sharded handle after wr_acs_begin only");
+    if (ipc_handle) WR_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle), a->d_slab));
+    if (raw_pointer) *raw_pointer = a->d_slab;
     return WR_OK;
 }
 
-static int install_peers(wr_acs* a, const std::vector<const uint32_t*> (&tab)[2])
+static int install_peers(wr_acs* a, const std::vector<const unsigned char*>& slabs)
 {
-    for (int b = 0; b < 2; b++)
-        WR_CUDA(cudaMemcpyAsync(a->d_peer_tab[b], tab[b].data(), (size_t)a->nranks * sizeof(uint32_t*), cudaMemcpyHostToDevice, a->stream));
+    std::vector<const void*> tab((size_t)6 * a->nranks);
+    for (int r = 0; r < a->nranks; r++)
+        for (int b = 0; b < 2; b++) {
+            tab[((size_t)0 * 2 + b) * a->nranks + r] = slabs[r] + a->off_ids[b];
+            tab[((size_t)1 * 2 + b) * a->nranks + r] = slabs[r] + a->off_dirs[b];
+            tab[((size_t)2 * 2 + b) * a->nranks + r] = slabs[r] + a->off_fin[b];
+        }
+    WR_CUDA(cudaMemcpyAsync(a->d_tabs, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, a->stream));
     WR_CUDA(cudaStreamSynchronize(a->stream));
     a->peers_set = true;
     return WR_OK;
@@ -763,53 +786,70 @@ static int install_peers(wr_acs* a, const std::vector<const uint32_t*> (&tab)[2]
 
 extern "C" int wr_acs_peer_import(wr_acs* a, const void* all_ipc_handles)
 {
-    WR_REQUIRE(a && all_ipc_handles && a->begun && a->nranks > 1 && a->d_export[0], WR_ERR_STATE, "wr_acs_peer_import: sharded handle after wr_acs_begin only");
+    WR_REQUIRE(a && all_ipc_handles && a->begun && a->nranks > 1 && a->d_slab, WR_ERR_STATE, "wr_acs_peer_import: sharded handle after wr_acs_begin only");
     WR_CUDA(cudaSetDevice(a->device));
     const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all_ipc_handles);
-    std::vector<const uint32_t*> tab[2];
-    for (int b = 0; b < 2; b++) tab[b].resize(a->nranks);
-    for (int r = 0; r < a->nranks; r++)
-        for (int b = 0; b < 2; b++) {
-            if (r == a->rank) { tab[b][r] = a->d_export[b]; continue; }
-            void* p = nullptr;
-            WR_CUDA(cudaIpcOpenMemHandle(&p, h[2 * r + b], cudaIpcMemLazyEnablePeerAccess));
-            a->ipc_opened.push_back(p);
-            tab[b][r] = static_cast<const uint32_t*>(p);
-        }
-    return install_peers(a, tab);
+    std::vector<const unsigned char*> slabs(a->nranks);
+    for (int r = 0; r < a->nranks; r++) {
+        if (r == a->rank) { slabs[r] = a->d_slab; continue; }
+        void* p = nullptr;
+        WR_CUDA(cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess));
+        a->ipc_opened.push_back(p);
+        slabs[r] = static_cast<const unsigned char*>(p);
+    }
+    return install_peers(a, slabs);
 }
 
 extern "C" int wr_acs_peer_set_pointers(wr_acs* a, void* const* all_raw_pointers)
 {
-    WR_REQUIRE(a && all_raw_pointers && a->begun && a->nranks > 1 && a->d_export[0], WR_ERR_STATE, "wr_acs_peer_set_pointers: sharded handle after wr_acs_begin only");
-    std::vector<const uint32_t*> tab[2];
-    for (int b = 0; b < 2; b++) {
-        tab[b].resize(a->nranks);
-        for (int r = 0; r < a->nranks; r++) tab[b][r] = r == a->rank ? a->d_export[b] : static_cast<const uint32_t*>(all_raw_pointers[2 * r + b]);
-    }
-    return install_peers(a, tab);
+    WR_REQUIRE(a && all_raw_pointers && a->begun && a->nranks > 1 && a->d_slab, WR_ERR_STATE, "wr_acs_peer_set_pointers: sharded handle after wr_acs_begin only");
+    std::vector<const unsigned char*> slabs(a->nranks);
+    for (int r = 0; r < a->nranks; r++) slabs[r] = r == a->rank ? a->d_slab : static_cast<const unsigned char*>(all_raw_pointers[r]);
+    return install_peers(a, slabs);
 }
 
-// Owner-computes finish: this rank keeps only the records of ITS slot slice (stable partition of the merged list),
-// sorts them, evaporates the whole field and applies its slice's deposits, listing the final values for the peers.
-extern "C" int wr_acs_finish_iteration_sliced(wr_acs* a)
+// Steps 3-6 of the peer-memory protocol, one call, no host synchronisation: global ranking + best decision (the new
+// best trail is read from its owner's HBM), deposit records of ALL eligible ants generated from the owners' trails in
+// global (rank, step) order, then either the replicated update (sliced = 0: slot sort + fused update of everything)
+// or the owner-computes update (sliced = 1: this rank keeps, sorts and applies the records of its slot slice and lists
+// the final values; follow with a barrier and wr_acs_pull_finals).
+extern "C" int wr_acs_finish_iteration_peer(wr_acs* a, const int* dev_all_steps, int sliced)
 {
-    WR_REQUIRE(a && a->begun && a->nranks > 1, WR_ERR_STATE, "wr_acs_finish_iteration_sliced: sharded handle only");
-    WR_REQUIRE(a->peers_set, WR_ERR_STATE, "wr_acs_finish_iteration_sliced: exchange the peer buffers first (wr_acs_peer_export / _import)");
-    WR_REQUIRE(a->p.update_mode == WR_UPDATE_FUSED, WR_ERR_STATE, "wr_acs_finish_iteration_sliced: needs update_mode WR_UPDATE_FUSED");
+    WR_REQUIRE(a && dev_all_steps && a->begun && a->nranks > 1, WR_ERR_STATE, "wr_acs_finish_iteration_peer: sharded handle only");
+    WR_REQUIRE(a->peers_set, WR_ERR_STATE, "wr_acs_finish_iteration_peer: exchange the peer buffers first (wr_acs_peer_export / _import)");
+    WR_REQUIRE(!sliced || a->p.update_mode == WR_UPDATE_FUSED, WR_ERR_STATE, "wr_acs_finish_iteration_peer: the owner-computes update needs WR_UPDATE_FUSED");
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
+    WR_CUDA(cudaMemcpyAsync(a->d_ant_steps, dev_all_steps, (size_t)std::max(a->colony_max, 1) * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    int st = launch_rank(a, a->d_ant_steps);
+    if (st != WR_OK) return st;
+    const uint32_t* const* ids_tab = reinterpret_cast<const uint32_t* const*>(a->tab(0, a->parity));
+    const uint8_t* const* dirs_tab = reinterpret_cast<const uint8_t* const*>(a->tab(1, a->parity));
+    k_best_copy_peer<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, ids_tab, dirs_tab, a->cap, a->chunk, (int)a->goal);
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    k_deposit_gen<false, true><<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_rec_off, nullptr, nullptr, a->cap, 0, a->chunk,
+                                                         (int)a->goal, a->d_Ltab, a->d_onbest, a->sort_recs.keys_a, a->sort_recs.vals_a, nullptr,
+                                                         ids_tab, dirs_tab);
+    WR_CUDA(cudaGetLastError());
+    a->warm_by_pull = sliced != 0;
+    if (!sliced) {
+        st = launch_update(a);
+        if (st != WR_OK) return st;
+        k_iter_end<<<1, 1, 0, s>>>(a->d_state);
+        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+        WR_CUDA(cudaGetLastError());
+        return WR_OK;
+    }
     const unsigned t_lo = (unsigned)(((unsigned long long)a->ntiles * a->rank) / a->nranks);
     const unsigned t_hi = (unsigned)(((unsigned long long)a->ntiles * (a->rank + 1)) / a->nranks);
-    int st = sort_partition(&a->sort_recs, a->dptr_nrec(), t_lo * (uint32_t)kUpdTile, (t_hi - t_lo) * (uint32_t)kUpdTile, s, a->d_nq);
+    st = sort_partition(&a->sort_recs, a->dptr_nrec(), t_lo * (uint32_t)kUpdTile, (t_hi - t_lo) * (uint32_t)kUpdTile, s, a->d_nq);
     if (st != WR_OK) return st;
     st = sort_pairs(&a->sort_recs, a->d_nq, a->slot_bits, s, &a->recs_in_b, true);
     if (st != WR_OK) return st;
     const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
     const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    a->slice_parity ^= 1u;
-    uint32_t* fin = a->d_export[a->slice_parity];
+    uint32_t* fin = a->fin_buf(a->parity);
     WR_CUDA(cudaMemsetAsync(fin, 0, 4 * sizeof(uint32_t), s));
     st = launch_fused(a, ck, cv, a->d_nq, fin);
     if (st != WR_OK) return st;
@@ -818,14 +858,15 @@ extern "C" int wr_acs_finish_iteration_sliced(wr_acs* a)
     return WR_OK;
 }
 
-// After a barrier across ranks (every rank has finished wr_acs_finish_iteration_sliced): overwrite the slots the
-// other ranks own with their final values, read straight from their HBM.
+// After a barrier across ranks (every rank has finished the sliced wr_acs_finish_iteration_peer): overwrite the slots
+// the other ranks own with their final values, read straight from their HBM.
 extern "C" int wr_acs_pull_finals(wr_acs* a)
 {
     WR_REQUIRE(a && a->begun && a->nranks > 1 && a->peers_set, WR_ERR_STATE, "wr_acs_pull_finals: bad state");
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
-    k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(a->d_tau, walk_warm() ? a->d_heur : nullptr, a->d_peer_tab[a->slice_parity], a->nranks, a->rank);
+    k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(a->d_tau, walk_warm() ? a->d_heur : nullptr, reinterpret_cast<const uint32_t* const*>(a->tab(2, a->parity)),
+                                              a->nranks, a->rank);
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     WR_CUDA(cudaGetLastError());
     return WR_OK;

@@ -474,6 +474,26 @@ __global__ void k_best_copy(const IterState* st, int* best_n, uint32_t* best_ids
     if (blockIdx.x == 0 && threadIdx.x == 0) *best_n = steps + 1;
 }
 
+// Peer-memory variant (sharded colonies on NVLink): the trail is read straight from the HBM of the rank that walked
+// the ant — ids_tab[r] / dirs_tab[r] are rank r's trail buffers (peer pointers), chunk ants per rank.
+__global__ void k_best_copy_peer(const IterState* st, int* best_n, uint32_t* best_ids, uint8_t* best_dirs, uint32_t* onbest,
+                                 const uint32_t* const* __restrict__ ids_tab, const uint8_t* const* __restrict__ dirs_tab, int cap, int chunk, int goal)
+{
+    if (!st->best_changed) return;
+    const int steps = st->best_steps;
+    const int owner = st->best_ant / chunk;
+    const size_t off = (size_t)(st->best_ant - owner * chunk) * cap;
+    const uint32_t* path_ids = ids_tab[owner];
+    const uint8_t* path_dirs = dirs_tab[owner];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= steps; i += gridDim.x * blockDim.x) {
+        uint32_t id = i < steps ? path_ids[off + i] : (uint32_t)goal;
+        best_ids[i] = id;
+        if (i < steps) best_dirs[i] = path_dirs[off + i];
+        atomicOr(&onbest[id >> 5], 1u << (id & 31));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *best_n = steps + 1;
+}
+
 // Sharded colonies: the rank that walked the new best ant publishes its trail in a buffer that is
 // zero everywhere else, so an integer all_reduce(SUM) hands every rank the same words.
 // Layout: [0] = 1 if filled, [1 .. cap+1] node ids (goal included), [cap+2 .. 2*cap+1] chosen slots.
@@ -511,19 +531,27 @@ __global__ void k_best_install(const IterState* st, int* best_n, uint32_t* best_
 // rank order inside every slot — the order the reference adds them in.
 //   value = (lambda - order)*Q/L_ant + float(onBest)*lambda*Q/L_best      (:210-211)
 // ------------------------------------------------------------------------------------------
-template <bool ATOMIC>
+// PEER: ids_tab / dirs_tab name every rank's trail buffers (peer pointers over NVLink), so each rank generates the
+// records of ALL eligible ants itself, in global (rank, step) order — no record exchange, no host-sized collective.
+template <bool ATOMIC, bool PEER = false>
 __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const uint32_t* __restrict__ rank_keys,
                                                       const uint32_t* __restrict__ rank_vals, const uint32_t* __restrict__ rec_off,
                                                       const uint32_t* __restrict__ path_ids, const uint8_t* __restrict__ path_dirs, int cap,
                                                       int shard_first, int shard_chunk,
                                                       int goal, const float* __restrict__ Ltab, const uint32_t* __restrict__ onbest,
-                                                      uint32_t* __restrict__ rec_keys, uint32_t* __restrict__ rec_vals, float* tau)
+                                                      uint32_t* __restrict__ rec_keys, uint32_t* __restrict__ rec_vals, float* tau,
+                                                      const uint32_t* const* __restrict__ ids_tab = nullptr,
+                                                      const uint8_t* const* __restrict__ dirs_tab = nullptr)
 {
     const int r = blockIdx.x;
     if (r >= st->n_eligible) return;
     const int steps = (int)rank_keys[r];
     const int ant_global = (int)rank_vals[r];
-    if (ant_global < shard_first || ant_global >= shard_first + shard_chunk) return;   // another rank holds this trail
+    if (PEER) {
+        const int owner = ant_global / shard_chunk;
+        path_ids = ids_tab[owner]; path_dirs = dirs_tab[owner];
+        shard_first = owner * shard_chunk;
+    } else if (ant_global < shard_first || ant_global >= shard_first + shard_chunk) return;   // another rank holds this trail
     const size_t ant = (size_t)(ant_global - shard_first);
     const int order = r + 1;
     const float lambda = st->lambda, Q = st->Q;

@@ -1,31 +1,36 @@
 """Ant-sharded search across ranks: one process per GPU, torch.distributed for the plumbing.
 
-SURVEY.md §8e: within an iteration the pheromone field is read-only, so ants are independent units
-with ONE exchange step per iteration.  The grid and the pheromone field are replicated on every GPU;
-rank r constructs ants [r*chunk, (r+1)*chunk) of the global colony (Philox is keyed by the global
-ant index).  Per iteration:
+SURVEY.md §8e: within an iteration the pheromone field is read-only, so ants are independent units with ONE
+exchange step per iteration.  The grid and the pheromone field are replicated on every GPU; rank r constructs ants
+[r*chunk, (r+1)*chunk) of the global colony (Philox is keyed by the global ant index).
 
-  1. local ant construction (K2)                                         wr_acs_walk
-  2. all_gather of per-ant step counts (4 B per ant)                     -> every rank ranks the whole colony
-  3. ranking + best decision, identical on every rank                    wr_acs_rank_global
-  4. all_reduce(SUM, int32) of the best-candidate buffer (only the owner of the new best ant
-     holds non-zero words)                                               wr_acs_apply_best
-  5. deposit records of the local ants at their GLOBAL (rank, step) positions, zeros elsewhere,
-     all_reduce(SUM, int32) of keys and values                           wr_acs_build_records
-  6. owner-computes update (default): the slot space is cut into one tile-aligned slice per rank; every rank
-     keeps the merged records of ITS slice (stable partition), sorts and applies them while evaporating the
-     whole field, and lists the final value of every slot it touched       wr_acs_finish_iteration_sliced
-  7. barrier, then every rank pulls the peers' lists straight out of their HBM over NVLink (kernel-side peer
-     loads through CUDA IPC pointers, no host-sized collective)             wr_acs_pull_finals
-     (`sliced=False`: step 6 = slot sort + fused update of ALL records on every rank, wr_acs_finish_iteration)
+PEER protocol (default on NVLink/NVSwitch boxes) — one small collective per iteration, no host synchronisation:
 
-Every reduced position has exactly one non-zero contributor, so integer SUM is a merge, the merged
-deposit list equals the single-GPU list and the pheromone field stays bit-identical on all ranks and
-to a 1-GPU run — no floating-point reduction order is involved.  (The dense alternative — all_reduce
-of a delta field, 3.2 GB at 512^3 — moves 20-200x more bytes over NVLink and is not reproducible.)
+  0. once per search: every rank exports ONE CUDA IPC handle of the slab that holds what its peers read (ant trails
+     and the list of final slot values, double-buffered by iteration parity)            wr_acs_peer_export / _import
+  1. local ant construction (K2), trails written into the slab                          wr_acs_walk
+  2. all_gather of per-ant step counts (4 B per ant) — also the barrier that makes the trails visible
+  3. every rank: global ranking + best decision; the new best trail and the trails of ALL eligible ants are read
+     straight out of their owners' HBM over NVLink (kernel-side peer loads) and the deposit records are generated
+     locally in global (rank, step) order                                               wr_acs_finish_iteration_peer
+  4a. sliced = False: slot sort + fused evaporation/deposit (K3) of all records, identical on every rank
+  4b. sliced = True (default): owner-computes update — the slot space is cut into one tile-aligned slice per rank;
+      every rank keeps (stable partition), sorts and applies only ITS slice's records (1/world of the sort and of the
+      dependent add chains) while evaporating the whole field, and lists the final value of every slot it touched;
+      barrier; every rank pulls the peers' lists out of their HBM and overwrites those slots  wr_acs_pull_finals
 
-The exchange logic is written against a small backend interface so that it runs under gloo on CPU
-in tests (tests/test_dist_gloo.py); `GpuBackend` is the product backend over the C ABI.
+NCCL-only protocol (`peer=False`; also what the CPU/gloo test drives): steps 3-4 become
+  all_reduce(SUM, int32) of the best-candidate buffer (only the owner of the new best ant holds non-zero words),
+  deposit records of the local ants at their GLOBAL positions + all_reduce(SUM, int32) of keys and values (every
+  position has exactly one non-zero contributor, so integer SUM is a merge), replicated sort + update.
+
+Either way the deposit list equals the single-GPU list, so the pheromone field stays bit-identical on all ranks and
+to a 1-GPU run — no floating-point reduction order is involved.  (The dense alternative — all_reduce of a delta
+field, 3.2 GB at 512^3 — moves 20-200x more bytes over NVLink and is not reproducible.)
+
+The exchange logic is written against a small backend interface so that it runs under gloo on CPU in tests
+(tests/test_dist_gloo.py); `GpuBackend` is the product backend over the C ABI; `LocalShards` drives all shards of a
+colony from one process on one GPU (tests/test_gpu_shards_local.py).
 """
 import ctypes as C
 
@@ -86,28 +91,27 @@ class GpuBackend:
     def finish_iteration(self):
         check(lib().wr_acs_finish_iteration(self.h))
 
-    # ---- owner-computes deposits ----------------------------------------------------------------------
-    def export_handles(self):
-        """-> (128 bytes of CUDA IPC handles, [2 raw device pointers]) of this rank's two final-value lists."""
-        h = (C.c_ubyte * 128)(); raw = (C.c_void_p * 2)()
-        check(lib().wr_acs_peer_export(self.h, h, raw))
-        return bytes(h), [raw[0], raw[1]]
+    # ---- NVLink peer-memory protocol ------------------------------------------------------------------
+    def export_handle(self):
+        """-> (64 bytes: CUDA IPC handle of this rank's slab, raw device pointer of the slab)."""
+        h = (C.c_ubyte * 64)(); raw = C.c_void_p()
+        check(lib().wr_acs_peer_export(self.h, h, C.byref(raw)))
+        return bytes(h), raw.value
 
     def peer_setup(self, world, group=None):
-        """Exchange the IPC handles of the final-value lists (once per begin)."""
-        mine, _ = self.export_handles()
+        """Exchange the IPC handles of the slabs (once per begin)."""
+        mine, _ = self.export_handle()
         t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.device)
-        allh = torch.empty(128 * world, dtype=torch.uint8, device=self.device)
+        allh = torch.empty(64 * world, dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(allh, t, group=group)
-        buf = allh.cpu().numpy().tobytes()
-        check(lib().wr_acs_peer_import(self.h, buf))
+        check(lib().wr_acs_peer_import(self.h, allh.cpu().numpy().tobytes()))
 
     def set_peer_pointers(self, all_raw):
         arr = (C.c_void_p * len(all_raw))(*all_raw)
         check(lib().wr_acs_peer_set_pointers(self.h, arr))
 
-    def finish_iteration_sliced(self):
-        check(lib().wr_acs_finish_iteration_sliced(self.h))
+    def finish_iteration_peer(self, all_steps, sliced):
+        check(lib().wr_acs_finish_iteration_peer(self.h, C.c_void_p(all_steps.data_ptr()), 1 if sliced else 0))
 
     def pull_finals(self):
         check(lib().wr_acs_pull_finals(self.h))
@@ -115,23 +119,27 @@ class GpuBackend:
 
 class ShardedSearch:
     """Drives one ant-sharded search.  `backend` defaults to the GPU backend of `acs`.
-    sliced: owner-computes update (steps 6-7 above); None = on when the backend supports it (WR_SHARD_SLICED=0 disables)."""
+    peer:   NVLink peer-memory protocol; None = on when the backend supports it (WR_SHARD_PEER=0 disables).
+    sliced: owner-computes update (step 4b); None = on with the peer protocol (WR_SHARD_SLICED=0 disables)."""
 
-    def __init__(self, acs, rank, world, group=None, backend=None, sliced=None):
+    def __init__(self, acs, rank, world, group=None, backend=None, peer=None, sliced=None):
         import os
         self.rank, self.world, self.group = rank, world, group
         self.backend = backend if backend is not None else GpuBackend(acs)
         self.backend.set_shard(rank, world)
+        if peer is None:
+            peer = hasattr(self.backend, "finish_iteration_peer") and os.environ.get("WR_SHARD_PEER", "1") != "0"
+        self.peer = bool(peer) and world > 1
         if sliced is None:
-            sliced = world > 1 and hasattr(self.backend, "finish_iteration_sliced") and os.environ.get("WR_SHARD_SLICED", "1") != "0"
-        self.sliced = bool(sliced) and world > 1
+            sliced = os.environ.get("WR_SHARD_SLICED", "1") != "0"
+        self.sliced = bool(sliced) and self.peer
         self._all = None
         self._bar = None
-        self.bytes_exchanged = 0
+        self.bytes_exchanged = 0     # through collectives (peer loads are not counted here)
 
     def begin(self, predict_path_len):
         self.backend.begin(predict_path_len)
-        if self.sliced:
+        if self.peer:
             self.backend.peer_setup(self.world, self.group)
 
     def iterate(self, n=1):
@@ -142,6 +150,13 @@ class ShardedSearch:
                 self._all = torch.empty(local.numel() * self.world, dtype=local.dtype, device=local.device)
                 self._bar = torch.zeros(1, dtype=torch.int32, device=local.device)
             dist.all_gather_into_tensor(self._all, local, group=self.group)
+            if self.peer:
+                b.finish_iteration_peer(self._all, self.sliced)
+                if self.sliced:
+                    dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.group)   # barrier: every rank's list is complete
+                    b.pull_finals()
+                self.bytes_exchanged += 4 * (self._all.numel() + (1 if self.sliced else 0))
+                continue
             cand = b.rank_global(self._all)                    # zeros unless this rank owns the new best ant
             dist.all_reduce(cand, op=dist.ReduceOp.SUM, group=self.group)
             b.apply_best()
@@ -149,21 +164,17 @@ class ShardedSearch:
             if keys.numel():
                 dist.all_reduce(keys, op=dist.ReduceOp.SUM, group=self.group)
                 dist.all_reduce(vals, op=dist.ReduceOp.SUM, group=self.group)
-            if self.sliced:
-                b.finish_iteration_sliced()
-                dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.group)   # barrier: every rank's list is complete
-                b.pull_finals()
-            else:
-                b.finish_iteration()
-            self.bytes_exchanged += 4 * (self._all.numel() + cand.numel() + 2 * keys.numel() + 1)
+            b.finish_iteration()
+            self.bytes_exchanged += 4 * (self._all.numel() + cand.numel() + 2 * keys.numel())
 
 
 class LocalShards:
-    """The same protocol for `world` shards of one colony that live in ONE process on ONE GPU (tests, debugging): the
-    collectives become tensor operations on the shared stream, the peer buffers plain device pointers."""
+    """The peer protocol for `world` shards of one colony that live in ONE process on ONE GPU (tests, debugging): the
+    all_gather becomes a concatenation on the shared stream, the peer slabs plain device pointers."""
 
-    def __init__(self, searches):
+    def __init__(self, searches, sliced=True):
         self.world = len(searches)
+        self.sliced = sliced
         self.backends = [GpuBackend(a) for a in searches]
         stream = torch.cuda.current_stream().cuda_stream
         for r, b in enumerate(self.backends):
@@ -174,7 +185,7 @@ class LocalShards:
         raws = []
         for b in self.backends:
             b.begin(predict_path_len)
-            raws += b.export_handles()[1]
+            raws.append(b.export_handle()[1])
         for b in self.backends:
             b.set_peer_pointers(raws)
 
@@ -182,18 +193,8 @@ class LocalShards:
         bs = self.backends
         for _ in range(n):
             allsteps = torch.cat([b.walk() for b in bs])
-            cands = [b.rank_global(allsteps) for b in bs]
-            tot = torch.stack(cands).sum(0, dtype=torch.int32)
-            for b, c in zip(bs, cands):
-                c.copy_(tot)
-                b.apply_best()
-            recs = [b.build_records() for b in bs]
-            if recs[0][0].numel():
-                ks = torch.stack([k for k, _ in recs]).sum(0, dtype=torch.int32)
-                vs = torch.stack([v for _, v in recs]).sum(0, dtype=torch.int32)
-                for k, v in recs:
-                    k.copy_(ks); v.copy_(vs)
             for b in bs:
-                b.finish_iteration_sliced()
-            for b in bs:
-                b.pull_finals()
+                b.finish_iteration_peer(allsteps, self.sliced)
+            if self.sliced:
+                for b in bs:
+                    b.pull_finals()
