@@ -186,8 +186,8 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     _lib.check(_lib.lib().wr_acs_set_stream(acs._a, stream.cuda_stream))
     acs.setEndpoints(wl["start"], wl["goal"])
+    from welding_robot_b200.dist import ShardedSearch
     if world > 1:
-        from welding_robot_b200.dist import ShardedSearch
         driver = ShardedSearch(acs, rank, world)
         driver.begin(PREDICT)
         step = lambda: driver.iterate(args.iters)  # noqa: E731
@@ -243,15 +243,22 @@ def run_ours(args):
 
     # ---- end to end through the public API from HOST buffers -------------------------------------------
     e2e = None
-    if world == 1:
+    if True:
         pinned = torch.from_numpy(wl["isfree"]).pin_memory()
         host_free = pinned.numpy()
         e2e_steps = max(1, min(args.steps, 5))
+
         def e2e_step():
             a2 = make_search(host_free)
             a2.setEndpoints(wl["start"], wl["goal"])
-            a2.begin(PREDICT)
-            a2.iterate(args.iters)
+            if world > 1:
+                _lib.check(_lib.lib().wr_acs_set_stream(a2._a, stream.cuda_stream))
+                d2 = ShardedSearch(a2, rank, world)
+                d2.begin(PREDICT)                                                       # + exchange of the peer-slab IPC handles
+                d2.iterate(args.iters)
+            else:
+                a2.begin(PREDICT)
+                a2.iterate(args.iters)
             ids, dirs, L = a2.bestPath()                                                # D2H: the result
             n = a2.counters()["ant_steps"]
             del a2
@@ -260,17 +267,25 @@ def run_ours(args):
         for _ in range(2):          # untimed: the first searches grow the stream-ordered memory pool by a second handle's worth
             e2e_step()
         tot_steps, d2h = 0, 0
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             n, d2h = e2e_step()
             tot_steps += n
-        torch.cuda.synchronize()
+        barrier()
         dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            sN = torch.tensor([tot_steps], device="cuda", dtype=torch.int64)
+            dist.all_reduce(sN, op=dist.ReduceOp.SUM)
+            tot_steps = int(sN.item())
         e2e = {"value": tot_steps / dt, "unit": "ant-steps/s", "h2d_bytes_per_step": int(host_free.nbytes + 3 * CUBE * 4 + 16),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "what": "per step, from host buffers: wr_grid_create_from_occupancy (16.8 MB H2D) -> wr_acs_create -> wr_acs_begin -> "
-                       "%d x wr_acs_iterate -> wr_acs_best (D2H)" % args.iters}
+               "what": "per step and per rank, from host buffers: wr_grid_create_from_occupancy (16.8 MB H2D) -> wr_acs_create -> wr_acs_begin -> "
+                       "%d x iterate%s -> wr_acs_best (D2H); wall clock between barriers, max over ranks"
+                       % (args.iters, " (sharded: + peer-slab handle exchange)" if world > 1 else "")}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -296,11 +311,14 @@ def run_ours(args):
                    "grid": [CUBE, CUBE, CUBE], "natural_grid": list(wl["natural"]), "ants": colony, "iters_per_step": args.iters,
                    "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic", "fused_tma"][args.update_mode],
                    "parallelism": "ants sharded x%d" % world,
+                   "exchange": ("none (1 GPU)" if world == 1 else
+                                ("NVLink peer memory (trails read from their owners' HBM), %s update" % ("owner-computes (slot slices)" if driver.sliced else "replicated"))
+                                if driver.peer else "NCCL all_reduce merges, replicated update"),
                    "l2_rule": "inputs larger than L2: the 403 MB pheromone field is streamed from HBM every iteration"},
         "acs_iterations_per_s": iters_done / (ms * 1e-3),
         "ant_steps": steps_done, "arrived_local": c1["arrived"] - c0["arrived"], "ants_local": c1["ants"] - c0["ants"],
         "mean_steps_per_ant": local_steps / ants_done,
-        "gpu_launches": launches_per_iteration(args.update_mode) * iters_done,
+        "gpu_launches": (launches_per_iteration(args.update_mode) + (6 if world > 1 else 0)) * iters_done,
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
         "roofline": {"kernel": "k_walk (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
                      "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk"), "peak_source": hbm_src,
@@ -332,6 +350,7 @@ def launches_per_iteration(update_mode):
     n = 1 + 1 + 3 + 1 + sort(cap_bits) + 1 + 2 + 1   # L2 warm-up, iter_begin, walk x2 + queue reset, rank keys, sort, rank finish, best x2, iter_end
     if update_mode == 2:
         return n + 2
+    # sharded (peer protocol, owner-computes): + partition pass (4) + pull (1) + best copy from the owner (1) - warm-up (done by the pull)
     return n + 1 + sort(slot_bits) + 2           # deposit gen, sort, (tile offsets + fused) | (evaporate + apply)
 
 

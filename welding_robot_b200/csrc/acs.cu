@@ -92,6 +92,7 @@ struct wr_acs {
     unsigned ntiles = 0;
     int cap = 0, rank_bits = 0, slot_bits = 0;
     int table_log2 = 9, gtable_log2 = 0;
+    int table_entries = 512;          // k_walk2: entries per ant (768 by default: two 16-ant CTAs per SM)
     int64_t start = -1, goal = -1;
     bool begun = false;
     int colony_max = 0, w_max = 0;
@@ -243,7 +244,7 @@ static int walk_warm()
 }
 static size_t walk_smem(const wr_acs* a)
 {
-    if (walk_version(a->g) == 2) return 192 + ((size_t)kAntsPerCta << a->table_log2) * sizeof(unsigned long long);
+    if (walk_version(a->g) == 2) return 192 + (size_t)kAntsPerCta * a->table_entries * sizeof(unsigned long long);
     const size_t coord_bytes = ((size_t)(a->g->rx + a->g->ry + a->g->rz + 6) * 4 + 15) & ~(size_t)15;
     return coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
 }
@@ -308,6 +309,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     a->cap = p->step_cap > 0 ? p->step_cap : (int)std::min<size_t>(g->N - 1, 65532);
     a->rank_bits = ceil_log2((unsigned long long)a->cap + 2);
     a->table_log2 = p->walk_table_log2 > 0 ? p->walk_table_log2 : 9;
+    a->table_entries = p->walk_table_log2 > 0 ? (1 << p->walk_table_log2) : 768;
     if (a->table_log2 < 4 || a->table_log2 > 10) { delete a; set_error("wr_acs_create: walk_table_log2 must be in [4,10]"); return WR_ERR_INVALID; }
 #define WR_CUDA_A(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); wr_acs_destroy(a); return WR_ERR_CUDA; } } while (0)
     WR_CUDA_A(cudaGetDevice(&a->device));
@@ -481,7 +483,7 @@ static int launch_walk(wr_acs* a)
     w.shard_first = a->rank * a->chunk; w.shard_chunk = a->chunk;
     w.ant_steps = a->d_local_steps;
     w.path_ids = a->d_path_ids; w.path_dirs = a->d_path_dirs;
-    w.table_log2 = a->table_log2; w.overflow_list = a->d_overflow;
+    w.table_log2 = a->table_log2; w.table_entries = a->table_entries; w.overflow_list = a->d_overflow;
     w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks; w.gtab = a->d_gmasks; w.gtable_log2 = a->gtable_log2; w.resume = a->d_resume;
     const int ver = walk_version(g);
     const size_t smem1 = walk_smem(a);

@@ -38,7 +38,8 @@ struct WalkArgs {
     int* ant_steps;          // [chunk]  steps, -1 dead, -2 pending (table overflow -> pass 2)
     uint32_t* path_ids;      // [chunk][cap]   node the ant stood on before step i
     uint8_t* path_dirs;      // [chunk][cap]   slot chosen at step i
-    int table_log2;          // shared-memory (pass 1) or global (pass 2) visited-tile table size
+    int table_log2;          // k_walk: shared-memory (pass 1) or global (pass 2) visited-tile table size
+    int table_entries;       // k_walk2: shared-memory visited-tile entries per ant (any size; the HBM tables of pass 2 have 1 << gtable_log2)
     uint32_t* overflow_list; // [chunk]
     uint32_t* gkeys;         // HBM visited tables, one per overflowed ant: [chunk][1 << gtable_log2]
     unsigned long long* gmasks;

@@ -22,7 +22,8 @@ constexpr uint32_t kPackMul = 0x00101010u;                    // gathers the fiv
 constexpr uint32_t kKeyTag = 0x80000000u;                     // a stored key is never 0 (0 = empty entry)
 
 __device__ __forceinline__ uint32_t pack_xyz(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 10) | ((uint32_t)z << 20); }
-__device__ __forceinline__ uint32_t tile_hash(uint32_t key, int hshift) { return (key * 2654435761u) >> hshift; }
+// table sizes need not be powers of two (768 entries per ant = two CTAs per SM): Fibonacci hash, then multiply-high range reduction
+__device__ __forceinline__ uint32_t tile_hash(uint32_t key, uint32_t entries) { return __umulhi(key * 2654435761u, entries); }
 
 // visited-table access: 32-bit shared-window addresses for the on-chip tables (a generic pointer makes the compiler
 // re-derive the shared window base inside the step loop), plain global pointers for the HBM tables of pass 2
@@ -84,8 +85,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
     const int gbase = lane & 24;
     const int k = lane & 7;
     const int g = threadIdx.x >> 3;
-    const int E = 1 << a.table_log2;
-    const int hshift = 32 - a.table_log2;
+    const int E = GLOBAL ? (1 << a.gtable_log2) : a.table_entries;   // entries of the table this kernel probes
     uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(move_lut);
     TabRef<GLOBAL> tab;
     tab.gp = a.gtab;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
             if (k == 0) {   // addStartNode :81-86
                 const uint32_t key = (P & kPackKey) | kKeyTag;
                 const uint32_t bit = (((P & kPackLow) * kPackMul) >> 20) & 31u;
-                tab.store(tile_hash(key, hshift), ((unsigned long long)key << 32) | (unsigned long long)(1u << bit));
+                tab.store(tile_hash(key, (uint32_t)E), ((unsigned long long)key << 32) | (unsigned long long)(1u << bit));
             }
         }
         __syncwarp();
@@ -205,10 +205,10 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
             const uint32_t key = (Pk & kPackKey) | kKeyTag;
             const uint32_t bitm = 1u << ((((Pk & kPackLow) * kPackMul) >> 20) & 31u);
             const bool open_k = (k < 6) && heur_v != kClosedSlot;   // NaN (duplicate plane) stays open, as in the reference
-            unsigned slot = tile_hash(key, hshift);
+            unsigned slot = tile_hash(key, (uint32_t)E);
             unsigned long long e = tab.load(slot);
             while (open_k && (uint32_t)(e >> 32) != key && (uint32_t)(e >> 32) != 0u) {   // collisions are rare at load <= 3/4
-                slot = (slot + 1) & (E - 1);
+                slot = slot + 1 < (unsigned)E ? slot + 1 : 0u;
                 e = tab.load(slot);
             }
             const bool found = (uint32_t)(e >> 32) == key;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
                 int o = 0;
                 if (parked && k == 0) o = (int)atomicAdd(&st->overflow_n, 1u);
                 o = __shfl_sync(FULL, o, 0, 8);
-                const int Eg = 1 << a.gtable_log2, gsh = 32 - a.gtable_log2;
+                const int Eg = 1 << a.gtable_log2;
                 for (unsigned rest = pm; rest; rest &= rest - 1) {   // zero each parked ant's HBM table with the whole warp
                     const int src = __ffs(rest) - 1;
                     const int oo = __shfl_sync(FULL, o, src);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
                     for (int i = k; i < E; i += kGroup) {
                         const unsigned long long t = tab.load(i);
                         if (t == 0ull) continue;
-                        unsigned sl = tile_hash((uint32_t)(t >> 32), gsh);
+                        unsigned sl = tile_hash((uint32_t)(t >> 32), (uint32_t)Eg);
                         while (atomicCAS(&ntab[sl], 0ull, t) != 0ull) sl = (sl + 1) & (Eg - 1);
                     }
                     if (k == 0) {
