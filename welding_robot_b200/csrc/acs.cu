@@ -244,7 +244,7 @@ static int walk_warm()
 }
 static size_t walk_smem(const wr_acs* a)
 {
-    if (walk_version(a->g) == 2) return 192 + (size_t)kAntsPerCta * a->table_entries * sizeof(unsigned long long);
+    if (walk_version(a->g) == 2) return kWalk2Lut + 128 + (size_t)kAntsPerCta * a->table_entries * sizeof(unsigned long long);
     const size_t coord_bytes = ((size_t)(a->g->rx + a->g->ry + a->g->rz + 6) * 4 + 15) & ~(size_t)15;
     return coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
 }
@@ -327,8 +327,10 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     // L after s steps: precision added s times in float (Agent::addNextNode :78)
     a->h_Ltab.resize((size_t)a->cap + 2);
     { float L = 0; a->h_Ltab[0] = 0; for (int s = 1; s <= a->cap + 1; s++) { L += g->precision; a->h_Ltab[s] = L; } }
+    a->h_Ltab.push_back(kClosedSlot);   // + the marker k_walk2's idle lanes read (not part of the table)
     WR_CUDA_A(dmalloc(&a->d_Ltab, a->h_Ltab.size() * sizeof(float), a->stream));
     WR_CUDA_A(cudaMemcpyAsync(a->d_Ltab, a->h_Ltab.data(), a->h_Ltab.size() * sizeof(float), cudaMemcpyHostToDevice, a->stream));
+    a->h_Ltab.pop_back();
     WR_CUDA_A(dmalloc(&a->d_best_n, sizeof(int), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_best_n, 0, sizeof(int), a->stream));
     WR_CUDA_A(dmalloc(&a->d_best_ids, ((size_t)a->cap + 2) * sizeof(uint32_t), a->stream));
@@ -476,6 +478,7 @@ static int launch_walk(wr_acs* a)
     const wr_grid* g = a->g;
     WalkArgs w;
     w.st = a->d_state; w.tau = a->d_tau; w.heur = a->d_heur; w.coords = g->d_coords;
+    w.closed_marker = a->d_Ltab + a->h_Ltab.size();   // one float behind the length table
     w.rx = g->rx; w.ry = g->ry; w.rz = g->rz;
     w.start = (int)a->start; w.goal = (int)a->goal;
     w.seed_lo = (uint32_t)a->p.seed; w.seed_hi = (uint32_t)(a->p.seed >> 32);
@@ -495,7 +498,7 @@ static int launch_walk(wr_acs* a)
         // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
         k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
         w.table_log2 = a->gtable_log2;
-        launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, 192, a->stream);
+        launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, kWalk2Lut + 128, a->stream);
     } else {
         const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15;   // + guard elements
         k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);

@@ -27,6 +27,7 @@ struct WalkArgs {
     IterState* st;
     const float* tau;        // [N][6] node-major ("edge-major": a node's 6 directed slots are contiguous)
     const float* heur;       // [N][6]  1 + beta*cos(theta) per directed slot for the current goal (k_heuristic)
+    const float* closed_marker;   // one float = kClosedSlot (k_walk2's idle lanes read it)
     const float* coords;     // xs | ys | zs
     int rx, ry, rz;
     int start, goal;

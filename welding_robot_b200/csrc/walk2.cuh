@@ -19,6 +19,7 @@ namespace wr {
 constexpr uint32_t kPackLow = 0x00100C03u;                    // x bits 0-1, y bits 10-11, z bit 20: position inside a 4x4x2 tile
 constexpr uint32_t kPackKey = 0x3FFFFFFFu & ~kPackLow;        // the tile
 constexpr uint32_t kPackMul = 0x00101010u;                    // gathers the five position bits at 20..24 (no carries: partial products are disjoint)
+constexpr int kWalk2Lut = 1024;                                // bytes of the move table at the start of k_walk2's shared memory
 constexpr uint32_t kKeyTag = 0x80000000u;                     // a stored key is never 0 (0 = empty entry)
 
 __device__ __forceinline__ uint32_t pack_xyz(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 10) | ((uint32_t)z << 20); }
@@ -69,14 +70,18 @@ template <bool GLOBAL, bool ALPHA1, int PREFETCH>
 __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    int2* move_lut = reinterpret_cast<int2*>(smem_raw);                        // [8]  slot c -> {node-id stride, packed-coordinate delta}
-    uint32_t* ntiles_s = reinterpret_cast<uint32_t*>(smem_raw + 64);            // [16] tiles in the ant's table
-    volatile uint32_t* flag_s = reinterpret_cast<volatile uint32_t*>(smem_raw + 128);   // [16] table reached 3/4 -> park after this step
-    unsigned long long* tab_s = reinterpret_cast<unsigned long long*>(smem_raw + 192);  // [16][E]
-    if (threadIdx.x < 8) {
-        const int c = threadIdx.x;
+    // [0, 1024): move table indexed by the 6-bit pick ballot: the winner is its highest set bit c (the roulette scans
+    //            5 -> 0) -> {node-id stride, packed-coordinate delta, c, -}; one LDS.128 replaces find-leading-one + index math
+    // [1024, 1088): tiles in each ant's table; [1088, 1152): table reached 3/4; [1152, ...): tables [16][E]
+    int4* move_lut = reinterpret_cast<int4*>(smem_raw);
+    uint32_t* ntiles_s = reinterpret_cast<uint32_t*>(smem_raw + kWalk2Lut);
+    volatile uint32_t* flag_s = reinterpret_cast<volatile uint32_t*>(smem_raw + kWalk2Lut + 64);
+    unsigned long long* tab_s = reinterpret_cast<unsigned long long*>(smem_raw + kWalk2Lut + 128);
+    if (threadIdx.x < 64) {
+        const int pbv = threadIdx.x;
+        const int c = pbv ? 31 - __clz(pbv) : 0;
         const int dx = (c == 3) - (c == 2), dy = (c == 4) - (c == 1), dz = (c == 5) - (c == 0);
-        move_lut[c] = make_int2(dx + dy * a.rx + dz * a.rx * a.ry, dx + dy * 1024 + dz * 1048576);
+        move_lut[pbv] = pbv ? make_int4(dx + dy * a.rx + dz * a.rx * a.ry, dx + dy * 1024 + dz * 1048576, c, 0) : make_int4(0, 0, 0, 0);
     }
     __syncthreads();
 
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
     TabRef<GLOBAL> tab;
     tab.gp = a.gtab;
     tab.sa = (uint32_t)__cvta_generic_to_shared(tab_s + (size_t)g * E);
-    uint32_t flag_sa = (uint32_t)__cvta_generic_to_shared(smem_raw + 128 + 4 * g);
+    uint32_t flag_sa = (uint32_t)__cvta_generic_to_shared(smem_raw + kWalk2Lut + 64 + 4 * g);
     // opaque to the optimiser: otherwise it re-derives the shared-window base (S2UR + ULEA) inside the step loop
     asm volatile("" : "+r"(lut_sa), "+r"(tab.sa), "+r"(flag_sa));
 
@@ -99,7 +104,9 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
     const uint32_t dPk = (uint32_t)(dxk + dyk * 1024 + dzk * 1048576);
     const int kk6 = k < 6 ? k : 5;                                             // idle lanes re-read slot 5 (same sector)
     const float* tau_k = a.tau + kk6;
-    const float* heur_k_base = a.heur + kk6;
+    // idle lanes (k = 6, 7) read a constant "closed" marker with a zero row stride, so `open` is one compare for every lane
+    const float* heur_k_base = k < 6 ? a.heur + k : a.closed_marker;
+    const int heur_row = k < 6 ? 6 : 0;
     const long long stride_k = (long long)(dxk + dyk * rx + dzk * rxy);
     const long long last_node = (long long)rxy * a.rz - 1;
     // lane masks of the descending prefix chain: lane k adds v_j only for j >= k
@@ -168,10 +175,11 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
         uint32_t* pid = a.path_ids + (size_t)ant_local * cap;
         uint8_t* pdir = a.path_dirs + (size_t)ant_local * cap;
 
-        while (__any_sync(FULL, live)) {
-            // ---- the loads of this step ---------------------------------------------------------
-            const float tau_v = __ldg(tau_k + (size_t)cur * 6);
-            const float heur_v = __ldg(heur_k_base + (size_t)cur * 6);
+        // this lane's slot of the current row; reloaded as soon as the next node is known, ahead of the move's side effects
+        float tau_v = __ldg(tau_k + (size_t)cur * 6);
+        float heur_v = __ldg(heur_k_base + (size_t)cur * heur_row);
+
+        auto step = [&]() {
             if (PREFETCH) {   // the row of neighbour k is the next step's row if k wins: pull both arrays' lines towards the SM now
                 long long nb = (long long)cur + stride_k;
                 nb = nb < 0 ? 0 : (nb > last_node ? last_node : nb);
@@ -180,16 +188,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
                 if (PREFETCH == 1) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(pt));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(ph));
-                } else if (PREFETCH == 3) {
-                    // real loads, one step ahead: a 24-byte row touches one or two 32-byte sectors, so its first and last word
-                    // cover it.  ptxas drops loads whose result is dead, so the words are folded into `sink` one step later
-                    // (by then they have landed) and `sink` reaches a store that never executes.
-                    sink ^= pre0 ^ pre1;
-                    sink ^= pre2 ^ pre3;
-                    pre0 = __ldg(reinterpret_cast<const uint32_t*>(pt));
-                    pre1 = __ldg(reinterpret_cast<const uint32_t*>(pt) + 5);
-                    pre2 = __ldg(reinterpret_cast<const uint32_t*>(ph));
-                    pre3 = __ldg(reinterpret_cast<const uint32_t*>(ph) + 5);
                 } else {
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(pt));
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(ph));
@@ -204,7 +202,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
             const uint32_t Pk = P + dPk;
             const uint32_t key = (Pk & kPackKey) | kKeyTag;
             const uint32_t bitm = 1u << ((((Pk & kPackLow) * kPackMul) >> 20) & 31u);
-            const bool open_k = (k < 6) && heur_v != kClosedSlot;   // NaN (duplicate plane) stays open, as in the reference
+            const bool open_k = heur_v != kClosedSlot;   // NaN (duplicate plane) stays open, as in the reference; idle lanes read the marker
             unsigned slot = tile_hash(key, (uint32_t)E);
             unsigned long long e = tab.load(slot);
             while (open_k && (uint32_t)(e >> 32) != key && (uint32_t)(e >> 32) != 0u) {   // collisions are rare at load <= 3/4
@@ -223,7 +221,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
             const float v3 = __shfl_sync(FULL, info, 3, 8), v4 = __shfl_sync(FULL, info, 4, 8), v5 = __shfl_sync(FULL, info, 5, 8);
             const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, v0), v1), v2), v3), v4), v5);
             const float rnd = __fmul_rn(u, total);
-            // this lane's prob_sum: v5 + v4 + ... + v_k, then +0 (the identity: every v is >= +0 or NaN), so one chain serves all lanes
+            // this lane's prob_sum: v5 + v4 + ... + v_k, then +0 (the identity of the chain), so one chain serves all lanes
             float mine = __fadd_rn(0.0f, v5);
             mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v4) & m4));
             mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v3) & m3));
@@ -231,15 +229,22 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
             mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v1) & m1));
             mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v0) & m0));
             const bool pick = cand && (mine >= rnd);
-            const unsigned pb = (__ballot_sync(FULL, pick) >> gbase) & 0x3Fu;
-            const int c = 31 - __clz((int)(pb | 1u));                  // first hit scanning 5 -> 0 (pb == 0 handled below)
-            // ---- outcome -------------------------------------------------------------------------
+            const unsigned pb = (__ballot_sync(FULL, pick) >> gbase) & 0x3Fu;   // the first hit scanning 5 -> 0 is its highest set bit
+            // ---- the move: one table look-up on the ballot, then the next row's loads go out at once ---------------
+            int4 mv;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(mv.x), "=r"(mv.y), "=r"(mv.z), "=r"(mv.w) : "r"(lut_sa + pb * 16u) : "memory");
+            const int c = mv.z;
             const bool stepok = live && pb != 0;
+            const int prev = cur, at = steps;
+            if (stepok) { cur += mv.x; P += (uint32_t)mv.y; steps++; }
+            tau_v = __ldg(tau_k + (size_t)cur * 6);
+            heur_v = __ldg(heur_k_base + (size_t)cur * heur_row);
+            // ---- outcome -------------------------------------------------------------------------
             if (live && !stepok) reason = cb == 0 ? 1 : 2;              // :162-166 / fall-through :191-192
             if (stepok && k == c) {   // the winning lane performs the move's side effects: tabu insert + addNextNode (:73-79)
                 tab.store(slot, ((unsigned long long)key << 32) | (unsigned long long)(emask | bitm));
-                pid[steps] = (uint32_t)cur;
-                pdir[steps] = (uint8_t)c;
+                pid[at] = (uint32_t)prev;
+                pdir[at] = (uint8_t)c;
                 if (!GLOBAL && !found) {   // tile count lives next to the flag: [flag_sa - 64]
                     uint32_t n;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n) : "r"(flag_sa - 64u) : "memory");
@@ -248,9 +253,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
                     if (n > limit) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(flag_sa), "r"(1u) : "memory");
                 }
             }
-            int2 mv;
-            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(mv.x), "=r"(mv.y) : "r"(lut_sa + (uint32_t)c * 8u) : "memory");
-            if (stepok) { cur += mv.x; P += (uint32_t)mv.y; steps++; }
             const bool arrived = stepok && cur == goal;              // :182-186
             const bool over = !GLOBAL && stepok && !arrived && flag != 0u;
             const bool capped = stepok && !arrived && !over && steps >= cap;   // a deviation the oracle mirrors; the reference is unbounded
@@ -258,6 +260,10 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
             reason = capped ? 3 : reason;
             live = stepok && !arrived && !over && !capped;
             __syncwarp();
+        };
+        while (__any_sync(FULL, live)) {   // two steps per trip: halves the cost of the loop's vote + branch; a finished ant just idles
+            step();
+            step();
         }
         // ---- park the ants whose shared-memory table filled up: move the visited set to an HBM table sized for the step
         //      cap and record where to resume; pass 2 (GLOBAL) continues them from the very step they stopped at ---------
