@@ -52,42 +52,84 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled in
+    process every few ms (a 4 ms step leaves no room for `nvidia-smi -lms`' start-up); where pynvml cannot initialise the
+    recipe's `nvidia-smi --query-gpu` loop is the fallback.  Only samples taken between mark_begin() and mark_end() count."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc = index, [], None     # rows: (t, sm_mhz, sm_max_mhz, [reasons])
+        self.t0 = self.t1 = None
+        self.quit = threading.Event()
+        self.ready = threading.Event()
+        self.source = None
+
+    def _nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+        self.source = "nvml"
+        while not self.quit.is_set():
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            self.rows.append((time.perf_counter(), sm, mx, [n for n, b in names if bits & b]))
+            self.ready.set()
+            time.sleep(0.003)
+
+    def _smi(self):
+        self.source = "nvidia-smi"
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            c = [v.strip() for v in line.split(",")]
+            try:
+                sm, mx = float(c[0]), float(c[1])
+            except (ValueError, IndexError):
+                continue
+            rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]) if v.lower().startswith("active")]
+            self.rows.append((time.perf_counter(), sm, mx, rs))
+            self.ready.set()
+            if self.quit.is_set():
+                break
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            return
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self._nvml()
+        except Exception:
+            try:
+                self._smi()
+            except OSError:
+                pass
+        self.ready.set()
+
+    def mark_begin(self):
+        self.ready.wait(10.0)       # first sample is in before the timed region starts
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
+        self.quit.set()
         if self.proc is not None:
             self.proc.terminate()
 
     def summary(self):
-        def num(v):
-            try:
-                return float(v)
-            except ValueError:
-                return None
-        sm = [num(r[0]) for r in self.rows if r and num(r[0]) is not None]
-        mx = [num(r[1]) for r in self.rows if len(r) > 1 and num(r[1]) is not None]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or float("inf"))]
+        window = "timed region"
+        if not rows:                # never silently empty: say that the window is wider
+            rows, window = list(self.rows), "whole run (no sample fell inside the timed region)"
+        sm = [r[1] for r in rows]
+        mx = [r[2] for r in rows]
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "source": self.source, "window": window}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -209,7 +251,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.2)
+        sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -218,6 +260,7 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    sampler.mark_end()
     sampler.stop()
     c1 = acs.counters()
     kms = acs.kernelMs()
@@ -320,8 +363,8 @@ def run_ours(args):
         "mean_steps_per_ant": local_steps / ants_done,
         "gpu_launches": (launches_per_iteration(args.update_mode) + (6 if world > 1 else 0)) * iters_done,
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
-        "roofline": {"kernel": "k_walk (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
-                     "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk"), "peak_source": hbm_src,
+        "roofline": {"kernel": "k_walk2 (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
+                     "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk2", traffic.get("k_walk")), "peak_source": hbm_src,
                      "algorithmic_bytes_per_launch": WALK_BYTES_PER_STEP * (local_steps / iters_done),
                      "note": "30 B algorithmic per ant-step; a walk is a chain of dependent gathers, so with 4096 ants the kernel is "
                              "latency-bound, not bandwidth-bound (see DESIGN.md)"},
