@@ -84,7 +84,7 @@ typedef struct {
     float tau0;           /* initial pheromone, :324 (1)                           */
     int fixed_colony;     /* 0: adaptive colony_num of :247; >0: that many ants    */
     int step_cap;         /* 0: auto (min(N-1, 65534)); else max steps per ant     */
-    int K;                /* neighbourhood: 6 (reference)                          */
+    int K;                /* neighbourhood: 6 (reference) or 26 (the extension disabled at :367-385; one GPU) */
     uint64_t seed;        /* Philox key; draw = f(seed; iteration, ant, step)      */
     int update_mode;      /* WR_UPDATE_*                                           */
     int walk_table_log2;  /* log2 of per-ant shared-memory visited-tile slots (0: default 9) */
@@ -123,7 +123,7 @@ int wr_acs_reset(wr_acs* a);                                        /* reset() :
  * (0 if none yet); ids gets min(*n, cap) node ids, dirs min(*n-1, cap) slot indices; *L = best.L
  * (+inf if none). */
 int wr_acs_best(wr_acs* a, int64_t* ids, int* dirs, int cap, int* n, float* L);
-int wr_acs_download_pheromone(wr_acs* a, float* tau, size_t n);     /* N*K floats, node-major, slots [-z,-y,-x,+x,+y,+z] */
+int wr_acs_download_pheromone(wr_acs* a, float* tau, size_t n);     /* N*K floats, node-major; K = 6: slots [-z,-y,-x,+x,+y,+z]; K = 26: the (dz,dy,dx) enumeration of :355-359 without the centre */
 int wr_acs_upload_pheromone(wr_acs* a, const float* tau, size_t n);
 /* last iteration's colony (parity checks): size, lambda, Q of :247-249 */
 int wr_acs_last_colony(wr_acs* a, int* colony, float* lambda, float* Q);

@@ -66,7 +66,7 @@ def test_occupancy_entry_point_round_trip(wr):
 # ---------------------------------------------------------------------------------------------
 def make_pair(wr, oracle, tris, precision, wall, **params):
     G = oracle.Grid.from_triangles(tris, precision, wall, oracle.VOX_AABB)
-    op = {k: v for k, v in params.items() if k in ("alpha", "beta", "rho", "tau0", "fixed_colony", "step_cap", "seed")}
+    op = {k: v for k, v in params.items() if k in ("alpha", "beta", "rho", "tau0", "fixed_colony", "step_cap", "seed", "K")}
     A = oracle.Acs(G, **op)
     g = wr.ACS_Rank(**params)
     g.creatGridMap(tris, precision, wall)
@@ -154,6 +154,82 @@ def test_fixed_colony_step_cap_and_table_overflow(wr, oracle, meshes, table_log2
     gc = g.counters()
     assert (gc["table_overflows"] > 0) == (table_log2 == 4)
     assert gc["dead_step_cap"] == A.counters()["dead_step_cap"]
+
+
+# ---------------------------------------------------------------------------------------------
+# K = 26: the neighbourhood the reference scaffolds and disables (ACSRank_3D.hpp:367-385); the oracle's K = 26 mode is
+# the specification (same enumeration, lengths precision*1.414f / precision*1.732f, every slot evaporated)
+# ---------------------------------------------------------------------------------------------
+def slot26_offsets():
+    out = []
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if (dx, dy, dz) != (0, 0, 0):
+                    out.append((dx, dy, dz))
+    return out
+
+
+@pytest.mark.parametrize("update_mode", [0, 1])
+def test_k26_adaptive_colony_bit_exact(wr, oracle, meshes, update_mode):
+    """cubic.stl @ (0.005, 10), adaptive colony, K = 26: every ant's visited-node sequence, length (float sums of three
+    step lengths in path order), rank, the best path and the whole 26-slot pheromone field, bit for bit."""
+    A, g = make_pair(wr, oracle, meshes["cubic"], 0.005, 10, seed=0x5EED, update_mode=update_mode, K=26)
+    ok, s, e = A.set_points(C1_POINTS[0], C1_POINTS[5])
+    assert g.setPoints(C1_POINTS[0], C1_POINTS[5]) and ok
+    A.begin(0.5); g.begin(0.5)
+    assert np.array_equal(A.pheromone().view(np.uint32), g.pheromone().view(np.uint32))   # initFromGridMap: tau0 / 0 on out-of-bounds slots
+    for it in range(10):
+        A.iterate(1); g.iterate(1)
+        compare_iteration(A, g, check_tau=it in (0, 1, 9))
+    A.iterate(30); g.iterate(30)
+    compare_iteration(A, g)
+    oc, gc = A.counters(), g.counters()
+    for key in ("ant_steps", "ants", "arrived", "dead_no_candidate", "dead_fallthrough", "dead_step_cap", "iterations"):
+        assert oc[key] == gc[key], key
+    assert gc["arrived"] > 0
+    # the moves really are 26-connected: some diagonal slot was taken, and ids follow the slot enumeration
+    ids, dirs, L = g.bestPath()
+    rx, ry = g.rangeX, g.rangeY
+    off = slot26_offsets()
+    assert np.array_equal(np.diff(ids), np.array([off[d][0] + off[d][1] * rx + off[d][2] * rx * ry for d in dirs]))
+    assert any(sum(1 for c in off[d] if c) > 1 for d in dirs)
+
+
+@pytest.mark.parametrize("table_log2", [4, 9])
+def test_k26_fixed_colony_step_cap_table_overflow_and_nan(wr, oracle, meshes, table_log2):
+    """K = 26 with a fixed colony, a step cap that some ants hit and — with a 16-slot visited table — the park/resume path
+    (pass 2 with tables in HBM, L carried in the parked state); then the NaN-plane pair (every ant dies)."""
+    A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=11, fixed_colony=384, step_cap=200, walk_table_log2=table_log2, K=26)
+    ids = np.flatnonzero(A.grid.isfree())
+    s, e = int(ids[10]), int(ids[-10])
+    A.set_endpoints(s, e); g.setEndpoints(s, e)
+    A.begin(1.0); g.begin(1.0)
+    for it in range(5):
+        A.iterate(1); g.iterate(1)
+        compare_iteration(A, g)
+    gc = g.counters()
+    assert (gc["table_overflows"] > 0) == (table_log2 == 4)
+    assert gc["dead_step_cap"] == A.counters()["dead_step_cap"]
+    A.reset(); g.reset()
+    assert np.array_equal(A.pheromone().view(np.uint32), g.pheromone().view(np.uint32))
+
+
+def test_k26_nan_plane(wr, oracle, meshes):
+    A, g = make_pair(wr, oracle, meshes["cubic"], 0.005, 10, seed=0x5EED, K=26)
+    ok, s, e = A.set_points(*C1_NAN_PAIR)
+    assert g.setPoints(*C1_NAN_PAIR) and (g._start_id, g._goal_id) == (s, e)
+    A.begin(0.5); A.iterate(4); g.begin(0.5); g.iterate(4)
+    compare_iteration(A, g)
+    assert A.counters()["dead_fallthrough"] == g.counters()["dead_fallthrough"]
+
+
+def test_k26_rejected_for_sharded_handles(wr, meshes):
+    g = wr.ACS_Rank(K=26)
+    g.creatGridMap(meshes["cubic"], 0.0123, 1)
+    g.initFromGridMap()
+    from welding_robot_b200 import _lib
+    assert _lib.lib().wr_acs_set_shard(g._a, 0, 2) == -1   # WR_ERR_INVALID
 
 
 def test_atomic_update_within_tolerance(wr, oracle, meshes):

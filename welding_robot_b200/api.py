@@ -435,7 +435,7 @@ class ACS_Rank(GridMap):
 
     # -- introspection (parity tests, bench) -----------------------------------------------
     def pheromone(self):
-        out = np.zeros(self.size_of_map() * 6, np.float32)
+        out = np.zeros(self.size_of_map() * int(self.params.K), np.float32)
         check(lib().wr_acs_download_pheromone(self._need(), ptr(out), out.size))
         return out
 

@@ -12,6 +12,7 @@
 
 #include "acs_kernels.cuh"
 #include "walk2.cuh"
+#include "walk26.cuh"
 #include "wr_internal.cuh"
 
 namespace wr {
@@ -89,6 +90,8 @@ struct wr_acs {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     size_t N = 0, n_slots = 0, n_slots_pad = 0;
+    int K = 6;                        // directed slots per node: 6 (the reference) or 26 (walk26.cuh)
+    float* d_ant_L = nullptr;         // K = 26: length of every ant of the last iteration (+inf: dead)
     unsigned ntiles = 0;
     int cap = 0, rank_bits = 0, slot_bits = 0;
     int table_log2 = 9, gtable_log2 = 0;
@@ -151,7 +154,7 @@ struct wr_acs {
 static void free_colony_buffers(wr_acs* a)
 {
     cudaStream_t s = a->stream;
-    pool_free(a->d_ant_steps, s); pool_free(a->d_overflow, s);
+    pool_free(a->d_ant_steps, s); pool_free(a->d_overflow, s); pool_free(a->d_ant_L, s); a->d_ant_L = nullptr;
     if (!a->d_slab) { pool_free(a->d_path_ids, s); pool_free(a->d_path_dirs, s); }
     pool_free(a->d_gkeys, s); pool_free(a->d_gmasks, s); pool_free(a->d_resume, s); a->d_resume = nullptr; pool_free(a->d_rec_off, s); pool_free(a->d_order, s);
     if (a->d_local_steps != a->d_ant_steps) pool_free(a->d_local_steps, s);
@@ -206,6 +209,7 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
         WR_CUDA(dmalloc(&a->d_path_dirs, chunk * cap, a->stream));
     }
     WR_CUDA(dmalloc(&a->d_overflow, chunk * sizeof(uint32_t), a->stream));
+    if (a->K == kK26) WR_CUDA(dmalloc(&a->d_ant_L, chunk * sizeof(float), a->stream));
     WR_CUDA(dmalloc(&a->d_rec_off, cm * sizeof(uint32_t), a->stream));
     WR_CUDA(dmalloc(&a->d_order, cm * sizeof(int), a->stream));
     WR_CUDA(cudaMemsetAsync(a->d_order, 0, cm * sizeof(int), a->stream));
@@ -244,6 +248,7 @@ static int walk_warm()
 }
 static size_t walk_smem(const wr_acs* a)
 {
+    if (a->K == kK26) return ((size_t)kWalk26Ants << a->table_log2) * 12;
     if (walk_version(a->g) == 2) return kWalk2Lut + 128 + (size_t)kAntsPerCta * a->table_entries * sizeof(unsigned long long);
     const size_t coord_bytes = ((size_t)(a->g->rx + a->g->ry + a->g->rz + 6) * 4 + 15) & ~(size_t)15;
     return coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
@@ -295,19 +300,20 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
 {
     WR_REQUIRE(g && p && out, WR_ERR_INVALID, "wr_acs_create: null");
     *out = nullptr;
-    WR_REQUIRE(p->K == 6, WR_ERR_INVALID, "wr_acs_create: only K = 6 (the reference's neighbourhood) is implemented");
+    WR_REQUIRE(p->K == 6 || p->K == kK26, WR_ERR_INVALID, "wr_acs_create: K must be 6 (the reference's neighbourhood) or 26 (its disabled extension)");
     WR_REQUIRE(p->alpha >= 0 && p->alpha < 64, WR_ERR_INVALID, "wr_acs_create: alpha out of range");
     WR_REQUIRE(p->update_mode >= WR_UPDATE_FUSED && p->update_mode <= WR_UPDATE_FUSED_TMA, WR_ERR_INVALID, "wr_acs_create: bad update_mode");
-    WR_REQUIRE((unsigned long long)g->N * 6 < 0xFFFFFFFFull - kUpdTile, WR_ERR_INVALID, "wr_acs_create: grid too large for 32-bit slot ids");
+    WR_REQUIRE((unsigned long long)g->N * p->K < 0xFFFFFFFFull - kUpdTile, WR_ERR_INVALID, "wr_acs_create: grid too large for 32-bit slot ids");
     WR_REQUIRE(g->N >= 2, WR_ERR_INVALID, "wr_acs_create: grid too small");
     wr_acs* a = new wr_acs();
     a->g = g; a->p = *p; a->N = g->N;
-    a->n_slots = g->N * 6;
+    a->K = p->K;
+    a->n_slots = g->N * (size_t)p->K;
     a->n_slots_pad = (a->n_slots + kUpdTile - 1) / kUpdTile * kUpdTile;
     a->ntiles = (unsigned)(a->n_slots_pad / kUpdTile);
     a->slot_bits = ceil_log2(a->n_slots);
     a->cap = p->step_cap > 0 ? p->step_cap : (int)std::min<size_t>(g->N - 1, 65532);
-    a->rank_bits = ceil_log2((unsigned long long)a->cap + 2);
+    a->rank_bits = a->K == kK26 ? 31 : ceil_log2((unsigned long long)a->cap + 2);   // K = 26 ranks by the bits of L (<= +inf = 0x7F800000)
     a->table_log2 = p->walk_table_log2 > 0 ? p->walk_table_log2 : 9;
     a->table_entries = p->walk_table_log2 > 0 ? (1 << p->walk_table_log2) : 768;
     if (a->table_log2 < 4 || a->table_log2 > 10) { delete a; set_error("wr_acs_create: walk_table_log2 must be in [4,10]"); return WR_ERR_INVALID; }
@@ -317,7 +323,8 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     a->own_stream = true;
     WR_CUDA_A(dmalloc(&a->d_tau, a->n_slots_pad * sizeof(float), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_tau, 0, a->n_slots_pad * sizeof(float), a->stream));
-    k_tau_init<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, p->tau0);
+    if (a->K == kK26) k_tau_init26<<<(unsigned)((a->n_slots + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, p->tau0);
+    else k_tau_init<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, p->tau0);
     WR_CUDA_A(cudaGetLastError());
     WR_CUDA_A(dmalloc(&a->d_state, sizeof(IterState), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_state, 0, sizeof(IterState), a->stream));
@@ -343,12 +350,15 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
         WR_CUDA_A(cudaFuncSetAttribute(k_update_tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const size_t ws = walk_smem(a);
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
+        if (a->K == kK26) WR_CUDA_A(cudaFuncSetAttribute(k_walk26<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        else {
         WR_CUDA_A(cudaFuncSetAttribute(k_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        }
     }
     WR_CUDA_A(cudaStreamSynchronize(a->stream));
 #undef WR_CUDA_A
@@ -438,7 +448,11 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     if (st != WR_OK) return st;
     a->colony_max = cm;
     if (!a->d_heur) WR_CUDA(dmalloc(&a->d_heur, a->n_slots_pad * sizeof(float), a->stream));
-    if (a->heur_goal != a->goal) {   // selectNext's geometric factor, tabulated once per goal
+    if (a->heur_goal != a->goal && a->K == kK26) {
+        k_heuristic26<<<(unsigned)((a->n_slots + 255) / 256), 256, 0, a->stream>>>(a->d_heur, a->g->d_coords, a->g->d_bits, a->g->rx, a->g->ry, a->g->rz, a->N,
+                                                                                  (int)a->goal, a->p.beta);
+        a->heur_goal = a->goal;
+    } else if (a->heur_goal != a->goal) {   // selectNext's geometric factor, tabulated once per goal
         k_heuristic<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_heur, a->g->d_coords, a->g->d_bits, a->g->rx, a->g->ry, a->g->rz, a->N, (int)a->goal,
                                                                             a->p.beta);
         a->heur_goal = a->goal;
@@ -467,7 +481,7 @@ static void launch_walk2(const WalkArgs& w, bool alpha1, int prefetch, int block
 // before k_iter_begin: pull the rows under last iteration's deposits into L2 (see k_path_warm)
 static void launch_warm(wr_acs* a)
 {
-    if (!walk_warm() || walk_version(a->g) != 2 || a->p.update_mode == WR_UPDATE_ATOMIC) return;
+    if (!walk_warm() || walk_version(a->g) != 2 || a->p.update_mode == WR_UPDATE_ATOMIC || a->K != 6) return;
     if (a->warm_by_pull) return;   // owner-computes update: k_pull_finals has just touched the rows under the deposits
     const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
     k_path_warm<<<kNumSMs, 256, 0, a->stream>>>(a->d_state, ck, a->d_tau, a->d_heur);
@@ -488,6 +502,18 @@ static int launch_walk(wr_acs* a)
     w.path_ids = a->d_path_ids; w.path_dirs = a->d_path_dirs;
     w.table_log2 = a->table_log2; w.table_entries = a->table_entries; w.overflow_list = a->d_overflow;
     w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks; w.gtab = a->d_gmasks; w.gtable_log2 = a->gtable_log2; w.resume = a->d_resume;
+    w.precision = g->precision; w.ant_L = a->d_ant_L;
+    if (a->K == kK26) {
+        const size_t smem = walk_smem(a);
+        const int per_sm = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 16));
+        const int blocks = std::max(1, std::min((a->chunk + kWalk26Ants - 1) / kWalk26Ants, kNumSMs * per_sm));
+        k_walk26<false><<<blocks, kWalk26Threads, smem, a->stream>>>(w);
+        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);   // pass 2: resume the ants that parked on a full shared-memory table
+        w.table_log2 = a->gtable_log2;
+        k_walk26<true><<<std::max(1, std::min((a->chunk + kWalk26Ants - 1) / kWalk26Ants, kNumSMs * 4)), kWalk26Threads, 0, a->stream>>>(w);
+        WR_CUDA(cudaGetLastError());
+        return WR_OK;
+    }
     const int ver = walk_version(g);
     const size_t smem1 = walk_smem(a);
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem1 + 1024)));
@@ -518,10 +544,12 @@ static int launch_rank(wr_acs* a, const int* d_all_steps)
 {
     const int cm = std::max(a->colony_max, 1);
     cudaStream_t s = a->stream;
-    k_rank_keys<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->cap, a->sort_ants.keys_a, a->sort_ants.vals_a);
+    if (a->K == kK26) k_rank_keys26<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->d_ant_L, a->sort_ants.keys_a, a->sort_ants.vals_a);
+    else k_rank_keys<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->cap, a->sort_ants.keys_a, a->sort_ants.vals_a);
     int st = sort_pairs(&a->sort_ants, a->dptr_colony(), a->rank_bits, s, &a->ants_in_b);
     if (st != WR_OK) return st;
-    k_rank_finish<<<1, 1024, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->cap, a->d_Ltab, a->d_rec_off, a->d_order);
+    k_rank_finish<<<1, 1024, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->cap, a->d_Ltab, a->d_rec_off, a->d_order,
+                                     a->K == kK26 ? d_all_steps : nullptr);
     k_best_clear<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_onbest);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
@@ -535,11 +563,12 @@ static int launch_deposit_gen(wr_acs* a)
     if (a->p.update_mode == WR_UPDATE_ATOMIC) {
         k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
         k_deposit_gen<true><<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_rec_off, a->d_path_ids, a->d_path_dirs, a->cap,
-                                                     first, a->chunk, (int)a->goal, a->d_Ltab, a->d_onbest, nullptr, nullptr, a->d_tau);
+                                                     first, a->chunk, (int)a->goal, a->d_Ltab, a->d_onbest, nullptr, nullptr, a->d_tau, nullptr, nullptr, a->K,
+                                                     a->K == kK26 ? a->d_ant_steps : nullptr);
     } else {
         k_deposit_gen<false><<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_rec_off, a->d_path_ids, a->d_path_dirs, a->cap,
                                                       first, a->chunk, (int)a->goal, a->d_Ltab, a->d_onbest, a->sort_recs.keys_a,
-                                                      a->sort_recs.vals_a, nullptr);
+                                                      a->sort_recs.vals_a, nullptr, nullptr, nullptr, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
     }
     WR_CUDA(cudaGetLastError());
     return WR_OK;
@@ -676,6 +705,7 @@ extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks)
     WR_REQUIRE(a && nranks >= 1 && rank >= 0 && rank < nranks, WR_ERR_INVALID, "wr_acs_set_shard: bad argument");
     WR_REQUIRE(!a->begun || (a->rank == rank && a->nranks == nranks), WR_ERR_STATE, "wr_acs_set_shard: set the shard before wr_acs_begin");
     WR_REQUIRE(nranks == 1 || a->p.update_mode != WR_UPDATE_ATOMIC, WR_ERR_INVALID, "wr_acs_set_shard: sharded colonies use the rank-ordered update modes");
+    WR_REQUIRE(nranks == 1 || a->K == 6, WR_ERR_INVALID, "wr_acs_set_shard: the K = 26 extension runs on one GPU (ranks would have to exchange lengths as well as step counts)");
     a->rank = rank; a->nranks = nranks;
     return WR_OK;
 }
@@ -962,6 +992,7 @@ extern "C" int wr_acs_last_ant(wr_acs* a, int k, int64_t* ids, int* dirs, int ca
     if (order) *order = ord;
     if (steps < 0) { *L = INFINITY; *n = 0; return WR_OK; }   // the trail of a dead ant is not kept
     *L = a->h_Ltab[steps];
+    if (a->K == kK26) WR_CUDA(cudaMemcpy(L, a->d_ant_L + (k - first), sizeof(float), cudaMemcpyDeviceToHost));
     *n = steps + 1;
     const size_t off = (size_t)(k - first) * a->cap;
     if (ids && cap > 0) {

@@ -46,7 +46,9 @@ struct WalkArgs {
     unsigned long long* gmasks;
     unsigned long long* gtab;   // k_walk2: HBM visited tables of 64-bit entries (aliases gmasks)
     int gtable_log2;
-    int4* resume;            // [chunk] state of an overflowed ant: {cur, steps, ntiles, -}
+    int4* resume;            // [chunk] state of an overflowed ant: {cur, steps, ntiles, bits of L (K = 26)}
+    float precision;         // K = 26 (walk26.cuh): step lengths precision, precision*1.414f, precision*1.732f
+    float* ant_L;            // K = 26: [chunk] length of the finished ant, +inf if it died (for K = 6 L is a function of steps)
 };
 
 __device__ __forceinline__ float pow_int(float x, int y)
@@ -401,8 +403,8 @@ __global__ void k_rank_keys(const IterState* st, const int* __restrict__ ant_ste
 // (L finite and order <= lambda-1) and the record offset of every eligible rank.
 __global__ void __launch_bounds__(1024) k_rank_finish(IterState* st, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                        int cap, const float* __restrict__ Ltab, uint32_t* __restrict__ rec_off,
-                                                       int* __restrict__ order_of_ant)
-{
+                                                       int* __restrict__ order_of_ant, const int* __restrict__ steps26 = nullptr)
+{   // steps26 != nullptr (K = 26): keys are the bits of L (k_rank_keys26) and an ant's step count comes from steps26[ant]
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry, elig_total;
     const int n = st->colony;
@@ -410,7 +412,12 @@ __global__ void __launch_bounds__(1024) k_rank_finish(IterState* st, const uint3
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         carry = 0; elig_total = 0;
-        if (n > 0) {
+        if (n > 0 && steps26) {
+            const float L0 = __uint_as_float(keys[0]);
+            if (L0 < st->best_L) {                  // agentK.L < best.L  (:263); a dead ant's +inf never is
+                st->best_steps = steps26[vals[0]]; st->best_L = L0; st->best_changed = 1; st->best_ant = (int)vals[0];
+            }
+        } else if (n > 0) {
             int s = (int)keys[0];
             if (s <= cap && s < st->best_steps) {   // agentK.L < best.L  (:263)
                 st->best_steps = s; st->best_L = Ltab[s]; st->best_changed = 1; st->best_ant = (int)vals[0];
@@ -422,10 +429,11 @@ __global__ void __launch_bounds__(1024) k_rank_finish(IterState* st, const uint3
         const int r = base + threadIdx.x;
         uint32_t len = 0; bool el = false;
         if (r < n) {
-            const int s = (int)keys[r];
+            const int s = steps26 ? steps26[vals[r]] : (int)keys[r];
+            const bool arrived = steps26 ? keys[r] != 0x7F800000u : s <= cap;
             const int order = r + 1;
             order_of_ant[vals[r]] = order;
-            el = s <= cap && !((float)order > __fsub_rn(lambda, 1.0f));   // :200
+            el = arrived && !((float)order > __fsub_rn(lambda, 1.0f));   // :200
             len = el ? (uint32_t)s : 0u;
         }
         uint32_t incl = len;
@@ -543,12 +551,14 @@ __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const 
                                                       int goal, const float* __restrict__ Ltab, const uint32_t* __restrict__ onbest,
                                                       uint32_t* __restrict__ rec_keys, uint32_t* __restrict__ rec_vals, float* tau,
                                                       const uint32_t* const* __restrict__ ids_tab = nullptr,
-                                                      const uint8_t* const* __restrict__ dirs_tab = nullptr)
-{
+                                                      const uint8_t* const* __restrict__ dirs_tab = nullptr, int K = 6,
+                                                      const int* __restrict__ steps26 = nullptr)
+{   // steps26 != nullptr (K = 26): rank_keys holds the bits of the ant's L, its step count is steps26[ant]
     const int r = blockIdx.x;
     if (r >= st->n_eligible) return;
-    const int steps = (int)rank_keys[r];
     const int ant_global = (int)rank_vals[r];
+    const int steps = steps26 ? steps26[ant_global] : (int)rank_keys[r];
+    const float L_ant = steps26 ? __uint_as_float(rank_keys[r]) : Ltab[steps];
     if (PEER) {
         const int owner = ant_global / shard_chunk;
         path_ids = ids_tab[owner]; path_dirs = dirs_tab[owner];
@@ -557,7 +567,7 @@ __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const 
     const size_t ant = (size_t)(ant_global - shard_first);
     const int order = r + 1;
     const float lambda = st->lambda, Q = st->Q;
-    const float base = __fdiv_rn(__fmul_rn(__fsub_rn(lambda, (float)order), Q), Ltab[steps]);
+    const float base = __fdiv_rn(__fmul_rn(__fsub_rn(lambda, (float)order), Q), L_ant);
     const float elite = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, lambda), Q), st->best_L);
     const float with_elite = __fadd_rn(base, elite), without = __fadd_rn(base, 0.0f);
     const uint32_t off = rec_off[r];
@@ -568,7 +578,7 @@ __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const 
         const uint32_t next = (i + 1 < steps) ? pid[i + 1] : (uint32_t)goal;
         const bool onb = ((onbest[node >> 5] >> (node & 31)) & 1u) && ((onbest[next >> 5] >> (next & 31)) & 1u);
         const float val = onb ? with_elite : without;
-        const uint32_t slot = node * 6u + pdir[i];
+        const uint32_t slot = node * (uint32_t)K + pdir[i];
         if (ATOMIC) atomicAdd(&tau[slot], val);
         else { rec_keys[off + i] = slot; rec_vals[off + i] = __float_as_uint(val); }
     }
