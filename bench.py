@@ -284,6 +284,41 @@ def run_ours(args):
             t_ms = acs.benchKernel(which, 20)
             alone[name] = {"ms": t_ms, "GBps": UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (t_ms * 1e-3) / 1e9}
 
+    # ---- the K = 26 neighbourhood (north_star's "26-neighbour" scores; the reference disables it, so it is reported next to
+    #      the K = 6 parity workload, never instead of it): same grid, colony and endpoints, 112 B per ant-step --------------
+    k26 = None
+    if world == 1 and not args.no_k26:
+        a26 = wr.ACS_Rank(seed=SEED, fixed_colony=args.ants, step_cap=STEP_CAP, update_mode=args.update_mode, K=26)
+        a26.creatFromOccupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], PRECISION)
+        with contextlib.redirect_stdout(io.StringIO()):
+            a26.initFromGridMap()
+        _lib.check(_lib.lib().wr_acs_set_stream(a26._a, stream.cuda_stream))
+        a26.setEndpoints(wl["start"], wl["goal"])
+        a26.begin(PREDICT)
+        a26.iterate(3 * args.iters)
+        a26.sync()
+        a26.setTiming(True)
+        d0 = a26.counters()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n26 = 6 * args.iters
+        f0.record(stream)
+        a26.iterate(n26)
+        f1.record(stream)
+        torch.cuda.synchronize()
+        ms26 = f0.elapsed_time(f1)
+        d1 = a26.counters()
+        k26ms = a26.kernelMs()
+        st26 = d1["ant_steps"] - d0["ant_steps"]
+        hbm26, _ = peaks()
+        w26 = 112 * st26 / (k26ms["walk"] * 1e-3) / 1e9
+        u26 = UPDATE_BYTES_PER_SLOT * n_nodes * 26 * n26 / (k26ms["update"] * 1e-3) / 1e9
+        k26 = {"ant_steps_per_s": st26 / (ms26 * 1e-3), "acs_iterations_per_s": n26 / (ms26 * 1e-3), "iterations": n26,
+               "mean_steps_per_ant": st26 / max(1, d1["ants"] - d0["ants"]), "arrived": d1["arrived"] - d0["arrived"],
+               "kernel_ms_per_iteration": {k: v / n26 for k, v in k26ms.items()},
+               "walk_GBps_at_112B_per_step": w26, "walk_frac_of_hbm": w26 / hbm26,
+               "update_GBps": u26, "update_frac_of_hbm": u26 / hbm26, "pheromone_field_bytes": n_nodes * 26 * 4}
+        del a26
+
     # ---- end to end through the public API from HOST buffers -------------------------------------------
     e2e = None
     if True:
@@ -361,7 +396,7 @@ def run_ours(args):
         "acs_iterations_per_s": iters_done / (ms * 1e-3),
         "ant_steps": steps_done, "arrived_local": c1["arrived"] - c0["arrived"], "ants_local": c1["ants"] - c0["ants"],
         "mean_steps_per_ant": local_steps / ants_done,
-        "gpu_launches": (launches_per_iteration(args.update_mode) + (6 if world > 1 else 0)) * iters_done,
+        "gpu_launches": int(round(launches_per_iteration(args.update_mode, colony, args.iters, world > 1) * iters_done)),
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
         "roofline": {"kernel": "k_walk2 (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
                      "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk2", traffic.get("k_walk")), "peak_source": hbm_src,
@@ -380,21 +415,27 @@ def run_ours(args):
     }
     if e2e:
         out["e2e"] = e2e
+    if k26:
+        out["k26_extension"] = k26
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(out))
 
 
-def launches_per_iteration(update_mode):
-    """Kernels of OURS launched per ACS iteration (welding_robot_b200/csrc/acs.cu)."""
+def launches_per_iteration(update_mode, colony=ANTS_PER_GPU, iters=5, sharded=False):
+    """Kernels of OURS launched per ACS iteration (welding_robot_b200/csrc/acs.cu: wr_acs_iterate / the sharded sequence)."""
     cap_bits = int(np.ceil(np.log2(STEP_CAP + 2)))
     slot_bits = int(np.ceil(np.log2(CUBE ** 3 * 6)))
     sort = lambda bits: 3 * ((bits + 9) // 10)  # noqa: E731  hist + scan + scatter per pass of <= 10-bit digits (radix_sort.cu)
-    n = 1 + 1 + 3 + 1 + sort(cap_bits) + 1 + 2 + 1   # L2 warm-up, iter_begin, walk x2 + queue reset, rank keys, sort, rank finish, best x2, iter_end
+    rank = 1 if colony <= 8192 else 1 + sort(cap_bits) + 2      # k_rank_small | keys + sort + finish + best clear
+    # L2 warm-up, iter_begin, walk pass 1 + 2, ranking, best copy, iter_end (single GPU: once per wr_acs_iterate call)
+    n = 1 + 1 + 2 + rank + 1 + (1 if sharded else 1.0 / iters)
     if update_mode == 2:
         return n + 2
-    # sharded (peer protocol, owner-computes): + partition pass (4) + pull (1) + best copy from the owner (1) - warm-up (done by the pull)
-    return n + 1 + sort(slot_bits) + 2           # deposit gen, sort, (tile offsets + fused) | (evaporate + apply)
+    n += 1 + sort(slot_bits) + 2                                  # deposit gen, slot sort, (tile offsets + fused) | (evaporate + apply)
+    if sharded:
+        n += 6                                                    # partition pass (4), pull of the peers' final values, memset of the queue words
+    return n
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -513,6 +554,7 @@ def main():
     ap.add_argument("--max-workers", type=int, default=16)
     ap.add_argument("--port", action="store_true", help="time the oracle port instead of oracle/_ref")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-k26", action="store_true", help="skip the K = 26 extension leg")
     ap.add_argument("--worker-mode", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--worker", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -13,8 +13,9 @@ import welding_robot_b200 as wr  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 wl = bench.build_workload_gpu()
-acs = wr.ACS_Rank(seed=1, fixed_colony=4096, step_cap=8192, update_mode=mode)
+acs = wr.ACS_Rank(seed=1, fixed_colony=4096, step_cap=8192, update_mode=mode, K=K)
 acs.creatFromOccupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], bench.PRECISION)
 with contextlib.redirect_stdout(io.StringIO()):
     acs.initFromGridMap()

@@ -13,6 +13,7 @@
 #include "acs_kernels.cuh"
 #include "walk2.cuh"
 #include "walk26.cuh"
+#include "rank_small.cuh"
 #include "wr_internal.cuh"
 
 namespace wr {
@@ -144,6 +145,7 @@ struct wr_acs {
     bool ants_in_b = false, recs_in_b = false;
     size_t alloc_colony = 0;
     PhaseTimer timer;
+    bool upd_q_zeroed = false;        // this iteration's k_iter_begin already cleared d_upd_q (wr_acs_iterate)
 
     const void** tab(int kind, unsigned par) const { return d_tabs + ((size_t)kind * 2 + par) * nranks; }
     uint32_t* fin_buf(unsigned par) const { return reinterpret_cast<uint32_t*>(d_slab + off_fin[par]); }
@@ -348,6 +350,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     {
         size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
         WR_CUDA_A(cudaFuncSetAttribute(k_update_tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WR_CUDA_A(cudaFuncSetAttribute(k_rank_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmallSmem));
         const size_t ws = walk_smem(a);
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         if (a->K == kK26) WR_CUDA_A(cudaFuncSetAttribute(k_walk26<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
@@ -508,7 +511,6 @@ static int launch_walk(wr_acs* a)
         const int per_sm = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 16));
         const int blocks = std::max(1, std::min((a->chunk + kWalk26Ants - 1) / kWalk26Ants, kNumSMs * per_sm));
         k_walk26<false><<<blocks, kWalk26Threads, smem, a->stream>>>(w);
-        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);   // pass 2: resume the ants that parked on a full shared-memory table
         w.table_log2 = a->gtable_log2;
         k_walk26<true><<<std::max(1, std::min((a->chunk + kWalk26Ants - 1) / kWalk26Ants, kNumSMs * 4)), kWalk26Threads, 0, a->stream>>>(w);
         WR_CUDA(cudaGetLastError());
@@ -522,13 +524,11 @@ static int launch_walk(wr_acs* a)
         const bool alpha1 = a->p.alpha == 1;
         launch_walk2<false>(w, alpha1, walk_prefetch(), blocks1, smem1, a->stream);
         // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
-        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
         w.table_log2 = a->gtable_log2;
         launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, kWalk2Lut + 128, a->stream);
     } else {
         const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15;   // + guard elements
         k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-        k_queue_reset<<<1, 1, 0, a->stream>>>(a->d_state);
         w.table_log2 = a->gtable_log2;
         k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
     }
@@ -544,6 +544,15 @@ static int launch_rank(wr_acs* a, const int* d_all_steps)
 {
     const int cm = std::max(a->colony_max, 1);
     cudaStream_t s = a->stream;
+    static const bool small_ok = [] { const char* e = getenv("WR_RANK_SMALL"); return !e || atoi(e) != 0; }();
+    if (small_ok && cm <= kRankSmallMax) {   // the whole ranking in one single-CTA kernel (rank_small.cuh)
+        k_rank_small<<<1, kRankSmallThreads, kRankSmallSmem, s>>>(a->d_state, d_all_steps, a->K == kK26 ? a->d_ant_L : nullptr, a->cap, a->rank_bits, a->d_Ltab,
+                                                                   a->sort_ants.keys_a, a->sort_ants.vals_a, a->d_rec_off, a->d_order, a->d_best_n, a->d_best_ids,
+                                                                   a->d_onbest);
+        a->ants_in_b = false;
+        WR_CUDA(cudaGetLastError());
+        return WR_OK;
+    }
     if (a->K == kK26) k_rank_keys26<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->d_ant_L, a->sort_ants.keys_a, a->sort_ants.vals_a);
     else k_rank_keys<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->cap, a->sort_ants.keys_a, a->sort_ants.vals_a);
     int st = sort_pairs(&a->sort_ants, a->dptr_colony(), a->rank_bits, s, &a->ants_in_b);
@@ -579,7 +588,8 @@ static int launch_deposit_gen(wr_acs* a)
 static int launch_fused(wr_acs* a, const uint32_t* ck, const uint32_t* cv, const int* d_n = nullptr, uint32_t* fin = nullptr)
 {
     cudaStream_t s = a->stream;
-    WR_CUDA(cudaMemsetAsync(a->d_upd_q, 0, 4 * sizeof(uint32_t), s));
+    if (!a->upd_q_zeroed) WR_CUDA(cudaMemsetAsync(a->d_upd_q, 0, 4 * sizeof(uint32_t), s));
+    a->upd_q_zeroed = false;
     k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(d_n ? d_n : a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, a->d_dep_list, a->d_upd_q + 2);
     if (fin) k_update_fused<true><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, fin);
     else k_update_fused<false><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, nullptr);
@@ -625,7 +635,8 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
     for (int it = 0; it < n; it++) {
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
         launch_warm(a);
-        k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0);
+        k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->d_upd_q);
+        a->upd_q_zeroed = true;
         int st = launch_walk(a);
         if (st != WR_OK) return st;
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
@@ -638,7 +649,8 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
         if (st != WR_OK) return st;
         st = launch_update(a);
         if (st != WR_OK) return st;
-        k_iter_end<<<1, 1, 0, s>>>(a->d_state);
+        a->upd_q_zeroed = false;
+        if (it == n - 1) k_iter_end<<<1, 1, 0, s>>>(a->d_state);   // otherwise folded into the next k_iter_begin
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     }
     WR_CUDA(cudaGetLastError());

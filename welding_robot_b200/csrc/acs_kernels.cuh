@@ -74,15 +74,19 @@ __global__ void k_begin(IterState* st, float predict)
     st->n_eligible = 0; st->n_records = 0;
 }
 
-__global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, float precision, float tau0)
+// advance: the previous iteration's k_iter_end folded in (iterations enqueued back to back); upd_q: the fused update's
+// three queue words, zeroed here instead of by a memset launch in front of k_tile_offsets.
+__global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, float precision, float tau0, int advance = 0, uint32_t* upd_q = nullptr)
 {   // :247-249
+    if (advance) { st->iter++; st->cnt[6]++; }
+    if (upd_q) { upd_q[0] = 0; upd_q[1] = 0; upd_q[2] = 0; upd_q[3] = 0; }
     float best_L = st->best_L, predict = st->predict;
     int colony = fixed_colony > 0 ? fixed_colony : (int)(0.35 * (double)(best_L < predict ? best_L : predict) / (double)precision);
     colony = max(0, min(colony, colony_max));
     float lambda = (float)(0.2 * (double)colony);
     float Q = __fmul_rn(__fdiv_rn(tau0, lambda), (best_L == INFINITY ? predict : best_L));
     st->colony = colony; st->lambda = lambda; st->Q = Q;
-    st->queue = 0; st->overflow_n = 0; st->best_changed = 0;
+    st->queue = 0; st->queue2 = 0; st->overflow_n = 0; st->best_changed = 0;
     st->n_eligible = 0; st->n_records = 0;
 }
 
@@ -92,7 +96,6 @@ __global__ void k_iter_end(IterState* st)
     st->cnt[6]++;
 }
 
-__global__ void k_queue_reset(IterState* st) { st->queue = 0; }
 
 // ------------------------------------------------------------------------------------------
 // Heuristic table for the current goal: heur[node][k] = 1 + beta*cos(theta), theta between (goal - node) and
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
 
     while (true) {
         unsigned q0 = 0;
-        if (lane == 0) q0 = atomicAdd(&st->queue, 4u);
+        if (lane == 0) q0 = atomicAdd(GLOBAL ? &st->queue2 : &st->queue, 4u);
         q0 = __shfl_sync(FULL, q0, 0);
         if (q0 >= (unsigned)local_n) break;                       // warp-uniform
         const unsigned q = q0 + (unsigned)(lane >> 3);

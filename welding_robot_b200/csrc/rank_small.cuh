@@ -1,0 +1,171 @@
+// Colony ranking in ONE kernel for colonies of up to kRankSmallMax ants (the reference's adaptive colonies are tens of
+// ants, BASELINE's C2 colony is 4096): keys, stable LSD radix sort, best decision, eligibility, record offsets and the
+// old best path's membership bits — what launch_rank otherwise spreads over k_rank_keys + 3 kernels per sort pass +
+// k_rank_finish + k_best_clear (10 dependent launches whose cost is launch latency, not work).
+//
+// Sort: a single CTA of 1024 threads, keys and values ping-pong in shared memory, 8-bit digits.  Warp w owns the
+// contiguous index block [w*chunk, (w+1)*chunk) and walks it 32 keys at a time, so "earlier index" = (earlier warp) or
+// (same warp, earlier round) or (same round, lower lane): a key's position inside its digit is
+//     prefix over (digit, warp) of the per-warp counts  +  count of this warp's earlier rounds  +  match-any rank
+// which makes every pass stable, hence the result the oracle's total order (key, ant index).
+#pragma once
+#include "acs_kernels.cuh"
+
+namespace wr {
+
+constexpr int kRankSmallMax = 8192;
+constexpr int kRankSmallThreads = 1024;
+constexpr int kRankSmallRounds = kRankSmallMax / kRankSmallThreads;   // 32-key rounds per warp
+// dynamic shared memory: keys[2][max] + vals[2][max] (u32) + whist[32][256] (u32)
+constexpr size_t kRankSmallSmem = (size_t)4 * kRankSmallMax * sizeof(uint32_t) + (size_t)32 * 256 * sizeof(uint32_t);
+
+// steps26 / ant_L: K = 26 (key = bits of L); else key = steps (cap+1 for a dead ant), as k_rank_keys / k_rank_keys26.
+__global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st, const int* __restrict__ ant_steps, const float* __restrict__ ant_L, int cap,
+                                                                   int key_bits, const float* __restrict__ Ltab, uint32_t* __restrict__ out_keys,
+                                                                   uint32_t* __restrict__ out_vals, uint32_t* __restrict__ rec_off,
+                                                                   int* __restrict__ order_of_ant, const int* __restrict__ best_n,
+                                                                   const uint32_t* __restrict__ best_ids, uint32_t* onbest)
+{
+    extern __shared__ __align__(16) uint32_t rs_smem[];
+    uint32_t* kbuf[2] = {rs_smem, rs_smem + kRankSmallMax};
+    uint32_t* vbuf[2] = {rs_smem + 2 * kRankSmallMax, rs_smem + 3 * kRankSmallMax};
+    uint32_t* whist = rs_smem + 4 * kRankSmallMax;   // [warp][digit]
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry, elig_total;
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n = st->colony;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool k26 = ant_L != nullptr;
+    const int rounds = (n + kRankSmallThreads - 1) / kRankSmallThreads;   // per warp
+    const int chunk = rounds * 32;
+
+    // ---- keys (k_rank_keys / k_rank_keys26) ----
+    for (int i = threadIdx.x; i < n; i += kRankSmallThreads) {
+        const int s = ant_steps[i];
+        kbuf[0][i] = k26 ? (s < 0 ? 0x7F800000u : __float_as_uint(ant_L[i])) : (s < 0 ? (uint32_t)(cap + 1) : (uint32_t)s);
+        vbuf[0][i] = (uint32_t)i;
+    }
+    __syncthreads();
+
+    // ---- stable LSD radix sort, 8 bits per pass ----
+    int src = 0;
+    for (int shift = 0; shift < key_bits; shift += 8, src ^= 1) {
+        const uint32_t* ki = kbuf[src];
+        const uint32_t* vi = vbuf[src];
+        for (int d = lane; d < 256; d += 32) whist[w * 256 + d] = 0;
+        __syncwarp();
+        uint32_t local[kRankSmallRounds];   // position of this thread's key of round r among its warp's keys of the same digit
+#pragma unroll
+        for (int r = 0; r < kRankSmallRounds; r++) {
+            if (r < rounds) {   // warp-uniform
+                const int idx = w * chunk + r * 32 + lane;
+                const bool ok = idx < n;
+                const uint32_t d = ok ? ((ki[idx] >> shift) & 255u) : 256u;
+                const unsigned peers = __match_any_sync(FULL, d);
+                const uint32_t base = ok ? whist[w * 256 + d] : 0u;
+                local[r] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+                __syncwarp();
+                if (ok && lane == __ffs(peers) - 1) whist[w * 256 + d] = base + (uint32_t)__popc(peers);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the 8192 counters in (digit, warp) order: thread t owns digit t/4, warps (t%4)*8 .. +7
+        {
+            const int d = threadIdx.x >> 2, w0 = (threadIdx.x & 3) * 8;
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { c[j] = whist[(w0 + j) * 256 + d]; sum += c[j]; }
+            uint32_t incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+            if (lane == 31) warp_sum[w] = incl;
+            __syncthreads();
+            if (w == 0) {
+                const uint32_t s = warp_sum[lane];
+                uint32_t si = s;
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, si, o); if (lane >= o) si += u; }
+                warp_sum[lane] = si - s;
+            }
+            __syncthreads();
+            uint32_t run = warp_sum[w] + (incl - sum);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { whist[(w0 + j) * 256 + d] = run; run += c[j]; }
+        }
+        __syncthreads();
+        uint32_t* ko = kbuf[src ^ 1];
+        uint32_t* vo = vbuf[src ^ 1];
+#pragma unroll
+        for (int r = 0; r < kRankSmallRounds; r++) {
+            if (r < rounds) {
+                const int idx = w * chunk + r * 32 + lane;
+                if (idx < n) {
+                    const uint32_t key = ki[idx];
+                    const uint32_t pos = whist[w * 256 + ((key >> shift) & 255u)] + local[r];
+                    ko[pos] = key; vo[pos] = vi[idx];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t* keys = kbuf[src];
+    const uint32_t* vals = vbuf[src];
+
+    // ---- k_rank_finish: best decision (:263-264), eligibility (:200), record offsets ----
+    const float lambda = st->lambda;
+    if (threadIdx.x == 0) {
+        carry = 0; elig_total = 0;
+        if (n > 0 && k26) {
+            const float L0 = __uint_as_float(keys[0]);
+            if (L0 < st->best_L) { st->best_steps = ant_steps[vals[0]]; st->best_L = L0; st->best_changed = 1; st->best_ant = (int)vals[0]; }
+        } else if (n > 0) {
+            const int s = (int)keys[0];
+            if (s <= cap && s < st->best_steps) { st->best_steps = s; st->best_L = Ltab[s]; st->best_changed = 1; st->best_ant = (int)vals[0]; }
+        }
+    }
+    __syncthreads();
+    for (int base = 0; base < n; base += kRankSmallThreads) {
+        const int r = base + threadIdx.x;
+        uint32_t len = 0; bool el = false;
+        if (r < n) {
+            const uint32_t key = keys[r], ant = vals[r];
+            out_keys[r] = key; out_vals[r] = ant;
+            const int s = k26 ? ant_steps[ant] : (int)key;
+            const bool arrived = k26 ? key != 0x7F800000u : s <= cap;
+            const int order = r + 1;
+            order_of_ant[ant] = order;
+            el = arrived && !((float)order > __fsub_rn(lambda, 1.0f));   // :200
+            len = el ? (uint32_t)s : 0u;
+        }
+        uint32_t incl = len;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) warp_sum[w] = incl;
+        const unsigned em = __ballot_sync(FULL, el);
+        if (lane == 0 && em) atomicAdd(&elig_total, (uint32_t)__popc(em));
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t s = warp_sum[lane];
+            uint32_t si = s;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, si, o); if (lane >= o) si += u; }
+            warp_sum[lane] = si - s;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sum[w] + (incl - len);
+        if (r < n) rec_off[r] = excl;
+        __syncthreads();
+        if (threadIdx.x == kRankSmallThreads - 1) carry = excl + len;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { st->n_eligible = (int)elig_total; st->n_records = (int)carry; st->cnt[7] += carry; }
+
+    // ---- k_best_clear: best = agentK (:264) drops the old best path's membership bits ----
+    if (st->best_changed) {   // written by thread 0 before the barrier above
+        const int nb = *best_n;
+        for (int i = threadIdx.x; i < nb; i += kRankSmallThreads) {
+            const uint32_t id = best_ids[i];
+            atomicAnd(&onbest[id >> 5], ~(1u << (id & 31)));
+        }
+    }
+}
+
+}  // namespace wr

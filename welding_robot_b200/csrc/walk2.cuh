@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
 
     while (true) {
         unsigned q0 = 0;
-        if (lane == 0) q0 = atomicAdd(&st->queue, 4u);
+        if (lane == 0) q0 = atomicAdd(GLOBAL ? &st->queue2 : &st->queue, 4u);
         q0 = __shfl_sync(FULL, q0, 0);
         if (q0 >= (unsigned)local_n) break;                                    // warp-uniform
         const unsigned q = q0 + (unsigned)(lane >> 3);

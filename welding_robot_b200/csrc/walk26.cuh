@@ -97,7 +97,7 @@ __global__ void k_rank_keys26(const IterState* st, const int* __restrict__ ant_s
 // L} and is resumed by pass 2 (GLOBAL) — exact, its draws are a pure function of (iteration, ant, step).
 // ------------------------------------------------------------------------------------------
 template <bool GLOBAL>
-__global__ void __launch_bounds__(kWalk26Threads) k_walk26(WalkArgs a)
+__global__ void __launch_bounds__(kWalk26Threads, 7) k_walk26(WalkArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned FULL = 0xffffffffu;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kWalk26Threads) k_walk26(WalkArgs a)
 
     while (true) {
         unsigned q = 0;
-        if (lane == 0) q = atomicAdd(&st->queue, 1u);
+        if (lane == 0) q = atomicAdd(GLOBAL ? &st->queue2 : &st->queue, 1u);
         q = __shfl_sync(FULL, q, 0);
         if (q >= (unsigned)local_n) break;
         const int ant_local = GLOBAL ? (int)a.overflow_list[q] : (int)q;

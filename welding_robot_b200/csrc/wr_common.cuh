@@ -109,7 +109,8 @@ struct IterState {
     int best_ant;        // global ant index that produced it (this iteration)
     int n_eligible;      // ants that deposit this iteration (order <= lambda-1, arrived)
     int n_records;       // deposit records this iteration
-    unsigned queue;      // walk work queue
+    unsigned queue;      // walk work queue (pass 1)
+    unsigned queue2;     // pass 2 (resumed ants): its own counter, so no reset launch sits between the two passes
     unsigned overflow_n; // ants whose shared-memory visited table overflowed (pass 2)
     unsigned long long cnt[9];
 };
