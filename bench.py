@@ -248,6 +248,7 @@ def run_ours(args):
     # ---- timed region, device resident -------------------------------------------------------------
     acs.setTiming(True)
     c0 = acs.counters()
+    rs0 = acs.updateStats()["rankset_iterations"]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -264,6 +265,8 @@ def run_ours(args):
     sampler.stop()
     c1 = acs.counters()
     kms = acs.kernelMs()
+    upd_stats = acs.updateStats()
+    rs_iters = upd_stats["rankset_iterations"] - rs0        # timed iterations whose deposits went through rank sets (mode 4)
     acs.setTiming(False)
     local_steps = c1["ant_steps"] - c0["ant_steps"]
     steps_done = local_steps
@@ -387,7 +390,7 @@ def run_ours(args):
         "data": "synthetic: reference mesh fixture voxelised on the GPU, embedded in 256^3 free space; synthetic start/goal",
         "config": {"workload": "C2: ACSRank_3D, simplified_piece @256-long grid in 256^3, %d ants/GPU, K=6" % args.ants,
                    "grid": [CUBE, CUBE, CUBE], "natural_grid": list(wl["natural"]), "ants": colony, "iters_per_step": args.iters,
-                   "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic", "fused_tma"][args.update_mode],
+                   "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic", "fused_tma", "rankset"][args.update_mode],
                    "parallelism": "ants sharded x%d" % world,
                    "exchange": ("none (1 GPU)" if world == 1 else
                                 ("NVLink peer memory (trails read from their owners' HBM), %s update" % ("owner-computes (slot slices)" if driver.sliced else "replicated"))
@@ -396,7 +399,9 @@ def run_ours(args):
         "acs_iterations_per_s": iters_done / (ms * 1e-3),
         "ant_steps": steps_done, "arrived_local": c1["arrived"] - c0["arrived"], "ants_local": c1["ants"] - c0["ants"],
         "mean_steps_per_ant": local_steps / ants_done,
-        "gpu_launches": int(round(launches_per_iteration(args.update_mode, colony, args.iters, world > 1) * iters_done)),
+        "gpu_launches": int(round(launches_per_iteration(0 if args.update_mode == 4 else args.update_mode, colony, args.iters, world > 1) * (iters_done - rs_iters)
+                                  + launches_per_iteration(4, colony, args.iters, world > 1) * rs_iters)),
+        "deposit_path": {"rank_set_iterations": rs_iters, "record_iterations": iters_done - rs_iters, "last": upd_stats} if args.update_mode == 4 else None,
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
         "roofline": {"kernel": "k_walk2 (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
                      "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk2", traffic.get("k_walk")), "peak_source": hbm_src,
@@ -404,7 +409,8 @@ def run_ours(args):
                      "note": "30 B algorithmic per ant-step; a walk is a chain of dependent gathers, so with 4096 ants the kernel is "
                              "latency-bound, not bandwidth-bound (see DESIGN.md)"},
         "roofline_update": {"kernel": ["k_update_fused (K3: evaporation + rank-ordered deposits, one HBM pass)", "k_evaporate + k_deposit_apply (K3 split)",
-                                       "k_evaporate + atomic deposits (K3 atomic)", "k_update_tma_ring (K3 through a TMA ring)"][args.update_mode],
+                                       "k_evaporate + atomic deposits (K3 atomic)", "k_update_tma_ring (K3 through a TMA ring)",
+                                       "k_update_fused on record-path iterations | k_evaporate + k_rankset_apply on rank-set iterations (K3 adaptive)"][args.update_mode],
                             "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm,
                             "traffic": traffic.get("k_update_fused") if args.update_mode == 0 else None,
                             "algorithmic_bytes_per_launch": UPDATE_BYTES_PER_SLOT * n_nodes * 6,
@@ -430,8 +436,8 @@ def launches_per_iteration(update_mode, colony=ANTS_PER_GPU, iters=5, sharded=Fa
     rank = 1 if colony <= 8192 else 1 + sort(cap_bits) + 2      # k_rank_small | keys + sort + finish + best clear
     # L2 warm-up, iter_begin, walk pass 1 + 2, ranking, best copy, iter_end (single GPU: once per wr_acs_iterate call)
     n = 1 + 1 + 2 + rank + 1 + (1 if sharded else 1.0 / iters)
-    if update_mode == 2:
-        return n + 2
+    if update_mode == 2 or (update_mode == 4 and not sharded):
+        return n + (2 if update_mode == 2 else 3)                 # rank-set: gen, evaporate, apply
     n += 1 + sort(slot_bits) + 2                                  # deposit gen, slot sort, (tile offsets + fused) | (evaporate + apply)
     if sharded:
         n += 6                                                    # partition pass (4), pull of the peers' final values, memset of the queue words
@@ -549,7 +555,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5, help="ACS iterations per step")
     ap.add_argument("--ants", type=int, default=ANTS_PER_GPU, help="ants per GPU (default: the C2 colony; other values are exploration runs)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--update-mode", type=int, default=0)
+    ap.add_argument("--update-mode", type=int, default=4, help="WR_UPDATE_*: 4 = adaptive rank sets | sorted records + fused pass (default), 0 = fused")
     ap.add_argument("--cpu-ants", type=int, default=1024, help="colony size of the CPU sample")
     ap.add_argument("--max-workers", type=int, default=16)
     ap.add_argument("--port", action="store_true", help="time the oracle port instead of oracle/_ref")

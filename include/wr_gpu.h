@@ -94,7 +94,13 @@ enum {
     WR_UPDATE_FUSED = 0,     /* one HBM pass: tile streamed through registers, rank-ordered deposits applied while the tile is in L2 */
     WR_UPDATE_SPLIT = 1,     /* float4 evaporation pass, then rank-ordered deposit pass (same bits) */
     WR_UPDATE_ATOMIC = 2,    /* evaporation pass + atomicAdd deposits (fast, order not reproducible) */
-    WR_UPDATE_FUSED_TMA = 3  /* one HBM pass through a 4-stage TMA ring in shared memory (same bits; measurement variant) */
+    WR_UPDATE_FUSED_TMA = 3, /* one HBM pass through a 4-stage TMA ring in shared memory (same bits; measurement variant) */
+    WR_UPDATE_RANKSET = 4    /* adaptive: per touched slot the SET of depositing ranks (a deposit's value depends only on the rank and one
+                                bit of the slot) is built with atomicOr and applied as one ordered chain — no record sort — on the
+                                iterations where the colony's deposits are concentrated; sorted records + the fused pass (WR_UPDATE_FUSED)
+                                while it still wanders.  The choice is made on the device per iteration (no host sync); same additions in
+                                the same order either way, same bits.  Single-GPU handles of up to 4955 ants whose table fits in 4 GB;
+                                otherwise, and on sharded handles, it runs as WR_UPDATE_FUSED. */
 };
 
 int wr_acs_default_params(wr_acs_params* p);                        /* literals of initFromGridMap :319-325 */
@@ -137,6 +143,9 @@ int wr_acs_counters(wr_acs* a, uint64_t out[9]);
  * [0] walk [1] rank+best [2] deposit build+sort [3] update (evaporate+deposit) [4] whole iterations */
 int wr_acs_kernel_ms(wr_acs* a, float out[5]);
 int wr_acs_set_timing(wr_acs* a, int enabled);
+/* WR_UPDATE_RANKSET: [0] the last iteration took the rank-set path, [1] pheromone tiles that received deposits in the last
+ * record-path iteration, [2] distinct slots in the last rank-set iteration, [3] rank-set iterations since begin */
+int wr_acs_update_stats(wr_acs* a, uint32_t out[4]);
 /* measurement hook: run ONE kernel of the update path `reps` times back to back on the handle's
  * stream and report the average device time per launch (CUDA events).  which: 0 = fused update
  * (evaporation + the last iteration's deposit records), 1 = float4 evaporation pass alone,

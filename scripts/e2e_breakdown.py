@@ -12,7 +12,7 @@ import welding_robot_b200 as wr  # noqa: E402
 wl = bench.build_workload_gpu()
 for rep in range(8):
     t = [time.perf_counter()]
-    a = wr.ACS_Rank(seed=1, fixed_colony=4096, step_cap=8192)
+    a = wr.ACS_Rank(seed=1, fixed_colony=4096, step_cap=8192, update_mode=int(sys.argv[1]) if len(sys.argv) > 1 else 0)
     a.creatFromOccupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], bench.PRECISION); t.append(time.perf_counter())
     with contextlib.redirect_stdout(io.StringIO()):
         a.initFromGridMap()

@@ -100,7 +100,7 @@ def compare_iteration(A, g, check_tau=True, exact_tau=True):
             assert np.allclose(to, tg, rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("update_mode", [0, 1, 3])
+@pytest.mark.parametrize("update_mode", [0, 1, 3, 4])
 def test_c1_adaptive_colony_bit_exact(wr, oracle, meshes, update_mode):
     """cubic.stl @ (0.005, 10), reference defaults (adaptive colony), pair (0,5): every ant of
     every iteration, the best path and the whole pheromone field, bit for bit."""
@@ -170,7 +170,7 @@ def slot26_offsets():
     return out
 
 
-@pytest.mark.parametrize("update_mode", [0, 1])
+@pytest.mark.parametrize("update_mode", [0, 1, 4])
 def test_k26_adaptive_colony_bit_exact(wr, oracle, meshes, update_mode):
     """cubic.stl @ (0.005, 10), adaptive colony, K = 26: every ant's visited-node sequence, length (float sums of three
     step lengths in path order), rank, the best path and the whole 26-slot pheromone field, bit for bit."""
@@ -230,6 +230,35 @@ def test_k26_rejected_for_sharded_handles(wr, meshes):
     g.initFromGridMap()
     from welding_robot_b200 import _lib
     assert _lib.lib().wr_acs_set_shard(g._a, 0, 2) == -1   # WR_ERR_INVALID
+
+
+@pytest.mark.parametrize("K,policy", [(6, "1"), (26, "1"), (6, "0")])
+def test_rankset_update_mode_bit_exact(wr, oracle, meshes, K, policy, monkeypatch):
+    """WR_UPDATE_RANKSET (per-slot sets of depositing ranks instead of sorted records): same bits as the oracle with a
+    fixed colony (hot slots crossed by most eligible ranks take the warp-cooperative chain), across reset(), a second
+    search on the same handle, and a second handle that inherits the first one's parked (all-zero) table.  Policy 1 forces
+    the rank-set path on every iteration; policy 0 is the shipped device-side switch (thresholds lowered so that both
+    paths and both transitions occur within the run)."""
+    monkeypatch.setenv("WR_RANKSET_POLICY", policy)
+    if policy == "0":
+        monkeypatch.setenv("WR_RANKSET_ON", "100000"); monkeypatch.setenv("WR_RANKSET_OFF", "9000")
+    for rep in range(2):
+        A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=21 + rep, fixed_colony=640, step_cap=300, update_mode=4, K=K)
+        ids = np.flatnonzero(A.grid.isfree())
+        for (s, e) in [(int(ids[10]), int(ids[-10])), (int(ids[200]), int(ids[-300]))]:
+            A.set_endpoints(s, e); g.setEndpoints(s, e)
+            A.begin(1.0); g.begin(1.0)
+            for it in range(4):
+                A.iterate(1); g.iterate(1)
+                compare_iteration(A, g)
+            A.iterate(12); g.iterate(12)
+            compare_iteration(A, g)
+            A.reset(); g.reset()
+            assert np.array_equal(A.pheromone().view(np.uint32), g.pheromone().view(np.uint32))
+        assert g.counters()["deposit_records"] > 0
+        st = g.updateStats()
+        assert st["rankset_iterations"] > 0, st
+        del g
 
 
 def test_atomic_update_within_tolerance(wr, oracle, meshes):

@@ -470,6 +470,12 @@ class ACS_Rank(GridMap):
         check(lib().wr_acs_kernel_ms(self._need(), ptr(out)))
         return dict(walk=float(out[0]), rank=float(out[1]), deposit_build=float(out[2]), update=float(out[3]), total=float(out[4]))
 
+    def updateStats(self):
+        """WR_UPDATE_RANKSET: which deposit path the last iteration took and how concentrated the deposits were."""
+        out = np.zeros(4, np.uint32)
+        check(lib().wr_acs_update_stats(self._need(), ptr(out)))
+        return dict(rankset_last=int(out[0]), deposit_tiles=int(out[1]), distinct_slots=int(out[2]), rankset_iterations=int(out[3]))
+
     def benchKernel(self, which, reps=20):
         """Average device ms of one update-path kernel run alone (0 fused update, 1 float4 evaporation, 2 D2D copy, 3 all-TMA ring variant)."""
         ms = C.c_float()

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -14,6 +15,7 @@
 #include "walk2.cuh"
 #include "walk26.cuh"
 #include "rank_small.cuh"
+#include "rankset.cuh"
 #include "wr_internal.cuh"
 
 namespace wr {
@@ -145,17 +147,104 @@ struct wr_acs {
     bool ants_in_b = false, recs_in_b = false;
     size_t alloc_colony = 0;
     PhaseTimer timer;
+    // WR_UPDATE_RANKSET (rankset.cuh)
+    bool want_rankset = false, rankset = false;
+    RankSet rs = {};
+    size_t rs_entries = 0, rs_list_cap = 0;
+    int rs_policy = 0;                // 0 adaptive, 1 rank sets always, 2 records always (WR_RANKSET_POLICY)
+    // adaptive choice: device -> host feedback through mapped pinned memory, host kept <= kRsAhead iterations ahead
+    uint32_t* h_feedback = nullptr;   // {generation << 16 | iteration, path of the previous iteration, deposit tiles, distinct slots}
+    uint32_t* d_feedback = nullptr;   // the same words as the device sees them
+    uint32_t rs_generation = 0;       // bumped by wr_acs_begin: feedback of an earlier search on the same stream is ignored
+    int rs_choice = 0;                // path of the iteration being enqueued
+    static constexpr int kRsAhead = 4;
+    cudaEvent_t rs_ev[kRsAhead] = {};
+    unsigned long long rs_enqueued = 0;
+    unsigned rs_on = 1600, rs_off = 60000;   // switch thresholds: deposit tiles / distinct slots (WR_RANKSET_ON / WR_RANKSET_OFF)
     bool upd_q_zeroed = false;        // this iteration's k_iter_begin already cleared d_upd_q (wr_acs_iterate)
 
     const void** tab(int kind, unsigned par) const { return d_tabs + ((size_t)kind * 2 + par) * nranks; }
     uint32_t* fin_buf(unsigned par) const { return reinterpret_cast<uint32_t*>(d_slab + off_fin[par]); }
     const int* dptr_colony() const { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + offsetof(IterState, colony)); }
     const int* dptr_nrec() const { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + offsetof(IterState, n_records)); }
+    // record count the record path's kernels see: 0 on iterations an adaptive handle runs through rank sets
+    const int* dptr_nrec_upd() const
+    {
+        return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + (rankset ? offsetof(IterState, n_records_sort) : offsetof(IterState, n_records)));
+    }
 };
+
+// A rank-set table is all zeros whenever no iteration is in flight (k_rankset_apply clears what k_rankset_gen set), so a
+// destroyed handle's table can be handed to the next handle of the same shape without the 1-2 GB memset: one parked
+// table per process (searches created in a loop, one per request, are the e2e pattern).
+struct RankSetCache {
+    int device = -1;
+    size_t entries = 0, list_cap = 0;
+    int w_max = 0;
+    RankSet rs = {};   // all six buffers travel together, so a handle that adopts them adds no traffic to the memory pool
+};
+static RankSetCache g_rs_cache;
+static std::mutex g_rs_cache_mu;   // handles may be created and destroyed on different host threads
+
+// Feedback words (device -> host, mapped pinned memory): pinned allocations cost milliseconds, handles are created per
+// request, so one page is pinned per process and handles borrow a 16-byte slot of it.
+struct FeedbackPage {
+    uint32_t* host = nullptr;
+    uint32_t* dev = nullptr;
+    bool used[256] = {};
+};
+static FeedbackPage g_feedback;
+
+static int feedback_acquire(uint32_t** h, uint32_t** d)
+{
+    std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+    if (!g_feedback.host) {
+        WR_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_feedback.host), 256 * 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        WR_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_feedback.dev), g_feedback.host, 0));
+    }
+    for (int i = 0; i < 256; i++)
+        if (!g_feedback.used[i]) {
+            g_feedback.used[i] = true;
+            *h = g_feedback.host + 4 * i; *d = g_feedback.dev + 4 * i;
+            (*h)[0] = 0; (*h)[1] = 0; (*h)[2] = 0xFFFFFFFFu; (*h)[3] = 0xFFFFFFFFu;
+            return WR_OK;
+        }
+    *h = nullptr; *d = nullptr;   // all slots taken: the handle runs without feedback (records path only)
+    return WR_OK;
+}
+static void feedback_release(uint32_t* h)
+{
+    if (!h) return;
+    std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+    g_feedback.used[(h - g_feedback.host) / 4] = false;
+}
+
+// The rank-set buffers outlive handles (they are parked between searches), so they come from cudaMalloc, not from the
+// stream-ordered pool whose blocks are tied to the allocating handle's stream.
+static void rankset_release_buffers(RankSet& rs, cudaStream_t)
+{
+    cudaFree(rs.ent); cudaFree(rs.rows); cudaFree(rs.list); cudaFree(rs.touched); cudaFree(rs.count); cudaFree(rs.vtab);
+    rs = RankSet{};
+}
+
+static void free_rankset(wr_acs* a)
+{
+    cudaStream_t s = a->stream;
+    if (a->rs.ent) {
+        cudaStreamSynchronize(s);   // the table is clean once the stream has drained
+        std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+        if (g_rs_cache.rs.ent) rankset_release_buffers(g_rs_cache.rs, s);
+        g_rs_cache.device = a->device; g_rs_cache.entries = a->rs_entries; g_rs_cache.list_cap = a->rs_list_cap; g_rs_cache.w_max = a->w_max;
+        g_rs_cache.rs = a->rs;
+    }
+    a->rs = RankSet{};
+    a->rankset = false; a->rs_entries = 0;
+}
 
 static void free_colony_buffers(wr_acs* a)
 {
     cudaStream_t s = a->stream;
+    free_rankset(a);
     pool_free(a->d_ant_steps, s); pool_free(a->d_overflow, s); pool_free(a->d_ant_L, s); a->d_ant_L = nullptr;
     if (!a->d_slab) { pool_free(a->d_path_ids, s); pool_free(a->d_path_dirs, s); }
     pool_free(a->d_gkeys, s); pool_free(a->d_gmasks, s); pool_free(a->d_resume, s); a->d_resume = nullptr; pool_free(a->d_rec_off, s); pool_free(a->d_order, s);
@@ -226,7 +315,46 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     WR_CUDA(dmalloc(&a->d_resume, chunk * sizeof(int4), a->stream));
     int st = sort_plan_create(&a->sort_ants, cm, a->stream);
     if (st != WR_OK) return st;
-    st = sort_plan_create(&a->sort_recs, rec_max, a->stream);
+    // WR_UPDATE_RANKSET: open-addressed table sized for the worst case (every record a distinct slot) at load <= 1/2
+    a->rankset = false;
+    if (a->want_rankset && a->nranks == 1) {
+        const int nwords = (a->w_max + 31) / 32, rw = nwords;
+        size_t T = 1024;
+        while (T < 2 * rec_max) T <<= 1;
+        if (nwords <= kRankSetMaxWords && T * rw * sizeof(uint32_t) <= ((size_t)4 << 30) && T <= ((size_t)1 << 31)) {
+            cudaStream_t s = a->stream;
+            const size_t list_cap = rec_max + 1;
+            {
+                std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+                if (g_rs_cache.rs.ent && g_rs_cache.device == a->device && g_rs_cache.entries == T && g_rs_cache.rs.nwords == nwords &&
+                    g_rs_cache.list_cap == list_cap && g_rs_cache.w_max == a->w_max) {
+                    a->rs = g_rs_cache.rs;
+                    g_rs_cache = RankSetCache();
+                }
+            }
+            if (!a->rs.ent) {
+                WR_CUDA(cudaMalloc(&a->rs.ent, T * sizeof(unsigned long long)));
+                WR_CUDA(cudaMalloc(&a->rs.rows, T * rw * sizeof(uint32_t)));
+                WR_CUDA(cudaMemsetAsync(a->rs.ent, 0, T * sizeof(unsigned long long), s));
+                WR_CUDA(cudaMemsetAsync(a->rs.rows, 0, T * rw * sizeof(uint32_t), s));
+                WR_CUDA(cudaMalloc(&a->rs.list, list_cap * sizeof(uint32_t)));
+                WR_CUDA(cudaMalloc(&a->rs.touched, list_cap * sizeof(uint32_t)));
+                WR_CUDA(cudaMalloc(&a->rs.count, 4 * sizeof(uint32_t)));
+                WR_CUDA(cudaMalloc(&a->rs.vtab, (size_t)2 * (a->w_max + 1) * sizeof(float)));
+            }
+            WR_CUDA(cudaMemsetAsync(a->rs.count, 0, 4 * sizeof(uint32_t), s));
+            a->rs_entries = T; a->rs_list_cap = list_cap;
+            a->rs.tmask = (uint32_t)(T - 1); a->rs.shift = 32 - ceil_log2(T);
+            a->rs.nwords = nwords;
+            if (!a->rs_ev[0]) {
+                int rc = feedback_acquire(&a->h_feedback, &a->d_feedback);
+                if (rc != WR_OK) return rc;
+                for (cudaEvent_t& e : a->rs_ev) WR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
+            a->rankset = true;
+        }
+    }
+    st = sort_plan_create(&a->sort_recs, rec_max, a->stream);   // the record list and its slot sort
     if (st != WR_OK) return st;
     a->alloc_colony = cm;
     return WR_OK;
@@ -241,6 +369,11 @@ static int walk_version(const wr_grid* g)
 static int walk_prefetch()
 {
     static const int env = [] { const char* e = getenv("WR_WALK_PREFETCH"); return e ? atoi(e) : 2; }();
+    return env;
+}
+static int stream_cs()
+{
+    static const int env = [] { const char* e = getenv("WR_STREAM_CS"); return e ? atoi(e) : 1; }();   // evict-first streaming of the tiles without deposits (default on)
     return env;
 }
 static int walk_warm()
@@ -290,6 +423,8 @@ extern "C" int wr_acs_destroy(wr_acs* a)
     pool_free(a->d_best_n, s); pool_free(a->d_best_ids, s); pool_free(a->d_best_dirs, s); pool_free(a->d_tile_off, s); pool_free(a->d_dep_list, s);
     pool_free(a->d_upd_q, s);
     if (a->stream) cudaStreamSynchronize(a->stream);
+    feedback_release(a->h_feedback);
+    for (cudaEvent_t e : a->rs_ev) if (e) cudaEventDestroy(e);
     if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
     delete a;
     return WR_OK;
@@ -304,11 +439,17 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     *out = nullptr;
     WR_REQUIRE(p->K == 6 || p->K == kK26, WR_ERR_INVALID, "wr_acs_create: K must be 6 (the reference's neighbourhood) or 26 (its disabled extension)");
     WR_REQUIRE(p->alpha >= 0 && p->alpha < 64, WR_ERR_INVALID, "wr_acs_create: alpha out of range");
-    WR_REQUIRE(p->update_mode >= WR_UPDATE_FUSED && p->update_mode <= WR_UPDATE_FUSED_TMA, WR_ERR_INVALID, "wr_acs_create: bad update_mode");
+    WR_REQUIRE(p->update_mode >= WR_UPDATE_FUSED && p->update_mode <= WR_UPDATE_RANKSET, WR_ERR_INVALID, "wr_acs_create: bad update_mode");
     WR_REQUIRE((unsigned long long)g->N * p->K < 0xFFFFFFFFull - kUpdTile, WR_ERR_INVALID, "wr_acs_create: grid too large for 32-bit slot ids");
     WR_REQUIRE(g->N >= 2, WR_ERR_INVALID, "wr_acs_create: grid too small");
     wr_acs* a = new wr_acs();
     a->g = g; a->p = *p; a->N = g->N;
+    if (p->update_mode == WR_UPDATE_RANKSET) {   // the record path it alternates with (and falls back to) is FUSED
+        a->want_rankset = true; a->p.update_mode = WR_UPDATE_FUSED;
+        if (const char* e = getenv("WR_RANKSET_POLICY")) a->rs_policy = atoi(e);
+        if (const char* e = getenv("WR_RANKSET_ON")) a->rs_on = (unsigned)atoi(e);
+        if (const char* e = getenv("WR_RANKSET_OFF")) a->rs_off = (unsigned)atoi(e);
+    }
     a->K = p->K;
     a->n_slots = g->N * (size_t)p->K;
     a->n_slots_pad = (a->n_slots + kUpdTile - 1) / kUpdTile * kUpdTile;
@@ -462,6 +603,7 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     }
     k_begin<<<1, 1, 0, a->stream>>>(a->d_state, predict);
     WR_CUDA(cudaGetLastError());
+    a->rs_generation = (a->rs_generation + 1) & 0xFFFFu; a->rs_choice = 0; a->rs_enqueued = 0;
     a->begun = true;
     a->timer.used = 0;
     for (float& m : a->timer.ms) m = 0;
@@ -485,6 +627,10 @@ static void launch_walk2(const WalkArgs& w, bool alpha1, int prefetch, int block
 static void launch_warm(wr_acs* a)
 {
     if (!walk_warm() || walk_version(a->g) != 2 || a->p.update_mode == WR_UPDATE_ATOMIC || a->K != 6) return;
+    if (a->rankset && a->rs_enqueued > 0 && a->rs_choice) {   // rs_choice still names the previous iteration's path here
+        k_rankset_warm<<<kNumSMs, 256, 0, a->stream>>>(a->rs.touched, a->rs.count, a->d_tau, a->d_heur, a->d_state);
+        return;
+    }
     if (a->warm_by_pull) return;   // owner-computes update: k_pull_finals has just touched the rows under the deposits
     const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
     k_path_warm<<<kNumSMs, 256, 0, a->stream>>>(a->d_state, ck, a->d_tau, a->d_heur);
@@ -591,8 +737,8 @@ static int launch_fused(wr_acs* a, const uint32_t* ck, const uint32_t* cv, const
     if (!a->upd_q_zeroed) WR_CUDA(cudaMemsetAsync(a->d_upd_q, 0, 4 * sizeof(uint32_t), s));
     a->upd_q_zeroed = false;
     k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(d_n ? d_n : a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, a->d_dep_list, a->d_upd_q + 2);
-    if (fin) k_update_fused<true><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, fin);
-    else k_update_fused<false><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, nullptr);
+    if (fin) k_update_fused<true><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, fin, stream_cs());
+    else k_update_fused<false><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, nullptr, stream_cs());
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -605,13 +751,13 @@ static int launch_update(wr_acs* a)
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
         return WR_OK;   // evaporation + atomic deposits already issued by launch_deposit_gen
     }
-    int st = sort_pairs(&a->sort_recs, a->dptr_nrec(), a->slot_bits, s, &a->recs_in_b);
+    int st = sort_pairs(&a->sort_recs, a->dptr_nrec_upd(), a->slot_bits, s, &a->recs_in_b);
     if (st != WR_OK) return st;
     const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
     const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     if (a->p.update_mode == WR_UPDATE_FUSED) {
-        int rc = launch_fused(a, ck, cv);
+        int rc = launch_fused(a, ck, cv, a->dptr_nrec_upd());
         if (rc != WR_OK) return rc;
     } else if (a->p.update_mode == WR_UPDATE_FUSED_TMA) {
         k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
@@ -635,7 +781,21 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
     for (int it = 0; it < n; it++) {
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
         launch_warm(a);
-        k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->d_upd_q);
+        if (a->rankset) {   // which deposit path this iteration takes (see k_iter_begin)
+            if (a->rs_enqueued >= (unsigned long long)wr_acs::kRsAhead) WR_CUDA(cudaEventSynchronize(a->rs_ev[a->rs_enqueued % wr_acs::kRsAhead]));
+            if (a->rs_policy == 1 || a->rs_policy == 2) a->rs_choice = a->rs_policy == 1;
+            else {
+                const volatile uint32_t* f = a->h_feedback;
+                const uint32_t tag = f ? f[0] : 0u, prev = f ? f[1] : 0u, tiles = f ? f[2] : 0u, slots = f ? f[3] : 0u;
+                if (f && (tag >> 16) == a->rs_generation && (tag & 0xFFFFu) > 0) {
+                    if (!a->rs_choice && prev == 0 && tiles <= a->rs_on) a->rs_choice = 1;
+                    else if (a->rs_choice && prev == 1 && slots > a->rs_off) a->rs_choice = 0;
+                }
+            }
+        }
+        const bool rs_now = a->rankset && a->rs_choice;
+        k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->d_upd_q,
+                                     a->rankset ? a->rs.count : nullptr, rs_now ? 1 : 0, a->d_feedback, a->rs_generation);
         a->upd_q_zeroed = true;
         int st = launch_walk(a);
         if (st != WR_OK) return st;
@@ -645,10 +805,20 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
         k_best_copy<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_path_ids, a->d_path_dirs, a->cap,
                                       0, (int)a->goal);
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-        st = launch_deposit_gen(a);
-        if (st != WR_OK) return st;
-        st = launch_update(a);
-        if (st != WR_OK) return st;
+        if (rs_now) {   // rank sets instead of sorted records (rankset.cuh): gen | evaporation pass + one ordered chain per touched slot
+            k_rankset_gen<<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal, a->d_Ltab,
+                                                   a->d_onbest, a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
+            if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+            k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho, stream_cs());
+            k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs);
+            WR_CUDA(cudaGetLastError());
+        } else {
+            st = launch_deposit_gen(a);
+            if (st != WR_OK) return st;
+            st = launch_update(a);
+            if (st != WR_OK) return st;
+        }
+        if (a->rankset) { WR_CUDA(cudaEventRecord(a->rs_ev[a->rs_enqueued % wr_acs::kRsAhead], s)); a->rs_enqueued++; }
         a->upd_q_zeroed = false;
         if (it == n - 1) k_iter_end<<<1, 1, 0, s>>>(a->d_state);   // otherwise folded into the next k_iter_begin
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
@@ -1048,6 +1218,16 @@ extern "C" int wr_acs_kernel_ms(wr_acs* a, float out[5])
     return WR_OK;
 }
 
+extern "C" int wr_acs_update_stats(wr_acs* a, uint32_t out[4])
+{
+    WR_REQUIRE(a && out, WR_ERR_INVALID, "wr_acs_update_stats: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    IterState st;
+    WR_CUDA(cudaMemcpy(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost));
+    out[0] = (uint32_t)st.use_rankset; out[1] = st.spread_tiles; out[2] = st.spread_slots; out[3] = st.rankset_iters;
+    return WR_OK;
+}
+
 extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch)
 {
     WR_REQUIRE(a && ms_per_launch && reps > 0 && which >= 0 && which <= 3, WR_ERR_INVALID, "wr_acs_bench_kernel: bad argument");
@@ -1061,15 +1241,20 @@ extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per
     if (which == 2) WR_CUDA(dmalloc(&scratch, a->n_slots_pad * sizeof(float), s));
     const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
     const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
+    const int* d_n = a->dptr_nrec();
+    if (a->rankset) {   // no record list in this mode: the fused kernels run with zero records (count[2] stays 0)
+        ck = cv = a->rs.list;
+        d_n = reinterpret_cast<const int*>(a->rs.count + 2);
+    }
     const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
     const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * 2);
     for (int r = -1; r < reps; r++) {   // one untimed warm-up launch
         if (r == 0) WR_CUDA(cudaEventRecord(e0, s));
         if (which == 0) {
-            int rc = launch_fused(a, ck, cv);
+            int rc = launch_fused(a, ck, cv, d_n);
             if (rc != WR_OK) return rc;
         } else if (which == 3) {
-            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
+            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(d_n, ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
             k_update_tma_ring<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
         } else if (which == 1) {
             k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);

@@ -71,14 +71,34 @@ __global__ void k_begin(IterState* st, float predict)
     st->best_changed = 0;
     st->best_ant = -1;
     st->colony = 0; st->lambda = 0; st->Q = 0;
-    st->n_eligible = 0; st->n_records = 0;
+    st->n_eligible = 0; st->n_records = 0; st->n_records_sort = 0;
+    st->use_rankset = 0; st->spread_tiles = 0xFFFFFFFFu; st->spread_slots = 0xFFFFFFFFu; st->rankset_iters = 0;
 }
 
 // advance: the previous iteration's k_iter_end folded in (iterations enqueued back to back); upd_q: the fused update's
 // three queue words, zeroed here instead of by a memset launch in front of k_tile_offsets.
-__global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, float precision, float tau0, int advance = 0, uint32_t* upd_q = nullptr)
+// rankset_count != nullptr: adaptive handle (WR_UPDATE_RANKSET).  use_rankset is the HOST's choice for this iteration: rank
+// sets pay off once the colony has converged on a few hundred slots, sorted records while it still wanders over ~10^6.
+// What the choice is based on — how concentrated the previous iteration's deposits were — is measured here and
+// published to the host through mapped pinned memory (feedback: {generation << 16 | iteration, path, tiles, slots}); the
+// host reads it without synchronising, a few iterations late (acs.cu keeps itself at most four iterations ahead of the
+// device), and only enqueues the kernels of the path it chose.  Either path gives the same bits, so the lag is invisible.
+__global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, float precision, float tau0, int advance = 0, uint32_t* upd_q = nullptr,
+                             uint32_t* rankset_count = nullptr, int use_rankset = 0, volatile uint32_t* feedback = nullptr, uint32_t generation = 0)
 {   // :247-249
     if (advance) { st->iter++; st->cnt[6]++; }
+    if (rankset_count) {
+        const int prev = st->use_rankset;
+        if (st->iter > 0) { if (prev) st->spread_slots = rankset_count[1]; else if (upd_q) st->spread_tiles = upd_q[2]; }
+        st->use_rankset = use_rankset;
+        if (use_rankset) st->rankset_iters++;
+        rankset_count[0] = 0;
+        if (feedback) {
+            feedback[1] = (uint32_t)prev; feedback[2] = st->spread_tiles; feedback[3] = st->spread_slots;
+            __threadfence_system();
+            feedback[0] = (generation << 16) | ((uint32_t)st->iter & 0xFFFFu);
+        }
+    }
     if (upd_q) { upd_q[0] = 0; upd_q[1] = 0; upd_q[2] = 0; upd_q[3] = 0; }
     float best_L = st->best_L, predict = st->predict;
     int colony = fixed_colony > 0 ? fixed_colony : (int)(0.35 * (double)(best_L < predict ? best_L : predict) / (double)precision);
@@ -457,7 +477,7 @@ __global__ void __launch_bounds__(1024) k_rank_finish(IterState* st, const uint3
         if (threadIdx.x == 1023) carry = excl + len;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { st->n_eligible = (int)elig_total; st->n_records = (int)carry; st->cnt[7] += carry; }
+    if (threadIdx.x == 0) { st->n_eligible = (int)elig_total; st->n_records = (int)carry; st->n_records_sort = st->use_rankset ? 0 : (int)carry; st->cnt[7] += carry; }
 }
 
 // best = agentK (:264): drop the old best path's membership bits ...
@@ -558,7 +578,7 @@ __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const 
                                                       const int* __restrict__ steps26 = nullptr)
 {   // steps26 != nullptr (K = 26): rank_keys holds the bits of the ant's L, its step count is steps26[ant]
     const int r = blockIdx.x;
-    if (r >= st->n_eligible) return;
+    if (r >= st->n_eligible || st->use_rankset) return;   // use_rankset: this iteration's deposits go through rank sets (rankset.cuh)
     const int ant_global = (int)rank_vals[r];
     const int steps = steps26 ? steps26[ant_global] : (int)rank_keys[r];
     const float L_ant = steps26 ? __uint_as_float(rank_keys[r]) : Ltab[steps];
@@ -696,8 +716,16 @@ __device__ __forceinline__ void apply_runs(float* buf, uint32_t base, const uint
 // ------------------------------------------------------------------------------------------
 // K3 split variants
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_evaporate(float4* __restrict__ tau4, size_t n4, float rho)
-{   // :268-272, 16 B per thread per trip, grid-stride
+__global__ void __launch_bounds__(256) k_evaporate(float4* __restrict__ tau4, size_t n4, float rho, int cs = 0)
+{   // :268-272, 16 B per thread per trip, grid-stride; cs: streaming (evict-first) accesses, see stream_tile
+    if (cs) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            float4 v = __ldcs(tau4 + i);
+            v.x = __fmul_rn(v.x, rho); v.y = __fmul_rn(v.y, rho); v.z = __fmul_rn(v.z, rho); v.w = __fmul_rn(v.w, rho);
+            __stcs(tau4 + i, v);
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 v = tau4[i];
         v.x = __fmul_rn(v.x, rho); v.y = __fmul_rn(v.y, rho); v.z = __fmul_rn(v.z, rho); v.w = __fmul_rn(v.w, rho);
@@ -812,17 +840,20 @@ __global__ void __launch_bounds__(kUpdThreads) k_update_tma_ring(float* tau, uns
 constexpr int kFusedCtasPerSm = 5;   // 48 registers per thread (the warp-cooperative chain) -> 5 x 256 threads per SM
 constexpr int kFusedChunk = 8;       // plain tiles per queue grab (128 KB)
 
+// CS: streaming (evict-first) loads and stores for tiles nobody touches again this iteration, so that the pass does not
+// leave L2 full of dirty pheromone lines when the next walk starts gathering rows.
+template <bool CS = false>
 __device__ __forceinline__ void stream_tile(float* tau, unsigned t, float rho, int tid)
 {
     constexpr int kVec = kUpdTile / 4 / kUpdThreads;   // float4 per thread per tile
     float4* g4 = reinterpret_cast<float4*>(tau + (size_t)t * kUpdTile);
     float4 v[kVec];
 #pragma unroll
-    for (int j = 0; j < kVec; j++) v[j] = g4[j * kUpdThreads + tid];
+    for (int j = 0; j < kVec; j++) v[j] = CS ? __ldcs(g4 + j * kUpdThreads + tid) : g4[j * kUpdThreads + tid];
 #pragma unroll
     for (int j = 0; j < kVec; j++) {
         v[j].x = __fmul_rn(v[j].x, rho); v[j].y = __fmul_rn(v[j].y, rho); v[j].z = __fmul_rn(v[j].z, rho); v[j].w = __fmul_rn(v[j].w, rho);
-        g4[j * kUpdThreads + tid] = v[j];
+        if (CS) __stcs(g4 + j * kUpdThreads + tid, v[j]); else g4[j * kUpdThreads + tid] = v[j];
     }
 }
 
@@ -834,7 +865,8 @@ __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(f
                                                                                 const uint32_t* __restrict__ rec_keys,
                                                                                 const uint32_t* __restrict__ rec_vals,
                                                                                 const uint32_t* __restrict__ tile_off,
-                                                                                const uint32_t* __restrict__ dep_list, uint32_t* q, uint32_t* fin)
+                                                                                const uint32_t* __restrict__ dep_list, uint32_t* q, uint32_t* fin,
+                                                                                int cs = 0)
 {
     __shared__ unsigned s_next;
     __shared__ uint32_t s_off[kFusedChunk + 1];
@@ -861,7 +893,7 @@ __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(f
         if (c0 >= ntiles) break;
         const unsigned c1 = min(c0 + kFusedChunk, ntiles);
         for (unsigned t = c0; t < c1; t++)
-            if (s_off[t - c0] == s_off[t - c0 + 1]) stream_tile(tau, t, rho, tid);
+            if (s_off[t - c0] == s_off[t - c0 + 1]) { if (cs) stream_tile<true>(tau, t, rho, tid); else stream_tile<false>(tau, t, rho, tid); }
         __syncthreads();   // s_off / s_next are reused by the next grab
     }
 }

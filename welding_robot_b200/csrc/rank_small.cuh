@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
         if (threadIdx.x == kRankSmallThreads - 1) carry = excl + len;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { st->n_eligible = (int)elig_total; st->n_records = (int)carry; st->cnt[7] += carry; }
+    if (threadIdx.x == 0) { st->n_eligible = (int)elig_total; st->n_records = (int)carry; st->n_records_sort = st->use_rankset ? 0 : (int)carry; st->cnt[7] += carry; }
 
     // ---- k_best_clear: best = agentK (:264) drops the old best path's membership bits ----
     if (st->best_changed) {   // written by thread 0 before the barrier above

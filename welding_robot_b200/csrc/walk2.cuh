@@ -53,7 +53,7 @@ template <bool GLOBAL> struct TabRef {
 // Must run BEFORE k_iter_begin (which clears n_records).
 __global__ void __launch_bounds__(256) k_path_warm(const IterState* st, const uint32_t* __restrict__ rec_keys, const float* tau, const float* heur)
 {
-    const int n = st->n_records;
+    const int n = st->n_records_sort;   // 0 when the last iteration's deposits went through rank sets (k_rankset_warm covers it)
     uint32_t acc = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t node = rec_keys[i] / 6u;

@@ -109,6 +109,11 @@ struct IterState {
     int best_ant;        // global ant index that produced it (this iteration)
     int n_eligible;      // ants that deposit this iteration (order <= lambda-1, arrived)
     int n_records;       // deposit records this iteration
+    int n_records_sort;  // = n_records, or 0 on iterations whose deposits go through rank sets (the record path's kernels then run empty)
+    int use_rankset;     // adaptive handles (WR_UPDATE_RANKSET): this iteration's deposit path, decided by k_iter_begin
+    unsigned spread_tiles;   // pheromone tiles that received deposits in the last record-path iteration
+    unsigned spread_slots;   // distinct slots that received deposits in the last rank-set iteration
+    unsigned rankset_iters;  // iterations that took the rank-set path since begin
     unsigned queue;      // walk work queue (pass 1)
     unsigned queue2;     // pass 2 (resumed ants): its own counter, so no reset launch sits between the two passes
     unsigned overflow_n; // ants whose shared-memory visited table overflowed (pass 2)
