@@ -75,16 +75,15 @@ def worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(600)
-def test_sharded_equals_single_gpu_world2():
+def run_world(world):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=500) for _ in procs]
@@ -92,3 +91,14 @@ def test_sharded_equals_single_gpu_world2():
         p.join(timeout=60)
     for rank, status, info in res:
         assert status == "ok", "rank %d: %s" % (rank, info)
+
+
+@pytest.mark.timeout(600)
+def test_sharded_equals_single_gpu_world2():
+    run_world(2)
+
+
+@pytest.mark.timeout(600)
+def test_sharded_equals_single_gpu_world4():
+    """four ranks: three peers to pull final values from, slot slices that do not divide evenly"""
+    run_world(4)

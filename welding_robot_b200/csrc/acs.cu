@@ -241,6 +241,21 @@ static void free_rankset(wr_acs* a)
     a->rankset = false; a->rs_entries = 0;
 }
 
+// Sharded searches created in a loop (one per request): the peer slab and the IPC mappings of the peers' slabs are kept
+// across handles.  cudaMalloc/cudaFree of a ~0.5 GB slab and cudaIpcOpenMemHandle/Close of every peer's cost tens of
+// milliseconds per search; a parked slab keeps its address, hence its IPC handle, hence the peers' mappings stay valid.
+struct SlabCache {
+    int device = -1;
+    size_t bytes = 0;
+    unsigned char* ptr = nullptr;
+};
+static SlabCache g_slab_cache;
+struct IpcMapping {
+    cudaIpcMemHandle_t handle;
+    void* ptr = nullptr;
+};
+static std::vector<IpcMapping> g_ipc_maps;   // one per peer rank (a process drives one GPU)
+
 static void free_colony_buffers(wr_acs* a)
 {
     cudaStream_t s = a->stream;
@@ -253,10 +268,15 @@ static void free_colony_buffers(wr_acs* a)
     a->d_ant_steps = nullptr; a->d_path_ids = nullptr; a->d_path_dirs = nullptr; a->d_overflow = nullptr;
     a->d_gkeys = nullptr; a->d_gmasks = nullptr; a->d_rec_off = nullptr; a->d_order = nullptr;
     sort_plan_destroy(&a->sort_ants, s); sort_plan_destroy(&a->sort_recs, s);
-    for (void* p : a->ipc_opened) cudaIpcCloseMemHandle(p);
-    a->ipc_opened.clear();
+    a->ipc_opened.clear();   // the mappings live in g_ipc_maps
     if (a->d_slab) {
-        cudaStreamSynchronize(s); cudaFree(a->d_slab); a->d_slab = nullptr;
+        cudaStreamSynchronize(s);
+        {
+            std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+            if (g_slab_cache.ptr) cudaFree(g_slab_cache.ptr);   // peers that still map it re-open on the next handle exchange
+            g_slab_cache.device = a->device; g_slab_cache.bytes = a->slab_bytes; g_slab_cache.ptr = a->d_slab;
+        }
+        a->d_slab = nullptr;
         a->d_path_ids = nullptr; a->d_path_dirs = nullptr;   // they pointed into the slab
     }
     pool_free(a->d_tabs, s); a->d_tabs = nullptr;
@@ -287,7 +307,14 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
         for (int b = 0; b < 2; b++) { a->off_dirs[b] = o; o += up(chunk * cap); }
         for (int b = 0; b < 2; b++) { a->off_fin[b] = o; o += up((4 + 2 * rec_max) * sizeof(uint32_t)); }
         a->slab_bytes = o;
-        WR_CUDA(cudaMalloc(&a->d_slab, a->slab_bytes));
+        {
+            std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+            if (g_slab_cache.ptr && g_slab_cache.device == a->device && g_slab_cache.bytes == a->slab_bytes) {
+                a->d_slab = g_slab_cache.ptr;
+                g_slab_cache = SlabCache();
+            }
+        }
+        if (!a->d_slab) WR_CUDA(cudaMalloc(&a->d_slab, a->slab_bytes));
         for (int b = 0; b < 2; b++) WR_CUDA(cudaMemsetAsync(a->d_slab + a->off_fin[b], 0, 4 * sizeof(uint32_t), a->stream));
         WR_CUDA(dmalloc(&a->d_tabs, (size_t)6 * a->nranks * sizeof(void*), a->stream));
         WR_CUDA(dmalloc(&a->d_nq, sizeof(int), a->stream));
@@ -1010,8 +1037,17 @@ extern "C" int wr_acs_peer_import(wr_acs* a, const void* all_ipc_handles)
     for (int r = 0; r < a->nranks; r++) {
         if (r == a->rank) { slabs[r] = a->d_slab; continue; }
         void* p = nullptr;
-        WR_CUDA(cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess));
-        a->ipc_opened.push_back(p);
+        {
+            std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+            if (g_ipc_maps.size() < (size_t)a->nranks) g_ipc_maps.resize(a->nranks);
+            IpcMapping& m = g_ipc_maps[r];
+            if (m.ptr && memcmp(&m.handle, &h[r], sizeof(cudaIpcMemHandle_t)) == 0) p = m.ptr;   // the peer re-used its parked slab
+            else {
+                if (m.ptr) { cudaIpcCloseMemHandle(m.ptr); m.ptr = nullptr; }
+                WR_CUDA(cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess));
+                m.handle = h[r]; m.ptr = p;
+            }
+        }
         slabs[r] = static_cast<const unsigned char*>(p);
     }
     return install_peers(a, slabs);

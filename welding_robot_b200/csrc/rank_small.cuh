@@ -1,5 +1,5 @@
 // Colony ranking in ONE kernel for colonies of up to kRankSmallMax ants (the reference's adaptive colonies are tens of
-// ants, BASELINE's C2 colony is 4096): keys, stable LSD radix sort, best decision, eligibility, record offsets and the
+// ants, BASELINE's C2 colony is 4096, four ranks of it 16384): keys, stable LSD radix sort, best decision, eligibility, record offsets and the
 // old best path's membership bits — what launch_rank otherwise spreads over k_rank_keys + 3 kernels per sort pass +
 // k_rank_finish + k_best_clear (10 dependent launches whose cost is launch latency, not work).
 //
@@ -13,11 +13,11 @@
 
 namespace wr {
 
-constexpr int kRankSmallMax = 8192;
+constexpr int kRankSmallMax = 16384;
 constexpr int kRankSmallThreads = 1024;
 constexpr int kRankSmallRounds = kRankSmallMax / kRankSmallThreads;   // 32-key rounds per warp
-// dynamic shared memory: keys[2][max] + vals[2][max] (u32) + whist[32][256] (u32)
-constexpr size_t kRankSmallSmem = (size_t)4 * kRankSmallMax * sizeof(uint32_t) + (size_t)32 * 256 * sizeof(uint32_t);
+// dynamic shared memory: keys[2][max] (u32) + vals[2][max] (u16: ant indices < 65536) + whist[32][256] (u32) = 224 KB
+constexpr size_t kRankSmallSmem = (size_t)2 * kRankSmallMax * sizeof(uint32_t) + (size_t)2 * kRankSmallMax * sizeof(uint16_t) + (size_t)32 * 256 * sizeof(uint32_t);
 
 // steps26 / ant_L: K = 26 (key = bits of L); else key = steps (cap+1 for a dead ant), as k_rank_keys / k_rank_keys26.
 __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st, const int* __restrict__ ant_steps, const float* __restrict__ ant_L, int cap,
@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
 {
     extern __shared__ __align__(16) uint32_t rs_smem[];
     uint32_t* kbuf[2] = {rs_smem, rs_smem + kRankSmallMax};
-    uint32_t* vbuf[2] = {rs_smem + 2 * kRankSmallMax, rs_smem + 3 * kRankSmallMax};
-    uint32_t* whist = rs_smem + 4 * kRankSmallMax;   // [warp][digit]
+    uint16_t* vbase = reinterpret_cast<uint16_t*>(rs_smem + 2 * kRankSmallMax);
+    uint16_t* vbuf[2] = {vbase, vbase + kRankSmallMax};
+    uint32_t* whist = rs_smem + 3 * kRankSmallMax;   // [warp][digit]
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry, elig_total;
 
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
     for (int i = threadIdx.x; i < n; i += kRankSmallThreads) {
         const int s = ant_steps[i];
         kbuf[0][i] = k26 ? (s < 0 ? 0x7F800000u : __float_as_uint(ant_L[i])) : (s < 0 ? (uint32_t)(cap + 1) : (uint32_t)s);
-        vbuf[0][i] = (uint32_t)i;
+        vbuf[0][i] = (uint16_t)i;
     }
     __syncthreads();
 
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
     int src = 0;
     for (int shift = 0; shift < key_bits; shift += 8, src ^= 1) {
         const uint32_t* ki = kbuf[src];
-        const uint32_t* vi = vbuf[src];
+        const uint16_t* vi = vbuf[src];
         for (int d = lane; d < 256; d += 32) whist[w * 256 + d] = 0;
         __syncwarp();
         uint32_t local[kRankSmallRounds];   // position of this thread's key of round r among its warp's keys of the same digit
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
         }
         __syncthreads();
         uint32_t* ko = kbuf[src ^ 1];
-        uint32_t* vo = vbuf[src ^ 1];
+        uint16_t* vo = vbuf[src ^ 1];
 #pragma unroll
         for (int r = 0; r < kRankSmallRounds; r++) {
             if (r < rounds) {
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
         __syncthreads();
     }
     const uint32_t* keys = kbuf[src];
-    const uint32_t* vals = vbuf[src];
+    const uint16_t* vals = vbuf[src];
 
     // ---- k_rank_finish: best decision (:263-264), eligibility (:200), record offsets ----
     const float lambda = st->lambda;

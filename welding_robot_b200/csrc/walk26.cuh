@@ -97,7 +97,7 @@ __global__ void k_rank_keys26(const IterState* st, const int* __restrict__ ant_s
 // L} and is resumed by pass 2 (GLOBAL) — exact, its draws are a pure function of (iteration, ant, step).
 // ------------------------------------------------------------------------------------------
 template <bool GLOBAL>
-__global__ void __launch_bounds__(kWalk26Threads, 7) k_walk26(WalkArgs a)
+__global__ void __launch_bounds__(kWalk26Threads) k_walk26(WalkArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned FULL = 0xffffffffu;
