@@ -38,6 +38,18 @@ SEED = 1
 PRECISION = 0.823812 / 235.5
 WALL = 10
 CUBE = 256
+MESH = "simplified_piece"
+LABEL = "C2: ACSRank_3D, simplified_piece @256-long grid in 256^3"
+
+
+def select_workload(name):
+    """C2 (BASELINE.json configs[1]) is the bench workload; C3 (configs[2]: origin_piece at a 512-long grid in 512^3, 8192 ants per
+    GPU, the pheromone field 3.2 GB per GPU) is the multi-GPU scaling case north_star names — an exploration run, never the default."""
+    global CUBE, PRECISION, MESH, LABEL, ANTS_PER_GPU, STEP_CAP
+    if name == "C3":
+        CUBE, PRECISION, MESH = 512, 0.823812 / 491.5, "origin_piece"
+        ANTS_PER_GPU, STEP_CAP = 8192, 16384
+        LABEL = "C3: ACSRank_3D, origin_piece @512-long grid in 512^3"
 PREDICT = 1.0                # with a fixed colony only Q of the pre-arrival iterations depends on it (ACSRank_3D.hpp:249)
 WALK_BYTES_PER_STEP = 30     # SURVEY.md §8d: 4*K tau + K/8 occupancy + 4 id + 1 dir, K = 6
 UPDATE_BYTES_PER_SLOT = 8    # 4 read + 4 write per directed slot per iteration
@@ -173,7 +185,7 @@ def embed(free_zyx, gmin, gmax):
 def build_workload_gpu():
     """Natural grid from the product's GPU voxeliser (K1)."""
     import welding_robot_b200 as wr
-    tris = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))["simplified_piece"]
+    tris = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))[MESH]
     g = wr.GridMap()
     with contextlib.redirect_stdout(io.StringIO()):
         g.creatGridMap(tris, PRECISION, WALL)
@@ -188,7 +200,7 @@ def build_workload_cpu():
     """The same workload built on the CPU (reference arm): the oracle's box-restricted voxeliser gives
     the natural grid (the reference's own O(T*N) loop would need ~140 s for it)."""
     from oracle import oracle as O
-    tris = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))["simplified_piece"]
+    tris = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))[MESH]
     G = O.Grid.from_triangles(tris, PRECISION, WALL, O.VOX_AABB)
     rx, ry, rz = G.dims
     v = tris[:, 3:].reshape(-1, 3)
@@ -388,14 +400,14 @@ def run_ours(args):
         "metric": "ant-steps/s", "value": value, "unit": "ant-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic: reference mesh fixture voxelised on the GPU, embedded in 256^3 free space; synthetic start/goal",
-        "config": {"workload": "C2: ACSRank_3D, simplified_piece @256-long grid in 256^3, %d ants/GPU, K=6" % args.ants,
+        "config": {"workload": "%s, %d ants/GPU, K=6" % (LABEL, args.ants),
                    "grid": [CUBE, CUBE, CUBE], "natural_grid": list(wl["natural"]), "ants": colony, "iters_per_step": args.iters,
                    "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic", "fused_tma", "rankset"][args.update_mode],
                    "parallelism": "ants sharded x%d" % world,
                    "exchange": ("none (1 GPU)" if world == 1 else
                                 ("NVLink peer memory (trails read from their owners' HBM), %s update" % ("owner-computes (slot slices)" if driver.sliced else "replicated"))
                                 if driver.peer else "NCCL all_reduce merges, replicated update"),
-                   "l2_rule": "inputs larger than L2: the 403 MB pheromone field is streamed from HBM every iteration"},
+                   "l2_rule": "inputs larger than L2: the %d MB pheromone field is streamed from HBM every iteration" % (n_nodes * 6 * 4 // 1000000)},
         "acs_iterations_per_s": iters_done / (ms * 1e-3),
         "ant_steps": steps_done, "arrived_local": c1["arrived"] - c0["arrived"], "ants_local": c1["ants"] - c0["ants"],
         "mean_steps_per_ant": local_steps / ants_done,
@@ -536,7 +548,7 @@ def run_reference(args):
         "impl": "reference", "metric": "ant-steps/s", "value": value, "unit": "ant-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic: same C2 grid as the GPU arm, built on the CPU",
-        "config": {"workload": "C2: ACSRank_3D, simplified_piece @256-long grid in 256^3, %d ants/GPU, K=6" % ANTS_PER_GPU,
+        "config": {"workload": "%s, %d ants/GPU, K=6" % (LABEL, ANTS_PER_GPU),
                    "grid": [CUBE, CUBE, CUBE], "sample_ants": args.cpu_ants, "processes": workers},
         "cpu_baseline": {"value": value, "unit": "ant-steps/s", "cores": workers, "kind": res[0]["kind"],
                          "sample": "%d timed first-iterations of computeSolution (ACSRank_3D.hpp:220-305) with %d-ant colonies on the 256^3 grid, "
@@ -553,7 +565,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--iters", type=int, default=5, help="ACS iterations per step")
-    ap.add_argument("--ants", type=int, default=ANTS_PER_GPU, help="ants per GPU (default: the C2 colony; other values are exploration runs)")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3"], help="C2 = the bench workload; C3 = the 512^3 scaling case (exploration run)")
+    ap.add_argument("--ants", type=int, default=0, help="ants per GPU (default: the workload's colony; other values are exploration runs)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--update-mode", type=int, default=4, help="WR_UPDATE_*: 4 = adaptive rank sets | sorted records + fused pass (default), 0 = fused")
     ap.add_argument("--cpu-ants", type=int, default=1024, help="colony size of the CPU sample")
@@ -564,6 +577,11 @@ def main():
     ap.add_argument("--worker-mode", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--worker", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.ants <= 0:
+        args.ants = ANTS_PER_GPU
+    if args.workload != "C2":
+        args.no_k26 = True
     if args.impl == "reference":
         if args.worker_mode:
             reference_worker(args)

@@ -160,7 +160,7 @@ struct wr_acs {
     static constexpr int kRsAhead = 4;
     cudaEvent_t rs_ev[kRsAhead] = {};
     unsigned long long rs_enqueued = 0;
-    unsigned rs_on = 1600, rs_off = 60000;   // switch thresholds: deposit tiles / distinct slots (WR_RANKSET_ON / WR_RANKSET_OFF)
+    unsigned rs_on = 2000, rs_off = 120000;   // switch thresholds: deposit tiles / distinct slots (WR_RANKSET_ON / WR_RANKSET_OFF)
     bool upd_q_zeroed = false;        // this iteration's k_iter_begin already cleared d_upd_q (wr_acs_iterate)
 
     const void** tab(int kind, unsigned par) const { return d_tabs + ((size_t)kind * 2 + par) * nranks; }
