@@ -27,5 +27,5 @@ for target in (1, 2, 3, 5, 10, 15, 20, 25, 30, 35, 40, 50, 60, 80, 120):
     ms = acs.kernelMs(); c = acs.counters()
     d = {k: (ms[k] - (prev[k] if prev else 0.0)) / (target - done) for k in ms}
     print("mode %d K %d iter %3d..%3d: %s records/iter %d %s" % (mode, K, done + 1, target, {k: round(v, 4) for k, v in d.items()},
-                                                               (c["deposit_records"] - prec) // (target - done), acs.updateStats()), flush=True)
+                                                               (c["deposit_records"] - prec) // (target - done), (acs.updateStats(), acs.fieldStats())), flush=True)
     prev, prec, done = ms, c["deposit_records"], target

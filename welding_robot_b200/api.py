@@ -476,6 +476,12 @@ class ACS_Rank(GridMap):
         check(lib().wr_acs_update_stats(self._need(), ptr(out)))
         return dict(rankset_last=int(out[0]), deposit_tiles=int(out[1]), distinct_slots=int(out[2]), rankset_iterations=int(out[3]))
 
+    def fieldStats(self):
+        """Clean-tile field: (tiles the evaporation pass touches, tiles of the field)."""
+        out = np.zeros(2, np.uint64)
+        check(lib().wr_acs_field_stats(self._need(), ptr(out)))
+        return int(out[0]), int(out[1])
+
     def benchKernel(self, which, reps=20):
         """Average device ms of one update-path kernel run alone (0 fused update, 1 float4 evaporation, 2 D2D copy, 3 all-TMA ring variant)."""
         ms = C.c_float()

@@ -162,6 +162,10 @@ struct wr_acs {
     unsigned long long rs_enqueued = 0;
     unsigned rs_on = 2000, rs_off = 120000;   // switch thresholds: deposit tiles / distinct slots (WR_RANKSET_ON / WR_RANKSET_OFF)
     bool upd_q_zeroed = false;        // this iteration's k_iter_begin already cleared d_upd_q (wr_acs_iterate)
+    // clean-tile field (acs_kernels.cuh): per-tile dirty flags; lazy = in-bounds slots start as sentinels (FUSED / RANKSET handles)
+    uint8_t* d_dirty = nullptr;
+    bool lazy = false;
+    bool oob_zero = true;             // out-of-bounds slots still hold their initial 0 (until the first reset())
 
     const void** tab(int kind, unsigned par) const { return d_tabs + ((size_t)kind * 2 + par) * nranks; }
     uint32_t* fin_buf(unsigned par) const { return reinterpret_cast<uint32_t*>(d_slab + off_fin[par]); }
@@ -448,7 +452,7 @@ extern "C" int wr_acs_destroy(wr_acs* a)
     cudaStream_t s = a->stream;
     pool_free(a->d_tau, s); pool_free(a->d_heur, s); pool_free(a->d_state, s); pool_free(a->d_onbest, s); pool_free(a->d_Ltab, s);
     pool_free(a->d_best_n, s); pool_free(a->d_best_ids, s); pool_free(a->d_best_dirs, s); pool_free(a->d_tile_off, s); pool_free(a->d_dep_list, s);
-    pool_free(a->d_upd_q, s);
+    pool_free(a->d_upd_q, s); pool_free(a->d_dirty, s);
     if (a->stream) cudaStreamSynchronize(a->stream);
     feedback_release(a->h_feedback);
     for (cudaEvent_t e : a->rs_ev) if (e) cudaEventDestroy(e);
@@ -493,12 +497,23 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     a->own_stream = true;
     WR_CUDA_A(dmalloc(&a->d_tau, a->n_slots_pad * sizeof(float), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_tau, 0, a->n_slots_pad * sizeof(float), a->stream));
-    if (a->K == kK26) k_tau_init26<<<(unsigned)((a->n_slots + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, p->tau0);
-    else k_tau_init<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, p->tau0);
+    // clean-tile field for the modes whose kernels know the sentinel (FUSED and the adaptive RANKSET); WR_LAZY_TAU=0 materialises it
+    {
+        const char* e = getenv("WR_LAZY_TAU");
+        a->lazy = a->p.update_mode == WR_UPDATE_FUSED && !(e && atoi(e) == 0);
+    }
+    WR_CUDA_A(dmalloc(&a->d_dirty, (size_t)a->ntiles + 1, a->stream));
+    WR_CUDA_A(cudaMemsetAsync(a->d_dirty, a->lazy ? 0 : 1, (size_t)a->ntiles + 1, a->stream));
+    {
+        const float init_val = a->lazy ? -0.0f : p->tau0;   // -0.0f: the sentinel (kSentinelBits)
+        if (a->K == kK26) k_tau_init26<<<(unsigned)((a->n_slots + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, init_val);
+        else k_tau_init<<<(unsigned)((a->N + 255) / 256), 256, 0, a->stream>>>(a->d_tau, g->rx, g->ry, g->rz, a->N, init_val);
+    }
     WR_CUDA_A(cudaGetLastError());
     WR_CUDA_A(dmalloc(&a->d_state, sizeof(IterState), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_state, 0, sizeof(IterState), a->stream));
     k_begin<<<1, 1, 0, a->stream>>>(a->d_state, 0.0f);
+    k_set_base<<<1, 1, 0, a->stream>>>(a->d_state, p->tau0);
     WR_CUDA_A(dmalloc(&a->d_onbest, (a->N / 32 + 2) * sizeof(uint32_t), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_onbest, 0, (a->N / 32 + 2) * sizeof(uint32_t), a->stream));
     // L after s steps: precision added s times in float (Agent::addNextNode :78)
@@ -764,8 +779,10 @@ static int launch_fused(wr_acs* a, const uint32_t* ck, const uint32_t* cv, const
     if (!a->upd_q_zeroed) WR_CUDA(cudaMemsetAsync(a->d_upd_q, 0, 4 * sizeof(uint32_t), s));
     a->upd_q_zeroed = false;
     k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(d_n ? d_n : a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, a->d_dep_list, a->d_upd_q + 2);
-    if (fin) k_update_fused<true><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, fin, stream_cs());
-    else k_update_fused<false><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, nullptr, stream_cs());
+    if (fin) k_update_fused<true><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, fin, stream_cs(),
+                                                                                      a->d_state, a->d_dirty);
+    else k_update_fused<false><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, nullptr, stream_cs(),
+                                                                                 a->d_state, a->d_dirty);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -822,7 +839,7 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
         }
         const bool rs_now = a->rankset && a->rs_choice;
         k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->d_upd_q,
-                                     a->rankset ? a->rs.count : nullptr, rs_now ? 1 : 0, a->d_feedback, a->rs_generation);
+                                     a->rankset ? a->rs.count : nullptr, rs_now ? 1 : 0, a->d_feedback, a->rs_generation, a->p.rho);
         a->upd_q_zeroed = true;
         int st = launch_walk(a);
         if (st != WR_OK) return st;
@@ -836,8 +853,8 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
             k_rankset_gen<<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal, a->d_Ltab,
                                                    a->d_onbest, a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
             if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-            k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho, stream_cs());
-            k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs);
+            k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
+            k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty);
             WR_CUDA(cudaGetLastError());
         } else {
             st = launch_deposit_gen(a);
@@ -847,7 +864,7 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
         }
         if (a->rankset) { WR_CUDA(cudaEventRecord(a->rs_ev[a->rs_enqueued % wr_acs::kRsAhead], s)); a->rs_enqueued++; }
         a->upd_q_zeroed = false;
-        if (it == n - 1) k_iter_end<<<1, 1, 0, s>>>(a->d_state);   // otherwise folded into the next k_iter_begin
+        if (it == n - 1) k_iter_end<<<1, 1, 0, s>>>(a->d_state, a->p.rho);   // otherwise folded into the next k_iter_begin
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     }
     WR_CUDA(cudaGetLastError());
@@ -998,7 +1015,7 @@ extern "C" int wr_acs_finish_iteration(wr_acs* a)
     WR_REQUIRE(a && a->begun, WR_ERR_STATE, "wr_acs_finish_iteration: bad state");
     int st = launch_update(a);
     if (st != WR_OK) return st;
-    k_iter_end<<<1, 1, 0, a->stream>>>(a->d_state);
+    k_iter_end<<<1, 1, 0, a->stream>>>(a->d_state, a->p.rho);
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), a->stream);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
@@ -1088,7 +1105,7 @@ extern "C" int wr_acs_finish_iteration_peer(wr_acs* a, const int* dev_all_steps,
     if (!sliced) {
         st = launch_update(a);
         if (st != WR_OK) return st;
-        k_iter_end<<<1, 1, 0, s>>>(a->d_state);
+        k_iter_end<<<1, 1, 0, s>>>(a->d_state, a->p.rho);
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
         WR_CUDA(cudaGetLastError());
         return WR_OK;
@@ -1106,7 +1123,7 @@ extern "C" int wr_acs_finish_iteration_peer(wr_acs* a, const int* dev_all_steps,
     WR_CUDA(cudaMemsetAsync(fin, 0, 4 * sizeof(uint32_t), s));
     st = launch_fused(a, ck, cv, a->d_nq, fin);
     if (st != WR_OK) return st;
-    k_iter_end<<<1, 1, 0, s>>>(a->d_state);
+    k_iter_end<<<1, 1, 0, s>>>(a->d_state, a->p.rho);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -1119,7 +1136,7 @@ extern "C" int wr_acs_pull_finals(wr_acs* a)
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
     k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(a->d_tau, walk_warm() ? a->d_heur : nullptr, reinterpret_cast<const uint32_t* const*>(a->tab(2, a->parity)),
-                                              a->nranks, a->rank);
+                                              a->nranks, a->rank, a->d_dirty);
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
@@ -1137,7 +1154,13 @@ extern "C" int wr_acs_reset(wr_acs* a)
 {   // reset() :307-315: every slot (out-of-bounds ones included) back to tau0
     WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_reset: null");
     WR_CUDA(cudaSetDevice(a->device));
-    k_tau_fill<<<kNumSMs * 8, 256, 0, a->stream>>>(a->d_tau, a->n_slots, a->p.tau0);
+    if (a->lazy) {   // clean-tile field: back to all-sentinel with base = tau0; after the first reset only the dirty tiles need rewriting
+        k_tau_reset_tiles<<<kNumSMs * 8, 256, 0, a->stream>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->d_dirty, a->oob_zero ? 1 : 0);
+        a->oob_zero = false;
+    } else {
+        k_tau_fill<<<kNumSMs * 8, 256, 0, a->stream>>>(a->d_tau, a->n_slots, a->p.tau0);
+    }
+    k_set_base<<<1, 1, 0, a->stream>>>(a->d_state, a->p.tau0);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -1171,6 +1194,14 @@ extern "C" int wr_acs_download_pheromone(wr_acs* a, float* tau, size_t n)
     WR_REQUIRE(n >= a->n_slots, WR_ERR_CAPACITY, "wr_acs_download_pheromone: buffer too small");
     WR_CUDA(cudaStreamSynchronize(a->stream));
     WR_CUDA(cudaMemcpy(tau, a->d_tau, a->n_slots * sizeof(float), cudaMemcpyDeviceToHost));
+    if (a->lazy) {   // clean-tile field: a sentinel stands for the value every never-deposited slot holds now
+        IterState st;
+        WR_CUDA(cudaMemcpy(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost));
+        uint32_t* w = reinterpret_cast<uint32_t*>(tau);
+        uint32_t basebits;
+        memcpy(&basebits, &st.base, sizeof basebits);
+        for (size_t i = 0; i < a->n_slots; i++) if (w[i] == kSentinelBits) w[i] = basebits;
+    }
     return WR_OK;
 }
 extern "C" int wr_acs_upload_pheromone(wr_acs* a, const float* tau, size_t n)
@@ -1179,6 +1210,7 @@ extern "C" int wr_acs_upload_pheromone(wr_acs* a, const float* tau, size_t n)
     WR_REQUIRE(n == a->n_slots, WR_ERR_INVALID, "wr_acs_upload_pheromone: size mismatch");
     WR_CUDA(cudaStreamSynchronize(a->stream));
     WR_CUDA(cudaMemcpy(a->d_tau, tau, a->n_slots * sizeof(float), cudaMemcpyHostToDevice));
+    WR_CUDA(cudaMemset(a->d_dirty, 1, (size_t)a->ntiles + 1));   // explicit values everywhere: every tile takes part in the evaporation
     return WR_OK;
 }
 
@@ -1261,6 +1293,18 @@ extern "C" int wr_acs_update_stats(wr_acs* a, uint32_t out[4])
     IterState st;
     WR_CUDA(cudaMemcpy(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost));
     out[0] = (uint32_t)st.use_rankset; out[1] = st.spread_tiles; out[2] = st.spread_slots; out[3] = st.rankset_iters;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_field_stats(wr_acs* a, uint64_t out[2])
+{
+    WR_REQUIRE(a && out, WR_ERR_INVALID, "wr_acs_field_stats: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    std::vector<uint8_t> h(a->ntiles);
+    WR_CUDA(cudaMemcpy(h.data(), a->d_dirty, a->ntiles, cudaMemcpyDeviceToHost));
+    uint64_t n = 0;
+    for (uint8_t v : h) n += v ? 1 : 0;
+    out[0] = n; out[1] = a->ntiles;
     return WR_OK;
 }
 

@@ -23,6 +23,20 @@ constexpr int kUpdTile = 4096;                             // floats per TMA til
 constexpr int kUpdStages = 4;
 constexpr int kUpdThreads = 256;
 
+// ------------------------------------------------------------------------------------------
+// Clean-tile pheromone field.  The reference multiplies EVERY slot by rho every iteration (:268-272) — its wall-clock
+// bottleneck — but a slot that never received a deposit holds the same value as every other such slot: tau0 after
+// initFromGridMap/reset(), then fmul(.., rho) once per iteration.  That one float sequence is kept in IterState::base, the
+// slots themselves hold the sentinel -0.0f (which no real pheromone value can be, and which rho leaves unchanged:
+// -0 * rho = -0), and a 16 KB tile that holds nothing but sentinels (and the exact zeros of out-of-bounds slots) is
+// "clean": the evaporation pass skips it — no read, no write.  A reader substitutes base for the sentinel (one select per
+// walk step); the first deposit on a slot starts its chain from the base of that iteration, exactly the value the
+// reference's slot holds at that point, and marks the tile dirty for good.  Bits are identical by construction; what is
+// saved is the traffic of every tile the colony never touched (most of a 512^3 field).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kSentinelBits = 0x80000000u;
+__device__ __forceinline__ float tau_or_base(float v, float base) { return __float_as_uint(v) == kSentinelBits ? base : v; }
+
 struct WalkArgs {
     IterState* st;
     const float* tau;        // [N][6] node-major ("edge-major": a node's 6 directed slots are contiguous)
@@ -84,9 +98,10 @@ __global__ void k_begin(IterState* st, float predict)
 // host reads it without synchronising, a few iterations late (acs.cu keeps itself at most four iterations ahead of the
 // device), and only enqueues the kernels of the path it chose.  Either path gives the same bits, so the lag is invisible.
 __global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, float precision, float tau0, int advance = 0, uint32_t* upd_q = nullptr,
-                             uint32_t* rankset_count = nullptr, int use_rankset = 0, volatile uint32_t* feedback = nullptr, uint32_t generation = 0)
+                             uint32_t* rankset_count = nullptr, int use_rankset = 0, volatile uint32_t* feedback = nullptr, uint32_t generation = 0,
+                             float rho = 1.0f)
 {   // :247-249
-    if (advance) { st->iter++; st->cnt[6]++; }
+    if (advance) { st->iter++; st->cnt[6]++; st->base = __fmul_rn(st->base, rho); }
     if (rankset_count) {
         const int prev = st->use_rankset;
         if (st->iter > 0) { if (prev) st->spread_slots = rankset_count[1]; else if (upd_q) st->spread_tiles = upd_q[2]; }
@@ -110,11 +125,13 @@ __global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, fl
     st->n_eligible = 0; st->n_records = 0;
 }
 
-__global__ void k_iter_end(IterState* st)
+__global__ void k_iter_end(IterState* st, float rho)
 {
     st->iter++;
     st->cnt[6]++;
+    st->base = __fmul_rn(st->base, rho);   // the evaporation (:268-272) of every slot that never received a deposit
 }
+__global__ void k_set_base(IterState* st, float v) { st->base = v; }
 
 
 // ------------------------------------------------------------------------------------------
@@ -243,6 +260,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
     IterState* st = a.st;
     const int colony = st->colony;
     const uint32_t iter = (uint32_t)st->iter;
+    const float base_now = st->base;
     int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
     if (GLOBAL) local_n = (int)st->overflow_n;
     const int limit = (E >> 2) * 3;
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
             reason = capped ? 3 : reason;
             live = live && !capped;
             // ---- the loads of this step ---------------------------------------------------------
-            const float tau_k = __ldg(a.tau + (size_t)cur * 6 + kk6);
+            const float tau_k = tau_or_base(__ldg(a.tau + (size_t)cur * 6 + kk6), base_now);
             const float heur_k = __ldg(a.heur + (size_t)cur * 6 + kk6);
             // ---- Philox: one call yields the draws of 4 consecutive steps (the live ants of a warp are
             //      in lockstep, so the branch is warp-uniform) ---------------------------------------
@@ -619,9 +637,10 @@ __global__ void __launch_bounds__(128) k_deposit_gen(const IterState* st, const 
 // ------------------------------------------------------------------------------------------
 // EMIT (sharded colonies, owner-computes): every finished run also appends (slot, final value) to `fin` — the list the
 // other ranks pull over NVLink instead of redoing this rank's chains (fin[0] = count, records from word 4).
+// sent_val: what a slot that still holds the clean-field sentinel is worth after this iteration's evaporation (base * rho).
 template <bool EMIT = false>
 __device__ __forceinline__ void apply_runs(float* buf, uint32_t base, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                           uint32_t lo, uint32_t hi, uint32_t first, uint32_t stride, uint32_t* fin = nullptr)
+                                           uint32_t lo, uint32_t hi, uint32_t first, uint32_t stride, uint32_t* fin = nullptr, float sent_val = 0.0f)
 {
     const int lane = threadIdx.x & 31;
     for (uint32_t r0 = lo + first; r0 < hi; r0 += stride) {   // r0 is warp-uniform: all 32 lanes run the same trips
@@ -633,7 +652,7 @@ __device__ __forceinline__ void apply_runs(float* buf, uint32_t base, const uint
         uint32_t j = r;
         bool more = false;
         if (head) {
-            x = buf[key - base];
+            x = tau_or_base(buf[key - base], sent_val);
             do { x = __fadd_rn(x, __uint_as_float(vals[j])); j++; } while (j < hi && j < r + 8 && keys[j] == key);
             more = j < hi && keys[j] == key;
             if (!more) buf[key - base] = x;
@@ -730,6 +749,23 @@ __global__ void __launch_bounds__(256) k_evaporate(float4* __restrict__ tau4, si
         float4 v = tau4[i];
         v.x = __fmul_rn(v.x, rho); v.y = __fmul_rn(v.y, rho); v.z = __fmul_rn(v.z, rho); v.w = __fmul_rn(v.w, rho);
         tau4[i] = v;
+    }
+}
+
+// The same pass over the DIRTY tiles of a clean-tile field only (16 KB tiles, four float4 in flight per thread).
+__global__ void __launch_bounds__(256) k_evaporate_tiles(float4* __restrict__ tau4, unsigned ntiles, float rho, const uint8_t* __restrict__ dirty, int cs)
+{
+    for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (!dirty[t]) continue;
+        float4* p = tau4 + ((size_t)t << 10) + threadIdx.x;
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = cs ? __ldcs(p + 256 * j) : p[256 * j];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j].x = __fmul_rn(v[j].x, rho); v[j].y = __fmul_rn(v[j].y, rho); v[j].z = __fmul_rn(v[j].z, rho); v[j].w = __fmul_rn(v[j].w, rho);
+            if (cs) __stcs(p + 256 * j, v[j]); else p[256 * j] = v[j];
+        }
     }
 }
 
@@ -866,8 +902,9 @@ __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(f
                                                                                 const uint32_t* __restrict__ rec_vals,
                                                                                 const uint32_t* __restrict__ tile_off,
                                                                                 const uint32_t* __restrict__ dep_list, uint32_t* q, uint32_t* fin,
-                                                                                int cs = 0)
-{
+                                                                                int cs, const IterState* st, uint8_t* dirty)
+{   // dirty[t] = 0: tile t is clean (sentinels and exact zeros only) and is neither read nor written; see "Clean-tile pheromone field"
+    const float base_new = __fmul_rn(st->base, rho);
     __shared__ unsigned s_next;
     __shared__ uint32_t s_off[kFusedChunk + 1];
     const int tid = threadIdx.x;
@@ -880,9 +917,10 @@ __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(f
         if (i >= dep_n) break;
         const unsigned t = dep_list[i];
         const uint32_t lo = tile_off[t], hi = tile_off[t + 1];
-        stream_tile(tau, t, rho, tid);
+        if (dirty[t]) stream_tile(tau, t, rho, tid);   // CTA-uniform
         __syncthreads();   // the scaled tile is visible to the whole CTA
-        apply_runs<EMIT>(tau, 0u, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads, fin);
+        apply_runs<EMIT>(tau, 0u, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads, fin, base_new);
+        if (tid == 0) dirty[t] = 1;
     }
     while (true) {   // ---- everything else: pure streaming ----
         if (tid == 0) s_next = atomicAdd(&q[1], (unsigned)kFusedChunk);
@@ -893,7 +931,7 @@ __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(f
         if (c0 >= ntiles) break;
         const unsigned c1 = min(c0 + kFusedChunk, ntiles);
         for (unsigned t = c0; t < c1; t++)
-            if (s_off[t - c0] == s_off[t - c0 + 1]) { if (cs) stream_tile<true>(tau, t, rho, tid); else stream_tile<false>(tau, t, rho, tid); }
+            if (s_off[t - c0] == s_off[t - c0 + 1] && dirty[t]) { if (cs) stream_tile<true>(tau, t, rho, tid); else stream_tile<false>(tau, t, rho, tid); }
         __syncthreads();   // s_off / s_next are reused by the next grab
     }
 }
@@ -959,7 +997,8 @@ __global__ void k_save_result(const IterState* st, const int* __restrict__ best_
 // overwrites its own, so far only evaporated, copy.  bufs[p]: word 0 = count, records (slot, value bits) from word 4.
 // The same pass is the next walk's L2 warm-up (cf. k_path_warm): the slots that just received deposits are where the
 // colony walks next, so the tau lines are left dirty in L2 by the writes and the heuristic rows are touched here.
-__global__ void __launch_bounds__(256) k_pull_finals(float* tau, const float* __restrict__ heur, const uint32_t* const* __restrict__ bufs, int npeers, int me)
+__global__ void __launch_bounds__(256) k_pull_finals(float* tau, const float* __restrict__ heur, const uint32_t* const* __restrict__ bufs, int npeers, int me,
+                                                      uint8_t* dirty)
 {
     uint32_t acc = 0;
     for (int p = 0; p < npeers; p++) {
@@ -968,7 +1007,7 @@ __global__ void __launch_bounds__(256) k_pull_finals(float* tau, const float* __
         const uint2* rec = reinterpret_cast<const uint2*>(buf + 4);
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
             const uint2 r = __ldcg(rec + i);
-            if (p != me) tau[r.x] = __uint_as_float(r.y);
+            if (p != me) { tau[r.x] = __uint_as_float(r.y); dirty[r.x / (uint32_t)kUpdTile] = 1; }
             else acc ^= __ldcg(reinterpret_cast<const uint32_t*>(tau) + r.x);
             if (heur) acc ^= __ldcg(reinterpret_cast<const uint32_t*>(heur) + r.x);
         }
@@ -981,6 +1020,22 @@ __global__ void k_tau_fill(float* tau, size_t n, float v)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) tau[i] = v;
 }
+// reset() on a clean-tile field: every slot back to "tau0" = the sentinel with base = tau0.  all = 0: only the dirty tiles
+// need rewriting (after the first reset() the out-of-bounds slots hold the sentinel too, like the reference's, :307-315).
+__global__ void __launch_bounds__(256) k_tau_reset_tiles(float4* __restrict__ tau4, unsigned ntiles, uint8_t* __restrict__ dirty, int all)
+{
+    const float s = __uint_as_float(kSentinelBits);
+    const float4 v = make_float4(s, s, s, s);
+    for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (!all && !dirty[t]) continue;
+        float4* p = tau4 + ((size_t)t << 10) + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < 4; j++) p[256 * j] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) dirty[t] = 0;
+    }
+}
+// clean-tile form: the host passes the sentinel as tau0 (the in-bounds slots' value is then IterState::base)
 __global__ void k_tau_init(float* tau, int rx, int ry, int rz, unsigned long long N, float tau0)
 {   // out-of-bounds slots start at 0 (:396), in-bounds at tau0 (:401)
     unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -108,9 +108,10 @@ __global__ void __launch_bounds__(128) k_rankset_gen(const IterState* st, const 
 // Lane per entry; an entry with more than two non-empty row words is handed to the whole warp: the 32 values of a word are
 // fetched by the lanes at once and the dependent FADD chain runs on values exchanged by shuffle (a converged colony puts
 // ~0.2*colony ranks on every slot of the best path).  Absent ranks contribute +0, the identity of the chain.
-__global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, float* tau, RankSet rs)
+__global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, float* tau, RankSet rs, float rho, uint8_t* dirty)
 {
     if (!st->use_rankset) return;
+    const float base_new = __fmul_rn(st->base, rho);   // clean-tile field: a slot that still holds the sentinel is worth this after the evaporation
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t n = rs.count[0];
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
         }
         const bool heavy = has && __popc(wm) > 2;
         if (has && !heavy) {
-            float x = tau[slot];
+            float x = tau_or_base(tau[slot], base_new);
             for (uint32_t ws = wm; ws; ws &= ws - 1) {
                 const int w = __ffs(ws) - 1;
                 uint32_t m = row[w];
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
                 }
             }
             tau[slot] = x;
+            dirty[slot / (uint32_t)kUpdTile] = 1;
         }
         unsigned hm = __ballot_sync(FULL, heavy);
         while (hm) {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
             const uint32_t ss = __shfl_sync(FULL, slot, src);
             const uint32_t fs = __shfl_sync(FULL, flag, src);
             uint32_t* rrow = rs.rows + (size_t)hs * nwords;
-            float x = tau[ss];
+            float x = tau_or_base(tau[ss], base_new);
             const uint32_t mine = lane < nwords ? rrow[lane] : 0u;   // the row: one coalesced load, lane j holds word j (nwords <= 31)
             if (lane < nwords) rrow[lane] = 0u;
             for (int j0 = 0; j0 < nwords; j0 += 4) {   // four words per round: their value loads are in flight together
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
                     for (int i = 0; i < 32; i++) x = __fadd_rn(x, __shfl_sync(FULL, v[j], i));
                 }
             }
-            if (lane == 0) tau[ss] = x;
+            if (lane == 0) { tau[ss] = x; dirty[ss / (uint32_t)kUpdTile] = 1; }
         }
         __syncwarp();
         if (has) {   // leave the table empty for the next iteration; remember the slot for the walk's L2 warm-up

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
     IterState* st = a.st;
     const int colony = st->colony;
     const uint32_t iter = (uint32_t)st->iter;
+    const float base_now = st->base;   // clean-tile field: what a slot that never received a deposit is worth this iteration
     int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
     if (GLOBAL) local_n = (int)st->overflow_n;
     const uint32_t limit = (uint32_t)((E >> 2) * 3);
@@ -213,7 +214,8 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
             const uint32_t emask = found ? (uint32_t)e : 0u;
             const bool cand = live && open_k && !(emask & bitm);
             // ---- info = tau^alpha * (1 + beta*cos)  (:151-154; the factor is tabulated by k_heuristic) --------------
-            const float tpow = ALPHA1 ? tau_v : pow_int(tau_v, a.alpha);
+            const float tau_now = tau_or_base(tau_v, base_now);
+            const float tpow = ALPHA1 ? tau_now : pow_int(tau_now, a.alpha);
             const float info = cand ? __fmul_rn(tpow, heur_v) : 0.0f;
             // ---- roulette in the reference's order (:155, :172-181) ------------------------------
             const unsigned cb = (__ballot_sync(FULL, cand) >> gbase) & 0x3Fu;

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kWalk26Threads) k_walk26(WalkArgs a)
     IterState* st = a.st;
     const int colony = st->colony;
     const uint32_t iter = (uint32_t)st->iter;
+    const float base_now = st->base;
     int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
     if (GLOBAL) local_n = (int)st->overflow_n;
     const int limit = (E >> 2) * 3;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kWalk26Threads) k_walk26(WalkArgs a)
 
         while (true) {
             if (steps >= a.cap) { reason = 3; break; }   // step cap (a deviation the oracle mirrors)
-            const float tau_k = __ldg(a.tau + (size_t)cur * kK26 + kk);
+            const float tau_k = tau_or_base(__ldg(a.tau + (size_t)cur * kK26 + kk), base_now);
             const float heur_k = __ldg(a.heur + (size_t)cur * kK26 + kk);
             if ((steps & 3) == 0) philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
             const uint32_t rsel = (steps & 2) ? ((steps & 1) ? rw3 : rw2) : ((steps & 1) ? rw1 : rw0);

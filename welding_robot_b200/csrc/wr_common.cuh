@@ -108,6 +108,8 @@ struct IterState {
     int best_changed;    // set by the ranking kernel when this iteration improved the best
     int best_ant;        // global ant index that produced it (this iteration)
     int n_eligible;      // ants that deposit this iteration (order <= lambda-1, arrived)
+    float base;          // value of every in-bounds slot that never received a deposit since init/reset(): tau0 * rho^iterations, multiplied
+                         // once per iteration exactly like the slots themselves would be (clean-tile field, see acs_kernels.cuh)
     int n_records;       // deposit records this iteration
     int n_records_sort;  // = n_records, or 0 on iterations whose deposits go through rank sets (the record path's kernels then run empty)
     int use_rankset;     // adaptive handles (WR_UPDATE_RANKSET): this iteration's deposit path, decided by k_iter_begin
