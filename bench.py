@@ -261,6 +261,7 @@ def run_ours(args):
     acs.setTiming(True)
     c0 = acs.counters()
     rs0 = acs.updateStats()["rankset_iterations"]
+    dirty0, tiles_total = acs.fieldStats()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -277,8 +278,11 @@ def run_ours(args):
     sampler.stop()
     c1 = acs.counters()
     kms = acs.kernelMs()
+    sk_ms, sk_n = acs.streamKernelMs()                      # the streaming kernel alone, by its own events inside the loop
     upd_stats = acs.updateStats()
     rs_iters = upd_stats["rankset_iterations"] - rs0        # timed iterations whose deposits went through rank sets (mode 4)
+    dirty1, _ = acs.fieldStats()
+    dirty_tiles = 0.5 * (dirty0 + dirty1)                    # tiles the evaporation pass streams (clean-tile field), mean over the timed region
     acs.setTiming(False)
     local_steps = c1["ant_steps"] - c0["ant_steps"]
     steps_done = local_steps
@@ -292,12 +296,30 @@ def run_ours(args):
     iters_done = args.steps * args.iters
     value = steps_done / (ms * 1e-3)
 
-    # ---- kernels timed alone (burst roofline of K3) ---------------------------------------------------
+    # ---- kernels timed alone (burst roofline of K3): the single-pass fused kernel over the WHOLE field, i.e. on a handle whose
+    #      field is materialised (every tile dirty, WR_LAZY_TAU=0) and that carries the deposit records of a real iteration -------
     alone = {}
-    if world == 1:
+    if world == 1 and args.workload == "C2":
+        os.environ["WR_LAZY_TAU"] = "0"
+        dense = wr.ACS_Rank(seed=SEED, fixed_colony=colony, step_cap=STEP_CAP, update_mode=0)
+        dense.creatFromOccupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], PRECISION)
+        with contextlib.redirect_stdout(io.StringIO()):
+            dense.initFromGridMap()
+        del os.environ["WR_LAZY_TAU"]
+        _lib.check(_lib.lib().wr_acs_set_stream(dense._a, stream.cuda_stream))
+        dense.setEndpoints(wl["start"], wl["goal"])
+        dense.begin(PREDICT)
+        dense.iterate(3 * args.iters)
         for name, which in (("update_fused", 0), ("update_tma_ring", 3), ("evaporate_float4", 1), ("d2d_copy", 2)):
-            t_ms = acs.benchKernel(which, 20)
+            t_ms = dense.benchKernel(which, 20)
             alone[name] = {"ms": t_ms, "GBps": UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (t_ms * 1e-3) / 1e9}
+        alone["what"] = "dense field (every tile streamed), records of iteration %d of the same search; 805 MB per launch" % (3 * args.iters)
+        del dense
+        # the same kernel on the bench handle itself: its clean-tile field after the timed region, no records (rank-set phase)
+        t_ms = acs.benchKernel(0, 20)
+        dt, _ = acs.fieldStats()
+        alone["update_fused_dirty_tiles_only"] = {"ms": t_ms, "GBps": dt * 4096 * UPDATE_BYTES_PER_SLOT / (t_ms * 1e-3) / 1e9, "tiles_streamed": dt,
+                                                  "bytes": dt * 4096 * UPDATE_BYTES_PER_SLOT}
 
     # ---- the K = 26 neighbourhood (north_star's "26-neighbour" scores; the reference disables it, so it is reported next to
     #      the K = 6 parity workload, never instead of it): same grid, colony and endpoints, 112 B per ant-step --------------
@@ -326,12 +348,13 @@ def run_ours(args):
         st26 = d1["ant_steps"] - d0["ant_steps"]
         hbm26, _ = peaks()
         w26 = 112 * st26 / (k26ms["walk"] * 1e-3) / 1e9
-        u26 = UPDATE_BYTES_PER_SLOT * n_nodes * 26 * n26 / (k26ms["update"] * 1e-3) / 1e9
+        dt26, tt26 = a26.fieldStats()
+        u26 = UPDATE_BYTES_PER_SLOT * dt26 * 4096 * n26 / (k26ms["update"] * 1e-3) / 1e9
         k26 = {"ant_steps_per_s": st26 / (ms26 * 1e-3), "acs_iterations_per_s": n26 / (ms26 * 1e-3), "iterations": n26,
                "mean_steps_per_ant": st26 / max(1, d1["ants"] - d0["ants"]), "arrived": d1["arrived"] - d0["arrived"],
                "kernel_ms_per_iteration": {k: v / n26 for k, v in k26ms.items()},
                "walk_GBps_at_112B_per_step": w26, "walk_frac_of_hbm": w26 / hbm26,
-               "update_GBps": u26, "update_frac_of_hbm": u26 / hbm26, "pheromone_field_bytes": n_nodes * 26 * 4}
+               "update_GBps": u26, "update_frac_of_hbm": u26 / hbm26, "pheromone_field_bytes": n_nodes * 26 * 4, "dirty_tiles": dt26, "tiles": tt26}
         del a26
 
     # ---- end to end through the public API from HOST buffers -------------------------------------------
@@ -394,7 +417,11 @@ def run_ours(args):
     walk_ms = kms["walk"] / iters_done
     upd_ms = kms["update"] / iters_done
     walk_gbs = WALK_BYTES_PER_STEP * (local_steps / iters_done) / (walk_ms * 1e-3) / 1e9
-    upd_gbs = UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (upd_ms * 1e-3) / 1e9
+    upd_bytes = dirty_tiles * 4096 * UPDATE_BYTES_PER_SLOT     # what the pass reads + writes: 4096-float tiles, 8 B per slot
+    upd_phase_gbs = upd_bytes / (upd_ms * 1e-3) / 1e9
+    upd_kernel_ms = sk_ms / max(1, sk_n) if world == 1 else upd_ms
+    upd_gbs = upd_bytes / (upd_kernel_ms * 1e-3) / 1e9
+    upd_dense_gbs = UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (upd_ms * 1e-3) / 1e9
     ants_done = max(1, c1["ants"] - c0["ants"])
     out = {
         "metric": "ant-steps/s", "value": value, "unit": "ant-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -425,8 +452,15 @@ def run_ours(args):
                                        "k_update_fused on record-path iterations | k_evaporate + k_rankset_apply on rank-set iterations (K3 adaptive)"][args.update_mode],
                             "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm,
                             "traffic": traffic.get("k_update_fused") if args.update_mode == 0 else None,
-                            "algorithmic_bytes_per_launch": UPDATE_BYTES_PER_SLOT * n_nodes * 6,
-                            "peak_source": hbm_src, "timed": "inside the iteration loop"},
+                            "algorithmic_bytes_per_launch": upd_bytes,
+                            "reference_sweep_bytes": UPDATE_BYTES_PER_SLOT * n_nodes * 6, "reference_sweep_equivalent_GBps": upd_dense_gbs,
+                            "dirty_tiles": dirty_tiles, "tiles": tiles_total, "kernel_ms": upd_kernel_ms, "launches_timed": sk_n,
+                            "phase_ms": upd_ms, "phase_GBps": upd_phase_gbs,
+                            "note": "clean-tile field: the pass streams only the 16 KB tiles that ever received a deposit (8 B per slot of those); "
+                                    "`achieved` counts those bytes, `reference_sweep_equivalent_GBps` the reference's sweep of every slot (SURVEY 8d) over the same time",
+                            "peak_source": hbm_src,
+                            "timed": "the streaming kernel by its own CUDA-event pair inside the iteration loop (`kernel_ms`); `phase_ms` is the whole update "
+                                     "phase (k_tile_offsets / k_rankset_apply and launch gaps included)"},
         "kernels_alone": alone,
         "voxelise": {"triangles": wl["ntri"], "grid": list(wl["natural"]), "kernel_ms": wl["vox"]["kernel_ms"], "tests": wl["vox"]["tests"]},
         "clocks": sampler.summary(),

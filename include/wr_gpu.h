@@ -150,6 +150,9 @@ int wr_acs_update_stats(wr_acs* a, uint32_t out[4]);
  * deposit since init/reset() — the only tiles the evaporation pass reads and writes — [1] tiles of the field.  Slots that
  * never received a deposit all hold the same value (tau0 * rho per iteration, kept as one scalar); downloads materialise it. */
 int wr_acs_field_stats(wr_acs* a, uint64_t out[2]);
+/* cumulative device ms and launch count, since begin and with timing enabled, of the kernel that streams the pheromone field
+ * (k_update_fused or k_evaporate_tiles) measured by its own event pair inside the iteration loop */
+int wr_acs_stream_kernel_ms(wr_acs* a, float* ms, int* launches);
 /* measurement hook: run ONE kernel of the update path `reps` times back to back on the handle's
  * stream and report the average device time per launch (CUDA events).  which: 0 = fused update
  * (evaporation + the last iteration's deposit records), 1 = float4 evaporation pass alone,

@@ -261,6 +261,40 @@ def test_rankset_update_mode_bit_exact(wr, oracle, meshes, K, policy, monkeypatc
         del g
 
 
+@pytest.mark.parametrize("update_mode", [0, 4])
+def test_uploaded_pheromone_field_and_clean_tiles(wr, oracle, meshes, update_mode):
+    """wr_acs_upload_pheromone on a clean-tile handle (every tile becomes explicit) and the clean-tile bookkeeping itself:
+    a fresh field has no dirty tile, deposits dirty only the tiles they touch, reset() cleans them again — with the
+    downloaded field equal to the oracle's at every point."""
+    A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=5, fixed_colony=300, step_cap=250, update_mode=update_mode)
+    ids = np.flatnonzero(A.grid.isfree())
+    s, e = int(ids[30]), int(ids[len(ids) // 3])
+    A.set_endpoints(s, e); g.setEndpoints(s, e)
+    A.begin(1.0); g.begin(1.0)
+    dirty, tiles = g.fieldStats()
+    assert dirty == 0 and tiles > 0
+    assert np.array_equal(A.pheromone().view(np.uint32), g.pheromone().view(np.uint32))
+    A.iterate(3); g.iterate(3)
+    compare_iteration(A, g)
+    dirty, _ = g.fieldStats()
+    assert 0 < dirty <= tiles
+    A.reset(); g.reset()
+    assert g.fieldStats()[0] == 0
+    assert np.array_equal(A.pheromone().view(np.uint32), g.pheromone().view(np.uint32))
+    A.begin(1.0); g.begin(1.0)
+    A.iterate(2); g.iterate(2)
+    compare_iteration(A, g)
+    # an explicit field: random values everywhere (out-of-bounds slots included)
+    rng = np.random.default_rng(3)
+    tau = (0.25 + rng.random(A.pheromone().size)).astype(np.float32)
+    A.set_pheromone(tau); g.setPheromone(tau)
+    assert g.fieldStats()[0] == tiles
+    A.begin(1.0); g.begin(1.0)
+    for _ in range(3):
+        A.iterate(1); g.iterate(1)
+        compare_iteration(A, g)
+
+
 def test_atomic_update_within_tolerance(wr, oracle, meshes):
     A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=9, fixed_colony=256, step_cap=400, update_mode=2)
     ids = np.flatnonzero(A.grid.isfree())

@@ -476,6 +476,12 @@ class ACS_Rank(GridMap):
         check(lib().wr_acs_update_stats(self._need(), ptr(out)))
         return dict(rankset_last=int(out[0]), deposit_tiles=int(out[1]), distinct_slots=int(out[2]), rankset_iterations=int(out[3]))
 
+    def streamKernelMs(self):
+        """(cumulative device ms, launches) of the kernel that streams the pheromone field, timed inside the loop."""
+        ms = C.c_float(); n = C.c_int()
+        check(lib().wr_acs_stream_kernel_ms(self._need(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def fieldStats(self):
         """Clean-tile field: (tiles the evaporation pass touches, tiles of the field)."""
         out = np.zeros(2, np.uint64)

@@ -162,6 +162,24 @@ struct wr_acs {
     unsigned long long rs_enqueued = 0;
     unsigned rs_on = 2000, rs_off = 120000;   // switch thresholds: deposit tiles / distinct slots (WR_RANKSET_ON / WR_RANKSET_OFF)
     bool upd_q_zeroed = false;        // this iteration's k_iter_begin already cleared d_upd_q (wr_acs_iterate)
+    // device time of the streaming kernel alone (k_update_fused / k_evaporate_tiles), inside the loop: event pairs around it
+    std::vector<cudaEvent_t> sk_ev;
+    size_t sk_used = 0;
+    float sk_ms = 0;
+    int sk_launches = 0;
+    cudaEvent_t sk_next()
+    {
+        if (sk_used == sk_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); sk_ev.push_back(e); }
+        return sk_ev[sk_used++];
+    }
+    void sk_resolve()
+    {
+        for (size_t i = 0; i + 2 <= sk_used; i += 2) {
+            float t;
+            if (cudaEventElapsedTime(&t, sk_ev[i], sk_ev[i + 1]) == cudaSuccess) { sk_ms += t; sk_launches++; }
+        }
+        sk_used = 0;
+    }
     // clean-tile field (acs_kernels.cuh): per-tile dirty flags; lazy = in-bounds slots start as sentinels (FUSED / RANKSET handles)
     uint8_t* d_dirty = nullptr;
     bool lazy = false;
@@ -455,6 +473,7 @@ extern "C" int wr_acs_destroy(wr_acs* a)
     pool_free(a->d_upd_q, s); pool_free(a->d_dirty, s);
     if (a->stream) cudaStreamSynchronize(a->stream);
     feedback_release(a->h_feedback);
+    for (cudaEvent_t e : a->sk_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->rs_ev) if (e) cudaEventDestroy(e);
     if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
     delete a;
@@ -646,6 +665,7 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     k_begin<<<1, 1, 0, a->stream>>>(a->d_state, predict);
     WR_CUDA(cudaGetLastError());
     a->rs_generation = (a->rs_generation + 1) & 0xFFFFu; a->rs_choice = 0; a->rs_enqueued = 0;
+    a->sk_used = 0; a->sk_ms = 0; a->sk_launches = 0;
     a->begun = true;
     a->timer.used = 0;
     for (float& m : a->timer.ms) m = 0;
@@ -779,10 +799,12 @@ static int launch_fused(wr_acs* a, const uint32_t* ck, const uint32_t* cv, const
     if (!a->upd_q_zeroed) WR_CUDA(cudaMemsetAsync(a->d_upd_q, 0, 4 * sizeof(uint32_t), s));
     a->upd_q_zeroed = false;
     k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(d_n ? d_n : a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, a->d_dep_list, a->d_upd_q + 2);
+    if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
     if (fin) k_update_fused<true><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, fin, stream_cs(),
                                                                                       a->d_state, a->d_dirty);
     else k_update_fused<false><<<kNumSMs * kFusedCtasPerSm, kUpdThreads, 0, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off, a->d_dep_list, a->d_upd_q, nullptr, stream_cs(),
                                                                                  a->d_state, a->d_dirty);
+    if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -853,7 +875,9 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
             k_rankset_gen<<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal, a->d_Ltab,
                                                    a->d_onbest, a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
             if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+            if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
             k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
+            if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
             k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty);
             WR_CUDA(cudaGetLastError());
         } else {
@@ -1293,6 +1317,15 @@ extern "C" int wr_acs_update_stats(wr_acs* a, uint32_t out[4])
     IterState st;
     WR_CUDA(cudaMemcpy(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost));
     out[0] = (uint32_t)st.use_rankset; out[1] = st.spread_tiles; out[2] = st.spread_slots; out[3] = st.rankset_iters;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_stream_kernel_ms(wr_acs* a, float* ms, int* launches)
+{
+    WR_REQUIRE(a && ms && launches, WR_ERR_INVALID, "wr_acs_stream_kernel_ms: null");
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    a->sk_resolve();
+    *ms = a->sk_ms; *launches = a->sk_launches;
     return WR_OK;
 }
 
