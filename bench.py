@@ -449,9 +449,9 @@ def run_ours(args):
                              "latency-bound, not bandwidth-bound (see DESIGN.md)"},
         "roofline_update": {"kernel": ["k_update_fused (K3: evaporation + rank-ordered deposits, one HBM pass)", "k_evaporate + k_deposit_apply (K3 split)",
                                        "k_evaporate + atomic deposits (K3 atomic)", "k_update_tma_ring (K3 through a TMA ring)",
-                                       "k_update_fused on record-path iterations | k_evaporate + k_rankset_apply on rank-set iterations (K3 adaptive)"][args.update_mode],
+                                       "k_update_fused on record-path iterations | k_evaporate_tiles (+ k_rankset_apply) on rank-set iterations (K3 adaptive)"][args.update_mode],
                             "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm,
-                            "traffic": traffic.get("k_update_fused") if args.update_mode == 0 else None,
+                            "traffic": traffic.get("k_update_fused") if args.update_mode == 0 else (traffic.get("k_evaporate_tiles") if args.update_mode == 4 else None),
                             "algorithmic_bytes_per_launch": upd_bytes,
                             "reference_sweep_bytes": UPDATE_BYTES_PER_SLOT * n_nodes * 6, "reference_sweep_equivalent_GBps": upd_dense_gbs,
                             "dirty_tiles": dirty_tiles, "tiles": tiles_total, "kernel_ms": upd_kernel_ms, "launches_timed": sk_n,
