@@ -417,7 +417,7 @@ static int walk_version(const wr_grid* g)
 }
 static int walk_prefetch()
 {
-    static const int env = [] { const char* e = getenv("WR_WALK_PREFETCH"); return e ? atoi(e) : 2; }();
+    static const int env = [] { const char* e = getenv("WR_WALK_PREFETCH"); return e ? atoi(e) : -1; }();   // -1: chosen per iteration (launch_walk)
     return env;
 }
 static int stream_cs()
@@ -730,7 +730,12 @@ static int launch_walk(wr_acs* a)
     const int blocks1 = std::max(1, std::min((a->chunk + kAntsPerCta - 1) / kAntsPerCta, kNumSMs * std::min(per_sm, 16)));
     if (ver == 2) {
         const bool alpha1 = a->p.alpha == 1;
-        launch_walk2<false>(w, alpha1, walk_prefetch(), blocks1, smem1, a->stream);
+        // L1 prefetch of the six neighbour rows pays while the colony wanders (rows come from L2/HBM); once its deposits are
+        // concentrated — the same device feedback that selects the rank-set path — the rows are hot and the twelve prefetch
+        // instructions per step are pure issue cost (converged walk 0.346 -> 0.317 ms without them)
+        int pf = walk_prefetch();
+        if (pf < 0) pf = (a->rankset && a->rs_choice) ? 0 : 2;
+        launch_walk2<false>(w, alpha1, pf, blocks1, smem1, a->stream);
         // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
         w.table_log2 = a->gtable_log2;
         launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, kWalk2Lut + 128, a->stream);
