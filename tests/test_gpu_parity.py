@@ -295,6 +295,22 @@ def test_uploaded_pheromone_field_and_clean_tiles(wr, oracle, meshes, update_mod
         compare_iteration(A, g)
 
 
+@pytest.mark.parametrize("K", [6, 26])
+def test_large_colony_single_kernel_ranking(wr, oracle, meshes, K):
+    """20 000 ants: the colony is ranked by k_rank_mid (one launch, global ping-pong buffers, up to 65 536 ants); massive
+    ties in the keys (a few hundred distinct step counts), dead ants, every ant's rank compared with the oracle's total order."""
+    A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=31, fixed_colony=20000, step_cap=160, K=K)
+    ids = np.flatnonzero(A.grid.isfree())
+    s, e = int(ids[40]), int(ids[len(ids) // 2])
+    A.set_endpoints(s, e); g.setEndpoints(s, e)
+    A.begin(1.0); g.begin(1.0)
+    for _ in range(2):
+        A.iterate(1); g.iterate(1)
+        compare_iteration(A, g)
+    c = g.counters()
+    assert c["arrived"] > 0 and c["dead_step_cap"] > 0
+
+
 def test_atomic_update_within_tolerance(wr, oracle, meshes):
     A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=9, fixed_colony=256, step_cap=400, update_mode=2)
     ids = np.flatnonzero(A.grid.isfree())
