@@ -67,12 +67,15 @@ class GpuBackend:
 
     def begin(self, predict):
         self.acs.begin(predict)
+        self._local = None
 
     def walk(self):
         check(lib().wr_acs_walk(self.h))
-        p = C.c_void_p(); first = C.c_int(); count = C.c_int()
-        check(lib().wr_acs_local_steps_dev(self.h, C.byref(p), C.byref(first), C.byref(count)))
-        return _view(p.value, count.value, self.device)
+        if getattr(self, "_local", None) is None:   # the buffer of this rank's step counts does not move during a search: wrap it once
+            p = C.c_void_p(); first = C.c_int(); count = C.c_int()
+            check(lib().wr_acs_local_steps_dev(self.h, C.byref(p), C.byref(first), C.byref(count)))
+            self._local = _view(p.value, count.value, self.device)
+        return self._local
 
     def rank_global(self, all_steps):
         check(lib().wr_acs_rank_global(self.h, C.c_void_p(all_steps.data_ptr())))
@@ -111,7 +114,9 @@ class GpuBackend:
         check(lib().wr_acs_peer_set_pointers(self.h, arr))
 
     def finish_iteration_peer(self, all_steps, sliced):
-        check(lib().wr_acs_finish_iteration_peer(self.h, C.c_void_p(all_steps.data_ptr()), 1 if sliced else 0))
+        if getattr(self, "_all_ptr", None) is None or self._all_src is not all_steps:
+            self._all_src, self._all_ptr = all_steps, C.c_void_p(all_steps.data_ptr())
+        check(lib().wr_acs_finish_iteration_peer(self.h, self._all_ptr, 1 if sliced else 0))
 
     def pull_finals(self):
         check(lib().wr_acs_pull_finals(self.h))
