@@ -515,7 +515,8 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     WR_CUDA_A(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
     a->own_stream = true;
     WR_CUDA_A(dmalloc(&a->d_tau, a->n_slots_pad * sizeof(float), a->stream));
-    WR_CUDA_A(cudaMemsetAsync(a->d_tau, 0, a->n_slots_pad * sizeof(float), a->stream));
+    if (a->n_slots_pad > a->n_slots)   // the slots themselves are written by k_tau_init below; only the padding of the last tile needs zeros
+        WR_CUDA_A(cudaMemsetAsync(a->d_tau + a->n_slots, 0, (a->n_slots_pad - a->n_slots) * sizeof(float), a->stream));
     // clean-tile field for the modes whose kernels know the sentinel (FUSED and the adaptive RANKSET); WR_LAZY_TAU=0 materialises it
     {
         const char* e = getenv("WR_LAZY_TAU");
