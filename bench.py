@@ -479,7 +479,7 @@ def launches_per_iteration(update_mode, colony=ANTS_PER_GPU, iters=5, sharded=Fa
     cap_bits = int(np.ceil(np.log2(STEP_CAP + 2)))
     slot_bits = int(np.ceil(np.log2(CUBE ** 3 * 6)))
     sort = lambda bits: 3 * ((bits + 9) // 10)  # noqa: E731  hist + scan + scatter per pass of <= 10-bit digits (radix_sort.cu)
-    rank = 1 if colony <= 65536 else 1 + sort(cap_bits) + 2      # k_rank_small | keys + sort + finish + best clear
+    rank = 1 if colony <= 16384 else 1 + sort(cap_bits) + 2      # k_rank_small | keys + sort + finish + best clear
     # L2 warm-up, iter_begin, walk pass 1 + 2, ranking, best copy, iter_end (single GPU: once per wr_acs_iterate call)
     n = 1 + 1 + 2 + rank + 1 + (1 if sharded else 1.0 / iters)
     if update_mode == 2 or (update_mode == 4 and not sharded):

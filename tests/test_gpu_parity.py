@@ -296,9 +296,9 @@ def test_uploaded_pheromone_field_and_clean_tiles(wr, oracle, meshes, update_mod
 
 
 @pytest.mark.parametrize("K", [6, 26])
-def test_large_colony_single_kernel_ranking(wr, oracle, meshes, K):
-    """20 000 ants: the colony is ranked by k_rank_mid (one launch, global ping-pong buffers, up to 65 536 ants); massive
-    ties in the keys (a few hundred distinct step counts), dead ants, every ant's rank compared with the oracle's total order."""
+def test_large_colony_ranking(wr, oracle, meshes, K):
+    """20 000 ants: beyond the single-kernel ranking, the colony goes through the multi-kernel radix sort; massive ties in
+    the keys (a few hundred distinct step counts), dead ants, every ant's rank compared with the oracle's total order."""
     A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=31, fixed_colony=20000, step_cap=160, K=K)
     ids = np.flatnonzero(A.grid.isfree())
     s, e = int(ids[40]), int(ids[len(ids) // 2])

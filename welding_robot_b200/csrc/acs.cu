@@ -767,14 +767,6 @@ static int launch_rank(wr_acs* a, const int* d_all_steps)
         WR_CUDA(cudaGetLastError());
         return WR_OK;
     }
-    if (small_ok && cm <= kRankMidMax) {     // one kernel as well, ping-ponging through the global sort buffers
-        k_rank_mid<<<1, kRankSmallThreads, 0, s>>>(a->d_state, d_all_steps, a->K == kK26 ? a->d_ant_L : nullptr, a->cap, a->rank_bits, a->d_Ltab,
-                                                   a->sort_ants.keys_a, a->sort_ants.vals_a, a->sort_ants.keys_b, a->sort_ants.vals_b, a->d_rec_off, a->d_order,
-                                                   a->d_best_n, a->d_best_ids, a->d_onbest);
-        a->ants_in_b = false;
-        WR_CUDA(cudaGetLastError());
-        return WR_OK;
-    }
     if (a->K == kK26) k_rank_keys26<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->d_ant_L, a->sort_ants.keys_a, a->sort_ants.vals_a);
     else k_rank_keys<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->cap, a->sort_ants.keys_a, a->sort_ants.vals_a);
     int st = sort_pairs(&a->sort_ants, a->dptr_colony(), a->rank_bits, s, &a->ants_in_b);

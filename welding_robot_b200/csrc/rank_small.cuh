@@ -169,154 +169,4 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
     }
 }
 
-// The same ranking for colonies of up to kRankMidMax ants (eight ranks of the C2 colony = 32768, C3 = 65536): keys and
-// values ping-pong between the global sort buffers (L2-resident, <= 512 KB) instead of shared memory, the scatter re-derives
-// each key's position from running per-(warp, digit) offsets instead of keeping it in registers, and the prefix sum over the
-// ranks is two sequential sweeps per thread around one block scan instead of n/1024 block scans.  Still one launch.
-constexpr int kRankMidMax = 65536;
-
-__global__ void __launch_bounds__(kRankSmallThreads) k_rank_mid(IterState* st, const int* __restrict__ ant_steps, const float* __restrict__ ant_L, int cap,
-                                                                 int key_bits, const float* __restrict__ Ltab, uint32_t* keys_a, uint32_t* vals_a,
-                                                                 uint32_t* keys_b, uint32_t* vals_b, uint32_t* __restrict__ rec_off,
-                                                                 int* __restrict__ order_of_ant, const int* __restrict__ best_n,
-                                                                 const uint32_t* __restrict__ best_ids, uint32_t* onbest)
-{
-    __shared__ uint32_t whist[32 * 256];   // [warp][digit]
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t elig_total;
-    constexpr unsigned FULL = 0xffffffffu;
-    const int n = st->colony;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const bool k26 = ant_L != nullptr;
-    const int rounds = (n + kRankSmallThreads - 1) / kRankSmallThreads;   // 32-key rounds per warp
-    const int chunk = rounds * 32;
-
-    for (int i = threadIdx.x; i < n; i += kRankSmallThreads) {
-        const int s = ant_steps[i];
-        keys_a[i] = k26 ? (s < 0 ? 0x7F800000u : __float_as_uint(ant_L[i])) : (s < 0 ? (uint32_t)(cap + 1) : (uint32_t)s);
-        vals_a[i] = (uint32_t)i;
-    }
-    __syncthreads();
-
-    const int npass = (((key_bits + 7) / 8) + 1) & ~1;   // an even number of passes: the result lands in keys_a / vals_a again
-    for (int pass = 0; pass < npass; pass++) {
-        const int shift = pass * 8;
-        const uint32_t* ki = (pass & 1) ? keys_b : keys_a;
-        const uint32_t* vi = (pass & 1) ? vals_b : vals_a;
-        uint32_t* ko = (pass & 1) ? keys_a : keys_b;
-        uint32_t* vo = (pass & 1) ? vals_a : vals_b;
-        for (int d = lane; d < 256; d += 32) whist[w * 256 + d] = 0;
-        __syncwarp();
-        for (int r = 0; r < rounds; r++) {   // count
-            const int idx = w * chunk + r * 32 + lane;
-            const bool ok = idx < n;
-            const uint32_t d = ok ? ((shift < 32 ? ki[idx] >> shift : 0u) & 255u) : 256u;
-            const unsigned peers = __match_any_sync(FULL, d);
-            if (ok && lane == __ffs(peers) - 1) whist[w * 256 + d] += (uint32_t)__popc(peers);
-            __syncwarp();
-        }
-        __syncthreads();
-        {   // exclusive scan of the 8192 counters in (digit, warp) order: thread t owns digit t/4, warps (t%4)*8 .. +7
-            const int d = threadIdx.x >> 2, w0 = (threadIdx.x & 3) * 8;
-            uint32_t c[8], sum = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) { c[j] = whist[(w0 + j) * 256 + d]; sum += c[j]; }
-            uint32_t incl = sum;
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
-            if (lane == 31) warp_sum[w] = incl;
-            __syncthreads();
-            if (w == 0) {
-                const uint32_t s = warp_sum[lane];
-                uint32_t si = s;
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, si, o); if (lane >= o) si += u; }
-                warp_sum[lane] = si - s;
-            }
-            __syncthreads();
-            uint32_t run = warp_sum[w] + (incl - sum);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { whist[(w0 + j) * 256 + d] = run; run += c[j]; }
-        }
-        __syncthreads();
-        for (int r = 0; r < rounds; r++) {   // scatter: whist[w][d] is the running offset of this warp's next key with digit d
-            const int idx = w * chunk + r * 32 + lane;
-            const bool ok = idx < n;
-            const uint32_t key = ok ? ki[idx] : 0u;
-            const uint32_t d = ok ? ((shift < 32 ? key >> shift : 0u) & 255u) : 256u;
-            const unsigned peers = __match_any_sync(FULL, d);
-            const uint32_t base = ok ? whist[w * 256 + d] : 0u;
-            __syncwarp();
-            if (ok) {
-                const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-                ko[pos] = key; vo[pos] = vi[idx];
-                if (lane == __ffs(peers) - 1) whist[w * 256 + d] = base + (uint32_t)__popc(peers);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-    }
-    const uint32_t* keys = keys_a;
-    const uint32_t* vals = vals_a;
-
-    // ---- best decision (:263-264), eligibility (:200), record offsets ----
-    const float lambda = st->lambda;
-    if (threadIdx.x == 0) {
-        elig_total = 0;
-        if (n > 0 && k26) {
-            const float L0 = __uint_as_float(keys[0]);
-            if (L0 < st->best_L) { st->best_steps = ant_steps[vals[0]]; st->best_L = L0; st->best_changed = 1; st->best_ant = (int)vals[0]; }
-        } else if (n > 0) {
-            const int s = (int)keys[0];
-            if (s <= cap && s < st->best_steps) { st->best_steps = s; st->best_L = Ltab[s]; st->best_changed = 1; st->best_ant = (int)vals[0]; }
-        }
-    }
-    __syncthreads();
-    const int per = rounds;                      // ranks per thread: [t*per, (t+1)*per)
-    const int r0 = threadIdx.x * per, r1 = min(r0 + per, n);
-    uint32_t mysum = 0, myel = 0;
-    for (int r = r0; r < r1; r++) {
-        const uint32_t key = keys[r], ant = vals[r];
-        const int s = k26 ? ant_steps[ant] : (int)key;
-        const bool arrived = k26 ? key != 0x7F800000u : s <= cap;
-        const bool el = arrived && !((float)(r + 1) > __fsub_rn(lambda, 1.0f));   // :200
-        mysum += el ? (uint32_t)s : 0u;
-        myel += el ? 1u : 0u;
-    }
-    uint32_t incl = mysum;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
-    if (lane == 31) warp_sum[w] = incl;
-    uint32_t elw = myel;
-    for (int o = 16; o > 0; o >>= 1) elw += __shfl_down_sync(FULL, elw, o);
-    if (lane == 0 && elw) atomicAdd(&elig_total, elw);
-    __syncthreads();
-    if (w == 0) {
-        const uint32_t s = warp_sum[lane];
-        uint32_t si = s;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, si, o); if (lane >= o) si += u; }
-        warp_sum[lane] = si - s;
-        if (lane == 31) whist[0] = si;   // total
-    }
-    __syncthreads();
-    uint32_t run = warp_sum[w] + (incl - mysum);
-    for (int r = r0; r < r1; r++) {
-        const uint32_t key = keys[r], ant = vals[r];
-        const int s = k26 ? ant_steps[ant] : (int)key;
-        const bool arrived = k26 ? key != 0x7F800000u : s <= cap;
-        const bool el = arrived && !((float)(r + 1) > __fsub_rn(lambda, 1.0f));
-        order_of_ant[ant] = r + 1;
-        rec_off[r] = run;
-        run += el ? (uint32_t)s : 0u;
-    }
-    if (threadIdx.x == 0) {
-        const uint32_t total = whist[0];
-        st->n_eligible = (int)elig_total; st->n_records = (int)total; st->n_records_sort = st->use_rankset ? 0 : (int)total; st->cnt[7] += total;
-    }
-    if (st->best_changed) {   // best = agentK (:264) drops the old best path's membership bits; written by thread 0 before the barriers above
-        const int nb = *best_n;
-        for (int i = threadIdx.x; i < nb; i += kRankSmallThreads) {
-            const uint32_t id = best_ids[i];
-            atomicAnd(&onbest[id >> 5], ~(1u << (id & 31)));
-        }
-    }
-}
-
 }  // namespace wr
