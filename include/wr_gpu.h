@@ -103,6 +103,10 @@ enum {
                                 otherwise, and on sharded handles, it runs as WR_UPDATE_FUSED. */
 };
 
+/* Handles created in a loop (one search per request) re-use a few large buffers of their predecessors instead of allocating and
+ * zeroing them again: the rank-set table of WR_UPDATE_RANKSET, the peer slab of a sharded handle and the IPC mappings of the
+ * peers' slabs stay parked in the process after wr_acs_destroy.  wr_release_caches frees them (no search may be in flight). */
+int wr_release_caches(void);
 int wr_acs_default_params(wr_acs_params* p);                        /* literals of initFromGridMap :319-325 */
 int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out); /* initFromGridMap :317-410 */
 int wr_acs_destroy(wr_acs* a);

@@ -31,7 +31,7 @@ class AcsParams(C.Structure):
 
 
 # every symbol include/wr_gpu.h declares (tests check the library exports exactly these)
-SYMBOLS = """wr_last_error wr_version wr_device_count wr_set_device wr_stl_parse
+SYMBOLS = """wr_last_error wr_version wr_device_count wr_set_device wr_release_caches wr_stl_parse
 wr_grid_create_from_triangles wr_grid_create_from_occupancy wr_grid_destroy wr_grid_dims wr_grid_precision
 wr_grid_bbox wr_grid_coords wr_grid_download_bits wr_grid_download_isfree wr_grid_stats
 wr_acs_default_params wr_acs_create wr_acs_destroy wr_acs_set_points wr_acs_set_endpoints wr_acs_snap_points wr_acs_search_pairs wr_acs_begin
@@ -65,7 +65,7 @@ def lib():
     vp, i32, f32, u64, i64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_int64
     L.wr_last_error.restype = C.c_char_p
     sig = {
-        "wr_device_count": [vp], "wr_set_device": [i32],
+        "wr_device_count": [vp], "wr_set_device": [i32], "wr_release_caches": [],
         "wr_stl_parse": [vp, C.c_size_t, vp, i32, vp],
         "wr_grid_create_from_triangles": [vp, i32, f32, i32, vp],
         "wr_grid_create_from_occupancy": [vp, i32, i32, i32, vp, vp, vp, f32, vp],

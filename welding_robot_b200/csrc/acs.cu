@@ -453,6 +453,15 @@ extern "C" int wr_set_device(int device)
     return WR_OK;
 }
 
+extern "C" int wr_release_caches(void)
+{   // buffers parked between handles (rank-set table, peer slab, IPC mappings of the peers' slabs); call with no search in flight
+    std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+    if (g_rs_cache.rs.ent) { rankset_release_buffers(g_rs_cache.rs, nullptr); g_rs_cache = RankSetCache(); }
+    if (g_slab_cache.ptr) { cudaFree(g_slab_cache.ptr); g_slab_cache = SlabCache(); }
+    for (IpcMapping& m : g_ipc_maps) if (m.ptr) { cudaIpcCloseMemHandle(m.ptr); m.ptr = nullptr; }
+    return WR_OK;
+}
+
 extern "C" int wr_acs_default_params(wr_acs_params* p)
 {
     WR_REQUIRE(p, WR_ERR_INVALID, "wr_acs_default_params: null");
