@@ -86,7 +86,7 @@ typedef struct {
     int step_cap;         /* 0: auto (min(N-1, 65534)); else max steps per ant     */
     int K;                /* neighbourhood: 6 (reference) or 26 (the extension disabled at :367-385; one GPU) */
     uint64_t seed;        /* Philox key; draw = f(seed; iteration, ant, step)      */
-    int update_mode;      /* WR_UPDATE_*                                           */
+    int update_mode;      /* WR_UPDATE_*; default WR_UPDATE_RANKSET (adaptive)     */
     int walk_table_log2;  /* log2 of per-ant shared-memory visited-tile slots (0: default 9) */
 } wr_acs_params;
 

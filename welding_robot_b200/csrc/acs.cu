@@ -467,7 +467,7 @@ extern "C" int wr_acs_default_params(wr_acs_params* p)
     WR_REQUIRE(p, WR_ERR_INVALID, "wr_acs_default_params: null");
     p->alpha = 1; p->beta = 0.6; p->rho = 0.8; p->tau0 = 1;   // ACSRank_3D.hpp:319-324
     p->fixed_colony = 0; p->step_cap = 0; p->K = 6; p->seed = 0;
-    p->update_mode = WR_UPDATE_FUSED; p->walk_table_log2 = 0;
+    p->update_mode = WR_UPDATE_RANKSET; p->walk_table_log2 = 0;   // adaptive deposit path; runs as WR_UPDATE_FUSED where rank sets do not apply
     return WR_OK;
 }
 
