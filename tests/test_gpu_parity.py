@@ -295,6 +295,22 @@ def test_uploaded_pheromone_field_and_clean_tiles(wr, oracle, meshes, update_mod
         compare_iteration(A, g)
 
 
+def test_rankset_widest_rows(wr, oracle, meshes, monkeypatch):
+    """4900 ants: 981 eligible ranks = 31 row words, the widest rank-set row (summary bits 0..30 + the on-best bit 31);
+    the rank-set path forced on every iteration, a converging colony so that slots collect ranks from every word."""
+    monkeypatch.setenv("WR_RANKSET_POLICY", "1")
+    A, g = make_pair(wr, oracle, meshes["simplified_piece"], 0.02, 3, seed=41, fixed_colony=4900, step_cap=120, update_mode=4)
+    ids = np.flatnonzero(A.grid.isfree())
+    s, e = int(ids[60]), int(ids[len(ids) // 4])
+    A.set_endpoints(s, e); g.setEndpoints(s, e)
+    A.begin(1.0); g.begin(1.0)
+    for _ in range(4):
+        A.iterate(1); g.iterate(1)
+        compare_iteration(A, g)
+    st = g.updateStats()
+    assert st["rankset_iterations"] == 4 and g.counters()["deposit_records"] > 100000
+
+
 @pytest.mark.parametrize("K", [6, 26])
 def test_large_colony_ranking(wr, oracle, meshes, K):
     """20 000 ants: beyond the single-kernel ranking, the colony goes through the multi-kernel radix sort; massive ties in
