@@ -221,6 +221,7 @@ def run_ours(args):
         raise SystemExit("launch with `python -m torch.distributed.run --nproc-per-node %d bench.py --gpus %d ...`" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     _lib.check(_lib.lib().wr_set_device(local))
+    torch.cuda.set_stream(torch.cuda.Stream())   # a stream of our own (the default stream cannot be captured into CUDA graphs); events, NCCL and the handles all use it
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -258,7 +259,12 @@ def run_ours(args):
         step()
     barrier()
     # ---- timed region, device resident -------------------------------------------------------------
-    acs.setTiming(True)
+    # Single GPU: the timed region runs as a user would run it (no per-phase events, so the steady-state iterations go out as
+    # one CUDA graph each); the per-phase / per-kernel times are taken afterwards on a REPLAY of the same iterations (a fresh
+    # handle, same seed: the search is deterministic) with the event pairs enabled.  Sharded: events inside the timed region.
+    phase_in_timed = world > 1
+    if phase_in_timed:
+        acs.setTiming(True)
     c0 = acs.counters()
     rs0 = acs.updateStats()["rankset_iterations"]
     dirty0, tiles_total = acs.fieldStats()
@@ -277,8 +283,24 @@ def run_ours(args):
     sampler.mark_end()
     sampler.stop()
     c1 = acs.counters()
-    kms = acs.kernelMs()
-    sk_ms, sk_n = acs.streamKernelMs()                      # the streaming kernel alone, by its own events inside the loop
+    if phase_in_timed:
+        kms = acs.kernelMs()
+        sk_ms, sk_n = acs.streamKernelMs()                  # the streaming kernel alone, by its own events inside the loop
+    else:
+        rep = make_search(wl["isfree"])
+        _lib.check(_lib.lib().wr_acs_set_stream(rep._a, stream.cuda_stream))
+        rep.setEndpoints(wl["start"], wl["goal"])
+        rep.begin(PREDICT)
+        for _ in range(args.warmup):
+            rep.iterate(args.iters)
+        rep.sync()
+        rep.setTiming(True)
+        for _ in range(args.steps):
+            rep.iterate(args.iters)
+        kms = rep.kernelMs()
+        sk_ms, sk_n = rep.streamKernelMs()
+        assert rep.counters()["ant_steps"] == c1["ant_steps"], "replay diverged from the timed search"
+        del rep
     upd_stats = acs.updateStats()
     rs_iters = upd_stats["rankset_iterations"] - rs0        # timed iterations whose deposits went through rank sets (mode 4)
     dirty1, _ = acs.fieldStats()
@@ -442,6 +464,8 @@ def run_ours(args):
                                   + launches_per_iteration(4, colony, args.iters, world > 1) * rs_iters)),
         "deposit_path": {"rank_set_iterations": rs_iters, "record_iterations": iters_done - rs_iters, "last": upd_stats} if args.update_mode == 4 else None,
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
+        "kernel_ms_source": "events inside the timed region" if world > 1 else
+                            "replay of the timed iterations on a fresh handle with per-phase events (the timed region itself runs without them)",
         "roofline": {"kernel": "k_walk2 (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
                      "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk2", traffic.get("k_walk")), "peak_source": hbm_src,
                      "algorithmic_bytes_per_launch": WALK_BYTES_PER_STEP * (local_steps / iters_done),

@@ -162,6 +162,10 @@ struct wr_acs {
     unsigned long long rs_enqueued = 0;
     unsigned rs_on = 2000, rs_off = 120000;   // switch thresholds: deposit tiles / distinct slots (WR_RANKSET_ON / WR_RANKSET_OFF)
     bool upd_q_zeroed = false;        // this iteration's k_iter_begin already cleared d_upd_q (wr_acs_iterate)
+    // steady-state rank-set iteration (previous and current iteration on the rank-set path, folded k_iter_end, no timers) as ONE
+    // CUDA graph launch: 9 kernels whose arguments do not change within a search; re-captured after wr_acs_begin
+    cudaGraphExec_t rs_graph = nullptr;
+    bool rs_graph_failed = false;
     // device time of the streaming kernel alone (k_update_fused / k_evaporate_tiles), inside the loop: event pairs around it
     std::vector<cudaEvent_t> sk_ev;
     size_t sk_used = 0;
@@ -195,6 +199,12 @@ struct wr_acs {
         return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + (rankset ? offsetof(IterState, n_records_sort) : offsetof(IterState, n_records)));
     }
 };
+
+static void drop_steady_graph(wr_acs* a)
+{
+    if (a->rs_graph) { cudaGraphExecDestroy(a->rs_graph); a->rs_graph = nullptr; }
+    a->rs_graph_failed = false;
+}
 
 // A rank-set table is all zeros whenever no iteration is in flight (k_rankset_apply clears what k_rankset_gen set), so a
 // destroyed handle's table can be handed to the next handle of the same shape without the 1-2 GB memset: one parked
@@ -281,6 +291,7 @@ static std::vector<IpcMapping> g_ipc_maps;   // one per peer rank (a process dri
 static void free_colony_buffers(wr_acs* a)
 {
     cudaStream_t s = a->stream;
+    drop_steady_graph(a);
     free_rankset(a);
     pool_free(a->d_ant_steps, s); pool_free(a->d_overflow, s); pool_free(a->d_ant_L, s); a->d_ant_L = nullptr;
     if (!a->d_slab) { pool_free(a->d_path_ids, s); pool_free(a->d_path_dirs, s); }
@@ -585,6 +596,7 @@ extern "C" int wr_acs_set_stream(wr_acs* a, void* cuda_stream)
 {
     WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_set_stream: null");
     WR_CUDA(cudaStreamSynchronize(a->stream));
+    drop_steady_graph(a);
     if (a->own_stream) cudaStreamDestroy(a->stream);
     a->stream = (cudaStream_t)cuda_stream;
     a->own_stream = false;
@@ -675,6 +687,7 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     k_begin<<<1, 1, 0, a->stream>>>(a->d_state, predict);
     WR_CUDA(cudaGetLastError());
     a->rs_generation = (a->rs_generation + 1) & 0xFFFFu; a->rs_choice = 0; a->rs_enqueued = 0;
+    drop_steady_graph(a);   // endpoints, heuristic table and generation are baked into the captured launches
     a->sk_used = 0; a->sk_ms = 0; a->sk_launches = 0;
     a->begun = true;
     a->timer.used = 0;
@@ -696,10 +709,10 @@ static void launch_walk2(const WalkArgs& w, bool alpha1, int prefetch, int block
 }
 
 // before k_iter_begin: pull the rows under last iteration's deposits into L2 (see k_path_warm)
-static void launch_warm(wr_acs* a)
+static void launch_warm(wr_acs* a, bool prev_rankset)
 {
     if (!walk_warm() || walk_version(a->g) != 2 || a->p.update_mode == WR_UPDATE_ATOMIC || a->K != 6) return;
-    if (a->rankset && a->rs_enqueued > 0 && a->rs_choice) {   // rs_choice still names the previous iteration's path here
+    if (a->rankset && a->rs_enqueued > 0 && prev_rankset) {   // the previous iteration's deposits went through rank sets
         k_rankset_warm<<<kNumSMs, 256, 0, a->stream>>>(a->rs.touched, a->rs.count, a->d_tau, a->d_heur, a->d_state);
         return;
     }
@@ -852,6 +865,43 @@ static int launch_update(wr_acs* a)
     return WR_OK;
 }
 
+static bool graph_enabled()
+{
+    static const bool on = [] { const char* e = getenv("WR_GRAPH"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
+// One rank-set iteration whose predecessor was a rank-set iteration too, captured from the very launch sequence of
+// wr_acs_iterate (k_iter_end of the predecessor folded into k_iter_begin): L2 warm-up, iteration parameters, walk pass 1 + 2,
+// ranking, best copy, rank-set build, evaporation of the dirty tiles, ordered chains.  Every argument is fixed for the search.
+static int capture_steady_iteration(wr_acs* a)
+{
+    cudaStream_t s = a->stream;
+    if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) return WR_ERR_STATE;   // the default streams cannot be captured
+    WR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    launch_warm(a, true);
+    k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, 1, a->d_upd_q, a->rs.count, 1, a->d_feedback,
+                                 a->rs_generation, a->p.rho);
+    int st = launch_walk(a);
+    if (st == WR_OK) st = launch_rank(a, a->d_ant_steps);
+    k_best_copy<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_path_ids, a->d_path_dirs, a->cap, 0, (int)a->goal);
+    k_rankset_gen<<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal, a->d_Ltab, a->d_onbest,
+                                           a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
+    k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
+    k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (e != cudaSuccess || st != WR_OK || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return WR_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(&a->rs_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { a->rs_graph = nullptr; cudaGetLastError(); return WR_ERR_CUDA; }
+    return WR_OK;
+}
+
 extern "C" int wr_acs_iterate(wr_acs* a, int n)
 {
     WR_REQUIRE(a && n >= 0, WR_ERR_INVALID, "wr_acs_iterate: bad argument");
@@ -861,7 +911,7 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
     cudaStream_t s = a->stream;
     for (int it = 0; it < n; it++) {
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-        launch_warm(a);
+        const bool rs_prev = a->rankset && a->rs_choice;   // path of the previous iteration (what the L2 warm-up reads)
         if (a->rankset) {   // which deposit path this iteration takes (see k_iter_begin)
             if (a->rs_enqueued >= (unsigned long long)wr_acs::kRsAhead) WR_CUDA(cudaEventSynchronize(a->rs_ev[a->rs_enqueued % wr_acs::kRsAhead]));
             if (a->rs_policy == 1 || a->rs_policy == 2) a->rs_choice = a->rs_policy == 1;
@@ -875,6 +925,17 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
             }
         }
         const bool rs_now = a->rankset && a->rs_choice;
+        // steady state of a converged search: the whole iteration is one graph launch
+        if (rs_now && rs_prev && it > 0 && a->rs_enqueued > 0 && !a->timer.enabled && !a->rs_graph_failed && graph_enabled()) {
+            if (!a->rs_graph && capture_steady_iteration(a) != WR_OK) a->rs_graph_failed = true;
+            if (a->rs_graph) {
+                WR_CUDA(cudaGraphLaunch(a->rs_graph, s));
+                WR_CUDA(cudaEventRecord(a->rs_ev[a->rs_enqueued % wr_acs::kRsAhead], s)); a->rs_enqueued++;
+                if (it == n - 1) k_iter_end<<<1, 1, 0, s>>>(a->d_state, a->p.rho);
+                continue;
+            }
+        }
+        launch_warm(a, rs_prev);
         k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->d_upd_q,
                                      a->rankset ? a->rs.count : nullptr, rs_now ? 1 : 0, a->d_feedback, a->rs_generation, a->p.rho);
         a->upd_q_zeroed = true;
@@ -986,7 +1047,7 @@ extern "C" int wr_acs_walk(wr_acs* a)
         a->d_path_ids = reinterpret_cast<uint32_t*>(a->d_slab + a->off_ids[a->parity]);
         a->d_path_dirs = a->d_slab + a->off_dirs[a->parity];
     }
-    launch_warm(a);
+    launch_warm(a, false);
     k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0);
     WR_CUDA(cudaMemsetAsync(a->d_local_steps, 0xFF, (size_t)a->chunk * sizeof(int), s));   // -1: beyond the colony
     int st = launch_walk(a);
