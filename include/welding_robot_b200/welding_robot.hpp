@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <deque>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <set>
 #include <stdexcept>
@@ -80,6 +81,45 @@ public:
     bool isFree;
     unsigned long int id;
 };
+
+// ---- node-cuboid helpers (model_grid_map.hpp:90-138) ---------------------------------------------
+// Same contract as the reference's three templates: matrix[z][y][x], the callback sees every (z, y, x) in z -> y -> x
+// order, creat_* wants a NULL pointer and delete_* a live one.  The storage differs: one contiguous block of T plus two
+// pointer tables (three allocations instead of rz*ry + rz + 1), so a sweep over the cuboid is a linear scan.
+template <class T>
+void creat_all_nodes(T***& matrix, int rx, int ry, int rz, std::function<void(int, int, int)> f)
+{
+    if (matrix != NULL) throw wr::Error(WR_ERR_STATE, "creat_all_nodes: matrix already exists");
+    T* cells = new T[(size_t)rx * ry * rz];
+    T** rows = new T*[(size_t)ry * rz];
+    matrix = new T**[rz];
+    for (int z = 0; z < rz; z++) {
+        matrix[z] = rows + (size_t)z * ry;
+        for (int y = 0; y < ry; y++) rows[(size_t)z * ry + y] = cells + ((size_t)z * ry + y) * rx;
+    }
+    for (int z = 0; z < rz; z++)
+        for (int y = 0; y < ry; y++)
+            for (int x = 0; x < rx; x++) f(z, y, x);
+}
+
+template <class T>
+void for_each_nodes(T***& matrix, int rx, int ry, int rz, std::function<void(int, int, int)> f)
+{
+    if (matrix == NULL) throw wr::Error(WR_ERR_STATE, "for_each_nodes: no matrix");
+    for (int z = 0; z < rz; z++)
+        for (int y = 0; y < ry; y++)
+            for (int x = 0; x < rx; x++) f(z, y, x);
+}
+
+template <class T>
+void delete_all_nodes(T***& matrix, int /*rx*/, int /*ry*/, int /*rz*/)
+{
+    if (matrix == NULL) throw wr::Error(WR_ERR_STATE, "delete_all_nodes: no matrix");
+    delete[] matrix[0][0];   // the cells
+    delete[] matrix[0];      // the row table
+    delete[] matrix;
+    matrix = NULL;
+}
 
 template <class T>
 struct _Inf_of_Points_t {
@@ -155,7 +195,9 @@ public:
         printf("[Grid Map] %d nodes is created... \n", size_of_map());
         if (file_name != "") writeGridMap(file_name);
         printf("[Grid Map] Done! \r\n");
-        return nullptr;   // main.cpp:279 ignores the result; the cuboid is built by ptr_grid_map() on demand
+        // the reference returns its node cuboid (model_grid_map.hpp:297).  It is built here (24 B of host memory per
+        // node) unless the caller switched it off; ptr_grid_map() builds it on first use either way.
+        return materialise_cuboid ? ptr_grid_map() : nullptr;
     }
 
     // synthetic-grid entry point (an addition)
@@ -243,6 +285,7 @@ public:
     T precision = 0;
     int wall = 0;
     int rangeX = 0, rangeY = 0, rangeZ = 0;
+    bool materialise_cuboid = true;   // addition: false = creatGridMap returns NULL and leaves the cuboid to ptr_grid_map()
 
 protected:
     wr_grid* grid_ = nullptr;

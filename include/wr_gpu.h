@@ -85,7 +85,7 @@ typedef struct {
     int fixed_colony;     /* 0: adaptive colony_num of :247; >0: that many ants    */
     int step_cap;         /* 0: auto (min(N-1, 65534)); else max steps per ant     */
     int K;                /* neighbourhood: 6 (reference) or 26 (the extension disabled at :367-385; one GPU) */
-    uint64_t seed;        /* Philox key; draw = f(seed; iteration, ant, step)      */
+    uint64_t seed;        /* Philox key; draw = f(seed; search, iteration, ant, step) */
     int update_mode;      /* WR_UPDATE_*; default WR_UPDATE_RANKSET (adaptive)     */
     int walk_table_log2;  /* log2 of per-ant shared-memory visited-tile slots (0: default 9) */
 } wr_acs_params;
@@ -94,7 +94,7 @@ enum {
     WR_UPDATE_FUSED = 0,     /* one HBM pass: tile streamed through registers, rank-ordered deposits applied while the tile is in L2 */
     WR_UPDATE_SPLIT = 1,     /* float4 evaporation pass, then rank-ordered deposit pass (same bits) */
     WR_UPDATE_ATOMIC = 2,    /* evaporation pass + atomicAdd deposits (fast, order not reproducible) */
-    WR_UPDATE_FUSED_TMA = 3, /* one HBM pass through a 4-stage TMA ring in shared memory (same bits; measurement variant) */
+    /* 3 was a measurement variant (every tile through a TMA ring in shared memory); removed, rejected by wr_acs_create */
     WR_UPDATE_RANKSET = 4    /* adaptive: per touched slot the SET of depositing ranks (a deposit's value depends only on the rank and one
                                 bit of the slot) is built with atomicOr and applied as one ordered chain — no record sort — on the
                                 iterations where the colony's deposits are concentrated; sorted records + the fused pass (WR_UPDATE_FUSED)
@@ -124,8 +124,14 @@ int wr_acs_snap_points(wr_acs* a, const float* pts_xyz, int npoints, int64_t* id
  * index less.  Independent queries (BASELINE config 5) shard by giving every rank its own pairs. */
 int wr_acs_search_pairs(wr_acs* a, const int64_t* start_ids, const int64_t* goal_ids, int npairs, float predict_path_len,
                         int n_iterations, float* L, int* path_nodes, int64_t* path_ids, int* path_dirs, int path_cap);
-/* computeSolution :220-305 = wr_acs_begin(predict) + wr_acs_iterate(max_iteration) */
+/* computeSolution :220-305 = wr_acs_begin(predict) + wr_acs_iterate(max_iteration).
+ * Random draws: the reference draws every search of an ACS_Rank object from ONE continuous rand() stream (:169, seeded
+ * once at :327), so successive searches are independent.  Here a draw is Philox(seed; search, iteration, ant, step) and
+ * `search` is the number of wr_acs_begin calls the handle has seen before this one (0, 1, 2 ...; the pairs of
+ * wr_acs_search_pairs and the queries of wr_acs_search_batch take consecutive indices the same way).
+ * wr_acs_set_next_search overrides the index the NEXT wr_acs_begin takes (e.g. to re-run query q of a batch alone). */
 int wr_acs_begin(wr_acs* a, float predict_path_len);                /* :229-233 */
+int wr_acs_set_next_search(wr_acs* a, uint32_t index);
 int wr_acs_iterate(wr_acs* a, int n_iterations);                    /* loop body :237-299, n times; asynchronous */
 int wr_acs_sync(wr_acs* a);
 int wr_acs_reset(wr_acs* a);                                        /* reset() :307-315 */
@@ -134,6 +140,8 @@ int wr_acs_reset(wr_acs* a);                                        /* reset() :
  * (+inf if none). */
 int wr_acs_best(wr_acs* a, int64_t* ids, int* dirs, int cap, int* n, float* L);
 int wr_acs_download_pheromone(wr_acs* a, float* tau, size_t n);     /* N*K floats, node-major; K = 6: slots [-z,-y,-x,+x,+y,+z]; K = 26: the (dz,dy,dx) enumeration of :355-359 without the centre */
+/* upload materialises the field (every tile takes part in the evaporation from then on); on a clean-tile handle a
+ * -0.0f in the input is stored as +0.0f (the bit pattern of -0.0f is the handle's "never deposited" marker) */
 int wr_acs_upload_pheromone(wr_acs* a, const float* tau, size_t n);
 /* last iteration's colony (parity checks): size, lambda, Q of :247-249 */
 int wr_acs_last_colony(wr_acs* a, int* colony, float* lambda, float* Q);
@@ -160,11 +168,12 @@ int wr_acs_stream_kernel_ms(wr_acs* a, float* ms, int* launches);
 /* measurement hook: run ONE kernel of the update path `reps` times back to back on the handle's
  * stream and report the average device time per launch (CUDA events).  which: 0 = fused update
  * (evaporation + the last iteration's deposit records), 1 = float4 evaporation pass alone,
- * 2 = device-to-device copy of the pheromone field (in-run copy ceiling), 3 = the all-TMA ring
- * variant of the fused update (kept as a measurement point).  The field is
+ * 2 = device-to-device copy of the pheromone field (in-run copy ceiling).  The field is
  * multiplied by rho each time (which 0/1), so call it on a scratch search only. */
 int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch);
-/* use an existing CUDA stream (cudaStream_t as void*); default: a private non-blocking stream */
+/* use an existing CUDA stream (cudaStream_t as void*); default: a private non-blocking stream.  A sharded handle whose
+ * collectives are issued by somebody else (torch.distributed / NCCL on the caller's stream) MUST run on that stream:
+ * the protocol orders kernels and collectives by stream order alone (welding_robot_b200/dist.py binds it itself). */
 int wr_acs_set_stream(wr_acs* a, void* cuda_stream);
 
 /* ---- ant sharding across ranks: one process per GPU ----------------------

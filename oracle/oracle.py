@@ -74,6 +74,7 @@ def lib():
         L.wro_acs_set_endpoints.argtypes = [vp, C.c_int64, C.c_int64]
         L.wro_acs_begin.argtypes = [vp, C.c_float]
         L.wro_acs_iterate.argtypes = [vp, C.c_int]
+        L.wro_acs_set_next_search.argtypes = [vp, C.c_uint32]
         L.wro_acs_seq_seek.argtypes = [vp, C.c_uint64]
         L.wro_acs_seq_tell.restype = C.c_uint64
         L.wro_acs_seq_tell.argtypes = [vp]
@@ -238,6 +239,10 @@ class Acs:
         keep = lib().wro_acs_seq_tell(self.h)
         lib().wro_acs_begin(self.h, predict)
         lib().wro_acs_seq_seek(self.h, keep if seq_pos is None else seq_pos)
+
+    def set_next_search(self, idx):
+        """Keyed stream: the search index the next begin() takes (default: the number of begin() calls so far)."""
+        lib().wro_acs_set_next_search(self.h, idx)
 
     def iterate(self, n):
         r = lib().wro_acs_iterate(self.h, n)

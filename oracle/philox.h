@@ -54,11 +54,15 @@ static inline uint32_t wr_rand31(uint64_t seed, uint32_t a, uint32_t b, uint32_t
 }
 
 /* The 3-D search's keyed stream: one Philox block serves 4 consecutive steps of an ant —
- * draw(iteration, ant, step) = word (step & 3) of Philox(counter = (iteration, ant, step >> 2, stream)) >> 1.
- * Still a pure function of (seed; iteration, ant, step); the GPU evaluates a block once per 4 steps. */
-static inline uint32_t wr_rand31_step(uint64_t seed, uint32_t iteration, uint32_t ant, uint32_t step, uint32_t stream)
+ * draw(search, iteration, ant, step) = word (step & 3) of
+ *     Philox(counter = (iteration, ant, (step >> 2) | (search >> 16) << 16, stream + (search & 0xFFFF))) >> 1.
+ * `search` counts the computeSolution calls on one ACS_Rank object (0 for the first): the reference draws all its
+ * searches from ONE continuous rand() stream (ACSRank_3D.hpp:169, seeded once at :327), so successive searches are
+ * statistically independent; keying the counter by the search index keeps that property while a draw stays a pure
+ * function of (seed; search, iteration, ant, step).  step >> 2 < 2^14 (step cap 65532), so the halves do not overlap. */
+static inline uint32_t wr_rand31_step(uint64_t seed, uint32_t search, uint32_t iteration, uint32_t ant, uint32_t step, uint32_t stream)
 {
-    uint32_t ctr[4] = {iteration, ant, step >> 2, stream};
+    uint32_t ctr[4] = {iteration, ant, (step >> 2) | ((search >> 16) << 16), stream + (search & 0xFFFFu)};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t out[4];
     wr_philox4x32_10(ctr, key, out);

@@ -234,6 +234,7 @@ struct wro_acs {
     float predict;
     int iter;                     // iterations since begin()
     uint64_t seq_calls;           // SEQUENTIAL stream position
+    uint32_t search, next_search; // keyed stream: index of the current search (begin() calls so far - 1) / of the next one
     wro_ant best;
     std::vector<uint8_t> onbest;  // node-membership of the best path (findPathNode :101-108)
     std::vector<uint32_t> stamp;  // tabu (std::set in the reference, :70)
@@ -278,6 +279,7 @@ extern "C" wro_acs* wro_acs_create(const wro_grid* g, const wro_acs_params* p)
                     a->tau[id * a->K + k] = oob ? 0.f : p->tau0;
                 }
     a->start = a->goal = -1; a->predict = 0; a->iter = 0; a->seq_calls = 0;
+    a->search = 0; a->next_search = 0;
     a->best.L = WRO_INF_FLOAT; a->best.order = 0;
     a->onbest.assign(a->N, 0);
     a->stamp.assign(a->N, 0); a->serial = 0;
@@ -339,7 +341,10 @@ extern "C" void wro_acs_begin(wro_acs* a, float predict)
 {
     a->best.L = WRO_INF_FLOAT; /* best.path is left as is, like the reference */
     a->predict = predict; a->iter = 0; a->seq_calls = 0;
+    a->search = a->next_search++;
 }
+/* index the NEXT begin() takes in the keyed stream (queries of a batch are numbered by the caller) */
+extern "C" void wro_acs_set_next_search(wro_acs* a, uint32_t idx) { a->next_search = idx; }
 /* position of the sequential (n-th call) stream: the genuine all-pairs driver (:472-499) never
  * reseeds between pairs, so a pinning run seeks to the cumulative draw count before each pair */
 extern "C" void wro_acs_seq_seek(wro_acs* a, uint64_t pos) { a->seq_calls = pos; }
@@ -358,7 +363,7 @@ static inline uint32_t draw31(wro_acs* a, uint32_t iter, uint32_t ant, uint32_t 
         uint64_t n = a->seq_calls++;
         return wr_rand31(a->p.seed, (uint32_t)n, (uint32_t)(n >> 32), 0, WR_STREAM_SEQ);
     }
-    return wr_rand31_step(a->p.seed, iter, ant, step, WR_STREAM_ACS3D);
+    return wr_rand31_step(a->p.seed, a->search, iter, ant, step, WR_STREAM_ACS3D);
 }
 
 /* One construction step — :134-193.  Returns 1: moved and not at the goal, 0: stop.

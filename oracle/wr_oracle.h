@@ -67,7 +67,8 @@ void wro_acs_destroy(wro_acs* a);
 int wro_acs_set_points(wro_acs* a, const float s[3], const float e[3], int64_t ids[2]); /* :537-565 */
 int wro_acs_set_points_scan(wro_acs* a, const float s[3], const float e[3], int64_t ids[2]); /* literal full scan */
 int wro_acs_set_endpoints(wro_acs* a, int64_t start_id, int64_t goal_id);
-void wro_acs_begin(wro_acs* a, float predict_path_len);   /* :229-233 */
+void wro_acs_begin(wro_acs* a, float predict_path_len);   /* :229-233; takes the next search index of the keyed stream */
+void wro_acs_set_next_search(wro_acs* a, uint32_t idx);    /* keyed stream: search index the next begin() uses (default: begin() calls so far) */
 void wro_acs_seq_seek(wro_acs* a, uint64_t pos);           /* sequential-stream position (pinning runs) */
 uint64_t wro_acs_seq_tell(const wro_acs* a);
 int wro_acs_iterate(wro_acs* a, int n);                    /* n passes of the loop body :237-299 */

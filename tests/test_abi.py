@@ -80,3 +80,11 @@ def test_product_does_not_import_the_oracle():
                 for line in src.splitlines():
                     if re.search(r"(import|include|from|dlopen|CDLL).*oracle", line):
                         raise AssertionError("product file %s references oracle/: %s" % (os.path.join(d, f), line))
+
+
+def test_unknown_search_parameter_raises(L):
+    import welding_robot_b200 as wr
+    with pytest.raises(TypeError):
+        wr.ACS_Rank(step_caps=600)         # a typo must not silently run with defaults
+    a = wr.ACS_Rank(step_cap=600, max_iteration=7, alpha=2)
+    assert (a.params.step_cap, a.max_iteration, a.params.alpha) == (600, 7, 2)

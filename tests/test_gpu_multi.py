@@ -39,7 +39,6 @@ def worker(rank, world, port, q):
             with contextlib.redirect_stdout(io.StringIO()):
                 a.creatGridMap(tris, 0.012, 4)
                 a.initFromGridMap()
-            _lib.check(_lib.lib().wr_acs_set_stream(a._a, torch.cuda.current_stream().cuda_stream))
             free = np.flatnonzero(a.isfree())
             a.setEndpoints(int(free[11]), int(free[-11]))
             return a

@@ -100,7 +100,7 @@ def compare_iteration(A, g, check_tau=True, exact_tau=True):
             assert np.allclose(to, tg, rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("update_mode", [0, 1, 3, 4])
+@pytest.mark.parametrize("update_mode", [0, 1, 4])
 def test_c1_adaptive_colony_bit_exact(wr, oracle, meshes, update_mode):
     """cubic.stl @ (0.005, 10), reference defaults (adaptive colony), pair (0,5): every ant of
     every iteration, the best path and the whole pheromone field, bit for bit."""

@@ -269,11 +269,14 @@ class ACS_Rank(GridMap):
         self.params = AcsParams()
         check(lib().wr_acs_default_params(C.byref(self.params)))
         self.max_iteration = 150  # ACSRank_3D.hpp:322
+        known = {f[0] for f in AcsParams._fields_}
         for k, v in params.items():
             if k == "max_iteration":
                 self.max_iteration = v
-            else:
+            elif k in known:
                 setattr(self.params, k, v)
+            else:   # a typo must not silently run the search with defaults
+                raise TypeError("ACS_Rank: unknown parameter %r (known: max_iteration, %s)" % (k, ", ".join(sorted(known))))
         self._a = None
         self.best_matrix = None
         self.route_points = []
@@ -357,6 +360,10 @@ class ACS_Rank(GridMap):
 
     def begin(self, predict_path_len):
         check(lib().wr_acs_begin(self._need(), predict_path_len))
+
+    def setNextSearch(self, index):
+        """Philox: the search index the next begin() takes (default: the number of begin() calls so far)."""
+        check(lib().wr_acs_set_next_search(self._need(), index))
 
     def iterate(self, n=1):
         check(lib().wr_acs_iterate(self._need(), n))

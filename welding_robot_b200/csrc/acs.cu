@@ -100,6 +100,7 @@ struct wr_acs {
     int table_log2 = 9, gtable_log2 = 0;
     int table_entries = 512;          // k_walk2: entries per ant (768 by default: two 16-ant CTAs per SM)
     int64_t start = -1, goal = -1;
+    uint32_t search = 0, next_search = 0;   // Philox: index of the current computeSolution on this handle / of the next wr_acs_begin
     bool begun = false;
     int colony_max = 0, w_max = 0;
     // shard (multi-rank)
@@ -420,12 +421,6 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     return WR_OK;
 }
 
-// walk kernel generation: 2 (default) = k_walk2, 1 = k_walk (also taken when an axis exceeds the packed-coordinate range)
-static int walk_version(const wr_grid* g)
-{
-    static const int env = [] { const char* e = getenv("WR_WALK_V"); return e ? atoi(e) : 2; }();
-    return (env == 1 || g->rx > 1024 || g->ry > 1024 || g->rz > 1024) ? 1 : 2;
-}
 static int walk_prefetch()
 {
     static const int env = [] { const char* e = getenv("WR_WALK_PREFETCH"); return e ? atoi(e) : -1; }();   // -1: chosen per iteration (launch_walk)
@@ -444,9 +439,7 @@ static int walk_warm()
 static size_t walk_smem(const wr_acs* a)
 {
     if (a->K == kK26) return ((size_t)kWalk26Ants << a->table_log2) * 12;
-    if (walk_version(a->g) == 2) return kWalk2Lut + 128 + (size_t)kAntsPerCta * a->table_entries * sizeof(unsigned long long);
-    const size_t coord_bytes = ((size_t)(a->g->rx + a->g->ry + a->g->rz + 6) * 4 + 15) & ~(size_t)15;
-    return coord_bytes + ((size_t)kAntsPerCta << a->table_log2) * 12;
+    return kWalk2Lut + 128 + (size_t)kAntsPerCta * a->table_entries * sizeof(unsigned long long);
 }
 
 extern "C" const char* wr_last_error(void) { return g_err.c_str(); }
@@ -509,7 +502,9 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     *out = nullptr;
     WR_REQUIRE(p->K == 6 || p->K == kK26, WR_ERR_INVALID, "wr_acs_create: K must be 6 (the reference's neighbourhood) or 26 (its disabled extension)");
     WR_REQUIRE(p->alpha >= 0 && p->alpha < 64, WR_ERR_INVALID, "wr_acs_create: alpha out of range");
-    WR_REQUIRE(p->update_mode >= WR_UPDATE_FUSED && p->update_mode <= WR_UPDATE_RANKSET, WR_ERR_INVALID, "wr_acs_create: bad update_mode");
+    WR_REQUIRE(p->update_mode >= WR_UPDATE_FUSED && p->update_mode <= WR_UPDATE_RANKSET && p->update_mode != 3, WR_ERR_INVALID, "wr_acs_create: bad update_mode");
+    WR_REQUIRE(p->K != 6 || (g->rx <= 1024 && g->ry <= 1024 && g->rz <= 1024), WR_ERR_INVALID,
+               "wr_acs_create: a grid axis exceeds 1024 nodes (k_walk2 packs node coordinates into 10 bits per axis)");
     WR_REQUIRE((unsigned long long)g->N * p->K < 0xFFFFFFFFull - kUpdTile, WR_ERR_INVALID, "wr_acs_create: grid too large for 32-bit slot ids");
     WR_REQUIRE(g->N >= 2, WR_ERR_INVALID, "wr_acs_create: grid too small");
     wr_acs* a = new wr_acs();
@@ -571,14 +566,11 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     WR_CUDA_A(dmalloc(&a->d_dep_list, ((size_t)a->ntiles + 2) * sizeof(uint32_t), a->stream));
     WR_CUDA_A(dmalloc(&a->d_upd_q, 4 * sizeof(uint32_t), a->stream));
     {
-        size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
-        WR_CUDA_A(cudaFuncSetAttribute(k_update_tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         WR_CUDA_A(cudaFuncSetAttribute(k_rank_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmallSmem));
         const size_t ws = walk_smem(a);
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         if (a->K == kK26) WR_CUDA_A(cudaFuncSetAttribute(k_walk26<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         else {
-        WR_CUDA_A(cudaFuncSetAttribute(k_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
@@ -664,6 +656,13 @@ extern "C" int wr_acs_set_endpoints(wr_acs* a, int64_t s, int64_t e)
     return WR_OK;
 }
 
+extern "C" int wr_acs_set_next_search(wr_acs* a, uint32_t index)
+{
+    WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_set_next_search: null");
+    a->next_search = index;
+    return WR_OK;
+}
+
 extern "C" int wr_acs_begin(wr_acs* a, float predict)
 {
     WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_begin: null");
@@ -674,6 +673,7 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     int st = alloc_colony_buffers(a, cm);
     if (st != WR_OK) return st;
     a->colony_max = cm;
+    a->search = a->next_search++;
     if (!a->d_heur) WR_CUDA(dmalloc(&a->d_heur, a->n_slots_pad * sizeof(float), a->stream));
     if (a->heur_goal != a->goal && a->K == kK26) {
         k_heuristic26<<<(unsigned)((a->n_slots + 255) / 256), 256, 0, a->stream>>>(a->d_heur, a->g->d_coords, a->g->d_bits, a->g->rx, a->g->ry, a->g->rz, a->N,
@@ -711,7 +711,7 @@ static void launch_walk2(const WalkArgs& w, bool alpha1, int prefetch, int block
 // before k_iter_begin: pull the rows under last iteration's deposits into L2 (see k_path_warm)
 static void launch_warm(wr_acs* a, bool prev_rankset)
 {
-    if (!walk_warm() || walk_version(a->g) != 2 || a->p.update_mode == WR_UPDATE_ATOMIC || a->K != 6) return;
+    if (!walk_warm() || a->p.update_mode == WR_UPDATE_ATOMIC || a->K != 6) return;
     if (a->rankset && a->rs_enqueued > 0 && prev_rankset) {   // the previous iteration's deposits went through rank sets
         k_rankset_warm<<<kNumSMs, 256, 0, a->stream>>>(a->rs.touched, a->rs.count, a->d_tau, a->d_heur, a->d_state);
         return;
@@ -730,6 +730,7 @@ static int launch_walk(wr_acs* a)
     w.rx = g->rx; w.ry = g->ry; w.rz = g->rz;
     w.start = (int)a->start; w.goal = (int)a->goal;
     w.seed_lo = (uint32_t)a->p.seed; w.seed_hi = (uint32_t)(a->p.seed >> 32);
+    w.stream_word = kStreamAcs3D + (a->search & 0xFFFFu); w.block_hi = (a->search >> 16) << 16;
     w.alpha = a->p.alpha; w.beta = a->p.beta; w.cap = a->cap;
     w.shard_first = a->rank * a->chunk; w.shard_chunk = a->chunk;
     w.ant_steps = a->d_local_steps;
@@ -747,27 +748,19 @@ static int launch_walk(wr_acs* a)
         WR_CUDA(cudaGetLastError());
         return WR_OK;
     }
-    const int ver = walk_version(g);
     const size_t smem1 = walk_smem(a);
     const int per_sm = std::max(1, (int)((227 * 1024) / (smem1 + 1024)));
     const int blocks1 = std::max(1, std::min((a->chunk + kAntsPerCta - 1) / kAntsPerCta, kNumSMs * std::min(per_sm, 16)));
-    if (ver == 2) {
-        const bool alpha1 = a->p.alpha == 1;
-        // L1 prefetch of the six neighbour rows pays while the colony wanders (rows come from L2/HBM); once its deposits are
-        // concentrated — the same device feedback that selects the rank-set path — the rows are hot and the twelve prefetch
-        // instructions per step are pure issue cost (converged walk 0.346 -> 0.317 ms without them)
-        int pf = walk_prefetch();
-        if (pf < 0) pf = (a->rankset && a->rs_choice) ? 0 : 2;
-        launch_walk2<false>(w, alpha1, pf, blocks1, smem1, a->stream);
-        // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
-        w.table_log2 = a->gtable_log2;
-        launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, kWalk2Lut + 128, a->stream);
-    } else {
-        const size_t coord_bytes = ((size_t)(g->rx + g->ry + g->rz + 6) * 4 + 15) & ~(size_t)15;   // + guard elements
-        k_walk<false><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-        w.table_log2 = a->gtable_log2;
-        k_walk<true><<<a->walk2_blocks, kWalkThreads, coord_bytes, a->stream>>>(w);
-    }
+    const bool alpha1 = a->p.alpha == 1;
+    // L1 prefetch of the six neighbour rows pays while the colony wanders (rows come from L2/HBM); once its deposits are
+    // concentrated — the same device feedback that selects the rank-set path — the rows are hot and the twelve prefetch
+    // instructions per step are pure issue cost (converged walk 0.346 -> 0.317 ms without them)
+    int pf = walk_prefetch();
+    if (pf < 0) pf = (a->rankset && a->rs_choice) ? 0 : 2;
+    launch_walk2<false>(w, alpha1, pf, blocks1, smem1, a->stream);
+    // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
+    w.table_log2 = a->gtable_log2;
+    launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, kWalk2Lut + 128, a->stream);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -853,10 +846,6 @@ static int launch_update(wr_acs* a)
     if (a->p.update_mode == WR_UPDATE_FUSED) {
         int rc = launch_fused(a, ck, cv, a->dptr_nrec_upd());
         if (rc != WR_OK) return rc;
-    } else if (a->p.update_mode == WR_UPDATE_FUSED_TMA) {
-        k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(a->dptr_nrec(), ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
-        const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
-        k_update_tma_ring<<<std::min<unsigned>(a->ntiles, kNumSMs * 2), kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
     } else {
         k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
         k_deposit_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, ck, cv, a->d_tau);
@@ -1309,7 +1298,17 @@ extern "C" int wr_acs_upload_pheromone(wr_acs* a, const float* tau, size_t n)
     WR_REQUIRE(a && tau, WR_ERR_INVALID, "wr_acs_upload_pheromone: null");
     WR_REQUIRE(n == a->n_slots, WR_ERR_INVALID, "wr_acs_upload_pheromone: size mismatch");
     WR_CUDA(cudaStreamSynchronize(a->stream));
-    WR_CUDA(cudaMemcpy(a->d_tau, tau, a->n_slots * sizeof(float), cudaMemcpyHostToDevice));
+    if (a->lazy) {
+        // clean-tile field: the bit pattern of -0.0f is the "never deposited" sentinel, which every kernel replaces by
+        // IterState::base.  An uploaded -0.0f is a VALUE (it compares equal to 0 and evaporates to -0 like +0 to +0), so it
+        // is stored as +0.0f: the same number in every comparison and product the search performs on it.
+        std::vector<float> h(tau, tau + a->n_slots);
+        uint32_t* w = reinterpret_cast<uint32_t*>(h.data());
+        for (size_t i = 0; i < a->n_slots; i++) if (w[i] == kSentinelBits) w[i] = 0u;
+        WR_CUDA(cudaMemcpy(a->d_tau, h.data(), a->n_slots * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        WR_CUDA(cudaMemcpy(a->d_tau, tau, a->n_slots * sizeof(float), cudaMemcpyHostToDevice));
+    }
     WR_CUDA(cudaMemset(a->d_dirty, 1, (size_t)a->ntiles + 1));   // explicit values everywhere: every tile takes part in the evaporation
     return WR_OK;
 }
@@ -1419,7 +1418,7 @@ extern "C" int wr_acs_field_stats(wr_acs* a, uint64_t out[2])
 
 extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch)
 {
-    WR_REQUIRE(a && ms_per_launch && reps > 0 && which >= 0 && which <= 3, WR_ERR_INVALID, "wr_acs_bench_kernel: bad argument");
+    WR_REQUIRE(a && ms_per_launch && reps > 0 && which >= 0 && which <= 2, WR_ERR_INVALID, "wr_acs_bench_kernel: bad argument");
     WR_REQUIRE(a->begun, WR_ERR_STATE, "wr_acs_bench_kernel: call wr_acs_begin first");
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
@@ -1435,16 +1434,11 @@ extern "C" int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per
         ck = cv = a->rs.list;
         d_n = reinterpret_cast<const int*>(a->rs.count + 2);
     }
-    const size_t smem = (size_t)kUpdStages * kUpdTile * sizeof(float) + kUpdStages * sizeof(uint64_t);
-    const unsigned blocks = std::min<unsigned>(a->ntiles, kNumSMs * 2);
     for (int r = -1; r < reps; r++) {   // one untimed warm-up launch
         if (r == 0) WR_CUDA(cudaEventRecord(e0, s));
         if (which == 0) {
             int rc = launch_fused(a, ck, cv, d_n);
             if (rc != WR_OK) return rc;
-        } else if (which == 3) {
-            k_tile_offsets<<<(a->ntiles + 1 + 255) / 256, 256, 0, s>>>(d_n, ck, a->d_tile_off, a->ntiles, nullptr, nullptr);
-            k_update_tma_ring<<<blocks, kUpdThreads, smem, s>>>(a->d_tau, a->ntiles, a->p.rho, ck, cv, a->d_tile_off);
         } else if (which == 1) {
             k_evaporate<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->n_slots_pad / 4, a->p.rho);
         } else {

@@ -1,5 +1,5 @@
 // Device kernels of the rank-based 3-D ant colony search (ACS_Rank, core/ACSRank_3D.hpp).
-//   K2  k_walk            ant construction (selectNext :134-193 + the ant loop :252-265)
+//   K2  k_walk2 (walk2.cuh) ant construction (selectNext :134-193 + the ant loop :252-265)
 //   --  k_rank_*          colony ranking, best tracking (:263-264, :273-274)
 //   --  k_deposit_gen     deposit records of update_pheromone (:198-215)
 //   K3  k_update_fused    evaporation (:268-272) + rank-ordered deposits in ONE HBM pass (TMA)
@@ -46,6 +46,8 @@ struct WalkArgs {
     int rx, ry, rz;
     int start, goal;
     uint32_t seed_lo, seed_hi;
+    uint32_t stream_word;    // Philox counter word 3: kStreamAcs3D + (search & 0xFFFF)   (search = index of this computeSolution on the handle)
+    uint32_t block_hi;       // OR-ed into counter word 2 (step >> 2): (search >> 16) << 16
     int alpha;
     float beta;
     int cap;                 // max steps per ant
@@ -53,7 +55,7 @@ struct WalkArgs {
     int* ant_steps;          // [chunk]  steps, -1 dead, -2 pending (table overflow -> pass 2)
     uint32_t* path_ids;      // [chunk][cap]   node the ant stood on before step i
     uint8_t* path_dirs;      // [chunk][cap]   slot chosen at step i
-    int table_log2;          // k_walk: shared-memory (pass 1) or global (pass 2) visited-tile table size
+    int table_log2;          // k_walk26: shared-memory (pass 1) or global (pass 2) visited-tile table size
     int table_entries;       // k_walk2: shared-memory visited-tile entries per ant (any size; the HBM tables of pass 2 have 1 << gtable_log2)
     uint32_t* overflow_list; // [chunk]
     uint32_t* gkeys;         // HBM visited tables, one per overflowed ant: [chunk][1 << gtable_log2]
@@ -183,245 +185,6 @@ __global__ void __launch_bounds__(256) k_heuristic(float* __restrict__ heur, con
     }
     float2* o = reinterpret_cast<float2*>(heur + id * 6);
     o[0] = make_float2(h[0], h[1]); o[1] = make_float2(h[2], h[3]); o[2] = make_float2(h[4], h[5]);
-}
-
-// ------------------------------------------------------------------------------------------
-// K2: one ant per 8-lane group, 4 ants per warp, 16 per CTA; persistent warps pull 4 ants at a time
-// from a device-side queue and step them in LOCKSTEP, so every warp collective runs with the full
-// mask (one SHFL / VOTE instruction each; sub-warp masks held in registers make the compiler emit a
-// MATCH/REDUX/WARPSYNC sequence per collective — measured 421 instructions per warp-step, see
-// profiles/).  A step is straight-line predicated code: an ant that has arrived or died just idles
-// until its three warp mates are done.
-//
-// Lane k < 6 owns neighbour slot k: it loads tau[cur][k] (the six lanes of a group read 24
-// contiguous bytes: one coalesced request), probes the visited set for its neighbour and evaluates
-// tau^alpha * (1 + beta*cos).  The roulette needs the reference's exact summation order (ascending
-// for `total`, descending for `prob_sum`), so the six scores are exchanged with width-8 shuffles and
-// every lane re-adds them sequentially — two chains of 6 dependent FADDs, cheap next to the
-// pheromone gather.  Non-candidates carry info = +0, which is the identity of the chain.
-// The walk of one ant is a chain of dependent steps, so with a few thousand ants the kernel is
-// bound by the latency of one step, not by bandwidth: everything in the step is about a short
-// critical path (one Philox call per 4 steps, |d| instead of sqrt(d*d), unconditional first probe).
-//
-// Visited set ("tabu", std::set at :70): an open-addressed hash of 4x4x4-node tiles, 64-bit
-// occupancy mask per tile, in shared memory.  A lattice walk re-visits the same few tiles, so a
-// 512-slot table (6 KB) holds walks of thousands of steps.  An ant that fills its table to 3/4
-// moves its visited set to a table in HBM sized for the step cap (parallel CAS inserts), parks its
-// state, and is RESUMED by pass 2 (GLOBAL = true) from the step it stopped at — exact, because its
-// draws are a pure function of (iteration, ant, step).  Keeping the two table kinds in two launches
-// lets the common path keep shared-memory addressing (a run-time switch costs 8-13 % per step).
-// ------------------------------------------------------------------------------------------
-template <bool GLOBAL>
-__global__ void __launch_bounds__(kWalkThreads) k_walk(WalkArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    // move table: slot c -> {node-id stride, dx, dy, dz} (one LDS.128 per step instead of a dozen compares)
-    int4* move_lut = reinterpret_cast<int4*>(smem_raw);
-    const int ncoord = a.rx + a.ry + a.rz + 6;   // the visited tables start behind this (reserved) region
-    if (threadIdx.x < 8) {
-        const int c = threadIdx.x;
-        const int dx = (c == 3) - (c == 2), dy = (c == 4) - (c == 1), dz = (c == 5) - (c == 0);
-        move_lut[c] = make_int4(dx + dy * a.rx + dz * a.rx * a.ry, dx, dy, dz);
-    }
-    __syncthreads();
-
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int gbase = lane & 24;
-    const int k = lane & 7;
-    const int g = threadIdx.x >> 3;
-    const int E = 1 << a.table_log2;
-    const int hshift = 32 - a.table_log2;
-
-    unsigned long long* masks;
-    uint32_t* keys;
-    if (GLOBAL) {
-        keys = a.gkeys; masks = a.gmasks;   // re-pointed per ant below
-    } else {
-        unsigned long long* mbase = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)ncoord * 4 + 15) & ~(size_t)15));
-        masks = mbase + (size_t)g * E;
-        keys = reinterpret_cast<uint32_t*>(mbase + (size_t)kAntsPerCta * E) + (size_t)g * E;
-    }
-
-    const int rx = a.rx, ry = a.ry;
-    const int rxy = rx * ry;
-    const int TX = (rx + 3) >> 2, TY = (ry + 3) >> 2;
-    const int dxk = (k == 3) - (k == 2), dyk = (k == 4) - (k == 1), dzk = (k == 5) - (k == 0);
-    const int stride_k = dxk + dyk * rx + dzk * rxy;
-    const int axis_k = (k == 2 || k == 3) ? 0 : ((k == 1 || k == 4) ? 1 : 2);   // which component of b is non-zero
-    const int dk = dxk + dyk + dzk;                                          // +-1 along that axis (0 for the idle lanes)
-    const int kk6 = k < 6 ? k : 5;                                           // idle lanes re-read slot 5 (same sector)
-
-    const int sz = a.start / rxy, sy = (a.start % rxy) / rx, sx = a.start % rx;
-    const int gz = a.goal / rxy, gy = (a.goal % rxy) / rx, gx = a.goal % rx;
-    const bool alpha1 = a.alpha == 1;
-    const float beta = a.beta;
-
-    IterState* st = a.st;
-    const int colony = st->colony;
-    const uint32_t iter = (uint32_t)st->iter;
-    const float base_now = st->base;
-    int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
-    if (GLOBAL) local_n = (int)st->overflow_n;
-    const int limit = (E >> 2) * 3;
-
-    unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
-
-    while (true) {
-        unsigned q0 = 0;
-        if (lane == 0) q0 = atomicAdd(GLOBAL ? &st->queue2 : &st->queue, 4u);
-        q0 = __shfl_sync(FULL, q0, 0);
-        if (q0 >= (unsigned)local_n) break;                       // warp-uniform
-        const unsigned q = q0 + (unsigned)(lane >> 3);
-        const bool has = q < (unsigned)local_n;
-        const int ant_local = has ? (GLOBAL ? (int)a.overflow_list[q] : (int)q) : 0;
-        const uint32_t ant_global = (uint32_t)(a.shard_first + ant_local);
-
-        int cur = a.start, x = sx, y = sy, z = sz, steps = 0, ntiles = 1;
-        uint32_t rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0;
-        if (GLOBAL) {   // resume a parked ant: its visited set already lives in HBM table q
-            keys = a.gkeys + (size_t)(has ? q : 0) * E;
-            masks = a.gmasks + (size_t)(has ? q : 0) * E;
-            if (has) {
-                const int4 r = a.resume[q];
-                cur = r.x; steps = r.y; ntiles = r.z;
-                z = cur / rxy; y = (cur % rxy) / rx; x = cur % rx;
-                philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
-            }
-        } else {
-            for (int i = k; i < E; i += kGroup) keys[i] = kEmptyKey;
-            __syncwarp();
-            if (k == 0) {   // addStartNode :81-86
-                uint32_t tile = (uint32_t)(((z >> 2) * TY + (y >> 2)) * TX + (x >> 2));
-                unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
-                unsigned slot = (tile * 2654435761u) >> hshift;
-                keys[slot] = tile; masks[slot] = 1ull << bit;
-            }
-        }
-        __syncwarp();
-
-        bool live = has;
-        int result = -1;   // >= 0: steps of an ant that arrived, -1: dead, -2: pending (table overflow -> pass 2)
-        int reason = 0;    // why a dead ant died: 1 no candidate, 2 roulette fall-through, 3 step cap
-        uint32_t* pid = a.path_ids + (size_t)ant_local * a.cap;
-        uint8_t* pdir = a.path_dirs + (size_t)ant_local * a.cap;
-
-        while (__any_sync(FULL, live)) {
-            // ---- step cap (a deviation the oracle mirrors; the reference is unbounded) ------------
-            const bool capped = live && steps >= a.cap;
-            reason = capped ? 3 : reason;
-            live = live && !capped;
-            // ---- the loads of this step ---------------------------------------------------------
-            const float tau_k = tau_or_base(__ldg(a.tau + (size_t)cur * 6 + kk6), base_now);
-            const float heur_k = __ldg(a.heur + (size_t)cur * 6 + kk6);
-            // ---- Philox: one call yields the draws of 4 consecutive steps (the live ants of a warp are
-            //      in lockstep, so the branch is warp-uniform) ---------------------------------------
-            if (live && (steps & 3) == 0) philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
-            const uint32_t rsel = (steps & 2) ? ((steps & 1) ? rw3 : rw2) : ((steps & 1) ? rw1 : rw0);
-            // (float)rand()/(float)RAND_MAX (:169): (float)RAND_MAX is 2^31, so the division is an exact scaling
-            const float u = __fmul_rn(__int2float_rn((int)(rsel >> 1)), 4.656612873077392578125e-10f);
-            // ---- neighbour k: bounds+free (open mask), tabu probe -------------------------------
-            const int nx = x + dxk, ny = y + dyk, nz = z + dzk;
-            const bool open_k = (k < 6) && heur_k != kClosedSlot;   // NaN (duplicate plane) stays open, as in the reference
-            const uint32_t tile = (uint32_t)(((nz >> 2) * TY + (ny >> 2)) * TX + (nx >> 2));
-            const unsigned bit = ((nz & 3) << 4) | ((ny & 3) << 2) | (nx & 3);
-            unsigned slot = (tile * 2654435761u) >> hshift;
-            uint32_t kk = keys[slot];
-            unsigned long long mm = masks[slot];
-            while (open_k && kk != tile && kk != kEmptyKey) {   // collisions are rare at load <= 3/4
-                slot = (slot + 1) & (E - 1);
-                kk = keys[slot]; mm = masks[slot];
-            }
-            const bool found = kk == tile;
-            const bool cand = live && open_k && !(found && ((mm >> bit) & 1ull));
-            // ---- info = tau^alpha * (1 + beta*cos)  (:151-154) ----------------------------------
-            // the geometric factor depends only on (node, slot, goal): k_heuristic tabulated it with the reference's
-            // operations when the endpoints were set, so a step gathers it next to the pheromone (same 24-byte row
-            // pattern) instead of redoing three coordinate look-ups, a square root and a division
-            const float tpow = alpha1 ? tau_k : pow_int(tau_k, a.alpha);
-            const float info = cand ? __fmul_rn(tpow, heur_k) : 0.0f;
-            const unsigned cb = (__ballot_sync(FULL, cand) >> gbase) & 0x3Fu;
-            // ---- roulette in the reference's order (:155, :172-181) ------------------------------
-            const float v0 = __shfl_sync(FULL, info, 0, 8), v1 = __shfl_sync(FULL, info, 1, 8), v2 = __shfl_sync(FULL, info, 2, 8);
-            const float v3 = __shfl_sync(FULL, info, 3, 8), v4 = __shfl_sync(FULL, info, 4, 8), v5 = __shfl_sync(FULL, info, 5, 8);
-            const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, v0), v1), v2), v3), v4), v5);
-            const float rnd = __fmul_rn(u, total);
-            // this lane's prob_sum: v5 + v4 + ... + v_k, then zeros (the identity), so one chain serves all lanes
-            const float mine = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, v5), k <= 4 ? v4 : 0.0f), k <= 3 ? v3 : 0.0f),
-                                                              k <= 2 ? v2 : 0.0f), k <= 1 ? v1 : 0.0f), k <= 0 ? v0 : 0.0f);
-            const bool pick = cand && (mine >= rnd);
-            const unsigned pb = (__ballot_sync(FULL, pick) >> gbase) & 0x3Fu;
-            const int c = (31 - __clz((int)(pb | 1u)));            // first hit scanning 5 -> 0 (pb == 0 handled below)
-            // ---- outcome -------------------------------------------------------------------------
-            const bool stepok = live && pb != 0;
-            reason = (live && !stepok) ? (cb == 0 ? 1 : 2) : reason;   // :162-166 / fall-through :191-192
-            // addNextNode (:73-79)
-            if (stepok && k == 0) { pid[steps] = (uint32_t)cur; pdir[steps] = (uint8_t)c; }
-            if (stepok && k == c) { keys[slot] = tile; masks[slot] = found ? (mm | (1ull << bit)) : (1ull << bit); }
-            const unsigned fb = (__ballot_sync(FULL, found) >> gbase) & 0x3Fu;
-            const int newtile = stepok ? (int)(((fb >> c) & 1u) ^ 1u) : 0;
-            const int4 mv = move_lut[c];
-            if (stepok) {
-                cur += mv.x; x += mv.y; y += mv.z; z += mv.w;
-                steps++;
-                ntiles += newtile;
-            }
-            const bool arrived = stepok && cur == a.goal;          // :182-186
-            const bool over = !GLOBAL && stepok && !arrived && newtile && ntiles > limit;
-            result = arrived ? steps : (over ? -2 : result);
-            live = stepok && !arrived && !over;
-            __syncwarp();
-            if (!GLOBAL && __any_sync(FULL, over)) {   // rare: an ant of this warp filled its shared-memory table to 3/4
-                int o = 0;
-                if (over && k == 0) o = (int)atomicAdd(&st->overflow_n, 1u);
-                o = __shfl_sync(FULL, o, 0, 8);
-                const int Eg = 1 << a.gtable_log2, gsh = 32 - a.gtable_log2;
-                uint32_t* nkeys = a.gkeys + (size_t)(over ? o : 0) * Eg;
-                unsigned long long* nmasks = a.gmasks + (size_t)(over ? o : 0) * Eg;
-                if (over) for (int i = k; i < Eg; i += kGroup) nkeys[i] = kEmptyKey;
-                __syncwarp();
-                if (over) {
-                    for (int i = k; i < E; i += kGroup) {
-                        const uint32_t t = keys[i];
-                        if (t == kEmptyKey) continue;
-                        unsigned sl = (t * 2654435761u) >> gsh;
-                        while (atomicCAS(&nkeys[sl], kEmptyKey, t) != kEmptyKey) sl = (sl + 1) & (Eg - 1);
-                        nmasks[sl] = masks[i];
-                    }
-                    if (k == 0) {
-                        a.resume[o] = make_int4(cur, steps, ntiles, 0);
-                        a.overflow_list[o] = (uint32_t)ant_local;
-                        a.ant_steps[ant_local] = -2;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        if (has && result != -2) {
-            c_arrived += result >= 0 ? 1 : 0;
-            c_nocand += (result < 0 && reason == 1) ? 1 : 0;
-            c_fall += (result < 0 && reason == 2) ? 1 : 0;
-            c_cap += (result < 0 && reason == 3) ? 1 : 0;
-        }
-        if (has) {
-            if (result == -2) {
-                c_over++;   // parked for pass 2 (its steps are counted there)
-            } else {
-                if (k == 0) a.ant_steps[ant_local] = result;
-                c_steps += (unsigned long long)steps; c_ants++;
-            }
-        }
-        __syncwarp();
-    }
-    if (k == 0) {
-        if (c_steps) atomicAdd(&st->cnt[0], c_steps);
-        if (c_ants) atomicAdd(&st->cnt[1], c_ants);
-        if (c_arrived) atomicAdd(&st->cnt[2], c_arrived);
-        if (c_nocand) atomicAdd(&st->cnt[3], c_nocand);
-        if (c_fall) atomicAdd(&st->cnt[4], c_fall);
-        if (c_cap) atomicAdd(&st->cnt[5], c_cap);
-        if (c_over) atomicAdd(&st->cnt[8], c_over);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -780,10 +543,9 @@ __global__ void __launch_bounds__(256) k_deposit_apply(const IterState* st, cons
 // ------------------------------------------------------------------------------------------
 // K3 fused: evaporation + rank-ordered deposits in a single HBM pass over the pheromone field, in
 // 16 KB tiles.  tile_off[t] .. tile_off[t+1] delimit tile t's (slot-sorted) records
-// (k_tile_offsets, binary search).  Two variants:
-//   k_update_tma_ring  every tile goes through a 4-stage TMA ring in shared memory (first design;
-//                      kept as a measurement point: 63 % of the measured copy bandwidth);
-//   k_update_fused     the shipped kernel, below.
+// (k_tile_offsets, binary search).  (A variant that staged every tile through a 4-stage TMA ring in shared memory was
+// measured in round 1 — 90 % of the copy bandwidth without records, 61-70 % with, it pays a load round trip per deposit
+// tile — and dropped; profiles/r1*_update_fused_ncu.md keep the numbers.)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys, int n, unsigned long long target)
 {
@@ -804,64 +566,6 @@ __global__ void k_tile_offsets(const int* __restrict__ d_n, const uint32_t* __re
     const int lo = lower_bound_key(keys, n, (unsigned long long)t * kUpdTile);
     tile_off[t] = (uint32_t)lo;
     if (dep_list && t < ntiles && lo < n && (unsigned long long)keys[lo] < (unsigned long long)(t + 1) * kUpdTile) dep_list[atomicAdd(dep_n, 1u)] = t;
-}
-
-__global__ void __launch_bounds__(kUpdThreads) k_update_tma_ring(float* tau, unsigned ntiles, float rho, const uint32_t* __restrict__ rec_keys,
-                                                                  const uint32_t* __restrict__ rec_vals, const uint32_t* __restrict__ tile_off)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stage = reinterpret_cast<float*>(smem_raw);                                  // [kUpdStages][kUpdTile]
-    uint64_t* full = reinterpret_cast<uint64_t*>(stage + (size_t)kUpdStages * kUpdTile);   // [kUpdStages]
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        for (int s = 0; s < kUpdStages; s++) tma::mbar_init(&full[s], 1);
-        tma::fence_barrier_init();
-    }
-    __syncthreads();
-    // contiguous tile range per CTA: a path's hot tiles are a fixed stride apart (one z-plane = 96 tiles at
-    // 256^3), which a round-robin assignment folds onto a few CTAs
-    const unsigned per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const unsigned first = blockIdx.x * per, stride = 1;
-    const unsigned cnt = first < ntiles ? min(per, ntiles - first) : 0;
-    constexpr uint32_t kBytes = kUpdTile * sizeof(float);
-    if (tid == 0) {
-        for (unsigned i = 0; i < (unsigned)(kUpdStages - 1) && i < cnt; i++) {
-            tma::mbar_arrive_expect_tx(&full[i], kBytes);
-            tma::bulk_g2s(stage + (size_t)i * kUpdTile, tau + (size_t)(first + i * stride) * kUpdTile, kBytes, &full[i]);
-        }
-    }
-    for (unsigned i = 0; i < cnt; i++) {
-        const unsigned s = i % kUpdStages;
-        const unsigned t = first + i * stride;
-        float* buf = stage + (size_t)s * kUpdTile;
-        tma::mbar_wait(&full[s], (i / kUpdStages) & 1u);
-        float4* b4 = reinterpret_cast<float4*>(buf);
-#pragma unroll
-        for (int j = 0; j < kUpdTile / 4 / kUpdThreads; j++) {
-            float4 v = b4[j * kUpdThreads + tid];
-            v.x = __fmul_rn(v.x, rho); v.y = __fmul_rn(v.y, rho); v.z = __fmul_rn(v.z, rho); v.w = __fmul_rn(v.w, rho);
-            b4[j * kUpdThreads + tid] = v;
-        }
-        const uint32_t lo = tile_off[t], hi = tile_off[t + 1];
-        if (lo < hi) {   // block-uniform
-            __syncthreads();
-            apply_runs(buf, t * (uint32_t)kUpdTile, rec_keys, rec_vals, lo, hi, (uint32_t)(tid & ~31), (uint32_t)kUpdThreads);
-        }
-        tma::fence_proxy_async();   // generic-proxy writes -> visible to the bulk store
-        __syncthreads();
-        if (tid == 0) {
-            tma::bulk_s2g(tau + (size_t)t * kUpdTile, buf, kBytes);
-            tma::bulk_commit();
-            const unsigned nxt = i + kUpdStages - 1;
-            if (nxt < cnt) {
-                tma::bulk_wait_read<1>();   // the store of tile i-1 has drained stage (i-1)%S
-                const unsigned ns = nxt % kUpdStages;
-                tma::mbar_arrive_expect_tx(&full[ns], kBytes);
-                tma::bulk_g2s(stage + (size_t)ns * kUpdTile, tau + (size_t)(first + nxt * stride) * kUpdTile, kBytes, &full[ns]);
-            }
-        }
-    }
-    if (tid == 0) tma::bulk_wait<0>();
 }
 
 // The shipped fused update.  A CTA owns a contiguous run of 16 KB tiles.  Every tile is streamed

@@ -1,14 +1,30 @@
-// K2, second generation of the ant-construction kernel (selectNext ACSRank_3D.hpp:134-193 + the ant loop :252-265).
-// Same parallelisation as k_walk (one ant per 8-lane group, 4 ants per warp in lockstep, persistent warps on a
-// device queue) and bit-identical results; what changed is the length of the per-step instruction stream, which is
-// what bounds a colony of a few thousand ants (profiles/: ~300 warp-instructions per step at ~6 cycles each):
+// K2, the ant-construction kernel (selectNext ACSRank_3D.hpp:134-193 + the ant loop :252-265).
+//
+// One ant per 8-lane group (6 neighbour lanes + 2 idle), 4 ants per warp, 16 per CTA; persistent warps pull 4 ants at a
+// time from a device-side queue and step them in LOCKSTEP, so every warp collective runs with the full mask (sub-warp
+// masks held in registers make the compiler emit a MATCH/REDUX/WARPSYNC sequence per collective — the first kernel
+// measured 421 instructions per warp-step that way).  A step is straight-line predicated code: an ant that has arrived
+// or died idles until its three warp mates are done.
+//
+// Lane k < 6 owns neighbour slot k: it loads tau[cur][k] and the tabulated geometric factor heur[cur][k] (the six lanes
+// of a group read 24 contiguous bytes per array: one request each), probes the visited set for its neighbour and
+// evaluates tau^alpha * (1 + beta*cos).  The roulette needs the reference's exact summation order (ascending for
+// `total`, descending for `prob_sum`), so the six scores are exchanged with width-8 shuffles and every lane re-adds them
+// sequentially — two chains of 6 dependent FADDs.  Non-candidates carry info = +0, the identity of the chain.
+// A walk is a chain of dependent steps, so a colony of a few thousand ants is bound by the latency of one step, not by
+// bandwidth; what this kernel is about is the length of the per-step instruction stream (~180 warp-instructions):
 //   * node coordinates live in ONE packed register  P = z<<20 | y<<10 | x  (a move is one add; needs dims <= 1024,
-//     larger grids take k_walk);
-//   * the visited set is an open-addressed table of 64-bit entries  (1<<31 | tile key) << 32 | 32-bit mask  over
-//     4x4x2-node tiles: one LDS.64 per probe, one STS.64 per insert, key = P & ~lowbits (one LOP3);
+//     wr_acs_create rejects larger grids);
+//   * the visited set ("tabu", std::set at :70) is an open-addressed table of 64-bit entries
+//     (1<<31 | tile key) << 32 | 32-bit mask  over 4x4x2-node tiles in shared memory: one LDS.64 per probe, one STS.64
+//     per insert, key = P & ~lowbits (one LOP3).  A lattice walk re-visits the same few tiles, so 768 entries (6 KB) hold
+//     walks of thousands of steps;
 //   * the chosen lane does everything that belongs to the move in one branch: visited insert, trail append
 //     (addNextNode :73-79), tile count; the table-full flag travels through shared memory instead of a vote;
-//   * parking an ant whose table filled up (-> pass 2 with a table in HBM) happens after the lockstep loop;
+//   * an ant whose table reaches 3/4 moves its visited set to a table in HBM sized for the step cap (parallel CAS
+//     inserts), parks its state after the lockstep loop and is RESUMED by pass 2 (GLOBAL = true) from the step it
+//     stopped at — exact, because its draws are a pure function of (search, iteration, ant, step).  Two launches keep
+//     shared-memory addressing on the common path (a run-time switch costs 8-13 % per step);
 //   * the uniform draws of four steps are converted to float once per Philox call; alpha == 1 (the reference's
 //     literal, :319) is a template parameter; the step cap is checked off the critical path.
 #pragma once
@@ -142,7 +158,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
         float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
         auto draw4 = [&](uint32_t block) {
             uint32_t w0, w1, w2, w3;
-            philox4(iter, ant_global, block, kStreamAcs3D, a.seed_lo, a.seed_hi, w0, w1, w2, w3);
+            philox4(iter, ant_global, block | a.block_hi, a.stream_word, a.seed_lo, a.seed_hi, w0, w1, w2, w3);
             // (float)rand()/(float)RAND_MAX (:169): (float)RAND_MAX is 2^31, so the division is an exact scaling
             u0 = __fmul_rn(__int2float_rn((int)(w0 >> 1)), 4.656612873077392578125e-10f);
             u1 = __fmul_rn(__int2float_rn((int)(w1 >> 1)), 4.656612873077392578125e-10f);

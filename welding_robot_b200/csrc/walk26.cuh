@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kWalk26Threads) k_walk26(WalkArgs a)
             const int4 r = a.resume[q];
             cur = r.x; steps = r.y; ntiles = r.z; L = __int_as_float(r.w);
             z = cur / rxy; y = (cur % rxy) / rx; x = cur % rx;
-            philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
+            philox4(iter, ant_global, ((uint32_t)steps >> 2) | a.block_hi, a.stream_word, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
         } else {
             for (int i = lane; i < E; i += 32) keys[i] = kEmptyKey;
             __syncwarp();
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kWalk26Threads) k_walk26(WalkArgs a)
             if (steps >= a.cap) { reason = 3; break; }   // step cap (a deviation the oracle mirrors)
             const float tau_k = tau_or_base(__ldg(a.tau + (size_t)cur * kK26 + kk), base_now);
             const float heur_k = __ldg(a.heur + (size_t)cur * kK26 + kk);
-            if ((steps & 3) == 0) philox4(iter, ant_global, (uint32_t)steps >> 2, kStreamAcs3D, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
+            if ((steps & 3) == 0) philox4(iter, ant_global, ((uint32_t)steps >> 2) | a.block_hi, a.stream_word, a.seed_lo, a.seed_hi, rw0, rw1, rw2, rw3);
             const uint32_t rsel = (steps & 2) ? ((steps & 1) ? rw3 : rw2) : ((steps & 1) ? rw1 : rw0);
             const float u = __fmul_rn(__int2float_rn((int)(rsel >> 1)), 4.656612873077392578125e-10f);   // (float)rand()/(float)RAND_MAX :169
             // ---- neighbour of this lane: open (in bounds and free, folded into the table), tabu probe ----

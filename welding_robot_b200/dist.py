@@ -57,10 +57,15 @@ class GpuBackend:
     """Per-rank compute over libwrgpu.so; every method is asynchronous on the handle's stream except
     build_records (reads the record count back)."""
 
-    def __init__(self, acs):
+    def __init__(self, acs, bind_stream=True):
         self.acs = acs
         self.h = acs._need()
         self.device = torch.device("cuda", torch.cuda.current_device())
+        # wr_acs_create gives every handle a private non-blocking stream, but the collectives of torch.distributed are
+        # ordered against torch's CURRENT stream only: the handle has to run on that stream, or the all_gather could read
+        # the step counts before the walk has written them (and peers could read trails that are still being written).
+        if bind_stream:
+            check(lib().wr_acs_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def set_shard(self, rank, world):
         check(lib().wr_acs_set_shard(self.h, rank, world))
