@@ -454,8 +454,8 @@ def run_ours(args):
                    "step_cap": STEP_CAP, "seed": SEED, "update_mode": ["fused", "split", "atomic", "fused_tma", "rankset"][args.update_mode],
                    "parallelism": "ants sharded x%d" % world,
                    "exchange": ("none (1 GPU)" if world == 1 else
-                                ("NVLink peer memory (trails read from their owners' HBM), %s update" % ("owner-computes (slot slices)" if driver.sliced else "replicated"))
-                                if driver.peer else "NCCL all_reduce merges, replicated update"),
+                                "NVLink peer memory inside the library's kernels (barrier flags, step counts, trails, rank-set blocks | final slot values); "
+                                "no collective in the iteration loop"),
                    "l2_rule": "inputs larger than L2: the %d MB pheromone field is streamed from HBM every iteration" % (n_nodes * 6 * 4 // 1000000)},
         "acs_iterations_per_s": iters_done / (ms * 1e-3),
         "ant_steps": steps_done, "arrived_local": c1["arrived"] - c0["arrived"], "ants_local": c1["ants"] - c0["ants"],

@@ -98,9 +98,10 @@ enum {
     WR_UPDATE_RANKSET = 4    /* adaptive: per touched slot the SET of depositing ranks (a deposit's value depends only on the rank and one
                                 bit of the slot) is built with atomicOr and applied as one ordered chain — no record sort — on the
                                 iterations where the colony's deposits are concentrated; sorted records + the fused pass (WR_UPDATE_FUSED)
-                                while it still wanders.  The choice is made on the device per iteration (no host sync); same additions in
-                                the same order either way, same bits.  Single-GPU handles of up to 4955 ants whose table fits in 4 GB;
-                                otherwise, and on sharded handles, it runs as WR_UPDATE_FUSED. */
+                                while it still wanders.  The choice for iteration n is a pure function of the statistics of iteration
+                                n-5 (read by the host without synchronising); same additions in the same order either way, same bits.
+                                Any colony size, one GPU or sharded; the table has a fixed capacity (142 MB) and a build that would
+                                exceed it falls back to an exact serial pass. */
 };
 
 /* Handles created in a loop (one search per request) re-use a few large buffers of their predecessors instead of allocating and
@@ -132,7 +133,7 @@ int wr_acs_search_pairs(wr_acs* a, const int64_t* start_ids, const int64_t* goal
  * wr_acs_set_next_search overrides the index the NEXT wr_acs_begin takes (e.g. to re-run query q of a batch alone). */
 int wr_acs_begin(wr_acs* a, float predict_path_len);                /* :229-233 */
 int wr_acs_set_next_search(wr_acs* a, uint32_t index);
-int wr_acs_iterate(wr_acs* a, int n_iterations);                    /* loop body :237-299, n times; asynchronous */
+int wr_acs_iterate(wr_acs* a, int n_iterations);                    /* loop body :237-299, n times; asynchronous; one GPU or sharded */
 int wr_acs_sync(wr_acs* a);
 int wr_acs_reset(wr_acs* a);                                        /* reset() :307-315 */
 /* getSolution :506-509 / Agent::getPath, nodeIndex :93-100.  *n = node count of the best path
@@ -176,52 +177,42 @@ int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch);
  * the protocol orders kernels and collectives by stream order alone (welding_robot_b200/dist.py binds it itself). */
 int wr_acs_set_stream(wr_acs* a, void* cuda_stream);
 
-/* ---- ant sharding across ranks: one process per GPU ----------------------
- * The pheromone field and the grid are replicated; rank r constructs ants
- * [r*chunk, (r+1)*chunk) of the global colony, chunk = ceil(colony_max / nranks).  Philox is keyed
- * by the GLOBAL ant index, so the result does not depend on the rank count.  One iteration is
- *     wr_acs_walk -> all_gather(local steps) -> wr_acs_rank_global -> all_reduce(best candidate)
- *     -> wr_acs_apply_best -> wr_acs_build_records -> all_reduce(record keys, record values)
- *     -> wr_acs_finish_iteration
- * with the collectives issued by the host on the handle's stream (NCCL through
- * torch.distributed; see welding_robot_b200/dist.py).  Every all_reduce is an integer SUM over
- * buffers in which exactly one rank holds a non-zero word per position, so the merged deposit
- * list — and with it the pheromone field on every rank — is bit-identical to a 1-GPU run. */
-int wr_acs_set_shard(wr_acs* a, int rank, int nranks);       /* before wr_acs_begin */
-int wr_acs_walk(wr_acs* a);                                  /* iteration parameters (:247-249) + local ant construction */
-/* this rank's steps: DEVICE int32[*count] (*count = chunk; -1 = dead or beyond the colony); *first = global index of entry 0 */
-int wr_acs_local_steps_dev(wr_acs* a, int** dev_steps, int* first, int* count);
-/* all ranks' steps concatenated in rank order (DEVICE int32[nranks*chunk]) -> global ranking, best decision,
- * deposit offsets; fills the best-candidate buffer (zeros unless this rank owns the new best ant) */
-int wr_acs_rank_global(wr_acs* a, const int* dev_all_steps);
-int wr_acs_best_candidate_dev(wr_acs* a, uint32_t** dev_words, size_t* nwords);   /* all_reduce(SUM, int32) this */
-int wr_acs_apply_best(wr_acs* a);                            /* install the (merged) new best path, if any */
-/* deposit records of this rank's ants at their global positions, zeros elsewhere; reads the record count back
- * (the one host sync of a sharded iteration).  all_reduce(SUM, int32) keys[0..*n) and vals[0..*n). */
-int wr_acs_build_records(wr_acs* a, uint32_t** dev_keys, uint32_t** dev_vals, int* n);
-int wr_acs_finish_iteration(wr_acs* a);                      /* slot sort + pheromone update + iteration counter */
-/* ---- the same over NVLink peer memory (default of welding_robot_b200/dist.py; needs P2P between the GPUs) ------------
- * Everything a peer reads lives in one slab per rank (ant trails and the list of final slot values, double-buffered by
- * iteration parity), exported once with ONE CUDA IPC handle.  An iteration is then
- *     wr_acs_walk -> all_gather(local steps) -> wr_acs_finish_iteration_peer(all_steps, sliced)
- *     [sliced: -> barrier (any collective) -> wr_acs_pull_finals]
- * with a single small collective and no host synchronisation: every rank ranks the colony, reads the new best trail
- * and the trails of ALL eligible ants straight out of their owners' HBM (kernel-side peer loads) and generates the
- * deposit records itself, in global (rank, step) order.
- *   sliced = 0: replicated update — slot sort + fused update of all records on every rank;
- *   sliced = 1: owner-computes update — the slot space is cut into nranks tile-aligned slices; rank r keeps (one stable
- *               partition pass), sorts and applies only the records of ITS slice — 1/nranks of the sort and of the
- *               dependent add chains — while evaporating the whole field, and lists the final value of every slot it
- *               touched; after the barrier wr_acs_pull_finals reads the peers' lists and overwrites those slots.
- * Both give the bits of the 1-GPU run.
- *   once after wr_acs_begin:  wr_acs_peer_export -> all_gather(handles) -> wr_acs_peer_import
- * ipc_handle: 64 bytes (cudaIpcMemHandle_t); all_ipc_handles: nranks x 64 bytes in rank order.  raw_pointer /
- * wr_acs_peer_set_pointers: the same for handles that live in ONE process (tests). */
-int wr_acs_peer_export(wr_acs* a, void* ipc_handle, void** raw_pointer);
-int wr_acs_peer_import(wr_acs* a, const void* all_ipc_handles);
+/* ---- ant sharding across ranks: one process per GPU ------------------------------------------------
+ * The pheromone field and the grid are replicated; rank r constructs ants [r*chunk, (r+1)*chunk) of the global colony,
+ * chunk = ceil(colony_max / nranks).  Philox is keyed by the GLOBAL ant index, so the result does not depend on the rank
+ * count: pheromone field (on every rank), best path and ranks are bit-identical to the 1-GPU run.
+ *
+ * The exchange runs over NVLink peer memory inside the library's own kernels — no collective library and no host
+ * synchronisation in the iteration loop.  Everything a peer reads lives in ONE slab per rank (barrier flags, step
+ * counts, ant trails, final slot values, published rank-set blocks), exported with one CUDA IPC handle per search.
+ * One iteration of wr_acs_iterate on a sharded handle:
+ *     walk (local ants; trails + step counts into the slab)
+ *     barrier (k_peer_barrier: release/acquire epoch words in the peers' slabs) ; gather of every rank's step counts
+ *     global ranking + best decision on every rank; the new best trail is read from its owner's HBM
+ *     deposits, by the path the search is in (chosen identically on every rank, see WR_UPDATE_RANKSET):
+ *       rank sets:      each rank builds the per-slot rank sets of ITS eligible ants (bits = global ranks), publishes its
+ *                       row blocks; barrier; every rank ORs the peers' blocks into its table, evaporates its field and
+ *                       applies the ordered chains — work per rank independent of the rank count
+ *       sorted records: each rank generates the records of all eligible ants from their owners' trails, keeps, sorts and
+ *                       applies the records of ITS slot slice while evaporating the whole field, lists the final values;
+ *                       barrier; every rank overwrites the slots the others own with their final values
+ *
+ * Setting up, either
+ *   (a) wr_comm_unique_id on one rank -> distribute the 128 bytes (any means) -> wr_acs_comm_init on every rank;
+ *       wr_acs_begin then exchanges the slab handles itself (ncclAllGather; libnccl.so.2 is opened at run time), or
+ *   (b) wr_acs_set_shard; after every wr_acs_begin: wr_acs_peer_export -> all_gather the 64-byte handles by your own
+ *       means (welding_robot_b200/dist.py uses torch.distributed) -> wr_acs_peer_import.
+ * raw_pointer / wr_acs_peer_set_pointers: the same for handles that live in ONE process on one GPU (tests); such
+ * handles must run on different streams and be iterated in turn, one iteration at a time.
+ * A sharded handle's stream must not be shared with work that could delay it behind a peer's (each barrier waits for
+ * every rank); a barrier that is not reached within 20 s (WR_PEER_TIMEOUT_MS) is reported by wr_acs_sync. */
+#define WR_COMM_ID_BYTES 128
+int wr_comm_unique_id(void* id128);                                       /* ncclGetUniqueId */
+int wr_acs_comm_init(wr_acs* a, const void* nccl_unique_id, int rank, int nranks);   /* before wr_acs_begin */
+int wr_acs_set_shard(wr_acs* a, int rank, int nranks);                    /* before wr_acs_begin */
+int wr_acs_peer_export(wr_acs* a, void* ipc_handle, void** raw_pointer);  /* ipc_handle: 64 bytes (cudaIpcMemHandle_t) */
+int wr_acs_peer_import(wr_acs* a, const void* all_ipc_handles);           /* nranks x 64 bytes in rank order */
 int wr_acs_peer_set_pointers(wr_acs* a, void* const* all_raw_pointers);
-int wr_acs_finish_iteration_peer(wr_acs* a, const int* dev_all_steps, int sliced);
-int wr_acs_pull_finals(wr_acs* a);
 
 /* ------------------------------------------------------------------------------------------
  * Seam ordering — replaces ACS_GTSP (core/ACS_GTSP.hpp), batched: B independent colonies on

@@ -43,18 +43,35 @@ def worker(rank, world, port, q):
             a.setEndpoints(int(free[11]), int(free[-11]))
             return a
 
-        single = make(); single.begin(1.0); single.iterate(6)
+        single = make(); single.begin(1.0); single.iterate(8)
         t1, b1, c1 = single.pheromone(), single.bestPath(), single.counters()
         chunk = (1001 + world - 1) // world
-        # NVLink peer-memory protocol with the owner-computes and with the replicated update, and the NCCL-only protocol
-        for peer, sliced in ((True, True), (True, False), (False, False)):
+        # deposit paths: sorted records only (owner-computes update), rank sets only (per-rank sets OR-merged over peer
+        # memory), the adaptive choice (thresholds set so that both paths and both transitions occur), and the fixed-capacity
+        # rank-set table overflowing into the exact serial pass; rendezvous through torch.distributed or through the
+        # library's own NCCL bootstrap (wr_comm_unique_id / wr_acs_comm_init)
+        for policy, env, own_comm in (("2", {}, False), ("1", {}, False), ("0", {"WR_RANKSET_ON": "100000", "WR_RANKSET_OFF": "2500"}, False),
+                                      ("1", {"WR_RANKSET_LOG2": "9"}, False), ("1", {}, True)):
+            os.environ["WR_RANKSET_POLICY"] = policy
+            os.environ.update(env)
             sharded = make()
-            S = ShardedSearch(sharded, rank, world, peer=peer, sliced=sliced)
-            assert (S.peer, S.sliced) == (peer, sliced)
-            S.begin(1.0); S.iterate(6)
-            torch.cuda.synchronize()
+            for k in ["WR_RANKSET_POLICY"] + list(env):
+                del os.environ[k]
+            if own_comm:
+                uid = np.zeros(128, np.uint8)
+                if rank == 0:
+                    _lib.check(_lib.lib().wr_comm_unique_id(uid.ctypes.data))
+                box = [uid.tobytes()]
+                dist.broadcast_object_list(box, src=0)
+                _lib.check(_lib.lib().wr_acs_comm_init(sharded._a, box[0], rank, world))
+                sharded.begin(1.0)                      # exchanges the slab handles itself (ncclAllGather)
+                sharded.iterate(3); sharded.iterate(5)
+            else:
+                S = ShardedSearch(sharded, rank, world)
+                S.begin(1.0); S.iterate(3); S.iterate(5)
+            sharded.sync()
             t2 = sharded.pheromone()
-            assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), "sharded pheromone field differs from the 1-GPU field (%s, %s)" % (peer, sliced)
+            assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), "sharded pheromone field differs from the 1-GPU field (%s, %s)" % (policy, env)
             b2 = sharded.bestPath()
             assert np.array_equal(b1[0], b2[0]) and np.array_equal(b1[1], b2[1]) and np.float32(b1[2]) == np.float32(b2[2])
             for k in range(rank * chunk, min((rank + 1) * chunk, 1001), 37):
@@ -64,8 +81,12 @@ def worker(rank, world, port, q):
             tot = torch.tensor([c2["ant_steps"], c2["ants"]], device="cuda", dtype=torch.int64)
             dist.all_reduce(tot)
             assert int(tot[0]) == c1["ant_steps"] and int(tot[1]) == c1["ants"]
+            st = sharded.updateStats()
+            assert (st["rankset_iterations"] > 0) == (policy != "2"), st
+            if policy == "0":
+                assert 0 < st["rankset_iterations"] < 8, st
             dist.barrier()
-            del S, sharded
+            del sharded
         q.put((rank, "ok", 0))
     except Exception:  # noqa: BLE001
         import traceback

@@ -1,7 +1,8 @@
-"""GPU, one device: the peer-memory protocol of a sharded colony (trails read through peer pointers, replicated or
-owner-computes update with final-value lists — welding_robot_b200/dist.py) with all shards living in ONE process,
-against the un-sharded search.
-Covers the device side of the multi-GPU protocol on a 1-GPU box; tests/test_gpu_multi.py runs it over NCCL + CUDA IPC."""
+"""GPU, one device: the peer-memory protocol of a sharded colony (barrier flags, step counts and trails read through peer
+pointers; rank sets built per shard and OR-merged, or sorted records with the owner-computes update and final-value
+lists — wr_acs_iterate on sharded handles) with all shards living in ONE process, against the un-sharded search.
+Covers the device side of the multi-GPU protocol on a 1-GPU box; tests/test_gpu_multi.py runs it over CUDA IPC between
+processes."""
 import contextlib
 import io
 import os
@@ -14,30 +15,37 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,colony,sliced", [(2, 1001, True), (3, 640, True), (2, 333, False)])
-def test_peer_protocol_shards_equal_unsharded(world, colony, sliced):
-    import torch
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,colony,policy,env", [(2, 1001, "2", {}), (3, 640, "1", {}), (2, 333, "0", {"WR_RANKSET_ON": "100000", "WR_RANKSET_OFF": "2500"}),
+                                                     (2, 777, "1", {"WR_RANKSET_LOG2": "9"}), (4, 6000, "1", {})])
+def test_peer_protocol_shards_equal_unsharded(world, colony, policy, env, monkeypatch):
     import welding_robot_b200 as wr
-    from welding_robot_b200 import _lib
     from welding_robot_b200.dist import LocalShards
+    monkeypatch.setenv("WR_PEER_TIMEOUT_MS", "15000")
     tris = np.load(os.path.join(GOLDEN, "meshes.npz"))["simplified_piece"]
 
-    def make():
-        a = wr.ACS_Rank(seed=21, fixed_colony=colony, step_cap=600)     # odd colony: ragged last chunk
+    def make(sharded):
+        if sharded:
+            monkeypatch.setenv("WR_RANKSET_POLICY", policy)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+        a = wr.ACS_Rank(seed=21, fixed_colony=colony, step_cap=600)     # odd colonies: ragged last chunk
         with contextlib.redirect_stdout(io.StringIO()):
             a.creatGridMap(tris, 0.012, 4)
             a.initFromGridMap()
-        _lib.check(_lib.lib().wr_acs_set_stream(a._a, torch.cuda.current_stream().cuda_stream))
+        monkeypatch.delenv("WR_RANKSET_POLICY", raising=False)
+        for k in env:
+            monkeypatch.delenv(k, raising=False)
         free = np.flatnonzero(a.isfree())
         a.setEndpoints(int(free[11]), int(free[-11]))
         return a
 
-    single = make(); single.begin(1.0)
-    shards = [make() for _ in range(world)]
-    S = LocalShards(shards, sliced=sliced); S.begin(1.0)
+    single = make(False); single.begin(1.0)
+    shards = [make(True) for _ in range(world)]
+    S = LocalShards(shards); S.begin(1.0)
     for its in (1, 1, 6):
         single.iterate(its); S.iterate(its)
-        torch.cuda.synchronize()
+        S.sync()
         t1 = single.pheromone()
         b1 = single.bestPath()
         for a in shards:
@@ -47,3 +55,6 @@ def test_peer_protocol_shards_equal_unsharded(world, colony, sliced):
     c1 = single.counters()
     assert sum(a.counters()["ant_steps"] for a in shards) == c1["ant_steps"]
     assert c1["deposit_records"] > 0 and all(a.counters()["deposit_records"] == c1["deposit_records"] for a in shards)
+    for a in shards:
+        st = a.updateStats()
+        assert (st["rankset_iterations"] > 0) == (policy != "2"), st

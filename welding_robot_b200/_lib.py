@@ -37,9 +37,7 @@ wr_grid_bbox wr_grid_coords wr_grid_download_bits wr_grid_download_isfree wr_gri
 wr_acs_default_params wr_acs_create wr_acs_destroy wr_acs_set_points wr_acs_set_endpoints wr_acs_snap_points wr_acs_search_pairs wr_acs_begin wr_acs_set_next_search
 wr_acs_iterate wr_acs_sync wr_acs_reset wr_acs_best wr_acs_download_pheromone wr_acs_upload_pheromone
 wr_acs_last_colony wr_acs_last_ant wr_acs_counters wr_acs_kernel_ms wr_acs_update_stats wr_acs_field_stats wr_acs_stream_kernel_ms wr_acs_set_timing wr_acs_bench_kernel wr_acs_set_stream
-wr_acs_set_shard wr_acs_walk wr_acs_local_steps_dev wr_acs_rank_global wr_acs_best_candidate_dev wr_acs_apply_best
-wr_acs_build_records wr_acs_finish_iteration wr_acs_peer_export wr_acs_peer_import wr_acs_peer_set_pointers
-wr_acs_finish_iteration_peer wr_acs_pull_finals
+wr_comm_unique_id wr_acs_comm_init wr_acs_set_shard wr_acs_peer_export wr_acs_peer_import wr_acs_peer_set_pointers
 wr_gtsp_create wr_gtsp_destroy wr_gtsp_iterate wr_gtsp_sync wr_gtsp_best wr_gtsp_download_pheromone wr_gtsp_tau0
 wr_gtsp_kernel_ms""".split()
 
@@ -80,10 +78,8 @@ def lib():
         "wr_acs_upload_pheromone": [vp, vp, C.c_size_t], "wr_acs_last_colony": [vp, vp, vp, vp],
         "wr_acs_last_ant": [vp, i32, vp, vp, i32, vp, vp, vp], "wr_acs_counters": [vp, vp], "wr_acs_kernel_ms": [vp, vp], "wr_acs_update_stats": [vp, vp], "wr_acs_field_stats": [vp, vp], "wr_acs_stream_kernel_ms": [vp, vp, vp],
         "wr_acs_set_timing": [vp, i32], "wr_acs_bench_kernel": [vp, i32, i32, vp], "wr_acs_set_stream": [vp, vp], "wr_acs_set_shard": [vp, i32, i32],
-        "wr_acs_walk": [vp], "wr_acs_local_steps_dev": [vp, vp, vp, vp], "wr_acs_rank_global": [vp, vp],
-        "wr_acs_best_candidate_dev": [vp, vp, vp], "wr_acs_apply_best": [vp], "wr_acs_build_records": [vp, vp, vp, vp],
-        "wr_acs_finish_iteration": [vp], "wr_acs_peer_export": [vp, vp, vp], "wr_acs_peer_import": [vp, vp],
-        "wr_acs_peer_set_pointers": [vp, vp], "wr_acs_finish_iteration_peer": [vp, vp, i32], "wr_acs_pull_finals": [vp],
+        "wr_comm_unique_id": [vp], "wr_acs_comm_init": [vp, vp, i32, i32],
+        "wr_acs_peer_export": [vp, vp, vp], "wr_acs_peer_import": [vp, vp], "wr_acs_peer_set_pointers": [vp, vp],
         "wr_gtsp_create": [vp, i32, i32, i32, i32, u64, vp], "wr_gtsp_destroy": [vp], "wr_gtsp_iterate": [vp, i32],
         "wr_gtsp_sync": [vp], "wr_gtsp_best": [vp, i32, vp, vp, vp], "wr_gtsp_download_pheromone": [vp, i32, vp],
         "wr_gtsp_tau0": [vp, vp], "wr_gtsp_kernel_ms": [vp, vp],

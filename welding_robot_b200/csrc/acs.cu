@@ -20,6 +20,8 @@
 
 namespace wr {
 
+constexpr uint32_t kPubBlocks = 262144;   // sharded colonies: row blocks a rank can publish per iteration (35.7 MB of its peer slab)
+
 static thread_local std::string g_err;
 void set_error(const char* fmt, ...)
 {
@@ -109,8 +111,12 @@ struct wr_acs {
     // handle, same layout on every rank): the ant trails and the list of final slot values of the owner-computes
     // update, each double-buffered by iteration parity.   [ids0 | ids1 | dirs0 | dirs1 | fin0 | fin1]
     unsigned char* d_slab = nullptr;
-    size_t slab_bytes = 0, off_ids[2] = {0, 0}, off_dirs[2] = {0, 0}, off_fin[2] = {0, 0};
-    const void** d_tabs = nullptr;    // device: [kind 0 ids,1 dirs,2 fin][parity][rank] -> pointer into rank's slab
+    size_t slab_bytes = 0, off_ids[2] = {0, 0}, off_dirs[2] = {0, 0}, off_fin[2] = {0, 0}, off_steps[2] = {0, 0}, off_pub = 0, off_flags = 0;
+    const void** d_tabs = nullptr;    // device: [kind 0 ids,1 dirs,2 fin,3 steps,4 publish area,5 barrier flags][parity][rank] -> pointer into rank's slab
+    void* comm = nullptr;             // NCCL communicator (wr_acs_comm_init): wr_acs_begin exchanges the peer slabs through it
+    uint32_t* d_epoch = nullptr;      // peer barrier: number of barriers this rank has passed since the slabs were exchanged
+    uint32_t* d_peer_err = nullptr;   // set by a barrier that timed out (a peer died): reported by wr_acs_sync
+    unsigned long long barrier_timeout_ns = 20000000000ull;
     std::vector<void*> ipc_opened;
     bool peers_set = false;
     int* d_nq = nullptr;              // records in this rank's slot slice
@@ -130,8 +136,6 @@ struct wr_acs {
     // per-colony buffers (sized at begin)
     int* d_ant_steps = nullptr;      // global colony order (ranking input)
     int* d_local_steps = nullptr;    // this rank's chunk (== d_ant_steps when nranks == 1)
-    uint32_t* d_cand = nullptr;      // best-candidate exchange buffer (sharded)
-    size_t cand_words = 0;
     uint32_t* d_path_ids = nullptr;
     uint8_t* d_path_dirs = nullptr;
     uint32_t* d_overflow = nullptr;
@@ -151,13 +155,15 @@ struct wr_acs {
     // WR_UPDATE_RANKSET (rankset.cuh)
     bool want_rankset = false, rankset = false;
     RankSet rs = {};
-    size_t rs_entries = 0, rs_list_cap = 0;
+    size_t rs_entries = 0;
+    int rs_groups = 1;                // apply launches per iteration: ceil(w_max / 1024)
     int rs_policy = 0;                // 0 adaptive, 1 rank sets always, 2 records always (WR_RANKSET_POLICY)
     // adaptive choice: device -> host feedback through mapped pinned memory, host kept <= kRsAhead iterations ahead
-    uint32_t* h_feedback = nullptr;   // {generation << 16 | iteration, path of the previous iteration, deposit tiles, distinct slots}
+    uint32_t* h_feedback = nullptr;   // ring of kFeedbackRing x {generation << 16 | iteration, path of the previous iteration, deposit tiles, row blocks}
     uint32_t* d_feedback = nullptr;   // the same words as the device sees them
     uint32_t rs_generation = 0;       // bumped by wr_acs_begin: feedback of an earlier search on the same stream is ignored
     int rs_choice = 0;                // path of the iteration being enqueued
+    uint8_t rs_history[16] = {};      // path of the last 16 iterations enqueued (index = iteration & 15)
     static constexpr int kRsAhead = 4;
     cudaEvent_t rs_ev[kRsAhead] = {};
     unsigned long long rs_enqueued = 0;
@@ -165,7 +171,7 @@ struct wr_acs {
     bool upd_q_zeroed = false;        // this iteration's k_iter_begin already cleared d_upd_q (wr_acs_iterate)
     // steady-state rank-set iteration (previous and current iteration on the rank-set path, folded k_iter_end, no timers) as ONE
     // CUDA graph launch: 9 kernels whose arguments do not change within a search; re-captured after wr_acs_begin
-    cudaGraphExec_t rs_graph = nullptr;
+    cudaGraphExec_t rs_graph[2] = {nullptr, nullptr};   // sharded handles: one per trail-buffer parity
     bool rs_graph_failed = false;
     // device time of the streaming kernel alone (k_update_fused / k_evaporate_tiles), inside the loop: event pairs around it
     std::vector<cudaEvent_t> sk_ev;
@@ -190,8 +196,13 @@ struct wr_acs {
     bool lazy = false;
     bool oob_zero = true;             // out-of-bounds slots still hold their initial 0 (until the first reset())
 
+    static constexpr int kTabKinds = 6;
     const void** tab(int kind, unsigned par) const { return d_tabs + ((size_t)kind * 2 + par) * nranks; }
     uint32_t* fin_buf(unsigned par) const { return reinterpret_cast<uint32_t*>(d_slab + off_fin[par]); }
+    uint32_t* pub_buf() const { return reinterpret_cast<uint32_t*>(d_slab + off_pub); }
+    const uint32_t* const* trail_ids_tab() const { return reinterpret_cast<const uint32_t* const*>(tab(0, parity)); }   // [rank] -> trail buffers of this iteration
+    const uint8_t* const* trail_dirs_tab() const { return reinterpret_cast<const uint8_t* const*>(tab(1, parity)); }
+    uint32_t* flags_buf() const { return reinterpret_cast<uint32_t*>(d_slab + off_flags); }
     const int* dptr_colony() const { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + offsetof(IterState, colony)); }
     const int* dptr_nrec() const { return reinterpret_cast<const int*>(reinterpret_cast<const char*>(d_state) + offsetof(IterState, n_records)); }
     // record count the record path's kernels see: 0 on iterations an adaptive handle runs through rank sets
@@ -203,7 +214,7 @@ struct wr_acs {
 
 static void drop_steady_graph(wr_acs* a)
 {
-    if (a->rs_graph) { cudaGraphExecDestroy(a->rs_graph); a->rs_graph = nullptr; }
+    for (cudaGraphExec_t& g : a->rs_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     a->rs_graph_failed = false;
 }
 
@@ -212,7 +223,8 @@ static void drop_steady_graph(wr_acs* a)
 // table per process (searches created in a loop, one per request, are the e2e pattern).
 struct RankSetCache {
     int device = -1;
-    size_t entries = 0, list_cap = 0;
+    size_t entries = 0;
+    uint32_t limit = 0;
     int w_max = 0;
     RankSet rs = {};   // all six buffers travel together, so a handle that adopts them adds no traffic to the memory pool
 };
@@ -220,7 +232,11 @@ static RankSetCache g_rs_cache;
 static std::mutex g_rs_cache_mu;   // handles may be created and destroyed on different host threads
 
 // Feedback words (device -> host, mapped pinned memory): pinned allocations cost milliseconds, handles are created per
-// request, so one page is pinned per process and handles borrow a 16-byte slot of it.
+// request, so one block is pinned per process and handles borrow a 128-byte slot of it (a ring of kFeedbackRing records:
+// the host reads the record of one specific, already finished iteration, so that its choice of the deposit path is a
+// pure function of the search — the same on every rank of a sharded colony, the same in every run).
+constexpr int kFeedbackRing = 8;
+constexpr int kFeedbackWords = 4 * kFeedbackRing;
 struct FeedbackPage {
     uint32_t* host = nullptr;
     uint32_t* dev = nullptr;
@@ -232,14 +248,14 @@ static int feedback_acquire(uint32_t** h, uint32_t** d)
 {
     std::lock_guard<std::mutex> lock(g_rs_cache_mu);
     if (!g_feedback.host) {
-        WR_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_feedback.host), 256 * 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        WR_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_feedback.host), 256 * kFeedbackWords * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
         WR_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_feedback.dev), g_feedback.host, 0));
     }
     for (int i = 0; i < 256; i++)
         if (!g_feedback.used[i]) {
             g_feedback.used[i] = true;
-            *h = g_feedback.host + 4 * i; *d = g_feedback.dev + 4 * i;
-            (*h)[0] = 0; (*h)[1] = 0; (*h)[2] = 0xFFFFFFFFu; (*h)[3] = 0xFFFFFFFFu;
+            *h = g_feedback.host + kFeedbackWords * i; *d = g_feedback.dev + kFeedbackWords * i;
+            for (int k = 0; k < kFeedbackWords; k++) (*h)[k] = 0xFFFFFFFFu;
             return WR_OK;
         }
     *h = nullptr; *d = nullptr;   // all slots taken: the handle runs without feedback (records path only)
@@ -249,25 +265,25 @@ static void feedback_release(uint32_t* h)
 {
     if (!h) return;
     std::lock_guard<std::mutex> lock(g_rs_cache_mu);
-    g_feedback.used[(h - g_feedback.host) / 4] = false;
+    g_feedback.used[(h - g_feedback.host) / kFeedbackWords] = false;
 }
 
 // The rank-set buffers outlive handles (they are parked between searches), so they come from cudaMalloc, not from the
 // stream-ordered pool whose blocks are tied to the allocating handle's stream.
 static void rankset_release_buffers(RankSet& rs, cudaStream_t)
 {
-    cudaFree(rs.ent); cudaFree(rs.rows); cudaFree(rs.list); cudaFree(rs.touched); cudaFree(rs.count); cudaFree(rs.vtab);
+    cudaFree(rs.key); cudaFree(rs.rows); cudaFree(rs.list); cudaFree(rs.touched); cudaFree(rs.count); cudaFree(rs.vtab);
     rs = RankSet{};
 }
 
 static void free_rankset(wr_acs* a)
 {
     cudaStream_t s = a->stream;
-    if (a->rs.ent) {
+    if (a->rs.key) {
         cudaStreamSynchronize(s);   // the table is clean once the stream has drained
         std::lock_guard<std::mutex> lock(g_rs_cache_mu);
-        if (g_rs_cache.rs.ent) rankset_release_buffers(g_rs_cache.rs, s);
-        g_rs_cache.device = a->device; g_rs_cache.entries = a->rs_entries; g_rs_cache.list_cap = a->rs_list_cap; g_rs_cache.w_max = a->w_max;
+        if (g_rs_cache.rs.key) rankset_release_buffers(g_rs_cache.rs, s);
+        g_rs_cache.device = a->device; g_rs_cache.entries = a->rs_entries; g_rs_cache.limit = a->rs.limit; g_rs_cache.w_max = a->w_max;
         g_rs_cache.rs = a->rs;
     }
     a->rs = RankSet{};
@@ -297,8 +313,8 @@ static void free_colony_buffers(wr_acs* a)
     pool_free(a->d_ant_steps, s); pool_free(a->d_overflow, s); pool_free(a->d_ant_L, s); a->d_ant_L = nullptr;
     if (!a->d_slab) { pool_free(a->d_path_ids, s); pool_free(a->d_path_dirs, s); }
     pool_free(a->d_gkeys, s); pool_free(a->d_gmasks, s); pool_free(a->d_resume, s); a->d_resume = nullptr; pool_free(a->d_rec_off, s); pool_free(a->d_order, s);
-    if (a->d_local_steps != a->d_ant_steps) pool_free(a->d_local_steps, s);
-    pool_free(a->d_cand, s); a->d_local_steps = nullptr; a->d_cand = nullptr;
+    a->d_local_steps = nullptr;   // aliases d_ant_steps (one GPU) or lives in the slab (sharded)
+    pool_free(a->d_epoch, s); a->d_epoch = nullptr; a->d_peer_err = nullptr;
     a->d_ant_steps = nullptr; a->d_path_ids = nullptr; a->d_path_dirs = nullptr; a->d_overflow = nullptr;
     a->d_gkeys = nullptr; a->d_gmasks = nullptr; a->d_rec_off = nullptr; a->d_order = nullptr;
     sort_plan_destroy(&a->sort_ants, s); sort_plan_destroy(&a->sort_recs, s);
@@ -332,14 +348,14 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     if (rec_max >= 0x7fffffffull) { set_error("colony %zu x step cap %zu needs too many deposit records; set step_cap", cm, cap); return WR_ERR_NOMEM; }
     WR_CUDA(dmalloc(&a->d_ant_steps, (chunk * a->nranks) * sizeof(int), a->stream));   // global colony: ranking reads all ranks' steps
     if (a->nranks > 1) {
-        WR_CUDA(dmalloc(&a->d_local_steps, chunk * sizeof(int), a->stream));
-        a->cand_words = 2 * cap + 2;
-        WR_CUDA(dmalloc(&a->d_cand, a->cand_words * sizeof(uint32_t), a->stream));
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
         size_t o = 0;
+        a->off_flags = o; o += up(4096);                                             // barrier flags: one epoch word per source rank
+        for (int b = 0; b < 2; b++) { a->off_steps[b] = o; o += up(chunk * sizeof(int)); }
         for (int b = 0; b < 2; b++) { a->off_ids[b] = o; o += up(chunk * cap * sizeof(uint32_t)); }
         for (int b = 0; b < 2; b++) { a->off_dirs[b] = o; o += up(chunk * cap); }
         for (int b = 0; b < 2; b++) { a->off_fin[b] = o; o += up((4 + 2 * rec_max) * sizeof(uint32_t)); }
+        a->off_pub = o; o += up(((size_t)4 + (size_t)kPubBlocks * kRsPubWords) * sizeof(uint32_t));
         a->slab_bytes = o;
         {
             std::lock_guard<std::mutex> lock(g_rs_cache_mu);
@@ -350,15 +366,24 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
         }
         if (!a->d_slab) WR_CUDA(cudaMalloc(&a->d_slab, a->slab_bytes));
         for (int b = 0; b < 2; b++) WR_CUDA(cudaMemsetAsync(a->d_slab + a->off_fin[b], 0, 4 * sizeof(uint32_t), a->stream));
-        WR_CUDA(dmalloc(&a->d_tabs, (size_t)6 * a->nranks * sizeof(void*), a->stream));
+        WR_CUDA(cudaMemsetAsync(a->d_slab + a->off_pub, 0, 4 * sizeof(uint32_t), a->stream));
+        WR_CUDA(dmalloc(&a->d_tabs, (size_t)wr_acs::kTabKinds * 2 * a->nranks * sizeof(void*), a->stream));
         WR_CUDA(dmalloc(&a->d_nq, sizeof(int), a->stream));
+        WR_CUDA(dmalloc(&a->d_epoch, 2 * sizeof(uint32_t), a->stream));
+        a->d_peer_err = a->d_epoch + 1;
         a->parity = 0;
         a->d_path_ids = reinterpret_cast<uint32_t*>(a->d_slab + a->off_ids[0]);
         a->d_path_dirs = a->d_slab + a->off_dirs[0];
+        a->d_local_steps = reinterpret_cast<int*>(a->d_slab + a->off_steps[0]);
     } else a->d_local_steps = a->d_ant_steps;
     if (a->nranks == 1) {
         WR_CUDA(dmalloc(&a->d_path_ids, chunk * cap * sizeof(uint32_t), a->stream));
         WR_CUDA(dmalloc(&a->d_path_dirs, chunk * cap, a->stream));
+        WR_CUDA(dmalloc(&a->d_tabs, (size_t)wr_acs::kTabKinds * 2 * sizeof(void*), a->stream));   // a one-rank table for the kernels that take one
+        const void* tab[wr_acs::kTabKinds * 2] = {};
+        tab[0] = tab[1] = a->d_path_ids; tab[2] = tab[3] = a->d_path_dirs;
+        WR_CUDA(cudaMemcpyAsync(a->d_tabs, tab, sizeof tab, cudaMemcpyHostToDevice, a->stream));
+        WR_CUDA(cudaStreamSynchronize(a->stream));   // `tab` is on the stack
     }
     WR_CUDA(dmalloc(&a->d_overflow, chunk * sizeof(uint32_t), a->stream));
     if (a->K == kK26) WR_CUDA(dmalloc(&a->d_ant_L, chunk * sizeof(float), a->stream));
@@ -376,44 +401,43 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     WR_CUDA(dmalloc(&a->d_resume, chunk * sizeof(int4), a->stream));
     int st = sort_plan_create(&a->sort_ants, cm, a->stream);
     if (st != WR_OK) return st;
-    // WR_UPDATE_RANKSET: open-addressed table sized for the worst case (every record a distinct slot) at load <= 1/2
+    // WR_UPDATE_RANKSET: open-addressed table of (slot, rank group) row blocks with a FIXED capacity (rankset.cuh): the path is
+    // only chosen while the colony's deposits are concentrated, an overflow falls back to an exact serial pass
     a->rankset = false;
-    if (a->want_rankset && a->nranks == 1) {
-        const int nwords = (a->w_max + 31) / 32, rw = nwords;
-        size_t T = 1024;
-        while (T < 2 * rec_max) T <<= 1;
-        if (nwords <= kRankSetMaxWords && T * rw * sizeof(uint32_t) <= ((size_t)4 << 30) && T <= ((size_t)1 << 31)) {
-            cudaStream_t s = a->stream;
-            const size_t list_cap = rec_max + 1;
-            {
-                std::lock_guard<std::mutex> lock(g_rs_cache_mu);
-                if (g_rs_cache.rs.ent && g_rs_cache.device == a->device && g_rs_cache.entries == T && g_rs_cache.rs.nwords == nwords &&
-                    g_rs_cache.list_cap == list_cap && g_rs_cache.w_max == a->w_max) {
-                    a->rs = g_rs_cache.rs;
-                    g_rs_cache = RankSetCache();
-                }
+    if (a->want_rankset) {
+        int log2R = 20;   // 2^20 blocks: 8 MB of keys + 134 MB of rows
+        if (const char* e = getenv("WR_RANKSET_LOG2")) log2R = std::max(6, std::min(26, atoi(e)));
+        const size_t R = (size_t)1 << log2R;
+        uint32_t limit = (uint32_t)(R / 2);
+        if (a->nranks > 1) limit = std::min<uint32_t>(limit, kPubBlocks);   // what fits in the publish area of the peer slab
+        cudaStream_t s = a->stream;
+        {
+            std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+            if (g_rs_cache.rs.key && g_rs_cache.device == a->device && g_rs_cache.entries == R && g_rs_cache.limit == limit && g_rs_cache.w_max == a->w_max) {
+                a->rs = g_rs_cache.rs;
+                g_rs_cache = RankSetCache();
             }
-            if (!a->rs.ent) {
-                WR_CUDA(cudaMalloc(&a->rs.ent, T * sizeof(unsigned long long)));
-                WR_CUDA(cudaMalloc(&a->rs.rows, T * rw * sizeof(uint32_t)));
-                WR_CUDA(cudaMemsetAsync(a->rs.ent, 0, T * sizeof(unsigned long long), s));
-                WR_CUDA(cudaMemsetAsync(a->rs.rows, 0, T * rw * sizeof(uint32_t), s));
-                WR_CUDA(cudaMalloc(&a->rs.list, list_cap * sizeof(uint32_t)));
-                WR_CUDA(cudaMalloc(&a->rs.touched, list_cap * sizeof(uint32_t)));
-                WR_CUDA(cudaMalloc(&a->rs.count, 4 * sizeof(uint32_t)));
-                WR_CUDA(cudaMalloc(&a->rs.vtab, (size_t)2 * (a->w_max + 1) * sizeof(float)));
-            }
-            WR_CUDA(cudaMemsetAsync(a->rs.count, 0, 4 * sizeof(uint32_t), s));
-            a->rs_entries = T; a->rs_list_cap = list_cap;
-            a->rs.tmask = (uint32_t)(T - 1); a->rs.shift = 32 - ceil_log2(T);
-            a->rs.nwords = nwords;
-            if (!a->rs_ev[0]) {
-                int rc = feedback_acquire(&a->h_feedback, &a->d_feedback);
-                if (rc != WR_OK) return rc;
-                for (cudaEvent_t& e : a->rs_ev) WR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            }
-            a->rankset = true;
         }
+        if (!a->rs.key) {
+            WR_CUDA(cudaMalloc(&a->rs.key, R * sizeof(unsigned long long)));
+            WR_CUDA(cudaMalloc(&a->rs.rows, R * kRsRowWords * sizeof(uint32_t)));
+            WR_CUDA(cudaMemsetAsync(a->rs.key, 0, R * sizeof(unsigned long long), s));
+            WR_CUDA(cudaMemsetAsync(a->rs.rows, 0, R * kRsRowWords * sizeof(uint32_t), s));
+            WR_CUDA(cudaMalloc(&a->rs.list, ((size_t)limit + 1) * sizeof(uint32_t)));
+            WR_CUDA(cudaMalloc(&a->rs.touched, ((size_t)limit + 1) * sizeof(uint32_t)));
+            WR_CUDA(cudaMalloc(&a->rs.count, 4 * sizeof(uint32_t)));
+            WR_CUDA(cudaMalloc(&a->rs.vtab, (size_t)2 * (a->w_max + 1) * sizeof(float)));
+        }
+        WR_CUDA(cudaMemsetAsync(a->rs.count, 0, 4 * sizeof(uint32_t), s));
+        a->rs_entries = R;
+        a->rs.rmask = (uint32_t)(R - 1); a->rs.shift = 32 - log2R; a->rs.limit = limit;
+        a->rs_groups = (a->w_max + kRsGroupRanks - 1) / kRsGroupRanks;
+        if (!a->rs_ev[0]) {
+            int rc = feedback_acquire(&a->h_feedback, &a->d_feedback);
+            if (rc != WR_OK) return rc;
+            for (cudaEvent_t& e : a->rs_ev) WR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        a->rankset = a->h_feedback != nullptr || a->rs_policy == 1;
     }
     st = sort_plan_create(&a->sort_recs, rec_max, a->stream);   // the record list and its slot sort
     if (st != WR_OK) return st;
@@ -460,9 +484,10 @@ extern "C" int wr_set_device(int device)
 extern "C" int wr_release_caches(void)
 {   // buffers parked between handles (rank-set table, peer slab, IPC mappings of the peers' slabs); call with no search in flight
     std::lock_guard<std::mutex> lock(g_rs_cache_mu);
-    if (g_rs_cache.rs.ent) { rankset_release_buffers(g_rs_cache.rs, nullptr); g_rs_cache = RankSetCache(); }
+    if (g_rs_cache.rs.key) { rankset_release_buffers(g_rs_cache.rs, nullptr); g_rs_cache = RankSetCache(); }
     if (g_slab_cache.ptr) { cudaFree(g_slab_cache.ptr); g_slab_cache = SlabCache(); }
     for (IpcMapping& m : g_ipc_maps) if (m.ptr) { cudaIpcCloseMemHandle(m.ptr); m.ptr = nullptr; }
+    comm_release();
     return WR_OK;
 }
 
@@ -515,6 +540,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
         if (const char* e = getenv("WR_RANKSET_ON")) a->rs_on = (unsigned)atoi(e);
         if (const char* e = getenv("WR_RANKSET_OFF")) a->rs_off = (unsigned)atoi(e);
     }
+    if (const char* e = getenv("WR_PEER_TIMEOUT_MS")) a->barrier_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
     a->K = p->K;
     a->n_slots = g->N * (size_t)p->K;
     a->n_slots_pad = (a->n_slots + kUpdTile - 1) / kUpdTile * kUpdTile;
@@ -567,6 +593,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     WR_CUDA_A(dmalloc(&a->d_upd_q, 4 * sizeof(uint32_t), a->stream));
     {
         WR_CUDA_A(cudaFuncSetAttribute(k_rank_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmallSmem));
+        WR_CUDA_A(cudaFuncSetAttribute(k_rank_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmallSmem));
         const size_t ws = walk_smem(a);
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         if (a->K == kK26) WR_CUDA_A(cudaFuncSetAttribute(k_walk26<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
@@ -656,6 +683,42 @@ extern "C" int wr_acs_set_endpoints(wr_acs* a, int64_t s, int64_t e)
     return WR_OK;
 }
 
+extern "C" int wr_acs_peer_export(wr_acs* a, void* ipc_handle, void** raw_pointer);
+extern "C" int wr_acs_peer_import(wr_acs* a, const void* all_ipc_handles);
+extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks);
+
+// wr_acs_begin of a handle that owns a communicator: all_gather of the slabs' CUDA IPC handles over NCCL
+static int exchange_slabs(wr_acs* a)
+{
+    unsigned char mine[64];
+    int rc = wr_acs_peer_export(a, mine, nullptr);
+    if (rc != WR_OK) return rc;
+    cudaStream_t s = a->stream;
+    unsigned char* d_buf = nullptr;
+    WR_CUDA(dmalloc(&d_buf, (size_t)64 * (a->nranks + 1), s));
+    WR_CUDA(cudaMemcpyAsync(d_buf, mine, 64, cudaMemcpyHostToDevice, s));
+    rc = comm_all_gather(a->comm, d_buf, d_buf + 64, 64, s);
+    std::vector<unsigned char> all((size_t)64 * a->nranks);
+    if (rc == WR_OK) {
+        WR_CUDA(cudaMemcpyAsync(all.data(), d_buf + 64, all.size(), cudaMemcpyDeviceToHost, s));
+        WR_CUDA(cudaStreamSynchronize(s));
+    }
+    pool_free(d_buf, s);
+    if (rc != WR_OK) return rc;
+    return wr_acs_peer_import(a, all.data());
+}
+
+extern "C" int wr_acs_comm_init(wr_acs* a, const void* nccl_unique_id, int rank, int nranks)
+{
+    WR_REQUIRE(a && nccl_unique_id, WR_ERR_INVALID, "wr_acs_comm_init: null");
+    int rc = wr_acs_set_shard(a, rank, nranks);
+    if (rc != WR_OK) return rc;
+    a->comm = nullptr;
+    if (nranks == 1) return WR_OK;
+    WR_CUDA(cudaSetDevice(a->device));
+    return comm_get(nccl_unique_id, rank, nranks, &a->comm);
+}
+
 extern "C" int wr_acs_set_next_search(wr_acs* a, uint32_t index)
 {
     WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_set_next_search: null");
@@ -692,6 +755,7 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     a->begun = true;
     a->timer.used = 0;
     for (float& m : a->timer.ms) m = 0;
+    if (a->nranks > 1 && a->comm) return exchange_slabs(a);   // without a communicator the caller exchanges them (wr_acs_peer_export / _import)
     return WR_OK;
 }
 
@@ -768,27 +832,23 @@ static int launch_walk(wr_acs* a)
 static const uint32_t* rank_keys(const wr_acs* a) { return a->ants_in_b ? a->sort_ants.keys_b : a->sort_ants.keys_a; }
 static const uint32_t* rank_vals(const wr_acs* a) { return a->ants_in_b ? a->sort_ants.vals_b : a->sort_ants.vals_a; }
 
-// colony ranking (:273-274), best decision (:263-264), deposit eligibility and offsets (:200)
+// colony ranking (:273-274), best decision (:263-264), deposit eligibility and offsets (:200): rank_small.cuh
 static int launch_rank(wr_acs* a, const int* d_all_steps)
 {
     const int cm = std::max(a->colony_max, 1);
     cudaStream_t s = a->stream;
-    static const bool small_ok = [] { const char* e = getenv("WR_RANK_SMALL"); return !e || atoi(e) != 0; }();
-    if (small_ok && cm <= kRankSmallMax) {   // the whole ranking in one single-CTA kernel (rank_small.cuh)
-        k_rank_small<<<1, kRankSmallThreads, kRankSmallSmem, s>>>(a->d_state, d_all_steps, a->K == kK26 ? a->d_ant_L : nullptr, a->cap, a->rank_bits, a->d_Ltab,
-                                                                   a->sort_ants.keys_a, a->sort_ants.vals_a, a->d_rec_off, a->d_order, a->d_best_n, a->d_best_ids,
-                                                                   a->d_onbest);
-        a->ants_in_b = false;
-        WR_CUDA(cudaGetLastError());
-        return WR_OK;
+    const float* d_L = a->K == kK26 ? a->d_ant_L : nullptr;
+    a->ants_in_b = false;
+    if (cm <= kRankSmallMax) {   // the whole ranking in one single-CTA kernel
+        k_rank_small<<<1, kRankSmallThreads, kRankSmallSmem, s>>>(a->d_state, d_all_steps, d_L, a->cap, a->rank_bits, a->d_Ltab, a->sort_ants.keys_a, a->sort_ants.vals_a,
+                                                                   a->d_rec_off, a->d_order, a->d_best_n, a->d_best_ids, a->d_onbest);
+    } else {                     // chunks of 16384 ants sorted in parallel, merged by rank counting, prefix-only finish
+        const int nchunks = (cm + kRankSmallMax - 1) / kRankSmallMax;
+        k_rank_chunks<<<nchunks, kRankSmallThreads, kRankSmallSmem, s>>>(a->d_state, d_all_steps, d_L, a->cap, a->rank_bits, a->sort_ants.keys_b, a->sort_ants.vals_b);
+        k_rank_merge<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, a->sort_ants.keys_b, a->sort_ants.vals_b, a->sort_ants.keys_a, a->sort_ants.vals_a, a->d_order);
+        k_rank_finish_prefix<<<1, 1024, 0, s>>>(a->d_state, a->sort_ants.keys_a, a->sort_ants.vals_a, a->cap, a->d_Ltab, a->d_rec_off, a->w_max,
+                                                a->K == kK26 ? d_all_steps : nullptr, a->d_best_n, a->d_best_ids, a->d_onbest);
     }
-    if (a->K == kK26) k_rank_keys26<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->d_ant_L, a->sort_ants.keys_a, a->sort_ants.vals_a);
-    else k_rank_keys<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, d_all_steps, a->cap, a->sort_ants.keys_a, a->sort_ants.vals_a);
-    int st = sort_pairs(&a->sort_ants, a->dptr_colony(), a->rank_bits, s, &a->ants_in_b);
-    if (st != WR_OK) return st;
-    k_rank_finish<<<1, 1024, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->cap, a->d_Ltab, a->d_rec_off, a->d_order,
-                                     a->K == kK26 ? d_all_steps : nullptr);
-    k_best_clear<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_onbest);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -812,7 +872,6 @@ static int launch_deposit_gen(wr_acs* a)
     return WR_OK;
 }
 
-// K3, shipped variant: tile offsets + list of deposit tiles, then the fused single-pass update
 // K3, shipped variant: tile offsets + list of deposit tiles, then the fused single-pass update
 static int launch_fused(wr_acs* a, const uint32_t* ck, const uint32_t* cv, const int* d_n = nullptr, uint32_t* fin = nullptr)
 {
@@ -854,16 +913,106 @@ static int launch_update(wr_acs* a)
     return WR_OK;
 }
 
+// ---- peer barrier of a sharded colony (k_peer_barrier) -------------------------------------------------------------------
+static void launch_barrier(wr_acs* a)
+{
+    k_peer_barrier<<<1, std::max(32, (a->nranks + 31) / 32 * 32), 0, a->stream>>>(reinterpret_cast<uint32_t* const*>(const_cast<void**>(a->tab(5, 0))), a->rank, a->nranks,
+                                                                                 a->d_epoch, a->d_peer_err, a->barrier_timeout_ns);
+}
+
+// ---- the rank-set deposit path (rankset.cuh): build [+ publish | barrier | merge], evaporate, one apply launch per rank group ----
+static int launch_rankset_update(wr_acs* a)
+{
+    cudaStream_t s = a->stream;
+    const int first = a->rank * a->chunk;
+    k_rankset_gen<<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal, a->d_Ltab, a->d_onbest,
+                                           a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr, first, a->chunk);
+    if (a->nranks > 1) {
+        k_rankset_publish<<<kNumSMs, 256, 0, s>>>(a->d_state, a->rs, a->pub_buf());
+        launch_barrier(a);
+        k_rankset_merge<<<kNumSMs * 2, 256, 0, s>>>(a->d_state, a->rs, reinterpret_cast<const uint32_t* const*>(a->tab(4, 0)), a->nranks, a->rank);
+    }
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
+    k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
+    if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
+    for (int g = 0; g < a->rs_groups; g++)
+        k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty, (uint32_t)g, g == a->rs_groups - 1 ? 1 : 0);
+    // overflow of the fixed-capacity table (flag raised by gen / merge): wipe what apply could not reach, deposit serially
+    k_rankset_wipe<<<kNumSMs * 2, 256, 0, s>>>(a->d_state, a->rs);
+    k_deposit_serial<<<1, 1024, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->trail_ids_tab(), a->trail_dirs_tab(), a->cap, a->chunk, (int)a->goal, a->d_Ltab,
+                                        a->d_onbest, a->rs.count + 3, a->d_tau, a->p.rho, a->d_dirty, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
+// ---- the sorted-record deposit path of a sharded colony: every rank generates the records of ALL eligible ants from their
+//      owners' trails (peer loads), keeps, sorts and applies its slot slice, lists the final values; barrier; pull ----
+static int launch_record_update_sharded(wr_acs* a)
+{
+    cudaStream_t s = a->stream;
+    k_deposit_gen<false, true><<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_rec_off, nullptr, nullptr, a->cap, 0, a->chunk,
+                                                         (int)a->goal, a->d_Ltab, a->d_onbest, a->sort_recs.keys_a, a->sort_recs.vals_a, nullptr,
+                                                         a->trail_ids_tab(), a->trail_dirs_tab());
+    WR_CUDA(cudaGetLastError());
+    const unsigned t_lo = (unsigned)(((unsigned long long)a->ntiles * a->rank) / a->nranks);
+    const unsigned t_hi = (unsigned)(((unsigned long long)a->ntiles * (a->rank + 1)) / a->nranks);
+    int st = sort_partition(&a->sort_recs, a->dptr_nrec_upd(), t_lo * (uint32_t)kUpdTile, (t_hi - t_lo) * (uint32_t)kUpdTile, s, a->d_nq);
+    if (st != WR_OK) return st;
+    st = sort_pairs(&a->sort_recs, a->d_nq, a->slot_bits, s, &a->recs_in_b, true);
+    if (st != WR_OK) return st;
+    const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
+    const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    uint32_t* fin = a->fin_buf(a->parity);
+    WR_CUDA(cudaMemsetAsync(fin, 0, 4 * sizeof(uint32_t), s));
+    st = launch_fused(a, ck, cv, a->d_nq, fin);
+    if (st != WR_OK) return st;
+    launch_barrier(a);   // every rank's list of final values is complete
+    k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(a->d_tau, walk_warm() ? a->d_heur : nullptr, reinterpret_cast<const uint32_t* const*>(a->tab(2, a->parity)),
+                                              a->nranks, a->rank, a->d_dirty, a->d_upd_q);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
 static bool graph_enabled()
 {
     static const bool on = [] { const char* e = getenv("WR_GRAPH"); return !e || atoi(e) != 0; }();
     return on;
 }
 
+// Everything of one iteration between the iteration parameters and the deposits: construction, [exchange of the step counts],
+// ranking, best path.
+static int launch_construct_and_rank(wr_acs* a)
+{
+    cudaStream_t s = a->stream;
+    if (a->nranks > 1) WR_CUDA(cudaMemsetAsync(a->d_local_steps, 0xFF, (size_t)a->chunk * sizeof(int), s));   // -1: beyond the colony
+    int st = launch_walk(a);
+    if (st != WR_OK) return st;
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    if (a->nranks > 1) {   // trails and step counts of every rank are complete and visible: barrier, then the global colony
+        launch_barrier(a);
+        const int total = a->chunk * a->nranks;
+        k_gather_steps<<<std::max(1, std::min((total + 255) / 256, kNumSMs * 2)), 256, 0, s>>>(reinterpret_cast<const int* const*>(a->tab(3, a->parity)), a->nranks, a->chunk,
+                                                                                                 a->d_ant_steps);
+    }
+    st = launch_rank(a, a->d_ant_steps);
+    if (st != WR_OK) return st;
+    if (a->nranks > 1)
+        k_best_copy_peer<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->trail_ids_tab(), a->trail_dirs_tab(), a->cap, a->chunk,
+                                           (int)a->goal);
+    else
+        k_best_copy<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_path_ids, a->d_path_dirs, a->cap, 0, (int)a->goal);
+    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    WR_CUDA(cudaGetLastError());
+    return WR_OK;
+}
+
 // One rank-set iteration whose predecessor was a rank-set iteration too, captured from the very launch sequence of
 // wr_acs_iterate (k_iter_end of the predecessor folded into k_iter_begin): L2 warm-up, iteration parameters, walk pass 1 + 2,
-// ranking, best copy, rank-set build, evaporation of the dirty tiles, ordered chains.  Every argument is fixed for the search.
-static int capture_steady_iteration(wr_acs* a)
+// ranking, best copy, rank-set build, evaporation of the dirty tiles, ordered chains.  Every argument is fixed for the search
+// (sharded handles alternate between two trail buffers, hence one graph per parity).
+static int capture_steady_iteration(wr_acs* a, cudaGraphExec_t* out)
 {
     cudaStream_t s = a->stream;
     if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) return WR_ERR_STATE;   // the default streams cannot be captured
@@ -871,13 +1020,8 @@ static int capture_steady_iteration(wr_acs* a)
     launch_warm(a, true);
     k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, 1, a->d_upd_q, a->rs.count, 1, a->d_feedback,
                                  a->rs_generation, a->p.rho);
-    int st = launch_walk(a);
-    if (st == WR_OK) st = launch_rank(a, a->d_ant_steps);
-    k_best_copy<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_path_ids, a->d_path_dirs, a->cap, 0, (int)a->goal);
-    k_rankset_gen<<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal, a->d_Ltab, a->d_onbest,
-                                           a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
-    k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
-    k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty);
+    int st = launch_construct_and_rank(a);
+    if (st == WR_OK) st = launch_rankset_update(a);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     if (e != cudaSuccess || st != WR_OK || !graph) {
@@ -885,9 +1029,29 @@ static int capture_steady_iteration(wr_acs* a)
         cudaGetLastError();
         return WR_ERR_CUDA;
     }
-    e = cudaGraphInstantiate(&a->rs_graph, graph, 0);
+    e = cudaGraphInstantiate(out, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { a->rs_graph = nullptr; cudaGetLastError(); return WR_ERR_CUDA; }
+    if (e != cudaSuccess) { *out = nullptr; cudaGetLastError(); return WR_ERR_CUDA; }
+    return WR_OK;
+}
+
+// Which deposit path iteration number `n` of this search takes.  Adaptive handles: the record the device published when
+// iteration n - kRsAhead started (statistics of iteration n - kRsAhead - 1; that iteration has finished, its event was
+// waited for) — a pure function of the search, so every rank of a sharded colony takes the same decision.
+static int choose_deposit_path(wr_acs* a)
+{
+    const unsigned long long n = a->rs_enqueued;
+    if (n >= (unsigned long long)wr_acs::kRsAhead) WR_CUDA(cudaEventSynchronize(a->rs_ev[n % wr_acs::kRsAhead]));
+    if (a->rs_policy == 1 || a->rs_policy == 2) a->rs_choice = a->rs_policy == 1;
+    else if (a->h_feedback && n > (unsigned long long)wr_acs::kRsAhead) {
+        const unsigned long long m = n - wr_acs::kRsAhead;
+        const volatile uint32_t* f = a->h_feedback + 4 * (m & 7u);
+        const uint32_t tag = f[0], prev = f[1], tiles = f[2], blocks = f[3];
+        if (tag == ((a->rs_generation << 16) | (uint32_t)(m & 0xFFFFu))) {
+            if (!a->rs_choice && prev == 0 && tiles <= a->rs_on) a->rs_choice = 1;
+            else if (a->rs_choice && prev == 1 && blocks > a->rs_off) a->rs_choice = 0;
+        }
+    }
     return WR_OK;
 }
 
@@ -895,30 +1059,27 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
 {
     WR_REQUIRE(a && n >= 0, WR_ERR_INVALID, "wr_acs_iterate: bad argument");
     WR_REQUIRE(a->begun, WR_ERR_STATE, "wr_acs_iterate: call wr_acs_begin first");
-    WR_REQUIRE(a->nranks == 1, WR_ERR_STATE, "wr_acs_iterate: a sharded handle iterates through wr_acs_walk ... wr_acs_finish_iteration");
+    WR_REQUIRE(a->nranks == 1 || a->peers_set, WR_ERR_STATE, "wr_acs_iterate: sharded handle: exchange the peer slabs first (wr_acs_comm_init, or wr_acs_peer_export / _import)");
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
+    const bool sharded = a->nranks > 1;
     for (int it = 0; it < n; it++) {
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
         const bool rs_prev = a->rankset && a->rs_choice;   // path of the previous iteration (what the L2 warm-up reads)
-        if (a->rankset) {   // which deposit path this iteration takes (see k_iter_begin)
-            if (a->rs_enqueued >= (unsigned long long)wr_acs::kRsAhead) WR_CUDA(cudaEventSynchronize(a->rs_ev[a->rs_enqueued % wr_acs::kRsAhead]));
-            if (a->rs_policy == 1 || a->rs_policy == 2) a->rs_choice = a->rs_policy == 1;
-            else {
-                const volatile uint32_t* f = a->h_feedback;
-                const uint32_t tag = f ? f[0] : 0u, prev = f ? f[1] : 0u, tiles = f ? f[2] : 0u, slots = f ? f[3] : 0u;
-                if (f && (tag >> 16) == a->rs_generation && (tag & 0xFFFFu) > 0) {
-                    if (!a->rs_choice && prev == 0 && tiles <= a->rs_on) a->rs_choice = 1;
-                    else if (a->rs_choice && prev == 1 && slots > a->rs_off) a->rs_choice = 0;
-                }
-            }
-        }
+        if (a->rankset) { int rc = choose_deposit_path(a); if (rc != WR_OK) return rc; }
         const bool rs_now = a->rankset && a->rs_choice;
+        if (sharded) {   // trails and step counts are double-buffered: a peer may still be reading the previous iteration's
+            a->parity ^= 1u;
+            a->d_path_ids = reinterpret_cast<uint32_t*>(a->d_slab + a->off_ids[a->parity]);
+            a->d_path_dirs = a->d_slab + a->off_dirs[a->parity];
+            a->d_local_steps = reinterpret_cast<int*>(a->d_slab + a->off_steps[a->parity]);
+        }
         // steady state of a converged search: the whole iteration is one graph launch
         if (rs_now && rs_prev && it > 0 && a->rs_enqueued > 0 && !a->timer.enabled && !a->rs_graph_failed && graph_enabled()) {
-            if (!a->rs_graph && capture_steady_iteration(a) != WR_OK) a->rs_graph_failed = true;
-            if (a->rs_graph) {
-                WR_CUDA(cudaGraphLaunch(a->rs_graph, s));
+            cudaGraphExec_t& gx = a->rs_graph[sharded ? a->parity : 0];
+            if (!gx && capture_steady_iteration(a, &gx) != WR_OK) a->rs_graph_failed = true;
+            if (gx) {
+                WR_CUDA(cudaGraphLaunch(gx, s));
                 WR_CUDA(cudaEventRecord(a->rs_ev[a->rs_enqueued % wr_acs::kRsAhead], s)); a->rs_enqueued++;
                 if (it == n - 1) k_iter_end<<<1, 1, 0, s>>>(a->d_state, a->p.rho);
                 continue;
@@ -928,29 +1089,16 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
         k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->d_upd_q,
                                      a->rankset ? a->rs.count : nullptr, rs_now ? 1 : 0, a->d_feedback, a->rs_generation, a->p.rho);
         a->upd_q_zeroed = true;
-        int st = launch_walk(a);
+        int st = launch_construct_and_rank(a);
         if (st != WR_OK) return st;
-        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-        st = launch_rank(a, a->d_ant_steps);
-        if (st != WR_OK) return st;
-        k_best_copy<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_path_ids, a->d_path_dirs, a->cap,
-                                      0, (int)a->goal);
-        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-        if (rs_now) {   // rank sets instead of sorted records (rankset.cuh): gen | evaporation pass + one ordered chain per touched slot
-            k_rankset_gen<<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_path_ids, a->d_path_dirs, a->cap, (int)a->goal, a->d_Ltab,
-                                                   a->d_onbest, a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
-            if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-            if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
-            k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
-            if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
-            k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty);
-            WR_CUDA(cudaGetLastError());
-        } else {
+        if (rs_now) st = launch_rankset_update(a);   // rank sets instead of sorted records (rankset.cuh)
+        else if (sharded) { st = launch_record_update_sharded(a); a->warm_by_pull = true; }
+        else {
             st = launch_deposit_gen(a);
-            if (st != WR_OK) return st;
-            st = launch_update(a);
-            if (st != WR_OK) return st;
+            if (st == WR_OK) st = launch_update(a);
         }
+        if (st != WR_OK) return st;
+        if (rs_now) a->warm_by_pull = false;
         if (a->rankset) { WR_CUDA(cudaEventRecord(a->rs_ev[a->rs_enqueued % wr_acs::kRsAhead], s)); a->rs_enqueued++; }
         a->upd_q_zeroed = false;
         if (it == n - 1) k_iter_end<<<1, 1, 0, s>>>(a->d_state, a->p.rho);   // otherwise folded into the next k_iter_begin
@@ -1021,92 +1169,9 @@ extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks)
     WR_REQUIRE(!a->begun || (a->rank == rank && a->nranks == nranks), WR_ERR_STATE, "wr_acs_set_shard: set the shard before wr_acs_begin");
     WR_REQUIRE(nranks == 1 || a->p.update_mode != WR_UPDATE_ATOMIC, WR_ERR_INVALID, "wr_acs_set_shard: sharded colonies use the rank-ordered update modes");
     WR_REQUIRE(nranks == 1 || a->K == 6, WR_ERR_INVALID, "wr_acs_set_shard: the K = 26 extension runs on one GPU (ranks would have to exchange lengths as well as step counts)");
+    WR_REQUIRE(nranks <= 256, WR_ERR_INVALID, "wr_acs_set_shard: at most 256 ranks");
+    WR_REQUIRE(nranks == 1 || a->p.update_mode == WR_UPDATE_FUSED, WR_ERR_INVALID, "wr_acs_set_shard: sharded colonies use WR_UPDATE_FUSED or WR_UPDATE_RANKSET");
     a->rank = rank; a->nranks = nranks;
-    return WR_OK;
-}
-
-extern "C" int wr_acs_walk(wr_acs* a)
-{
-    WR_REQUIRE(a && a->begun, WR_ERR_STATE, "wr_acs_walk: call wr_acs_begin first");
-    WR_CUDA(cudaSetDevice(a->device));
-    cudaStream_t s = a->stream;
-    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    if (a->d_slab) {   // trails are double-buffered: a peer may still be reading the previous iteration's
-        a->parity ^= 1u;
-        a->d_path_ids = reinterpret_cast<uint32_t*>(a->d_slab + a->off_ids[a->parity]);
-        a->d_path_dirs = a->d_slab + a->off_dirs[a->parity];
-    }
-    launch_warm(a, false);
-    k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0);
-    WR_CUDA(cudaMemsetAsync(a->d_local_steps, 0xFF, (size_t)a->chunk * sizeof(int), s));   // -1: beyond the colony
-    int st = launch_walk(a);
-    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    return st;
-}
-
-extern "C" int wr_acs_local_steps_dev(wr_acs* a, int** dev_steps, int* first, int* count)
-{
-    WR_REQUIRE(a && dev_steps && first && count && a->begun, WR_ERR_STATE, "wr_acs_local_steps_dev: call wr_acs_begin first");
-    *dev_steps = a->d_local_steps; *first = a->rank * a->chunk; *count = a->chunk;
-    return WR_OK;
-}
-
-extern "C" int wr_acs_rank_global(wr_acs* a, const int* dev_all_steps)
-{
-    WR_REQUIRE(a && dev_all_steps && a->begun, WR_ERR_STATE, "wr_acs_rank_global: bad state");
-    WR_CUDA(cudaSetDevice(a->device));
-    cudaStream_t s = a->stream;
-    WR_CUDA(cudaMemcpyAsync(a->d_ant_steps, dev_all_steps, (size_t)std::max(a->colony_max, 1) * sizeof(int), cudaMemcpyDeviceToDevice, s));
-    int st = launch_rank(a, a->d_ant_steps);
-    if (st != WR_OK) return st;
-    WR_CUDA(cudaMemsetAsync(a->d_cand, 0, a->cand_words * sizeof(uint32_t), s));
-    k_best_candidate<<<8, 256, 0, s>>>(a->d_state, a->d_cand, a->d_path_ids, a->d_path_dirs, a->cap, a->rank * a->chunk, a->chunk, (int)a->goal);
-    WR_CUDA(cudaGetLastError());
-    return WR_OK;
-}
-
-extern "C" int wr_acs_best_candidate_dev(wr_acs* a, uint32_t** dev_words, size_t* nwords)
-{
-    WR_REQUIRE(a && dev_words && nwords && a->begun, WR_ERR_STATE, "wr_acs_best_candidate_dev: bad state");
-    *dev_words = a->d_cand; *nwords = a->cand_words;
-    return WR_OK;
-}
-
-extern "C" int wr_acs_apply_best(wr_acs* a)
-{
-    WR_REQUIRE(a && a->begun, WR_ERR_STATE, "wr_acs_apply_best: bad state");
-    cudaStream_t s = a->stream;
-    k_best_install<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, a->d_cand, a->cap);
-    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    WR_CUDA(cudaGetLastError());
-    return WR_OK;
-}
-
-extern "C" int wr_acs_build_records(wr_acs* a, uint32_t** dev_keys, uint32_t** dev_vals, int* n)
-{
-    WR_REQUIRE(a && dev_keys && dev_vals && n && a->begun, WR_ERR_STATE, "wr_acs_build_records: bad state");
-    cudaStream_t s = a->stream;
-    IterState st;
-    WR_CUDA(cudaMemcpyAsync(&st, a->d_state, sizeof st, cudaMemcpyDeviceToHost, s));
-    WR_CUDA(cudaStreamSynchronize(s));   // the one host sync of a sharded iteration: the record count sizes the all_reduce
-    *n = st.n_records;
-    if (st.n_records > 0) {
-        WR_CUDA(cudaMemsetAsync(a->sort_recs.keys_a, 0, (size_t)st.n_records * sizeof(uint32_t), s));
-        WR_CUDA(cudaMemsetAsync(a->sort_recs.vals_a, 0, (size_t)st.n_records * sizeof(uint32_t), s));
-    }
-    int rc = launch_deposit_gen(a);
-    *dev_keys = a->sort_recs.keys_a; *dev_vals = a->sort_recs.vals_a;
-    return rc;
-}
-
-extern "C" int wr_acs_finish_iteration(wr_acs* a)
-{
-    WR_REQUIRE(a && a->begun, WR_ERR_STATE, "wr_acs_finish_iteration: bad state");
-    int st = launch_update(a);
-    if (st != WR_OK) return st;
-    k_iter_end<<<1, 1, 0, a->stream>>>(a->d_state, a->p.rho);
-    if (a->timer.enabled) cudaEventRecord(a->timer.next(), a->stream);
-    WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
 
@@ -1114,6 +1179,12 @@ extern "C" int wr_acs_finish_iteration(wr_acs* a)
 extern "C" int wr_acs_peer_export(wr_acs* a, void* ipc_handle, void** raw_pointer)
 {
     WR_REQUIRE(a && a->begun && a->nranks > 1 && a->d_slab, WR_ERR_STATE, "wr_acs_peer_export: sharded handle after wr_acs_begin only");
+    // the barrier epochs restart with every exchange: this rank's flag words and its epoch go back to 0 BEFORE the handle
+    // leaves (the exchange itself is a host-side barrier, so no peer can signal before every rank has done this)
+    WR_CUDA(cudaMemsetAsync(a->d_slab + a->off_flags, 0, 4096, a->stream));
+    WR_CUDA(cudaMemsetAsync(a->d_epoch, 0, 2 * sizeof(uint32_t), a->stream));
+    WR_CUDA(cudaStreamSynchronize(a->stream));
+    a->peers_set = false;
     if (ipc_handle) WR_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle), a->d_slab));
     if (raw_pointer) *raw_pointer = a->d_slab;
     return WR_OK;
@@ -1121,12 +1192,15 @@ extern "C" int wr_acs_peer_export(wr_acs* a, void* ipc_handle, void** raw_pointe
 
 static int install_peers(wr_acs* a, const std::vector<const unsigned char*>& slabs)
 {
-    std::vector<const void*> tab((size_t)6 * a->nranks);
+    std::vector<const void*> tab((size_t)wr_acs::kTabKinds * 2 * a->nranks);
     for (int r = 0; r < a->nranks; r++)
         for (int b = 0; b < 2; b++) {
             tab[((size_t)0 * 2 + b) * a->nranks + r] = slabs[r] + a->off_ids[b];
             tab[((size_t)1 * 2 + b) * a->nranks + r] = slabs[r] + a->off_dirs[b];
             tab[((size_t)2 * 2 + b) * a->nranks + r] = slabs[r] + a->off_fin[b];
+            tab[((size_t)3 * 2 + b) * a->nranks + r] = slabs[r] + a->off_steps[b];
+            tab[((size_t)4 * 2 + b) * a->nranks + r] = slabs[r] + a->off_pub;
+            tab[((size_t)5 * 2 + b) * a->nranks + r] = slabs[r] + a->off_flags;
         }
     WR_CUDA(cudaMemcpyAsync(a->d_tabs, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, a->stream));
     WR_CUDA(cudaStreamSynchronize(a->stream));
@@ -1167,75 +1241,16 @@ extern "C" int wr_acs_peer_set_pointers(wr_acs* a, void* const* all_raw_pointers
     return install_peers(a, slabs);
 }
 
-// Steps 3-6 of the peer-memory protocol, one call, no host synchronisation: global ranking + best decision (the new
-// best trail is read from its owner's HBM), deposit records of ALL eligible ants generated from the owners' trails in
-// global (rank, step) order, then either the replicated update (sliced = 0: slot sort + fused update of everything)
-// or the owner-computes update (sliced = 1: this rank keeps, sorts and applies the records of its slot slice and lists
-// the final values; follow with a barrier and wr_acs_pull_finals).
-extern "C" int wr_acs_finish_iteration_peer(wr_acs* a, const int* dev_all_steps, int sliced)
-{
-    WR_REQUIRE(a && dev_all_steps && a->begun && a->nranks > 1, WR_ERR_STATE, "wr_acs_finish_iteration_peer: sharded handle only");
-    WR_REQUIRE(a->peers_set, WR_ERR_STATE, "wr_acs_finish_iteration_peer: exchange the peer buffers first (wr_acs_peer_export / _import)");
-    WR_REQUIRE(!sliced || a->p.update_mode == WR_UPDATE_FUSED, WR_ERR_STATE, "wr_acs_finish_iteration_peer: the owner-computes update needs WR_UPDATE_FUSED");
-    WR_CUDA(cudaSetDevice(a->device));
-    cudaStream_t s = a->stream;
-    WR_CUDA(cudaMemcpyAsync(a->d_ant_steps, dev_all_steps, (size_t)std::max(a->colony_max, 1) * sizeof(int), cudaMemcpyDeviceToDevice, s));
-    int st = launch_rank(a, a->d_ant_steps);
-    if (st != WR_OK) return st;
-    const uint32_t* const* ids_tab = reinterpret_cast<const uint32_t* const*>(a->tab(0, a->parity));
-    const uint8_t* const* dirs_tab = reinterpret_cast<const uint8_t* const*>(a->tab(1, a->parity));
-    k_best_copy_peer<<<8, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, a->d_onbest, ids_tab, dirs_tab, a->cap, a->chunk, (int)a->goal);
-    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    k_deposit_gen<false, true><<<a->w_max, 128, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->d_rec_off, nullptr, nullptr, a->cap, 0, a->chunk,
-                                                         (int)a->goal, a->d_Ltab, a->d_onbest, a->sort_recs.keys_a, a->sort_recs.vals_a, nullptr,
-                                                         ids_tab, dirs_tab);
-    WR_CUDA(cudaGetLastError());
-    a->warm_by_pull = sliced != 0;
-    if (!sliced) {
-        st = launch_update(a);
-        if (st != WR_OK) return st;
-        k_iter_end<<<1, 1, 0, s>>>(a->d_state, a->p.rho);
-        if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-        WR_CUDA(cudaGetLastError());
-        return WR_OK;
-    }
-    const unsigned t_lo = (unsigned)(((unsigned long long)a->ntiles * a->rank) / a->nranks);
-    const unsigned t_hi = (unsigned)(((unsigned long long)a->ntiles * (a->rank + 1)) / a->nranks);
-    st = sort_partition(&a->sort_recs, a->dptr_nrec(), t_lo * (uint32_t)kUpdTile, (t_hi - t_lo) * (uint32_t)kUpdTile, s, a->d_nq);
-    if (st != WR_OK) return st;
-    st = sort_pairs(&a->sort_recs, a->d_nq, a->slot_bits, s, &a->recs_in_b, true);
-    if (st != WR_OK) return st;
-    const uint32_t* ck = a->recs_in_b ? a->sort_recs.keys_b : a->sort_recs.keys_a;
-    const uint32_t* cv = a->recs_in_b ? a->sort_recs.vals_b : a->sort_recs.vals_a;
-    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    uint32_t* fin = a->fin_buf(a->parity);
-    WR_CUDA(cudaMemsetAsync(fin, 0, 4 * sizeof(uint32_t), s));
-    st = launch_fused(a, ck, cv, a->d_nq, fin);
-    if (st != WR_OK) return st;
-    k_iter_end<<<1, 1, 0, s>>>(a->d_state, a->p.rho);
-    WR_CUDA(cudaGetLastError());
-    return WR_OK;
-}
-
-// After a barrier across ranks (every rank has finished the sliced wr_acs_finish_iteration_peer): overwrite the slots
-// the other ranks own with their final values, read straight from their HBM.
-extern "C" int wr_acs_pull_finals(wr_acs* a)
-{
-    WR_REQUIRE(a && a->begun && a->nranks > 1 && a->peers_set, WR_ERR_STATE, "wr_acs_pull_finals: bad state");
-    WR_CUDA(cudaSetDevice(a->device));
-    cudaStream_t s = a->stream;
-    k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(a->d_tau, walk_warm() ? a->d_heur : nullptr, reinterpret_cast<const uint32_t* const*>(a->tab(2, a->parity)),
-                                              a->nranks, a->rank, a->d_dirty);
-    if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    WR_CUDA(cudaGetLastError());
-    return WR_OK;
-}
-
 extern "C" int wr_acs_sync(wr_acs* a)
 {
     WR_REQUIRE(a, WR_ERR_INVALID, "wr_acs_sync: null");
     WR_CUDA(cudaStreamSynchronize(a->stream));
     if (a->timer.enabled) a->timer.resolve();
+    if (a->d_peer_err) {
+        uint32_t err = 0;
+        WR_CUDA(cudaMemcpy(&err, a->d_peer_err, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) { set_error("wr_acs_sync: a peer rank did not reach a barrier within %.1f s (results of this search are invalid)", a->barrier_timeout_ns * 1e-9); return WR_ERR_CUDA; }
+    }
     return WR_OK;
 }
 

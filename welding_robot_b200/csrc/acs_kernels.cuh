@@ -96,9 +96,11 @@ __global__ void k_begin(IterState* st, float predict)
 // rankset_count != nullptr: adaptive handle (WR_UPDATE_RANKSET).  use_rankset is the HOST's choice for this iteration: rank
 // sets pay off once the colony has converged on a few hundred slots, sorted records while it still wanders over ~10^6.
 // What the choice is based on — how concentrated the previous iteration's deposits were — is measured here and
-// published to the host through mapped pinned memory (feedback: {generation << 16 | iteration, path, tiles, slots}); the
-// host reads it without synchronising, a few iterations late (acs.cu keeps itself at most four iterations ahead of the
-// device), and only enqueues the kernels of the path it chose.  Either path gives the same bits, so the lag is invisible.
+// published to the host through mapped pinned memory (a ring of records {generation << 16 | iteration, path, tiles, row
+// blocks}); the host reads the record of the iteration that started kRsAhead iterations before the one it is enqueueing
+// (that iteration has finished: acs.cu keeps itself at most four iterations ahead of the device), and only enqueues
+// the kernels of the path it chose.  The choice is therefore a pure function of the search: identical on every rank of a
+// sharded colony (whose protocol depends on it) and in every run.  Either path gives the same bits.
 __global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, float precision, float tau0, int advance = 0, uint32_t* upd_q = nullptr,
                              uint32_t* rankset_count = nullptr, int use_rankset = 0, volatile uint32_t* feedback = nullptr, uint32_t generation = 0,
                              float rho = 1.0f)
@@ -109,11 +111,12 @@ __global__ void k_iter_begin(IterState* st, int fixed_colony, int colony_max, fl
         if (st->iter > 0) { if (prev) st->spread_slots = rankset_count[1]; else if (upd_q) st->spread_tiles = upd_q[2]; }
         st->use_rankset = use_rankset;
         if (use_rankset) st->rankset_iters++;
-        rankset_count[0] = 0;
-        if (feedback) {
-            feedback[1] = (uint32_t)prev; feedback[2] = st->spread_tiles; feedback[3] = st->spread_slots;
+        rankset_count[0] = 0; rankset_count[3] = 0;   // claimed blocks, overflow flag
+        if (feedback) {   // record of the iteration that starts now, in its slot of the ring (acs.cu reads the record of ONE specific iteration)
+            volatile uint32_t* f = feedback + 4 * ((uint32_t)st->iter & 7u);
+            f[1] = (uint32_t)prev; f[2] = st->spread_tiles; f[3] = st->spread_slots;
             __threadfence_system();
-            feedback[0] = (generation << 16) | ((uint32_t)st->iter & 0xFFFFu);
+            f[0] = (generation << 16) | ((uint32_t)st->iter & 0xFFFFu);
         }
     }
     if (upd_q) { upd_q[0] = 0; upd_q[1] = 0; upd_q[2] = 0; upd_q[3] = 0; }
@@ -190,87 +193,10 @@ __global__ void __launch_bounds__(256) k_heuristic(float* __restrict__ heur, con
 // ------------------------------------------------------------------------------------------
 // Ranking (:273-280) and best tracking (:263-264)
 // ------------------------------------------------------------------------------------------
-// key = steps for an ant that arrived, cap+1 for a dead one; value = ant index.  L is a strictly
-// increasing function of steps (L = precision added `steps` times, :78), so ordering by
-// (steps, ant) is ordering by (L, ant), the oracle's total order.
-__global__ void k_rank_keys(const IterState* st, const int* __restrict__ ant_steps, int cap, uint32_t* keys, uint32_t* vals)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st->colony) return;
-    int s = ant_steps[i];
-    keys[i] = s < 0 ? (uint32_t)(cap + 1) : (uint32_t)s;
-    vals[i] = (uint32_t)i;
-}
-
-// Single CTA.  From the sorted colony: the iteration's best (rank 1; lowest ant index among ties,
-// as the sequential `<` of :263 yields), the deposit eligibility of update_pheromone :200
-// (L finite and order <= lambda-1) and the record offset of every eligible rank.
-__global__ void __launch_bounds__(1024) k_rank_finish(IterState* st, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                       int cap, const float* __restrict__ Ltab, uint32_t* __restrict__ rec_off,
-                                                       int* __restrict__ order_of_ant, const int* __restrict__ steps26 = nullptr)
-{   // steps26 != nullptr (K = 26): keys are the bits of L (k_rank_keys26) and an ant's step count comes from steps26[ant]
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry, elig_total;
-    const int n = st->colony;
-    const float lambda = st->lambda;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        carry = 0; elig_total = 0;
-        if (n > 0 && steps26) {
-            const float L0 = __uint_as_float(keys[0]);
-            if (L0 < st->best_L) {                  // agentK.L < best.L  (:263); a dead ant's +inf never is
-                st->best_steps = steps26[vals[0]]; st->best_L = L0; st->best_changed = 1; st->best_ant = (int)vals[0];
-            }
-        } else if (n > 0) {
-            int s = (int)keys[0];
-            if (s <= cap && s < st->best_steps) {   // agentK.L < best.L  (:263)
-                st->best_steps = s; st->best_L = Ltab[s]; st->best_changed = 1; st->best_ant = (int)vals[0];
-            }
-        }
-    }
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int r = base + threadIdx.x;
-        uint32_t len = 0; bool el = false;
-        if (r < n) {
-            const int s = steps26 ? steps26[vals[r]] : (int)keys[r];
-            const bool arrived = steps26 ? keys[r] != 0x7F800000u : s <= cap;
-            const int order = r + 1;
-            order_of_ant[vals[r]] = order;
-            el = arrived && !((float)order > __fsub_rn(lambda, 1.0f));   // :200
-            len = el ? (uint32_t)s : 0u;
-        }
-        uint32_t incl = len;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-        if (lane == 31) warp_sum[w] = incl;
-        unsigned em = __ballot_sync(0xffffffffu, el);
-        if (lane == 0 && em) atomicAdd(&elig_total, (uint32_t)__popc(em));
-        __syncthreads();
-        if (w == 0) {
-            uint32_t s = warp_sum[lane], si = s;
-            for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += u; }
-            warp_sum[lane] = si - s;
-        }
-        __syncthreads();
-        const uint32_t excl = carry + warp_sum[w] + (incl - len);
-        if (r < n) rec_off[r] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + len;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { st->n_eligible = (int)elig_total; st->n_records = (int)carry; st->n_records_sort = st->use_rankset ? 0 : (int)carry; st->cnt[7] += carry; }
-}
-
-// best = agentK (:264): drop the old best path's membership bits ...
-__global__ void k_best_clear(const IterState* st, const int* __restrict__ best_n, const uint32_t* __restrict__ best_ids, uint32_t* onbest)
-{
-    if (!st->best_changed) return;
-    const int n = *best_n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t id = best_ids[i];
-        atomicAnd(&onbest[id >> 5], ~(1u << (id & 31)));
-    }
-}
+// The ranking itself lives in rank_small.cuh: key = steps for an ant that arrived, cap+1 for a dead one; value = ant index.
+// L is a strictly increasing function of steps (L = precision added `steps` times, :78), so ordering by (steps, ant) is
+// ordering by (L, ant), the oracle's total order.  best = agentK (:264): the ranking kernels drop the old best path's
+// membership bits ...
 // ... then copy the new one (path + chosen slots) and set its bits.  src_ids/src_dirs: the path
 // buffers of the ant that produced it (local ant index src_ant).
 __global__ void k_best_copy(const IterState* st, int* best_n, uint32_t* best_ids, uint8_t* best_dirs, uint32_t* onbest,
@@ -303,37 +229,6 @@ __global__ void k_best_copy_peer(const IterState* st, int* best_n, uint32_t* bes
         uint32_t id = i < steps ? path_ids[off + i] : (uint32_t)goal;
         best_ids[i] = id;
         if (i < steps) best_dirs[i] = path_dirs[off + i];
-        atomicOr(&onbest[id >> 5], 1u << (id & 31));
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *best_n = steps + 1;
-}
-
-// Sharded colonies: the rank that walked the new best ant publishes its trail in a buffer that is
-// zero everywhere else, so an integer all_reduce(SUM) hands every rank the same words.
-// Layout: [0] = 1 if filled, [1 .. cap+1] node ids (goal included), [cap+2 .. 2*cap+1] chosen slots.
-__global__ void k_best_candidate(const IterState* st, uint32_t* cand, const uint32_t* __restrict__ path_ids,
-                                 const uint8_t* __restrict__ path_dirs, int cap, int shard_first, int shard_chunk, int goal)
-{
-    if (!st->best_changed) return;
-    const int ant = st->best_ant;
-    if (ant < shard_first || ant >= shard_first + shard_chunk) return;
-    const int steps = st->best_steps;
-    const size_t off = (size_t)(ant - shard_first) * cap;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= steps; i += gridDim.x * blockDim.x) {
-        cand[1 + i] = i < steps ? path_ids[off + i] : (uint32_t)goal;
-        if (i < steps) cand[cap + 2 + i] = path_dirs[off + i];
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) cand[0] = 1u;
-}
-__global__ void k_best_install(const IterState* st, int* best_n, uint32_t* best_ids, uint8_t* best_dirs, uint32_t* onbest,
-                               const uint32_t* __restrict__ cand, int cap)
-{
-    if (!st->best_changed) return;
-    const int steps = st->best_steps;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= steps; i += gridDim.x * blockDim.x) {
-        const uint32_t id = cand[1 + i];
-        best_ids[i] = id;
-        if (i < steps) best_dirs[i] = (uint8_t)cand[cap + 2 + i];
         atomicOr(&onbest[id >> 5], 1u << (id & 31));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *best_n = steps + 1;
@@ -613,6 +508,7 @@ __global__ void __launch_bounds__(kUpdThreads, kFusedCtasPerSm) k_update_fused(f
     __shared__ uint32_t s_off[kFusedChunk + 1];
     const int tid = threadIdx.x;
     const unsigned dep_n = q[2];
+    if (EMIT && blockIdx.x == 0 && tid == 0) fin[1] = dep_n;   // sharded: this rank's share of the "tiles that received deposits" statistic
     while (true) {   // ---- tiles that receive deposits, first ----
         if (tid == 0) s_next = atomicAdd(&q[0], 1u);
         __syncthreads();
@@ -702,9 +598,14 @@ __global__ void k_save_result(const IterState* st, const int* __restrict__ best_
 // The same pass is the next walk's L2 warm-up (cf. k_path_warm): the slots that just received deposits are where the
 // colony walks next, so the tau lines are left dirty in L2 by the writes and the heuristic rows are touched here.
 __global__ void __launch_bounds__(256) k_pull_finals(float* tau, const float* __restrict__ heur, const uint32_t* const* __restrict__ bufs, int npeers, int me,
-                                                      uint8_t* dirty)
+                                                      uint8_t* dirty, uint32_t* upd_q)
 {
     uint32_t acc = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // tiles that received deposits on ANY rank (the slices are disjoint): the statistic k_iter_begin publishes
+        uint32_t tiles = 0;
+        for (int p = 0; p < npeers; p++) tiles += __ldcg(bufs[p] + 1);
+        upd_q[2] = tiles;
+    }
     for (int p = 0; p < npeers; p++) {
         const uint32_t* buf = bufs[p];
         const uint32_t cnt = __ldcg(buf);
@@ -717,6 +618,57 @@ __global__ void __launch_bounds__(256) k_pull_finals(float* tau, const float* __
         }
     }
     if (acc == 0x9E3779B9u && npeers < 0) tau[0] = 0.0f;   // keeps the warm-up loads alive; never true
+}
+
+// ------------------------------------------------------------------------------------------
+// Barrier between the ranks of a sharded colony, in peer memory (NVLink): every rank owns an array of epoch words, one
+// per source rank, in its slab.  Rank `me` writes its new epoch into word `me` of every peer's array (system-scope
+// release: everything this rank's earlier kernels wrote — trails, step counts, published row blocks, final values — is
+// visible to whoever acquires the word), then waits until every peer's word in its own array has reached the epoch.
+// No host involvement, no collective library in the iteration loop.  One CTA; thread t talks to rank t.
+// A peer that never arrives (its process died) would spin forever: after `timeout_ns` the kernel gives up, sets *err and
+// the host reports it at the next synchronisation.
+// k_gather_steps (next launch) then copies every rank's step counts into the global colony array the ranking reads.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_peer_barrier(uint32_t* const* __restrict__ flags_tab, int me, int nranks, uint32_t* epoch, uint32_t* err,
+                                                      unsigned long long timeout_ns)
+{
+    __shared__ uint32_t s_epoch;
+    const int t = threadIdx.x;
+    if (t == 0) s_epoch = *epoch + 1u;
+    __syncthreads();
+    const uint32_t e = s_epoch;
+    if (t < nranks && t != me) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags_tab[t] + me), "r"(e) : "memory");
+        const uint32_t* mine = flags_tab[me] + t;
+        const unsigned long long t0 = global_timer_ns();
+        while (true) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - e) >= 0) break;
+            if (global_timer_ns() - t0 > timeout_ns) { *err = 1u; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (t == 0) *epoch = e;
+}
+
+__global__ void __launch_bounds__(256) k_gather_steps(const int* const* __restrict__ steps_tab, int nranks, int chunk, int* __restrict__ all_steps)
+{
+    const int total = nranks * chunk;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / chunk;
+        all_steps[i] = __ldcg(steps_tab[r] + (i - r * chunk));
+    }
 }
 
 // reset() :307-315 and the initial field of initFromGridMap :391-401

@@ -19,23 +19,12 @@ constexpr int kRankSmallRounds = kRankSmallMax / kRankSmallThreads;   // 32-key 
 // dynamic shared memory: keys[2][max] (u32) + vals[2][max] (u16: ant indices < 65536) + whist[32][256] (u32) = 224 KB
 constexpr size_t kRankSmallSmem = (size_t)2 * kRankSmallMax * sizeof(uint32_t) + (size_t)2 * kRankSmallMax * sizeof(uint16_t) + (size_t)32 * 256 * sizeof(uint32_t);
 
-// steps26 / ant_L: K = 26 (key = bits of L); else key = steps (cap+1 for a dead ant), as k_rank_keys / k_rank_keys26.
-__global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st, const int* __restrict__ ant_steps, const float* __restrict__ ant_L, int cap,
-                                                                   int key_bits, const float* __restrict__ Ltab, uint32_t* __restrict__ out_keys,
-                                                                   uint32_t* __restrict__ out_vals, uint32_t* __restrict__ rec_off,
-                                                                   int* __restrict__ order_of_ant, const int* __restrict__ best_n,
-                                                                   const uint32_t* __restrict__ best_ids, uint32_t* onbest)
+// Keys + stable sort of ants [first, first + n) in shared memory; returns which ping-pong buffer holds the result
+// (kbuf[src] keys, vbuf[src] ant indices relative to `first`).  All 1024 threads of the CTA take part.
+__device__ __forceinline__ int rank_sort_chunk(uint32_t* const kbuf[2], uint16_t* const vbuf[2], uint32_t* whist, uint32_t* warp_sum, const int* __restrict__ ant_steps,
+                                               const float* __restrict__ ant_L, int first, int n, int cap, int key_bits)
 {
-    extern __shared__ __align__(16) uint32_t rs_smem[];
-    uint32_t* kbuf[2] = {rs_smem, rs_smem + kRankSmallMax};
-    uint16_t* vbase = reinterpret_cast<uint16_t*>(rs_smem + 2 * kRankSmallMax);
-    uint16_t* vbuf[2] = {vbase, vbase + kRankSmallMax};
-    uint32_t* whist = rs_smem + 3 * kRankSmallMax;   // [warp][digit]
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry, elig_total;
-
     constexpr unsigned FULL = 0xffffffffu;
-    const int n = st->colony;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const bool k26 = ant_L != nullptr;
     const int rounds = (n + kRankSmallThreads - 1) / kRankSmallThreads;   // per warp
@@ -43,8 +32,8 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
 
     // ---- keys (k_rank_keys / k_rank_keys26) ----
     for (int i = threadIdx.x; i < n; i += kRankSmallThreads) {
-        const int s = ant_steps[i];
-        kbuf[0][i] = k26 ? (s < 0 ? 0x7F800000u : __float_as_uint(ant_L[i])) : (s < 0 ? (uint32_t)(cap + 1) : (uint32_t)s);
+        const int s = ant_steps[first + i];
+        kbuf[0][i] = k26 ? (s < 0 ? 0x7F800000u : __float_as_uint(ant_L[first + i])) : (s < 0 ? (uint32_t)(cap + 1) : (uint32_t)s);
         vbuf[0][i] = (uint16_t)i;
     }
     __syncthreads();
@@ -109,6 +98,29 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
         }
         __syncthreads();
     }
+    return src;
+}
+
+// steps26 / ant_L: K = 26 (key = bits of L); else key = steps (cap+1 for a dead ant), as k_rank_keys / k_rank_keys26.
+__global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st, const int* __restrict__ ant_steps, const float* __restrict__ ant_L, int cap,
+                                                                   int key_bits, const float* __restrict__ Ltab, uint32_t* __restrict__ out_keys,
+                                                                   uint32_t* __restrict__ out_vals, uint32_t* __restrict__ rec_off,
+                                                                   int* __restrict__ order_of_ant, const int* __restrict__ best_n,
+                                                                   const uint32_t* __restrict__ best_ids, uint32_t* onbest)
+{
+    extern __shared__ __align__(16) uint32_t rs_smem[];
+    uint32_t* kbuf[2] = {rs_smem, rs_smem + kRankSmallMax};
+    uint16_t* vbase = reinterpret_cast<uint16_t*>(rs_smem + 2 * kRankSmallMax);
+    uint16_t* vbuf[2] = {vbase, vbase + kRankSmallMax};
+    uint32_t* whist = rs_smem + 3 * kRankSmallMax;   // [warp][digit]
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry, elig_total;
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n = st->colony;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool k26 = ant_L != nullptr;
+    const int src = rank_sort_chunk(kbuf, vbuf, whist, warp_sum, ant_steps, ant_L, 0, n, cap, key_bits);
     const uint32_t* keys = kbuf[src];
     const uint16_t* vals = vbuf[src];
 
@@ -163,6 +175,114 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
     if (st->best_changed) {   // written by thread 0 before the barrier above
         const int nb = *best_n;
         for (int i = threadIdx.x; i < nb; i += kRankSmallThreads) {
+            const uint32_t id = best_ids[i];
+            atomicAnd(&onbest[id >> 5], ~(1u << (id & 31)));
+        }
+    }
+}
+
+// ---- colonies beyond one CTA (C2 on eight GPUs: 32 768 ants; C3: 65 536) -----------------------------------------------------
+// k_rank_chunks: one CTA per chunk of kRankSmallMax ants sorts its chunk as above (chunks in parallel) -> chunk-sorted
+// (key, ant) lists in global memory.  k_rank_merge: an element's final position is its position in its own chunk plus, for
+// every other chunk, the number of elements that precede it there — keys <= its key in chunks of LOWER ant indices (ties go
+// to the lower index), keys < its key in the others: binary searches in L2-resident lists, one thread per element.
+// k_rank_finish_prefix: best decision, eligibility and record offsets; eligible ranks are a prefix of the sorted colony
+// (arrived ants first) no longer than w_max, so one CTA scans min(n, w_max + 1) elements instead of the colony.
+__global__ void __launch_bounds__(kRankSmallThreads) k_rank_chunks(const IterState* st, const int* __restrict__ ant_steps, const float* __restrict__ ant_L, int cap,
+                                                                    int key_bits, uint32_t* __restrict__ ck, uint32_t* __restrict__ cv)
+{
+    extern __shared__ __align__(16) uint32_t rs_smem[];
+    uint32_t* kbuf[2] = {rs_smem, rs_smem + kRankSmallMax};
+    uint16_t* vbase = reinterpret_cast<uint16_t*>(rs_smem + 2 * kRankSmallMax);
+    uint16_t* vbuf[2] = {vbase, vbase + kRankSmallMax};
+    uint32_t* whist = rs_smem + 3 * kRankSmallMax;
+    __shared__ uint32_t warp_sum[32];
+    const int n = st->colony;
+    const int first = blockIdx.x * kRankSmallMax;
+    if (first >= n) return;
+    const int nc = min(kRankSmallMax, n - first);
+    const int src = rank_sort_chunk(kbuf, vbuf, whist, warp_sum, ant_steps, ant_L, first, nc, cap, key_bits);
+    for (int i = threadIdx.x; i < nc; i += kRankSmallThreads) { ck[first + i] = kbuf[src][i]; cv[first + i] = (uint32_t)first + vbuf[src][i]; }
+}
+
+__global__ void __launch_bounds__(256) k_rank_merge(const IterState* st, const uint32_t* __restrict__ ck, const uint32_t* __restrict__ cv,
+                                                     uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals, int* __restrict__ order_of_ant)
+{
+    const int n = st->colony;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = ck[i];
+    const int mine = i / kRankSmallMax;
+    const int nchunks = (n + kRankSmallMax - 1) / kRankSmallMax;
+    int pos = i - mine * kRankSmallMax;
+    for (int c = 0; c < nchunks; c++) {
+        if (c == mine) continue;
+        const uint32_t* k = ck + (size_t)c * kRankSmallMax;
+        int lo = 0, hi = min(kRankSmallMax, n - c * kRankSmallMax);
+        if (c < mine) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] <= key) lo = mid + 1; else hi = mid; } }   // upper bound
+        else { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < key) lo = mid + 1; else hi = mid; } }           // lower bound
+        pos += lo;
+    }
+    const uint32_t ant = cv[i];
+    out_keys[pos] = key; out_vals[pos] = ant;
+    order_of_ant[ant] = pos + 1;
+}
+
+__global__ void __launch_bounds__(1024) k_rank_finish_prefix(IterState* st, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int cap,
+                                                              const float* __restrict__ Ltab, uint32_t* __restrict__ rec_off, int w_max,
+                                                              const int* __restrict__ steps26, const int* __restrict__ best_n,
+                                                              const uint32_t* __restrict__ best_ids, uint32_t* onbest)
+{   // steps26 != nullptr (K = 26): keys are the bits of L and an ant's step count comes from steps26[ant]
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry, elig_total;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n = st->colony;
+    const float lambda = st->lambda;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        carry = 0; elig_total = 0;
+        if (n > 0 && steps26) {
+            const float L0 = __uint_as_float(keys[0]);
+            if (L0 < st->best_L) { st->best_steps = steps26[vals[0]]; st->best_L = L0; st->best_changed = 1; st->best_ant = (int)vals[0]; }
+        } else if (n > 0) {
+            const int s = (int)keys[0];
+            if (s <= cap && s < st->best_steps) { st->best_steps = s; st->best_L = Ltab[s]; st->best_changed = 1; st->best_ant = (int)vals[0]; }
+        }
+    }
+    __syncthreads();
+    const int lim = min(n, w_max + 1);
+    for (int base = 0; base < lim; base += 1024) {
+        const int r = base + threadIdx.x;
+        uint32_t len = 0; bool el = false;
+        if (r < lim) {
+            const int s = steps26 ? steps26[vals[r]] : (int)keys[r];
+            const bool arrived = steps26 ? keys[r] != 0x7F800000u : s <= cap;
+            el = arrived && !((float)(r + 1) > __fsub_rn(lambda, 1.0f));   // :200
+            len = el ? (uint32_t)s : 0u;
+        }
+        uint32_t incl = len;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) warp_sum[w] = incl;
+        const unsigned em = __ballot_sync(FULL, el);
+        if (lane == 0 && em) atomicAdd(&elig_total, (uint32_t)__popc(em));
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t s = warp_sum[lane];
+            uint32_t si = s;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, si, o); if (lane >= o) si += u; }
+            warp_sum[lane] = si - s;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sum[w] + (incl - len);
+        if (r < lim) rec_off[r] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + len;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { st->n_eligible = (int)elig_total; st->n_records = (int)carry; st->n_records_sort = st->use_rankset ? 0 : (int)carry; st->cnt[7] += carry; }
+    if (st->best_changed) {   // k_best_clear: written by thread 0 before the first barrier above
+        const int nb = *best_n;
+        for (int i = threadIdx.x; i < nb; i += 1024) {
             const uint32_t id = best_ids[i];
             atomicAnd(&onbest[id >> 5], ~(1u << (id & 31)));
         }

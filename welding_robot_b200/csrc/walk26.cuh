@@ -10,8 +10,9 @@
 //   k_walk26         one ant per WARP: lane s < 26 owns slot s — the node's 26 pheromone values (104 contiguous bytes) and
 //                    its 26 heuristic factors are one coalesced request each; the roulette re-adds the 26 scores in the
 //                    reference's order (ascending total, descending prob_sum) from values exchanged by shuffle
-//   k_rank_keys26    an ant's length is no longer a function of its step count (three step lengths, float sums in path
-//                    order), so the colony is ranked by the bits of L (non-negative floats order like their bit patterns)
+//   ranking          an ant's length is no longer a function of its step count (three step lengths, float sums in path
+//                    order), so the colony is ranked by the bits of L (non-negative floats order like their bit patterns;
+//                    +inf for a dead ant): rank_small.cuh with ant_L != nullptr
 // Algorithmic bytes per ant-step: 4*26 tau + 26/8 occupancy + 4 id + 1 slot = 112 B.
 #pragma once
 #include "acs_kernels.cuh"
@@ -79,20 +80,10 @@ __global__ void __launch_bounds__(256) k_heuristic26(float* __restrict__ heur, c
     heur[idx] = v;
 }
 
-// key = bits of L for an ant that arrived (L >= 0, so the unsigned order of the bits is the order of the floats),
-// +inf for a dead one; value = ant index.  The stable sort then yields the oracle's total order (L, ant index).
-__global__ void k_rank_keys26(const IterState* st, const int* __restrict__ ant_steps, const float* __restrict__ ant_L, uint32_t* keys, uint32_t* vals)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st->colony) return;
-    keys[i] = ant_steps[i] < 0 ? 0x7F800000u : __float_as_uint(ant_L[i]);
-    vals[i] = (uint32_t)i;
-}
-
 // ------------------------------------------------------------------------------------------
 // K2 for K = 26: one ant per warp, persistent warps pulling ants from the device queue.  Everything in a step is
 // warp-uniform (one ant), so there is no predication on liveness: an ant that arrives, dies or parks leaves the loop.
-// Visited set: the same open-addressed hash of 4x4x4-node tiles as k_walk (u32 key + u64 mask per entry) in shared
+// Visited set: the same open-addressed hash of 4x4x4-node tiles (u32 key + u64 mask per entry) in shared
 // memory, one table per warp; an ant that fills it to 3/4 moves the set to its table in HBM, parks {node, steps, tiles,
 // L} and is resumed by pass 2 (GLOBAL) — exact, its draws are a pure function of (iteration, ant, step).
 // ------------------------------------------------------------------------------------------
