@@ -332,7 +332,7 @@ def run_ours(args):
         dense.setEndpoints(wl["start"], wl["goal"])
         dense.begin(PREDICT)
         dense.iterate(3 * args.iters)
-        for name, which in (("update_fused", 0), ("update_tma_ring", 3), ("evaporate_float4", 1), ("d2d_copy", 2)):
+        for name, which in (("update_fused", 0), ("evaporate_float4", 1), ("d2d_copy", 2)):
             t_ms = dense.benchKernel(which, 20)
             alone[name] = {"ms": t_ms, "GBps": UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (t_ms * 1e-3) / 1e9}
         alone["what"] = "dense field (every tile streamed), records of iteration %d of the same search; 805 MB per launch" % (3 * args.iters)
@@ -472,7 +472,7 @@ def run_ours(args):
                      "note": "30 B algorithmic per ant-step; a walk is a chain of dependent gathers, so with 4096 ants the kernel is "
                              "latency-bound, not bandwidth-bound (see DESIGN.md)"},
         "roofline_update": {"kernel": ["k_update_fused (K3: evaporation + rank-ordered deposits, one HBM pass)", "k_evaporate + k_deposit_apply (K3 split)",
-                                       "k_evaporate + atomic deposits (K3 atomic)", "k_update_tma_ring (K3 through a TMA ring)",
+                                       "k_evaporate + atomic deposits (K3 atomic)", "(removed)",
                                        "k_update_fused on record-path iterations | k_evaporate_tiles (+ k_rankset_apply) on rank-set iterations (K3 adaptive)"][args.update_mode],
                             "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm,
                             "traffic": traffic.get("k_update_fused") if args.update_mode == 0 else (traffic.get("k_evaporate_tiles") if args.update_mode == 4 else None),

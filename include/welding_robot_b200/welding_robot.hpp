@@ -440,8 +440,8 @@ public:
         for (int i = 0; i < point_num; i++) best_matrix[i] = new Agent<float>[point_num];
         initFromGridMap();
         checkRoutePoints();
-        // the pair loop of :472-499 runs on the device (wr_acs_search_pairs): snap every point once, search all pairs
-        // up to the first one the reference would reject, read everything back once
+        // the pair loop of :472-499 runs on the device: snap every point once, search all pairs up to the first one the
+        // reference would reject, read everything back once
         std::vector<float> xyz(3 * (size_t)point_num + 3);
         for (int i = 0; i < point_num; i++) { xyz[3 * i] = route_points[i].x; xyz[3 * i + 1] = route_points[i].y; xyz[3 * i + 2] = route_points[i].z; }
         std::vector<int64_t> node(point_num + 1, -1);
@@ -452,18 +452,20 @@ public:
         while (good < pairs.size() && node[pairs[good].first] >= 0 && node[pairs[good].second] >= 0) good++;
         std::vector<float> lens;
         if (good > 0) {
-            int dims[3]; wr::check(wr_grid_dims(grid_, dims));
-            const size_t nn = (size_t)dims[0] * dims[1] * dims[2];
-            const int cap = (params.step_cap > 0 ? params.step_cap : (int)std::min<size_t>(nn - 1, 65532)) + 1;
-            std::vector<int64_t> s_ids(good), g_ids(good), ids(good * (size_t)cap);
-            std::vector<int> cnt(good), dirs(good * (size_t)cap);
+            std::vector<int64_t> s_ids(good), g_ids(good);
+            std::vector<int> cnt(good);
             lens.resize(good);
             for (size_t q = 0; q < good; q++) { s_ids[q] = node[pairs[q].first]; g_ids[q] = node[pairs[q].second]; }
-            wr::check(wr_acs_search_pairs(acs_, s_ids.data(), g_ids.data(), (int)good, predict_path_len, max_iteration, lens.data(), cnt.data(),
-                                          ids.data(), dirs.data(), cap));
+            // all pairs advance concurrently (wr_acs_search_batch: same results as the pair-by-pair loop, bit for bit);
+            // the paths are fetched by their true length afterwards
+            wr::check(wr_acs_search_batch(acs_, s_ids.data(), g_ids.data(), (int)good, predict_path_len, max_iteration, lens.data(), cnt.data(), nullptr, nullptr, 0));
             for (size_t q = 0; q < good; q++) {
                 const int i = pairs[q].first, j = pairs[q].second;
-                make_agent(best_, ids.data() + q * cap, dirs.data() + q * cap, cnt[q], lens[q]);
+                std::vector<int64_t> ids((size_t)std::max(cnt[q], 1));
+                std::vector<int> dirs((size_t)std::max(cnt[q], 1));
+                int m = 0; float Lq = 0;
+                wr::check(wr_acs_result_path(acs_, (int)q, ids.data(), dirs.data(), cnt[q], &m, &Lq));
+                make_agent(best_, ids.data(), dirs.data(), cnt[q], lens[q]);
                 best_matrix[i][j] = best_;
                 best_matrix[j][i] = best_;
                 printf("[ACS 3D] <Point (%.3f, %.3f, %.3f) : Point (%.3f, %.3f, %.3f)> Path length: %.3f\r\n", route_points[i].x,

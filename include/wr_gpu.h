@@ -125,6 +125,20 @@ int wr_acs_snap_points(wr_acs* a, const float* pts_xyz, int npoints, int64_t* id
  * index less.  Independent queries (BASELINE config 5) shard by giving every rank its own pairs. */
 int wr_acs_search_pairs(wr_acs* a, const int64_t* start_ids, const int64_t* goal_ids, int npairs, float predict_path_len,
                         int n_iterations, float* L, int* path_nodes, int64_t* path_ids, int* path_dirs, int path_cap);
+/* The same searches advanced CONCURRENTLY: one launch per phase covers every (query, ant) pair — a 35- or 256-ant search
+ * alone leaves the GPU idle.  Per-query pheromone lives in one hash table keyed by (query, node) (a node without an entry
+ * is worth the scalar every never-deposited slot holds), the geometric factor is computed per step.  Results are
+ * bit-identical to wr_acs_search_pairs on the same handle state (query q takes Philox search index next_search + q either
+ * way).  Colonies above 4096 ants, K = 26, WR_UPDATE_ATOMIC and handles whose field is not in its initial / reset() state
+ * run as the sequential loop; so does a chunk whose table fills up.  Same arguments as wr_acs_search_pairs. */
+int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const int64_t* goal_ids, int nqueries, float predict_path_len,
+                        int n_iterations, float* L, int* path_nodes, int64_t* path_ids, int* path_dirs, int path_cap);
+/* Result `index` of the last wr_acs_search_pairs / wr_acs_search_batch (kept in the handle, packed by true length — call
+ * those with path_cap = 0 and fetch the paths here instead of passing rows of step_cap + 1 entries).  Like wr_acs_best. */
+int wr_acs_result_path(wr_acs* a, int index, int64_t* ids, int* dirs, int cap, int* n, float* L);
+/* batch path: [0] queries per chunk [1] entries of the pheromone table [2] entries used by the last chunk
+ * [3] chunks that fell back to the sequential loop since the handle was created */
+int wr_acs_batch_stats(wr_acs* a, uint64_t out[4]);
 /* computeSolution :220-305 = wr_acs_begin(predict) + wr_acs_iterate(max_iteration).
  * Random draws: the reference draws every search of an ACS_Rank object from ONE continuous rand() stream (:169, seeded
  * once at :327), so successive searches are independent.  Here a draw is Philox(seed; search, iteration, ant, step) and

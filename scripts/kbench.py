@@ -16,7 +16,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     acs.initFromGridMap()
 acs.setEndpoints(wl["start"], wl["goal"]); acs.begin(1.0)
 nbytes = 256 ** 3 * 6 * 8
-names = {0: "update_fused", 3: "update_tma_ring", 1: "evaporate_float4", 2: "d2d_copy"}
+names = {0: "update_fused", 1: "evaporate_float4", 2: "d2d_copy"}
 for label, iters in (("no records", 0), ("after 3 iterations", 3), ("after 60 iterations", 57)):
     if iters:
         acs.iterate(iters)

@@ -466,6 +466,7 @@ def test_search_pairs_equals_pair_by_pair_loop(wr, oracle, meshes):
         loop.append(g.bestPath())
         g.reset()
     tau_loop = g.pheromone()
+    g.setNextSearch(0)   # the pairs of searchPairs take consecutive Philox search indices, like the begin() calls of the loop above
     res = g.searchPairs([node[i] for i, _ in pairs], [node[j] for _, j in pairs], 0.5, iterations=30)
     for (ids, dirs, L), (ids2, dirs2, L2) in zip(loop, res):
         assert np.array_equal(ids, ids2) and np.array_equal(dirs, dirs2)

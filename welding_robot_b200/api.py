@@ -333,22 +333,34 @@ class ACS_Rank(GridMap):
     def stepCap(self):
         return self.params.step_cap if self.params.step_cap > 0 else min(self.size_of_map() - 1, 65532)
 
-    def searchPairs(self, start_ids, goal_ids, predict_path_len, iterations=None, with_paths=True):
+    def searchPairs(self, start_ids, goal_ids, predict_path_len, iterations=None, with_paths=True, batch=False):
         """The all-pairs loop (ACSRank_3D.hpp:472-499) on the device: per pair computeSolution + reset(), no host
-        synchronisation between pairs.  -> list of (ids, dirs, L) per pair (ids/dirs empty when no path)."""
+        synchronisation between pairs.  -> list of (ids, dirs, L) per pair (ids/dirs empty when no path).
+        batch=True: the same searches advanced concurrently (wr_acs_search_batch) — same results, bit for bit."""
         s = np.ascontiguousarray(start_ids, np.int64); g = np.ascontiguousarray(goal_ids, np.int64)
         n = len(s)
         it = self.max_iteration if iterations is None else iterations
-        cap = self.stepCap() + 1 if with_paths else 0
         L = np.zeros(max(n, 1), np.float32); cnt = np.zeros(max(n, 1), np.int32)
-        ids = np.zeros((max(n, 1), max(cap, 1)), np.int64); dirs = np.zeros((max(n, 1), max(cap, 1)), np.int32)
-        check(lib().wr_acs_search_pairs(self._need(), ptr(s), ptr(g), n, predict_path_len, it, ptr(L), ptr(cnt),
-                                        ptr(ids) if cap else None, ptr(dirs) if cap else None, cap))
+        fn = lib().wr_acs_search_batch if batch else lib().wr_acs_search_pairs
+        check(fn(self._need(), ptr(s), ptr(g), n, predict_path_len, it, ptr(L), ptr(cnt), None, None, 0))
         out = []
         for p in range(n):
-            k = int(cnt[p]) if cap else 0
-            out.append((ids[p, :k].copy(), dirs[p, :max(k - 1, 0)].copy(), float(L[p])))
+            k = int(cnt[p])
+            if not with_paths or k == 0:
+                out.append((np.zeros(0, np.int64), np.zeros(0, np.int32), float(L[p])))
+                continue
+            ids = np.zeros(k, np.int64); dirs = np.zeros(k, np.int32); m = C.c_int(); Lp = C.c_float()
+            check(lib().wr_acs_result_path(self._a, p, ptr(ids), ptr(dirs), k, C.byref(m), C.byref(Lp)))
+            out.append((ids, dirs[:k - 1].copy(), float(L[p])))
         return out
+
+    def searchBatch(self, start_ids, goal_ids, predict_path_len, iterations=None, with_paths=True):
+        return self.searchPairs(start_ids, goal_ids, predict_path_len, iterations, with_paths, batch=True)
+
+    def batchStats(self):
+        out = np.zeros(4, np.uint64)
+        check(lib().wr_acs_batch_stats(self._need(), ptr(out)))
+        return dict(queries_per_chunk=int(out[0]), table_entries=int(out[1]), entries_used=int(out[2]), fallbacks=int(out[3]))
 
     def checkRoutePoints(self):
         """ACSRank_3D.hpp:511-535."""
@@ -416,7 +428,7 @@ class ACS_Rank(GridMap):
         node = self.snapPoints(self.route_points) if point_num else np.zeros(0, np.int64)
         pairs = [(i, j) for i in range(point_num) for j in range(i + 1, point_num)]
         bad = next((q for q, (i, j) in enumerate(pairs) if node[i] < 0 or node[j] < 0), len(pairs))
-        res = self.searchPairs([node[i] for i, _ in pairs[:bad]], [node[j] for _, j in pairs[:bad]], predict_path_len) if bad else []
+        res = self.searchPairs([node[i] for i, _ in pairs[:bad]], [node[j] for _, j in pairs[:bad]], predict_path_len, batch=True) if bad else []
         lengths = []
         for (i, j), (ids, dirs, L) in zip(pairs[:bad], res):
             pi, pj = self.route_points[i], self.route_points[j]

@@ -16,6 +16,7 @@
 #include "walk26.cuh"
 #include "rank_small.cuh"
 #include "rankset.cuh"
+#include "batch.cuh"
 #include "wr_internal.cuh"
 
 namespace wr {
@@ -102,6 +103,12 @@ struct wr_acs {
     int table_log2 = 9, gtable_log2 = 0;
     int table_entries = 512;          // k_walk2: entries per ant (768 by default: two 16-ant CTAs per SM)
     int64_t start = -1, goal = -1;
+    // many searches (wr_acs_search_pairs / wr_acs_search_batch): packed results of the last call, batch buffers
+    std::vector<float> res_L; std::vector<int> res_n; std::vector<size_t> res_off; std::vector<uint32_t> res_ids; std::vector<uint8_t> res_dirs;
+    struct wr_batch* batch = nullptr;
+    uint32_t batch_last_entries = 0, batch_fallbacks = 0;
+    bool field_clean = true;          // the pheromone field is in its initial / reset() state
+    int gtable_log2_for_cap() const { int b = 0; while ((1ull << b) < (unsigned long long)cap + 3) b++; return b; }
     uint32_t search = 0, next_search = 0;   // Philox: index of the current computeSolution on this handle / of the next wr_acs_begin
     bool begun = false;
     int colony_max = 0, w_max = 0;
@@ -445,6 +452,11 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     return WR_OK;
 }
 
+static bool batch_enabled()
+{
+    static const bool on = [] { const char* e = getenv("WR_BATCH"); return !e || atoi(e) != 0; }();
+    return on;
+}
 static int walk_prefetch()
 {
     static const int env = [] { const char* e = getenv("WR_WALK_PREFETCH"); return e ? atoi(e) : -1; }();   // -1: chosen per iteration (launch_walk)
@@ -466,6 +478,7 @@ static size_t walk_smem(const wr_acs* a)
     return kWalk2Lut + 128 + (size_t)kAntsPerCta * a->table_entries * sizeof(unsigned long long);
 }
 
+static void free_batch(wr_acs* a);
 extern "C" const char* wr_last_error(void) { return g_err.c_str(); }
 extern "C" int wr_version(void) { return 100; }
 extern "C" int wr_device_count(int* count)
@@ -504,6 +517,7 @@ extern "C" int wr_acs_destroy(wr_acs* a)
 {
     if (!a) return WR_OK;
     if (a->stream) cudaStreamSynchronize(a->stream);
+    free_batch(a);
     free_colony_buffers(a);
     cudaStream_t s = a->stream;
     pool_free(a->d_tau, s); pool_free(a->d_heur, s); pool_free(a->d_state, s); pool_free(a->d_onbest, s); pool_free(a->d_Ltab, s);
@@ -1063,6 +1077,7 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
     WR_CUDA(cudaSetDevice(a->device));
     cudaStream_t s = a->stream;
     const bool sharded = a->nranks > 1;
+    if (n > 0) a->field_clean = false;
     for (int it = 0; it < n; it++) {
         if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
         const bool rs_prev = a->rankset && a->rs_choice;   // path of the previous iteration (what the L2 warm-up reads)
@@ -1108,61 +1123,340 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
     return WR_OK;
 }
 
-// searchBestPathOfPoints' loop (:472-499) on the device: every pair is a full computeSolution (begin + n iterations)
-// followed by reset(), enqueued back to back with NO host synchronisation in between; the results stay in HBM until
-// the single read-back at the end.
+// ---- many searches on one grid: the all-pairs loop of searchBestPathOfPoints (:472-499) / independent queries ------------
+// Results of the last wr_acs_search_pairs / wr_acs_search_batch stay in the handle (host memory, packed): paths are read back
+// by their true length (one count read-back, one packed copy) instead of as rows of step_cap + 1 entries.
+__global__ void k_pack_paths(const uint32_t* __restrict__ rows_ids, const uint8_t* __restrict__ rows_dirs, size_t row_stride, const int* __restrict__ counts,
+                             const unsigned long long* __restrict__ offs, uint32_t* __restrict__ out_ids, uint8_t* __restrict__ out_dirs)
+{
+    const int q = blockIdx.x;
+    const int n = counts[q];
+    const unsigned long long o = offs[q];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        out_ids[o + i] = rows_ids[(size_t)q * row_stride + i];
+        if (i + 1 < n) out_dirs[o + i] = rows_dirs[(size_t)q * row_stride + i];
+    }
+}
+
+// device rows [count][row_stride] + d_L/d_n[count] -> appended to the handle's result cache (synchronises the stream)
+static int collect_results(wr_acs* a, int count, const uint32_t* d_rows_ids, const uint8_t* d_rows_dirs, size_t row_stride, const float* d_L, const int* d_n)
+{
+    cudaStream_t s = a->stream;
+    std::vector<float> hL(count);
+    std::vector<int> hn(count);
+    WR_CUDA(cudaMemcpyAsync(hL.data(), d_L, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, s));
+    WR_CUDA(cudaMemcpyAsync(hn.data(), d_n, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, s));
+    WR_CUDA(cudaStreamSynchronize(s));
+    std::vector<unsigned long long> off(count);
+    unsigned long long total = 0;
+    for (int q = 0; q < count; q++) { off[q] = total; total += (unsigned long long)hn[q]; }
+    const size_t base = a->res_ids.size();
+    a->res_ids.resize(base + total); a->res_dirs.resize(base + total);
+    if (total > 0) {
+        unsigned long long* d_off = nullptr; uint32_t* d_pi = nullptr; uint8_t* d_pd = nullptr;
+        WR_CUDA(dmalloc(&d_off, (size_t)count * sizeof(unsigned long long), s));
+        WR_CUDA(dmalloc(&d_pi, total * sizeof(uint32_t), s));
+        WR_CUDA(dmalloc(&d_pd, total, s));
+        WR_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        k_pack_paths<<<count, 256, 0, s>>>(d_rows_ids, d_rows_dirs, row_stride, d_n, d_off, d_pi, d_pd);
+        WR_CUDA(cudaMemcpyAsync(a->res_ids.data() + base, d_pi, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        WR_CUDA(cudaMemcpyAsync(a->res_dirs.data() + base, d_pd, total, cudaMemcpyDeviceToHost, s));
+        WR_CUDA(cudaStreamSynchronize(s));
+        pool_free(d_off, s); pool_free(d_pi, s); pool_free(d_pd, s);
+    }
+    for (int q = 0; q < count; q++) { a->res_L.push_back(hL[q]); a->res_n.push_back(hn[q]); a->res_off.push_back(base + off[q]); }
+    return WR_OK;
+}
+
+// the searches [first, first + count) one after the other (begin + n iterations + reset(), enqueued back to back with no host
+// synchronisation), results appended to the cache
+static int run_pairs_sequential(wr_acs* a, const int64_t* start_ids, const int64_t* goal_ids, int first, int count, float predict, int n_iterations)
+{
+    cudaStream_t s = a->stream;
+    const size_t stride = (size_t)a->cap + 1;
+    float* d_L = nullptr; int* d_n = nullptr; uint32_t* d_ids = nullptr; uint8_t* d_dirs = nullptr;
+    WR_CUDA(dmalloc(&d_L, (size_t)count * sizeof(float), s));
+    WR_CUDA(dmalloc(&d_n, (size_t)count * sizeof(int), s));
+    WR_CUDA(dmalloc(&d_ids, (size_t)count * stride * sizeof(uint32_t), s));
+    WR_CUDA(dmalloc(&d_dirs, (size_t)count * stride, s));
+    int rc = WR_OK;
+    for (int p = 0; p < count && rc == WR_OK; p++) {
+        a->start = start_ids[first + p]; a->goal = goal_ids[first + p];
+        rc = wr_acs_begin(a, predict);
+        if (rc == WR_OK) rc = wr_acs_iterate(a, n_iterations);
+        if (rc != WR_OK) break;
+        k_save_result<<<4, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, p, (int)stride, d_L, d_n, d_ids, d_dirs);
+        rc = wr_acs_reset(a);
+    }
+    if (rc == WR_OK) rc = collect_results(a, count, d_ids, d_dirs, stride, d_L, d_n);
+    else cudaStreamSynchronize(s);
+    pool_free(d_L, s); pool_free(d_n, s); pool_free(d_ids, s); pool_free(d_dirs, s);
+    return rc;
+}
+
+static int check_queries(wr_acs* a, const char* who, const int64_t* start_ids, const int64_t* goal_ids, int n)
+{
+    for (int p = 0; p < n; p++) {
+        if (start_ids[p] < 0 || goal_ids[p] < 0) { set_error("%s: pair %d has an endpoint that did not snap to a free node", who, p); return WR_ERR_NOTFOUND; }
+        if ((size_t)start_ids[p] >= a->N || (size_t)goal_ids[p] >= a->N) { set_error("%s: id out of range", who); return WR_ERR_INVALID; }
+    }
+    return WR_OK;
+}
+
+// cache -> the caller's arrays
+static void export_results(const wr_acs* a, int n, float* L, int* path_nodes, int64_t* path_ids, int* path_dirs, int path_cap)
+{
+    for (int p = 0; p < n; p++) {
+        L[p] = a->res_L[p]; path_nodes[p] = a->res_n[p];
+        const int m = std::min(a->res_n[p], path_cap);
+        for (int i = 0; i < m; i++) path_ids[(size_t)p * path_cap + i] = a->res_ids[a->res_off[p] + i];
+        for (int i = 0; i + 1 < m; i++) path_dirs[(size_t)p * path_cap + i] = a->res_dirs[a->res_off[p] + i];
+    }
+}
+static void clear_results(wr_acs* a) { a->res_L.clear(); a->res_n.clear(); a->res_off.clear(); a->res_ids.clear(); a->res_dirs.clear(); }
+
 extern "C" int wr_acs_search_pairs(wr_acs* a, const int64_t* start_ids, const int64_t* goal_ids, int npairs, float predict, int n_iterations,
                                    float* L, int* path_nodes, int64_t* path_ids, int* path_dirs, int path_cap)
 {
     WR_REQUIRE(a && start_ids && goal_ids && L && path_nodes && npairs >= 0 && n_iterations >= 0, WR_ERR_INVALID, "wr_acs_search_pairs: bad argument");
     WR_REQUIRE(a->nranks == 1, WR_ERR_STATE, "wr_acs_search_pairs: independent searches are sharded by giving each rank its own pairs");
     WR_REQUIRE(path_cap >= 0 && (path_cap == 0 || (path_ids && path_dirs)), WR_ERR_INVALID, "wr_acs_search_pairs: path buffers missing");
-    for (int p = 0; p < npairs; p++) {
-        if (start_ids[p] < 0 || goal_ids[p] < 0) { set_error("wr_acs_search_pairs: pair %d has an endpoint that did not snap to a free node", p); return WR_ERR_NOTFOUND; }
-        WR_REQUIRE((size_t)start_ids[p] < a->N && (size_t)goal_ids[p] < a->N, WR_ERR_INVALID, "wr_acs_search_pairs: id out of range");
-    }
+    int rc = check_queries(a, "wr_acs_search_pairs", start_ids, goal_ids, npairs);
+    if (rc != WR_OK) return rc;
+    clear_results(a);
     if (npairs == 0) return WR_OK;
     WR_CUDA(cudaSetDevice(a->device));
-    cudaStream_t s = a->stream;
-    const int cap_out = std::min(path_cap, a->cap + 1);
-    const int cap_dev = std::max(cap_out, 1);
-    float* d_L = nullptr; int* d_n = nullptr; uint32_t* d_ids = nullptr; uint8_t* d_dirs = nullptr;
-    WR_CUDA(dmalloc(&d_L, (size_t)npairs * sizeof(float), s));
-    WR_CUDA(dmalloc(&d_n, (size_t)npairs * sizeof(int), s));
-    WR_CUDA(dmalloc(&d_ids, (size_t)npairs * cap_dev * sizeof(uint32_t), s));
-    WR_CUDA(dmalloc(&d_dirs, (size_t)npairs * cap_dev, s));
-    int rc = WR_OK;
-    for (int p = 0; p < npairs && rc == WR_OK; p++) {
-        a->start = start_ids[p]; a->goal = goal_ids[p];
-        rc = wr_acs_begin(a, predict);
-        if (rc == WR_OK) rc = wr_acs_iterate(a, n_iterations);
-        if (rc != WR_OK) break;
-        k_save_result<<<4, 256, 0, s>>>(a->d_state, a->d_best_n, a->d_best_ids, a->d_best_dirs, p, cap_out, d_L, d_n, d_ids, d_dirs);
-        rc = wr_acs_reset(a);
-    }
-    if (rc == WR_OK) {
-        std::vector<uint32_t> h_ids((size_t)npairs * cap_dev);
-        std::vector<uint8_t> h_dirs((size_t)npairs * cap_dev);
-        WR_CUDA(cudaMemcpyAsync(L, d_L, (size_t)npairs * sizeof(float), cudaMemcpyDeviceToHost, s));
-        WR_CUDA(cudaMemcpyAsync(path_nodes, d_n, (size_t)npairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-        if (cap_out > 0) {
-            WR_CUDA(cudaMemcpyAsync(h_ids.data(), d_ids, h_ids.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            WR_CUDA(cudaMemcpyAsync(h_dirs.data(), d_dirs, h_dirs.size(), cudaMemcpyDeviceToHost, s));
-        }
-        WR_CUDA(cudaStreamSynchronize(s));
-        for (int p = 0; p < npairs && cap_out > 0; p++) {
-            const int n = std::min(path_nodes[p], cap_out);
-            for (int i = 0; i < n; i++) path_ids[(size_t)p * path_cap + i] = h_ids[(size_t)p * cap_dev + i];
-            for (int i = 0; i + 1 < n; i++) path_dirs[(size_t)p * path_cap + i] = h_dirs[(size_t)p * cap_dev + i];
-        }
-    } else {
-        cudaStreamSynchronize(s);
-    }
-    pool_free(d_L, s); pool_free(d_n, s); pool_free(d_ids, s); pool_free(d_dirs, s);
+    rc = run_pairs_sequential(a, start_ids, goal_ids, 0, npairs, predict, n_iterations);
+    if (rc == WR_OK) export_results(a, npairs, L, path_nodes, path_ids, path_dirs, path_cap);
     return rc;
 }
 
+extern "C" int wr_acs_result_path(wr_acs* a, int index, int64_t* ids, int* dirs, int cap, int* n, float* L)
+{
+    WR_REQUIRE(a && n && L, WR_ERR_INVALID, "wr_acs_result_path: null");
+    WR_REQUIRE(index >= 0 && (size_t)index < a->res_L.size(), WR_ERR_INVALID, "wr_acs_result_path: no such result (run wr_acs_search_pairs / wr_acs_search_batch first)");
+    *n = a->res_n[index]; *L = a->res_L[index];
+    const int m = std::min(*n, cap);
+    if (ids) for (int i = 0; i < m; i++) ids[i] = a->res_ids[a->res_off[index] + i];
+    if (dirs) for (int i = 0; i + 1 < m; i++) dirs[i] = a->res_dirs[a->res_off[index] + i];
+    return WR_OK;
+}
+
+// ---- the same searches advanced CONCURRENTLY (batch.cuh) ---------------------------------------------------------------
+struct wr_batch {   // buffers of the batch path, kept by the handle between calls
+    BatchTable tab = {};
+    size_t T = 0;
+    BatchQuery* qs = nullptr;
+    long long *d_starts = nullptr, *d_goals = nullptr;
+    int* steps = nullptr;
+    uint32_t* path_ids = nullptr; uint8_t* path_dirs = nullptr;
+    uint32_t* ranked_keys = nullptr; uint16_t* ranked_vals = nullptr;
+    uint32_t* best_ids = nullptr; uint8_t* best_dirs = nullptr;
+    float* res_L = nullptr; int* res_n = nullptr;
+    uint32_t* overflow_list = nullptr; unsigned long long* gtab = nullptr; int4* resume = nullptr;
+    uint32_t pool = 0;
+    int qc = 0, cm = 0;   // queries per chunk / colony the per-query buffers were sized for
+    bool mem_limited = false;   // qc is what fits into memory, not what was asked for
+};
+
+static void free_batch(wr_acs* a)
+{
+    wr_batch* b = a->batch;
+    if (!b) return;
+    cudaStream_t s = a->stream;
+    cudaStreamSynchronize(s);
+    cudaFree(b->tab.ent); cudaFree(b->tab.list); cudaFree(b->tab.count);
+    void* ptrs[] = {b->qs, b->d_starts, b->d_goals, b->steps, b->path_ids, b->path_dirs, b->ranked_keys, b->ranked_vals, b->best_ids, b->best_dirs, b->res_L, b->res_n,
+                    b->overflow_list, b->gtab, b->resume};
+    for (void* p : ptrs) cudaFree(p);
+    delete b;
+    a->batch = nullptr;
+}
+
+static int batch_table_entries(int table_env_default)
+{
+    if (const char* e = getenv("WR_BATCH_TABLE")) return std::max(16, std::min(2048, atoi(e)));
+    return table_env_default;
+}
+
+// sizes the batch buffers for chunks of up to `want_q` queries of `cm` ants; *qc = queries per chunk that fit
+static int alloc_batch(wr_acs* a, int want_q, int cm, int* qc_out)
+{
+    const size_t cap = a->cap;
+    if (a->batch && a->batch->cm == cm && (a->batch->qc >= want_q || a->batch->mem_limited)) { *qc_out = a->batch->qc; return WR_OK; }
+    free_batch(a);
+    size_t free_b = 0, total_b = 0;
+    WR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (const char* e = getenv("WR_BATCH_MEM_MB")) free_b = std::min(free_b, (size_t)atoll(e) << 20);
+    const size_t per_q = (size_t)cm * cap * 5 + (size_t)cm * 10 + (cap + 1) * 5 + sizeof(BatchQuery) + 64;
+    const size_t fit = std::min<size_t>(std::max<size_t>(1, (free_b / 2) / per_q), (size_t)1 << 16);
+    const int qc = (int)std::min<size_t>((size_t)want_q, fit);
+    wr_batch* b = new wr_batch();
+    a->batch = b;
+    b->qc = qc; b->cm = cm; b->mem_limited = (size_t)want_q > fit;
+    // pheromone table: one for the whole chunk.  A quarter of the free memory at most, 2^17 entries (4 MB) per query at most
+    size_t T = (size_t)1 << 16;
+    while (T < (size_t)qc << 17 && T * 2 * 32 <= free_b / 4 && T < ((size_t)1 << 30)) T <<= 1;
+    if (const char* e = getenv("WR_BATCH_LOG2")) T = (size_t)1 << std::max(8, std::min(30, atoi(e)));
+    b->T = T;
+    b->tab.tmask = (uint32_t)(T - 1); b->tab.shift = 32 - ceil_log2(T); b->tab.limit = (uint32_t)(T / 2);
+    WR_CUDA(cudaMalloc(&b->tab.ent, T * 32));
+    WR_CUDA(cudaMalloc(&b->tab.list, (size_t)b->tab.limit * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&b->tab.count, 4 * sizeof(uint32_t)));
+    k_batch_fill<<<kNumSMs * 8, 256, 0, a->stream>>>(reinterpret_cast<uint4*>(b->tab.ent), T);
+    WR_CUDA(cudaMemsetAsync(b->tab.count, 0, 4 * sizeof(uint32_t), a->stream));
+    const size_t nq = qc;
+    WR_CUDA(cudaMalloc(&b->qs, nq * sizeof(BatchQuery)));
+    WR_CUDA(cudaMalloc(&b->d_starts, nq * sizeof(long long)));
+    WR_CUDA(cudaMalloc(&b->d_goals, nq * sizeof(long long)));
+    WR_CUDA(cudaMalloc(&b->steps, nq * cm * sizeof(int)));
+    WR_CUDA(cudaMalloc(&b->path_ids, nq * cm * cap * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&b->path_dirs, nq * cm * cap));
+    WR_CUDA(cudaMalloc(&b->ranked_keys, nq * cm * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&b->ranked_vals, nq * cm * sizeof(uint16_t)));
+    WR_CUDA(cudaMalloc(&b->best_ids, nq * (cap + 1) * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&b->best_dirs, nq * (cap + 1)));
+    WR_CUDA(cudaMalloc(&b->res_L, nq * sizeof(float)));
+    WR_CUDA(cudaMalloc(&b->res_n, nq * sizeof(int)));
+    // HBM visited tables for ants whose shared-memory table fills up: a pool (2 GB at most), handed out on demand
+    const size_t Eg = (size_t)1 << a->gtable_log2_for_cap();
+    size_t pool = std::min<size_t>(nq * cm, std::max<size_t>(16, ((size_t)2 << 30) / (Eg * 8)));
+    b->pool = (uint32_t)pool;
+    WR_CUDA(cudaMalloc(&b->overflow_list, pool * sizeof(uint32_t)));
+    WR_CUDA(cudaMalloc(&b->gtab, pool * Eg * sizeof(unsigned long long)));
+    WR_CUDA(cudaMalloc(&b->resume, pool * sizeof(int4)));
+    WR_CUDA(cudaGetLastError());
+    *qc_out = qc;
+    return WR_OK;
+}
+
+extern "C" int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const int64_t* goal_ids, int nq, float predict, int n_iterations,
+                                   float* L, int* path_nodes, int64_t* path_ids, int* path_dirs, int path_cap)
+{
+    WR_REQUIRE(a && start_ids && goal_ids && L && path_nodes && nq >= 0 && n_iterations >= 0, WR_ERR_INVALID, "wr_acs_search_batch: bad argument");
+    WR_REQUIRE(a->nranks == 1, WR_ERR_STATE, "wr_acs_search_batch: independent searches are sharded by giving each rank its own queries");
+    WR_REQUIRE(path_cap >= 0 && (path_cap == 0 || (path_ids && path_dirs)), WR_ERR_INVALID, "wr_acs_search_batch: path buffers missing");
+    int rc = check_queries(a, "wr_acs_search_batch", start_ids, goal_ids, nq);
+    if (rc != WR_OK) return rc;
+    clear_results(a);
+    if (nq == 0) return WR_OK;
+    WR_CUDA(cudaSetDevice(a->device));
+    cudaStream_t s = a->stream;
+    const int cm = a->p.fixed_colony > 0 ? a->p.fixed_colony : (int)(0.35 * (double)predict / (double)a->g->precision);   // :247 with best = inf
+    WR_REQUIRE(cm >= 0 && cm < (1 << 24), WR_ERR_INVALID, "wr_acs_search_batch: colony size out of range");
+    // What the batch path does not cover runs as the sequential loop (same results by definition): colonies that fill the
+    // GPU on their own, the K = 26 extension, the unordered atomic mode, a pheromone field that is not in its initial state
+    const bool batchable = cm >= 1 && cm <= kBatchMaxColony && a->K == 6 && a->p.update_mode != WR_UPDATE_ATOMIC && a->field_clean && nq > 1 && batch_enabled();
+    const uint32_t first_search = a->next_search;
+    if (!batchable) {
+        rc = run_pairs_sequential(a, start_ids, goal_ids, 0, nq, predict, n_iterations);
+        if (rc == WR_OK) export_results(a, nq, L, path_nodes, path_ids, path_dirs, path_cap);
+        return rc;
+    }
+    rc = grid_ensure_open6(a->g, s);
+    if (rc != WR_OK) return rc;
+    int qc = 0;
+    rc = alloc_batch(a, nq, cm, &qc);
+    if (rc != WR_OK) return rc;
+    wr_batch* b = a->batch;
+    const int entries = batch_table_entries(256);
+    const size_t smem1 = kWalk2Lut + 128 + (size_t)kAntsPerCta * entries * sizeof(unsigned long long);
+    WR_REQUIRE(smem1 <= 227 * 1024, WR_ERR_INVALID, "wr_acs_search_batch: WR_BATCH_TABLE too large");
+    const bool alpha1 = a->p.alpha == 1;
+    const int maxn = (std::max(cm, 32) + 31) / 32 * 32;
+    const size_t rank_smem = (size_t)12 * maxn + 32 * 256 * sizeof(uint32_t);
+    WR_CUDA(cudaFuncSetAttribute(k_walk_batch<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    WR_CUDA(cudaFuncSetAttribute(k_walk_batch<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    WR_CUDA(cudaFuncSetAttribute(k_batch_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
+    const int per_sm = std::max(1, std::min(16, (int)((227 * 1024) / (smem1 + 1024))));
+    BatchArgs w;
+    w.st = a->d_state; w.qs = b->qs; w.colony_max = cm; w.items_per_query = (cm + 3) / 4;
+    w.tab = b->tab; w.open6 = a->g->d_open6; w.coords = a->g->d_coords; w.rx = a->g->rx; w.ry = a->g->ry; w.rz = a->g->rz;
+    w.seed_lo = (uint32_t)a->p.seed; w.seed_hi = (uint32_t)(a->p.seed >> 32); w.alpha = a->p.alpha; w.beta = a->p.beta; w.cap = a->cap;
+    w.ant_steps = b->steps; w.path_ids = b->path_ids; w.path_dirs = b->path_dirs; w.table_entries = entries;
+    w.overflow_list = b->overflow_list; w.gtab = b->gtab; w.gtable_log2 = a->gtable_log2_for_cap(); w.resume = b->resume; w.pool = b->pool;
+    for (int c0 = 0; c0 < nq && rc == WR_OK; c0 += qc) {
+        const int n = std::min(qc, nq - c0);
+        w.nq = n;
+        std::vector<long long> hs(n), hg(n);
+        for (int q = 0; q < n; q++) { hs[q] = start_ids[c0 + q]; hg[q] = goal_ids[c0 + q]; }
+        WR_CUDA(cudaMemcpyAsync(b->d_starts, hs.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, s));
+        WR_CUDA(cudaMemcpyAsync(b->d_goals, hg.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, s));
+        WR_CUDA(cudaStreamSynchronize(s));   // hs / hg are on this frame
+        k_batch_begin<<<(n + 255) / 256, 256, 0, s>>>(a->d_state, b->qs, n, b->d_starts, b->d_goals, first_search + (uint32_t)c0, predict, a->p.tau0, b->tab.count);
+        const int items = n * w.items_per_query;
+        const int blocks1 = std::max(1, std::min((items + 3) / 4, kNumSMs * per_sm));
+        const int blocks2 = std::max(1, std::min((int)((b->pool + kAntsPerCta - 1) / kAntsPerCta), kNumSMs * 4));
+        for (int it = 0; it < n_iterations; it++) {
+            k_batch_iter_begin<<<(n + 255) / 256, 256, 0, s>>>(a->d_state, b->qs, n, a->p.fixed_colony, cm, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->p.rho);
+            if (alpha1) {
+                k_walk_batch<false, true><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                k_walk_batch<true, true><<<blocks2, kWalkThreads, kWalk2Lut + 128, s>>>(w);
+            } else {
+                k_walk_batch<false, false><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                k_walk_batch<true, false><<<blocks2, kWalkThreads, kWalk2Lut + 128, s>>>(w);
+            }
+            k_batch_rank<<<n, kRankSmallThreads, rank_smem, s>>>(a->d_state, b->qs, b->tab, b->steps, cm, maxn, a->cap, a->rank_bits, a->d_Ltab, b->ranked_keys, b->ranked_vals,
+                                                                  b->path_ids, b->path_dirs, b->best_ids, b->best_dirs);
+            k_batch_evaporate<<<kNumSMs * 8, 256, 0, s>>>(b->tab, a->p.rho);
+            k_batch_deposit<<<n, kBatchDepThreads, 0, s>>>(a->d_state, b->qs, b->tab, b->ranked_keys, b->ranked_vals, cm, b->path_ids, b->path_dirs, a->cap, a->d_Ltab, a->p.rho);
+        }
+        k_batch_results<<<(n + 255) / 256, 256, 0, s>>>(b->qs, n, b->res_L, b->res_n);
+        WR_CUDA(cudaGetLastError());
+        uint32_t cnt[4] = {0, 0, 0, 0};
+        WR_CUDA(cudaMemcpyAsync(cnt, b->tab.count, sizeof cnt, cudaMemcpyDeviceToHost, s));
+        WR_CUDA(cudaStreamSynchronize(s));
+        k_batch_wipe<<<kNumSMs * 4, 256, 0, s>>>(b->tab);
+        a->batch_last_entries = cnt[0];
+        if (cnt[1]) {   // pheromone table or overflow-table pool exhausted: this chunk's searches run one after the other instead
+            a->batch_fallbacks++;
+            k_batch_fill<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(b->tab.ent), b->T);   // entries claimed beyond the list
+            a->next_search = first_search + (uint32_t)c0;
+            rc = run_pairs_sequential(a, start_ids, goal_ids, c0, n, predict, n_iterations);
+        } else {
+            rc = collect_results(a, n, b->best_ids, b->best_dirs, (size_t)a->cap + 1, b->res_L, b->res_n);
+        }
+    }
+    a->next_search = first_search + (uint32_t)nq;
+    a->begun = false;
+    if (rc == WR_OK) rc = wr_acs_reset(a);   // the sequential loop ends every search with reset() (:481)
+    if (rc == WR_OK) export_results(a, nq, L, path_nodes, path_ids, path_dirs, path_cap);
+    return rc;
+}
+
+extern "C" int wr_acs_batch_stats(wr_acs* a, uint64_t out[4])
+{
+    WR_REQUIRE(a && out, WR_ERR_INVALID, "wr_acs_batch_stats: null");
+    out[0] = a->batch ? (uint64_t)a->batch->qc : 0; out[1] = a->batch ? (uint64_t)a->batch->T : 0;
+    out[2] = a->batch_last_entries; out[3] = a->batch_fallbacks;
+    return WR_OK;
+}
+
 // ---- ant sharding across ranks ------------------------------------------------------------------
+// CUDA loads a kernel's code the first time it is launched (lazy module loading), and loading may have to wait for running
+// kernels.  A sharded iteration contains kernels that WAIT for other handles' kernels (k_peer_barrier); if those handles live
+// in this process (several shards driven from one host thread) a first-time load behind a spinning barrier would wait for a
+// signal that this very thread has not enqueued yet.  So everything an iteration can launch is loaded up front.
+static int preload_iteration_kernels()
+{
+    static bool done = false;
+    if (done) return WR_OK;
+    cudaFuncAttributes at;
+#define WR_PRELOAD(f) WR_CUDA(cudaFuncGetAttributes(&at, f))
+    WR_PRELOAD(k_peer_barrier); WR_PRELOAD(k_gather_steps); WR_PRELOAD(k_rank_small); WR_PRELOAD(k_rank_chunks); WR_PRELOAD(k_rank_merge);
+    WR_PRELOAD(k_rank_finish_prefix); WR_PRELOAD(k_best_copy_peer); WR_PRELOAD(k_best_copy); WR_PRELOAD(k_rankset_gen); WR_PRELOAD(k_rankset_publish);
+    WR_PRELOAD(k_rankset_merge); WR_PRELOAD(k_evaporate_tiles); WR_PRELOAD(k_rankset_apply); WR_PRELOAD(k_rankset_wipe); WR_PRELOAD(k_deposit_serial);
+    WR_PRELOAD((k_deposit_gen<false, true>)); WR_PRELOAD(k_tile_offsets); WR_PRELOAD(k_update_fused<true>); WR_PRELOAD(k_update_fused<false>);
+    WR_PRELOAD(k_pull_finals); WR_PRELOAD(k_iter_begin); WR_PRELOAD(k_iter_end); WR_PRELOAD(k_path_warm); WR_PRELOAD(k_rankset_warm);
+    WR_PRELOAD((k_walk2<false, true, 0>)); WR_PRELOAD((k_walk2<false, true, 1>)); WR_PRELOAD((k_walk2<false, true, 2>)); WR_PRELOAD((k_walk2<false, true, 3>));
+    WR_PRELOAD((k_walk2<false, false, 0>)); WR_PRELOAD((k_walk2<true, true, 0>)); WR_PRELOAD((k_walk2<true, false, 0>));
+#undef WR_PRELOAD
+    int rc = sort_preload();
+    if (rc != WR_OK) return rc;
+    done = true;
+    return WR_OK;
+}
+
 extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks)
 {
     WR_REQUIRE(a && nranks >= 1 && rank >= 0 && rank < nranks, WR_ERR_INVALID, "wr_acs_set_shard: bad argument");
@@ -1170,6 +1464,7 @@ extern "C" int wr_acs_set_shard(wr_acs* a, int rank, int nranks)
     WR_REQUIRE(nranks == 1 || a->p.update_mode != WR_UPDATE_ATOMIC, WR_ERR_INVALID, "wr_acs_set_shard: sharded colonies use the rank-ordered update modes");
     WR_REQUIRE(nranks == 1 || a->K == 6, WR_ERR_INVALID, "wr_acs_set_shard: the K = 26 extension runs on one GPU (ranks would have to exchange lengths as well as step counts)");
     WR_REQUIRE(nranks <= 256, WR_ERR_INVALID, "wr_acs_set_shard: at most 256 ranks");
+    if (nranks > 1) { WR_CUDA(cudaSetDevice(a->device)); int rc = preload_iteration_kernels(); if (rc != WR_OK) return rc; }
     WR_REQUIRE(nranks == 1 || a->p.update_mode == WR_UPDATE_FUSED, WR_ERR_INVALID, "wr_acs_set_shard: sharded colonies use WR_UPDATE_FUSED or WR_UPDATE_RANKSET");
     a->rank = rank; a->nranks = nranks;
     return WR_OK;
@@ -1266,6 +1561,7 @@ extern "C" int wr_acs_reset(wr_acs* a)
     }
     k_set_base<<<1, 1, 0, a->stream>>>(a->d_state, a->p.tau0);
     WR_CUDA(cudaGetLastError());
+    a->field_clean = true;
     return WR_OK;
 }
 
@@ -1325,6 +1621,7 @@ extern "C" int wr_acs_upload_pheromone(wr_acs* a, const float* tau, size_t n)
         WR_CUDA(cudaMemcpy(a->d_tau, tau, a->n_slots * sizeof(float), cudaMemcpyHostToDevice));
     }
     WR_CUDA(cudaMemset(a->d_dirty, 1, (size_t)a->ntiles + 1));   // explicit values everywhere: every tile takes part in the evaporation
+    a->field_clean = false;
     return WR_OK;
 }
 

@@ -198,4 +198,15 @@ int sort_partition(SortPlan* p, const int* d_n, uint32_t lo, uint32_t span, cuda
     return WR_OK;
 }
 
+// force the lazy loading of this file's kernels (acs.cu: preload_iteration_kernels)
+int sort_preload()
+{
+    cudaFuncAttributes at;
+    WR_CUDA(cudaFuncGetAttributes(&at, k_sort_hist));
+    WR_CUDA(cudaFuncGetAttributes(&at, k_sort_scan_rows));
+    WR_CUDA(cudaFuncGetAttributes(&at, k_sort_scatter));
+    WR_CUDA(cudaFuncGetAttributes(&at, k_copy_count));
+    return WR_OK;
+}
+
 }  // namespace wr

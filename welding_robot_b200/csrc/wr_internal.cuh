@@ -40,6 +40,7 @@ void sort_plan_destroy(SortPlan* p, cudaStream_t s);
 int sort_pairs(SortPlan* p, const int* d_n, int key_bits, cudaStream_t s, bool* result_in_b, bool input_in_b = false);
 // stable partition: pairs with key in [lo, lo+span) to the front (their count -> *d_count_out); input keys_a/vals_a, result in keys_b/vals_b
 int sort_partition(SortPlan* p, const int* d_n, uint32_t lo, uint32_t span, cudaStream_t s, int* d_count_out);
+int sort_preload();
 
 // comm.cu — NCCL (opened at run time) for the rendezvous of a sharded colony
 int comm_get(const void* unique_id, int rank, int nranks, void** comm_out);
