@@ -210,6 +210,174 @@ def build_workload_cpu():
 
 
 # ---------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, as sub-records of the same line (short, bounded runs)
+# ---------------------------------------------------------------------------------------------------
+def synthetic_boxes(n, nboxes, seed):
+    """C5 grid: union of axis-aligned boxes (edges 4-48 cells), 10-cell free wall, coordinates = indices."""
+    rng = np.random.default_rng(seed)
+    occ = np.zeros((n, n, n), bool)
+    for _ in range(nboxes):
+        e = rng.integers(4, 49, 3)
+        c = [int(rng.integers(10, n - 10 - int(e[k]))) for k in range(3)]
+        occ[c[2]:c[2] + e[2], c[1]:c[1] + e[1], c[0]:c[0] + e[0]] = True
+    return (~occ).astype(np.uint8).ravel()
+
+
+def c5_queries(free, n, nq, seed=5):
+    ids = np.flatnonzero(free)
+    rng = np.random.default_rng(seed)
+    starts, goals = [], []
+    while len(starts) < nq:
+        s = int(ids[rng.integers(0, len(ids))])
+        sz, sy, sx = s // (n * n), (s // n) % n, s % n
+        d = int(rng.integers(64, 257))
+        for _ in range(64):      # a free cell at Manhattan distance d: random split of d over the axes
+            a = rng.multinomial(d, [1 / 3] * 3) * rng.choice([-1, 1], 3)
+            gz, gy, gx = sz + a[0], sy + a[1], sx + a[2]
+            if 0 <= gz < n and 0 <= gy < n and 0 <= gx < n and free[(gz * n + gy) * n + gx]:
+                starts.append(s); goals.append(int((gz * n + gy) * n + gx))
+                break
+    return starts, goals
+
+
+def sub_c5(rank, world, dist, nq=1024, iters=50, ants=256):
+    """BASELINE configs[4]: independent queries on a synthetic 512^3 obstacle grid, query q -> rank q mod world, no communication;
+    every rank advances its queries concurrently (wr_acs_search_batch)."""
+    import torch
+    import welding_robot_b200 as wr
+    from welding_robot_b200.dist import shard_queries
+    n = 512
+    free = synthetic_boxes(n, 4096, 4)
+    axis = np.arange(n, dtype=np.float32)
+    starts, goals = c5_queries(free, n, nq)
+    mine = shard_queries(nq, rank, world)
+    g = wr.ACS_Rank(seed=5, fixed_colony=ants, step_cap=4096)
+    g.creatFromOccupancy(free, axis, axis, axis, 1.0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        g.initFromGridMap()
+    s = [starts[q] for q in mine]; e = [goals[q] for q in mine]
+    g.searchBatch(s[:8], e[:8], 300.0, 3, with_paths=False)       # warm-up: buffers, kernels
+    g.setNextSearch(0)
+    g.sync()
+    c0 = g.counters()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = g.searchBatch(s, e, 300.0, iters, with_paths=True)     # paths read back: this is the e2e figure (queries in, paths out)
+    g.sync()
+    dt = time.perf_counter() - t0
+    steps = g.counters()["ant_steps"] - c0["ant_steps"]
+    found = int(sum(np.isfinite(r[2]) for r in res))
+    st = g.batchStats()
+    # the same queries one after the other (round 1's path), on a sample, and a sample against... nothing here: parity lives in tests/
+    k = min(8, len(s))
+    g.setNextSearch(0)
+    t1 = time.perf_counter()
+    seq = g.searchPairs(s[:k], e[:k], 300.0, iters, with_paths=True)
+    g.sync()
+    dt_seq = (time.perf_counter() - t1) / max(k, 1)
+    same = all(np.array_equal(a[0], b[0]) and (a[2] == b[2] or (np.isinf(a[2]) and np.isinf(b[2]))) for a, b in zip(seq, res[:k]))
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        v = torch.tensor([steps, found, int(same)], device="cuda", dtype=torch.int64); dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        steps, found, same = int(v[0]), int(v[1]), int(v[2]) == world
+    del g
+    return {"workload": "C5: %d start/goal queries on a synthetic 512^3 obstacle grid (%.1f %% occupied), %d ants x %d iterations each, Manhattan separation 64-256, "
+                        "query q -> rank q mod %d" % (nq, 100.0 * (1 - free.mean()), ants, iters, world),
+            "queries_per_s": nq / dt, "seconds": dt, "ant_steps_per_s": steps / dt, "acs_iterations_per_s": nq * iters / dt, "found": found,
+            "timed": "wall clock from host query lists to host paths (wr_acs_search_batch), max over ranks",
+            "batch": st, "sequential_ms_per_query_sample": 1e3 * dt_seq, "batch_equals_sequential_on_sample": bool(same)}
+
+
+def sub_c4(rank, world, dist, n=256, colonies=1024, iters=64):
+    """BASELINE configs[3]: ACS_GTSP seam ordering, 256 seams, 1024 colonies (colony b -> rank b mod world), 64 iterations."""
+    import torch
+    import welding_robot_b200 as wr
+    P = np.random.default_rng(3).random((n, 3))
+    D = np.sqrt(((P[:, None] - P[None]) ** 2).sum(-1))
+    D = np.round(D, 6)                                   # "%.6f", as a graph file would carry it
+    per = (colonies + world - 1) // world
+    first = rank * per
+    mine = max(0, min(per, colonies - first))
+    g = wr.ACS_GTSP(seed=3)
+    g.dis, g.city_num, g.cnt = D, n, n * (n - 1) // 2
+    g._create(max(mine, 1), first)
+    g.iterate(1)
+    check_sync = lambda: g.best(0)  # noqa: E731  (wr_gtsp_best synchronises)
+    check_sync()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    g.iterate(iters)
+    check_sync()
+    dt = time.perf_counter() - t0
+    ms = g.kernelMs()
+    Ls = [g.best(b)[1] for b in range(0, max(mine, 1), max(1, mine // 4))]
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+    return {"workload": "C4: ACS_GTSP, %d seams, %d colonies x %d iterations, colonies split over %d rank(s)" % (n, colonies, iters, world),
+            "colony_iterations_per_s": colonies * iters / dt, "ant_steps_per_s": colonies * iters * n * n / dt, "seconds": dt,
+            "phase_ms_rank0": ms, "algorithmic_GBps_at_40N2_B": colonies * iters * 40 * n * n / dt / 1e9, "sample_best_L": Ls}
+
+
+def sub_c3(rank, world, dist, stream, iters=10, ants_per_gpu=8192):
+    """BASELINE configs[2]: origin_piece at a 512-long grid in 512^3, 8192 ants per GPU (65 536 at 8), ant-sharded."""
+    import torch
+    import welding_robot_b200 as wr
+    from welding_robot_b200 import _lib
+    from welding_robot_b200.dist import ShardedSearch
+    global CUBE, PRECISION, MESH
+    keep = (CUBE, PRECISION, MESH)
+    CUBE, PRECISION, MESH = 512, 0.823812 / 491.5, "origin_piece"
+    try:
+        wl = build_workload_gpu()
+        a = wr.ACS_Rank(seed=2, fixed_colony=ants_per_gpu * world, step_cap=16384, update_mode=4)
+        a.creatFromOccupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], PRECISION)
+        with contextlib.redirect_stdout(io.StringIO()):
+            a.initFromGridMap()
+        _lib.check(_lib.lib().wr_acs_set_stream(a._a, stream.cuda_stream))
+        a.setEndpoints(wl["start"], wl["goal"])
+        if world > 1:
+            S = ShardedSearch(a, rank, world); S.begin(PREDICT); step = S.iterate
+        else:
+            a.begin(PREDICT); step = a.iterate
+        step(3)
+        a.sync()
+        a.setTiming(True)
+        c0 = a.counters()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step(iters)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        steps = a.counters()["ant_steps"] - c0["ant_steps"]
+        kms = a.kernelMs()
+        dirty, tiles = a.fieldStats()
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+            v = torch.tensor([steps], device="cuda", dtype=torch.int64); dist.all_reduce(v, op=dist.ReduceOp.SUM); steps = int(v.item())
+        del a
+        return {"workload": "C3: ACSRank_3D, origin_piece @512-long grid in 512^3, %d ants (%d per GPU), iterations 4-%d of one search" % (ants_per_gpu * world, ants_per_gpu, 3 + iters),
+                "ant_steps_per_s": steps / (ms * 1e-3), "acs_iterations_per_s": iters / (ms * 1e-3), "ms_per_iteration": ms / iters,
+                "kernel_ms_per_iteration_rank0": {k: v / iters for k, v in kms.items()}, "dirty_tiles": dirty, "tiles": tiles,
+                "pheromone_field_bytes": 512 ** 3 * 6 * 4, "natural_grid": list(wl["natural"])}
+    finally:
+        CUBE, PRECISION, MESH = keep
+
+
+def field_digest(acs):
+    """order-sensitive 64-bit digest of the downloaded pheromone field"""
+    t = acs.pheromone().view(np.uint32).astype(np.uint64)
+    w = (np.arange(t.size, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+    return int((t * w).sum(dtype=np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -379,6 +547,55 @@ def run_ours(args):
                "update_GBps": u26, "update_frac_of_hbm": u26 / hbm26, "pheromone_field_bytes": n_nodes * 26 * 4, "dirty_tiles": dt26, "tiles": tt26}
         del a26
 
+    # ---- sharded runs carry their own parity evidence: 3 iterations of a fresh sharded search against the same colony on
+    #      ONE GPU (rank 0), whole pheromone field + best path -------------------------------------------------------------
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        psh = make_search(wl["isfree"])
+        _lib.check(_lib.lib().wr_acs_set_stream(psh._a, stream.cuda_stream))
+        psh.setEndpoints(wl["start"], wl["goal"])
+        pd = ShardedSearch(psh, rank, world)
+        pd.begin(PREDICT); pd.iterate(3); psh.sync()
+        mine = (field_digest(psh), float(psh.bestPath()[2]), int(psh.bestPath()[0].sum()))
+        del pd, psh
+        ref = None
+        if rank == 0:
+            one = make_search(wl["isfree"])
+            one.setEndpoints(wl["start"], wl["goal"])
+            one.begin(PREDICT); one.iterate(3); one.sync()
+            ref = (field_digest(one), float(one.bestPath()[2]), int(one.bestPath()[0].sum()))
+            del one
+        allv = [None] * world
+        dist.all_gather_object(allv, mine)
+        box = [ref]
+        dist.broadcast_object_list(box, src=0)
+        parity = {"parity_check": "ok" if all(v == box[0] for v in allv) else "FAILED",
+                  "what": "3 iterations of a fresh %d-ant sharded search on every rank vs the same colony on one GPU (rank 0): digest of the whole "
+                          "pheromone field, best length, best path" % colony, "digests": [hex(v[0]) for v in allv], "single_gpu_digest": hex(box[0][0])}
+
+    # ---- what a user runs: begin + 150 iterations (the reference's max_iteration, ACSRank_3D.hpp:322), from host buffers --------
+    full = None
+    if world == 1 and args.workload == "C2" and not args.no_sub:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fs = make_search(wl["isfree"])
+        fs.setEndpoints(wl["start"], wl["goal"])
+        fs.begin(PREDICT)
+        fs.iterate(150)
+        ids, dirs, L = fs.bestPath()
+        dt_full = time.perf_counter() - t0
+        cf = fs.counters()
+        full = {"iterations": 150, "seconds_from_host_buffers": dt_full, "ant_steps": cf["ant_steps"], "ant_steps_per_s": cf["ant_steps"] / dt_full,
+                "acs_iterations_per_s": 150 / dt_full, "best_L": float(L), "best_path_nodes": int(len(ids)), "rank_set_iterations": fs.updateStats()["rankset_iterations"],
+                "what": "occupancy upload + wr_acs_create + wr_acs_begin + 150 x iterate + wr_acs_best, wall clock"}
+        del fs
+
+    subs = {}
+    if not args.no_sub and args.workload == "C2":
+        subs["C3"] = sub_c3(rank, world, dist, stream)
+        subs["C4"] = sub_c4(rank, world, dist)
+        subs["C5"] = sub_c5(rank, world, dist)
+
     # ---- end to end through the public API from HOST buffers -------------------------------------------
     e2e = None
     if True:
@@ -467,7 +684,10 @@ def run_ours(args):
         "kernel_ms_source": "events inside the timed region" if world > 1 else
                             "replay of the timed iterations on a fresh handle with per-phase events (the timed region itself runs without them)",
         "roofline": {"kernel": "k_walk2 (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
-                     "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk2", traffic.get("k_walk")), "peak_source": hbm_src,
+                     "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk2", traffic.get("k_walk")),
+                     "traffic_source": "static: dram__bytes_read+write per launch from the committed `ncu --set full` capture (profiles/), not measured in this run",
+                     "peak_source": hbm_src,
+                     "limiter": "step latency x longest ant, then instruction issue (not HBM: the gathers hit L2); see DESIGN.md section 4",
                      "algorithmic_bytes_per_launch": WALK_BYTES_PER_STEP * (local_steps / iters_done),
                      "note": "30 B algorithmic per ant-step; a walk is a chain of dependent gathers, so with 4096 ants the kernel is "
                              "latency-bound, not bandwidth-bound (see DESIGN.md)"},
@@ -476,6 +696,7 @@ def run_ours(args):
                                        "k_update_fused on record-path iterations | k_evaporate_tiles (+ k_rankset_apply) on rank-set iterations (K3 adaptive)"][args.update_mode],
                             "bound": "hbm", "achieved": upd_gbs, "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm,
                             "traffic": traffic.get("k_update_fused") if args.update_mode == 0 else (traffic.get("k_evaporate_tiles") if args.update_mode == 4 else None),
+                            "traffic_source": "static: committed ncu capture (profiles/), not measured in this run",
                             "algorithmic_bytes_per_launch": upd_bytes,
                             "reference_sweep_bytes": UPDATE_BYTES_PER_SLOT * n_nodes * 6, "reference_sweep_equivalent_GBps": upd_dense_gbs,
                             "dirty_tiles": dirty_tiles, "tiles": tiles_total, "kernel_ms": upd_kernel_ms, "launches_timed": sk_n,
@@ -491,6 +712,12 @@ def run_ours(args):
     }
     if e2e:
         out["e2e"] = e2e
+    if parity:
+        out.update(parity)
+    if full:
+        out["full_search"] = full
+    if subs:
+        out["other_configs"] = subs
     if k26:
         out["k26_extension"] = k26
     if not args.no_cpu_baseline and world == 1:
@@ -499,18 +726,25 @@ def run_ours(args):
 
 
 def launches_per_iteration(update_mode, colony=ANTS_PER_GPU, iters=5, sharded=False):
-    """Kernels of OURS launched per ACS iteration (welding_robot_b200/csrc/acs.cu: wr_acs_iterate / the sharded sequence)."""
-    cap_bits = int(np.ceil(np.log2(STEP_CAP + 2)))
+    """Kernels of OURS launched per ACS iteration (welding_robot_b200/csrc/acs.cu: wr_acs_iterate; a steady-state iteration that goes
+    out as one CUDA graph launch still runs the same kernels)."""
     slot_bits = int(np.ceil(np.log2(CUBE ** 3 * 6)))
     sort = lambda bits: 3 * ((bits + 9) // 10)  # noqa: E731  hist + scan + scatter per pass of <= 10-bit digits (radix_sort.cu)
-    rank = 1 if colony <= 16384 else 1 + sort(cap_bits) + 2      # k_rank_small | keys + sort + finish + best clear
-    # L2 warm-up, iter_begin, walk pass 1 + 2, ranking, best copy, iter_end (single GPU: once per wr_acs_iterate call)
-    n = 1 + 1 + 2 + rank + 1 + (1 if sharded else 1.0 / iters)
-    if update_mode == 2 or (update_mode == 4 and not sharded):
-        return n + (2 if update_mode == 2 else 3)                 # rank-set: gen, evaporate, apply
-    n += 1 + sort(slot_bits) + 2                                  # deposit gen, slot sort, (tile offsets + fused) | (evaporate + apply)
+    rank = 1 if colony <= 16384 else 3                           # k_rank_small | chunk sorts + merge + prefix finish
+    groups = (int(0.2 * colony) + 1 + 1023) // 1024              # apply launches of the rank-set path
+    # iter_begin, walk pass 1 + 2, ranking, best copy, iter_end (once per wr_acs_iterate call)
+    n = 1 + 2 + rank + 1 + 1.0 / iters
     if sharded:
-        n += 6                                                    # partition pass (4), pull of the peers' final values, memset of the queue words
+        n += 2                                                   # barrier + gather of the step counts
+    if update_mode == 2:
+        return n + 1 + 2                                         # L2 warm-up, evaporate, atomic deposits
+    if update_mode == 4:                                         # rank sets: L2 warm-up, gen, evaporate, apply x groups, wipe, serial fallback (both exit at once)
+        return n + 1 + 1 + 1 + groups + 2 + (3 if sharded else 0)   # sharded: + publish, barrier, merge
+    n += 1 + sort(slot_bits) + 2                                 # deposit gen, slot sort, tile offsets + fused
+    if sharded:
+        n += 4 + 2                                               # partition pass, barrier + pull of the peers' final values (which is also the L2 warm-up)
+    else:
+        n += 1                                                   # L2 warm-up
     return n
 
 
@@ -518,8 +752,9 @@ def launches_per_iteration(update_mode, colony=ANTS_PER_GPU, iters=5, sharded=Fa
 # the reference's CPU implementation (oracle/_ref = UNMODIFIED reference headers), or the oracle port
 # ---------------------------------------------------------------------------------------------------
 def reference_worker(args):
-    """One process: `warmup + steps` first-iterations of computeSolution (ACSRank_3D.hpp:220-305) with a
-    colony of `cpu_ants` on the C2 grid.  Prints {"kind", "ant_steps": [...], "seconds": [...], "init_s"}."""
+    """One process: `warmup + steps` first-iterations of computeSolution (ACSRank_3D.hpp:220-305) with the workload's own colony
+    (4096 ants) on the C2 grid, the pheromone field reset between steps (untimed) — the regime of the GPU arm's `e2e` leg
+    (fresh searches).  Stops early when the time budget is used up.  Prints {"kind", "ant_steps": [...], "seconds": [...], "init_s"}."""
     from oracle import oracle as O
     wl = build_workload_cpu()
     seed = SEED + 1000 * args.worker
@@ -528,6 +763,7 @@ def reference_worker(args):
     t0 = time.perf_counter()
     use_ref = O.have_ref() and not args.port
     steps, secs = [], []
+    budget = args.budget_s
     if use_ref:
         R = O.Ref()
         c0, c1 = wl["cmin"], wl["cmax"]
@@ -540,28 +776,36 @@ def reference_worker(args):
         R.acs_init()
         assert R.set_endpoints(wl["start"], wl["goal"])
         init_s = time.perf_counter() - t0
-        for _ in range(args.warmup + args.steps):
+        tb = time.perf_counter()
+        for i in range(args.warmup + args.steps):
             t1 = time.perf_counter()
-            calls = R.compute(predict, 1, seed)    # every successful step draws once (ACSRank_3D.hpp:169)
+            calls = R.compute(predict, 1, seed + i)    # every successful step draws once (ACSRank_3D.hpp:169)
             secs.append(time.perf_counter() - t1); steps.append(int(calls))
+            R.reset()                                  # reset() :307-315, untimed: every step is a fresh search
+            if i >= args.warmup and time.perf_counter() - tb > budget:
+                break
     else:
         G = O.Grid.from_occupancy(wl["isfree"], wl["xs"], wl["ys"], wl["zs"], PRECISION)
         A = O.Acs(G, seed=seed, rng_mode=O.RNG_SEQUENTIAL, sort_mode=O.SORT_STD)
         A.set_endpoints(wl["start"], wl["goal"])
         init_s = time.perf_counter() - t0
-        for _ in range(args.warmup + args.steps):
+        tb = time.perf_counter()
+        for i in range(args.warmup + args.steps):
             before = A.counters()["ant_steps"]
             t1 = time.perf_counter()
             A.begin(predict); A.iterate(1)
             secs.append(time.perf_counter() - t1); steps.append(A.counters()["ant_steps"] - before)
+            A.reset()
+            if i >= args.warmup and time.perf_counter() - tb > budget:
+                break
     print(json.dumps({"kind": "reference" if use_ref else "port", "ant_steps": steps[args.warmup:], "seconds": secs[args.warmup:], "init_s": init_s}))
 
 
-def run_reference_pool(args, steps, warmup, workers):
+def run_reference_pool(args, steps, warmup, workers, budget_s):
     """`workers` concurrent single-thread processes (the reference has no threads: independent searches
     are the only parallelism that keeps its arithmetic)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--worker-mode", "--steps", str(steps), "--warmup", str(warmup),
-           "--cpu-ants", str(args.cpu_ants)] + (["--port"] if args.port else [])
+           "--cpu-ants", str(args.cpu_ants), "--budget-s", str(budget_s), "--workload", args.workload] + (["--port"] if args.port else [])
     procs = [subprocess.Popen(cmd + ["--worker", str(i)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for i in range(workers)]
     res = []
     for p in procs:
@@ -569,9 +813,10 @@ def run_reference_pool(args, steps, warmup, workers):
         if p.returncode != 0:
             raise RuntimeError("reference worker failed:\n" + err[-2000:])
         res.append(json.loads(out.strip().splitlines()[-1]))
-    tot = sum(sum(r["ant_steps"]) for r in res)
-    wall = max(sum(r["seconds"]) for r in res)
-    return res, tot, wall
+    done = min(len(r["ant_steps"]) for r in res)            # every process contributes the same number of steps
+    tot = sum(sum(r["ant_steps"][:done]) for r in res)
+    wall = max(sum(r["seconds"][:done]) for r in res)
+    return res, tot, wall, done
 
 
 def host_workers(args):
@@ -586,11 +831,11 @@ def host_workers(args):
 
 
 def cpu_baseline(args):
-    """Bounded sample for the default run: ONE process, 1 warm-up + 2 timed first-iterations."""
-    res, tot, wall = run_reference_pool(args, steps=2, warmup=1, workers=1)
+    """Bounded sample for the default run: ONE process, 1 warm-up + 2 timed first-iterations of the workload's own colony."""
+    res, tot, wall, done = run_reference_pool(args, steps=2, warmup=1, workers=1, budget_s=30.0)
     return {"value": tot / wall, "unit": "ant-steps/s", "cores": 1, "kind": res[0]["kind"],
-            "sample": "2 iterations of computeSolution with %d of the %d ants on the same 256^3 grid (evaporation sweep of the whole field "
-                      "included), 1 process" % (args.cpu_ants, ANTS_PER_GPU),
+            "sample": "%d first-iterations of computeSolution with the workload's %d ants on the same 256^3 grid (evaporation sweep of the whole field "
+                      "included, reset() between them untimed), 1 process — the regime of the `e2e` leg" % (done, args.cpu_ants),
             "seconds": wall, "init_seconds": res[0]["init_s"], "ant_steps": tot}
 
 
@@ -598,20 +843,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 4)), min(args.warmup, 1)
+    steps, warmup = max(1, args.steps), min(args.warmup, 1)
     workers = host_workers(args)
-    res, tot, wall = run_reference_pool(args, steps, warmup, workers)
+    res, tot, wall, done = run_reference_pool(args, steps, warmup, workers, budget_s=150.0)
     value = tot / wall
     print(json.dumps({
-        "impl": "reference", "metric": "ant-steps/s", "value": value, "unit": "ant-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "impl": "reference", "metric": "ant-steps/s", "value": value, "unit": "ant-steps/s", "n_gpus": args.gpus, "steps": done, "warmup": warmup,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * wall / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic: same C2 grid as the GPU arm, built on the CPU",
         "config": {"workload": "%s, %d ants/GPU, K=6" % (LABEL, ANTS_PER_GPU),
-                   "grid": [CUBE, CUBE, CUBE], "sample_ants": args.cpu_ants, "processes": workers},
+                   "grid": [CUBE, CUBE, CUBE], "ants": args.cpu_ants, "processes": workers,
+                   "step": "one first-iteration of a fresh search with the full colony (the regime of the GPU arm's e2e leg); "
+                           "%d of the %d requested steps fit the 150 s budget" % (done, args.steps)},
         "cpu_baseline": {"value": value, "unit": "ant-steps/s", "cores": workers, "kind": res[0]["kind"],
                          "sample": "%d timed first-iterations of computeSolution (ACSRank_3D.hpp:220-305) with %d-ant colonies on the 256^3 grid, "
                                    "%d concurrent single-thread processes (independent searches), evaporation sweep included"
-                                   % (steps, args.cpu_ants, workers)},
+                                   % (done, args.cpu_ants, workers)},
         "e2e": {"value": value, "unit": "ant-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -627,17 +875,22 @@ def main():
     ap.add_argument("--ants", type=int, default=0, help="ants per GPU (default: the workload's colony; other values are exploration runs)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--update-mode", type=int, default=4, help="WR_UPDATE_*: 4 = adaptive rank sets | sorted records + fused pass (default), 0 = fused")
-    ap.add_argument("--cpu-ants", type=int, default=1024, help="colony size of the CPU sample")
+    ap.add_argument("--cpu-ants", type=int, default=0, help="colony size of the CPU arm (default: the workload's colony)")
     ap.add_argument("--max-workers", type=int, default=16)
     ap.add_argument("--port", action="store_true", help="time the oracle port instead of oracle/_ref")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-k26", action="store_true", help="skip the K = 26 extension leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records of the other BASELINE configurations (C3, C4, C5) and the full-search leg")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the sharded-vs-single-GPU self-check")
     ap.add_argument("--worker-mode", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--worker", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--budget-s", type=float, default=150.0, help=argparse.SUPPRESS)
     args = ap.parse_args()
     select_workload(args.workload)
     if args.ants <= 0:
         args.ants = ANTS_PER_GPU
+    if args.cpu_ants <= 0:
+        args.cpu_ants = ANTS_PER_GPU
     if args.workload != "C2":
         args.no_k26 = True
     if args.impl == "reference":

@@ -415,6 +415,26 @@ public:
         return &best_;
     }
     void counters(uint64_t out[9]) { need(); wr::check(wr_acs_counters(acs_, out)); }
+    // additions: the colony sharded by ants over `nranks` processes (one GPU each).  `nccl_unique_id`: the WR_COMM_ID_BYTES
+    // bytes rank 0 got from wr_comm_unique_id, handed to every rank by the caller's own means.  Call before computeSolution
+    // / begin; iterate() and computeSolution() then run the sharded protocol (include/wr_gpu.h) with the same results.
+    void commInit(const void* nccl_unique_id, int rank, int nranks) { need(); wr::check(wr_acs_comm_init(acs_, nccl_unique_id, rank, nranks)); }
+    void setEndpoints(int64_t start_id, int64_t goal_id) { need(); wr::check(wr_acs_set_endpoints(acs_, start_id, goal_id)); }
+    void sync() { need(); wr::check(wr_acs_sync(acs_)); }
+    std::vector<float> pheromone()
+    {
+        need();
+        std::vector<float> tau((size_t)size_of_map() * (size_t)params.K);
+        wr::check(wr_acs_download_pheromone(acs_, tau.data(), tau.size()));
+        return tau;
+    }
+    std::vector<uint8_t> isFreeArray()
+    {
+        std::vector<uint8_t> f((size_t)size_of_map());
+        wr::check(wr_grid_download_isfree(grid_, f.data(), f.size()));
+        return f;
+    }
+    wr_acs* handle() { need(); return acs_; }
 
     void searchBestPathOfPoints(float predict_path_len = 10, std::string read_file = "", std::string output_file = "")
     {   // :427-504

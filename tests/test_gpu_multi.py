@@ -122,3 +122,23 @@ def test_sharded_equals_single_gpu_world2():
 def test_sharded_equals_single_gpu_world4():
     """four ranks: three peers to pull final values from, slot slices that do not divide evenly"""
     run_world(4)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("ranks", [2])
+def test_cpp_harness_sharded_equals_single_gpu(ranks, tmp_path):
+    """examples/sharded_main: the C++ facade + wr_comm_unique_id / wr_acs_comm_init, one process per GPU, no Python in the
+    ranks: every rank's pheromone field digest, best length and best path equal the single-GPU run's."""
+    import subprocess
+    import torch
+    from test_oracle_golden import stl_bytes
+    if torch.cuda.device_count() < ranks:
+        pytest.skip("needs %d GPUs" % ranks)
+    exe = os.path.join(ROOT, "examples", "sharded_main")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-s"], check=True)
+    stl = tmp_path / "piece.stl"
+    stl.write_bytes(stl_bytes(dict(np.load(os.path.join(GOLDEN, "meshes.npz")))["simplified_piece"]))
+    r = subprocess.run([exe, str(stl), str(ranks), "0.012", "4", "2001", "10", str(tmp_path)], capture_output=True, text=True, timeout=500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "sharded == single GPU, bit for bit" in r.stdout

@@ -60,12 +60,13 @@ __device__ __forceinline__ uint32_t batch_find(const BatchTable& t, uint32_t nod
 {
     const unsigned long long want = (unsigned long long)(node + 1u) | ((unsigned long long)q << 32);
     uint32_t h = batch_hash(node, q) >> t.shift;
-    while (true) {
+    for (uint32_t probes = 0; probes <= t.tmask; probes++) {   // bounded: a failing batch (claims raced past the limit) may have filled a tiny table
         const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(t.ent + (size_t)h * kBatchEntryWords);
         if ((k & ~kBatchFlagBit) == want) return h;
         if (k == 0ull) return 0xFFFFFFFFu;
         h = (h + 1) & t.tmask;
     }
+    return 0xFFFFFFFFu;
 }
 
 // ... created if missing (its six slots hold the sentinel: the table is filled with sentinels, keys zero)
@@ -324,7 +325,9 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
             if (!(nb >= 1e-18f && nb <= 1e18f) && nb != 0.0f) nb = slow_norm1(d);
             const float heur_v = __fadd_rn(1.0f, __fmul_rn(beta, __fdiv_rn(__fmul_rn(ac, d), __fmul_rn(na, nb))));
             // ---- BATCH: pheromone of slot k: the node's entry, or the scalar if it has none ---------------------------
+            uint32_t probes = 0;
             while ((ekey.x != want0 || (ekey.y & 0x7FFFFFFFu) != qi) && (ekey.x | ekey.y) != 0u) {   // rare: linear probing at load <= 1/2
+                if (++probes > a.tab.tmask) { ekey = make_uint2(0u, 0u); break; }   // a full table: only in a batch that has already failed and will be re-run
                 eh = (eh + 1) & a.tab.tmask;
                 const uint32_t* e = ent + (size_t)eh * kBatchEntryWords;
                 ekey = __ldg(reinterpret_cast<const uint2*>(e));
