@@ -61,7 +61,7 @@ def test_c1_all_pairs_batch_equals_sequential_and_oracle(wr, oracle, meshes):
     (dict(fixed_colony=96, step_cap=300, alpha=2, beta=0.9, rho=0.7, tau0=0.5), {}),
     (dict(fixed_colony=150, step_cap=400), {"WR_BATCH_TABLE": "16"}),       # 16-entry visited tables: most ants park and resume from HBM tables
     (dict(fixed_colony=150, step_cap=300), {"WR_BATCH_LOG2": "10"}),        # 1024-entry pheromone table: the chunk falls back to the sequential loop
-    (dict(fixed_colony=64, step_cap=300), {"WR_BATCH_MEM_MB": "4"}),       # memory for a few queries per chunk only
+    (dict(fixed_colony=64, step_cap=300), {"WR_BATCH_MEM_MB": "4", "WR_BATCH_LOG2": "18"}),   # memory for a few queries per chunk only
 ])
 def test_fixed_colony_queries(wr, oracle, meshes, params, env, monkeypatch):
     for k, v in env.items():
@@ -77,7 +77,7 @@ def test_fixed_colony_queries(wr, oracle, meshes, params, env, monkeypatch):
     bat = g2.searchBatch(s, e, 1.0, iterations=12)
     same(seq, bat)
     st = g2.batchStats()
-    assert (st["fallbacks"] > 0) == ("WR_BATCH_LOG2" in env), st
+    assert (st["fallbacks"] > 0) == (env.get("WR_BATCH_LOG2") == "10"), st
     if "WR_BATCH_TABLE" in env:
         assert g2.counters()["table_overflows"] > 0
     if "WR_BATCH_MEM_MB" in env:

@@ -1254,6 +1254,7 @@ struct wr_batch {   // buffers of the batch path, kept by the handle between cal
     uint32_t* best_ids = nullptr; uint8_t* best_dirs = nullptr;
     float* res_L = nullptr; int* res_n = nullptr;
     uint32_t* overflow_list = nullptr; unsigned long long* gtab = nullptr; int4* resume = nullptr;
+    unsigned long long* cnt_save = nullptr;
     uint32_t pool = 0;
     int qc = 0, cm = 0;   // queries per chunk / colony the per-query buffers were sized for
     bool mem_limited = false;   // qc is what fits into memory, not what was asked for
@@ -1267,7 +1268,7 @@ static void free_batch(wr_acs* a)
     cudaStreamSynchronize(s);
     cudaFree(b->tab.ent); cudaFree(b->tab.list); cudaFree(b->tab.count);
     void* ptrs[] = {b->qs, b->d_starts, b->d_goals, b->steps, b->path_ids, b->path_dirs, b->ranked_keys, b->ranked_vals, b->best_ids, b->best_dirs, b->res_L, b->res_n,
-                    b->overflow_list, b->gtab, b->resume};
+                    b->overflow_list, b->gtab, b->resume, b->cnt_save};
     for (void* p : ptrs) cudaFree(p);
     delete b;
     a->batch = nullptr;
@@ -1325,6 +1326,7 @@ static int alloc_batch(wr_acs* a, int want_q, int cm, int* qc_out)
     WR_CUDA(cudaMalloc(&b->overflow_list, pool * sizeof(uint32_t)));
     WR_CUDA(cudaMalloc(&b->gtab, pool * Eg * sizeof(unsigned long long)));
     WR_CUDA(cudaMalloc(&b->resume, pool * sizeof(int4)));
+    WR_CUDA(cudaMalloc(&b->cnt_save, 16 * sizeof(unsigned long long)));
     WR_CUDA(cudaGetLastError());
     *qc_out = qc;
     return WR_OK;
@@ -1383,6 +1385,9 @@ extern "C" int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const in
         WR_CUDA(cudaMemcpyAsync(b->d_starts, hs.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, s));
         WR_CUDA(cudaMemcpyAsync(b->d_goals, hg.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, s));
         WR_CUDA(cudaStreamSynchronize(s));   // hs / hg are on this frame
+        // counters as they are before this chunk: a chunk that has to be re-run sequentially must not count twice
+        unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(a->d_state) + offsetof(IterState, cnt));
+        WR_CUDA(cudaMemcpyAsync(b->cnt_save, d_cnt, sizeof(unsigned long long) * 9, cudaMemcpyDeviceToDevice, s));
         k_batch_begin<<<(n + 255) / 256, 256, 0, s>>>(a->d_state, b->qs, n, b->d_starts, b->d_goals, first_search + (uint32_t)c0, predict, a->p.tau0, b->tab.count);
         const int items = n * w.items_per_query;
         const int blocks1 = std::max(1, std::min((items + 3) / 4, kNumSMs * per_sm));
@@ -1411,6 +1416,8 @@ extern "C" int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const in
         if (cnt[1]) {   // pheromone table or overflow-table pool exhausted: this chunk's searches run one after the other instead
             a->batch_fallbacks++;
             k_batch_fill<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(b->tab.ent), b->T);   // entries claimed beyond the list
+            WR_CUDA(cudaMemcpyAsync(d_cnt, b->cnt_save, sizeof(unsigned long long) * 9, cudaMemcpyDeviceToDevice, s));
+            k_set_base<<<1, 1, 0, s>>>(a->d_state, a->p.tau0);   // the batch advanced the handle's scalar; the dense field itself is untouched
             a->next_search = first_search + (uint32_t)c0;
             rc = run_pairs_sequential(a, start_ids, goal_ids, c0, n, predict, n_iterations);
         } else {
