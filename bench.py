@@ -427,12 +427,10 @@ def run_ours(args):
         step()
     barrier()
     # ---- timed region, device resident -------------------------------------------------------------
-    # Single GPU: the timed region runs as a user would run it (no per-phase events, so the steady-state iterations go out as
-    # one CUDA graph each); the per-phase / per-kernel times are taken afterwards on a REPLAY of the same iterations (a fresh
-    # handle, same seed: the search is deterministic) with the event pairs enabled.  Sharded: events inside the timed region.
-    phase_in_timed = world > 1
-    if phase_in_timed:
-        acs.setTiming(True)
+    # The timed region runs as a user would run it (no per-phase events, so the steady-state iterations go out as one CUDA graph
+    # each); the per-phase / per-kernel times are taken afterwards on a REPLAY of the same iterations (a fresh handle — on every
+    # rank, for a sharded search — same seed: the search is deterministic) with the event pairs enabled.
+    phase_in_timed = False
     c0 = acs.counters()
     rs0 = acs.updateStats()["rankset_iterations"]
     dirty0, tiles_total = acs.fieldStats()
@@ -458,13 +456,19 @@ def run_ours(args):
         rep = make_search(wl["isfree"])
         _lib.check(_lib.lib().wr_acs_set_stream(rep._a, stream.cuda_stream))
         rep.setEndpoints(wl["start"], wl["goal"])
-        rep.begin(PREDICT)
+        if world > 1:
+            rep_driver = ShardedSearch(rep, rank, world)
+            rep_driver.begin(PREDICT)
+            rep_step = rep_driver.iterate
+        else:
+            rep.begin(PREDICT)
+            rep_step = rep.iterate
         for _ in range(args.warmup):
-            rep.iterate(args.iters)
+            rep_step(args.iters)
         rep.sync()
         rep.setTiming(True)
         for _ in range(args.steps):
-            rep.iterate(args.iters)
+            rep_step(args.iters)
         kms = rep.kernelMs()
         sk_ms, sk_n = rep.streamKernelMs()
         assert rep.counters()["ant_steps"] == c1["ant_steps"], "replay diverged from the timed search"
@@ -658,7 +662,7 @@ def run_ours(args):
     walk_gbs = WALK_BYTES_PER_STEP * (local_steps / iters_done) / (walk_ms * 1e-3) / 1e9
     upd_bytes = dirty_tiles * 4096 * UPDATE_BYTES_PER_SLOT     # what the pass reads + writes: 4096-float tiles, 8 B per slot
     upd_phase_gbs = upd_bytes / (upd_ms * 1e-3) / 1e9
-    upd_kernel_ms = sk_ms / max(1, sk_n) if world == 1 else upd_ms
+    upd_kernel_ms = sk_ms / max(1, sk_n)
     upd_gbs = upd_bytes / (upd_kernel_ms * 1e-3) / 1e9
     upd_dense_gbs = UPDATE_BYTES_PER_SLOT * n_nodes * 6 / (upd_ms * 1e-3) / 1e9
     ants_done = max(1, c1["ants"] - c0["ants"])
@@ -681,8 +685,7 @@ def run_ours(args):
                                   + launches_per_iteration(4, colony, args.iters, world > 1) * rs_iters)),
         "deposit_path": {"rank_set_iterations": rs_iters, "record_iterations": iters_done - rs_iters, "last": upd_stats} if args.update_mode == 4 else None,
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
-        "kernel_ms_source": "events inside the timed region" if world > 1 else
-                            "replay of the timed iterations on a fresh handle with per-phase events (the timed region itself runs without them)",
+        "kernel_ms_source": "replay of the timed iterations on a fresh handle with per-phase events (the timed region itself runs without them)",
         "roofline": {"kernel": "k_walk2 (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
                      "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk2", traffic.get("k_walk")),
                      "traffic_source": "static: dram__bytes_read+write per launch from the committed `ncu --set full` capture (profiles/), not measured in this run",

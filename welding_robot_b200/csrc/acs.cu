@@ -120,6 +120,9 @@ struct wr_acs {
     unsigned char* d_slab = nullptr;
     size_t slab_bytes = 0, off_ids[2] = {0, 0}, off_dirs[2] = {0, 0}, off_fin[2] = {0, 0}, off_steps[2] = {0, 0}, off_pub = 0, off_flags = 0;
     const void** d_tabs = nullptr;    // device: [kind 0 ids,1 dirs,2 fin,3 steps,4 publish area,5 barrier flags][parity][rank] -> pointer into rank's slab
+    cudaStream_t side = nullptr;      // sharded rank-set iterations: the evaporation pass runs here, beside the exchange (barriers, ranking, merge)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool evap_forked = false;
     void* comm = nullptr;             // NCCL communicator (wr_acs_comm_init): wr_acs_begin exchanges the peer slabs through it
     uint32_t* d_epoch = nullptr;      // peer barrier: number of barriers this rank has passed since the slabs were exchanged
     uint32_t* d_peer_err = nullptr;   // set by a barrier that timed out (a peer died): reported by wr_acs_sync
@@ -452,6 +455,11 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
     return WR_OK;
 }
 
+static bool evap_overlap()
+{
+    static const bool on = [] { const char* e = getenv("WR_EVAP_OVERLAP"); return !e || atoi(e) != 0; }();
+    return on;
+}
 static bool batch_enabled()
 {
     static const bool on = [] { const char* e = getenv("WR_BATCH"); return !e || atoi(e) != 0; }();
@@ -527,6 +535,7 @@ extern "C" int wr_acs_destroy(wr_acs* a)
     feedback_release(a->h_feedback);
     for (cudaEvent_t e : a->sk_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->rs_ev) if (e) cudaEventDestroy(e);
+    if (a->side) { cudaStreamSynchronize(a->side); cudaStreamDestroy(a->side); cudaEventDestroy(a->ev_fork); cudaEventDestroy(a->ev_join); }
     if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
     delete a;
     return WR_OK;
@@ -947,13 +956,18 @@ static int launch_rankset_update(wr_acs* a)
         k_rankset_merge<<<kNumSMs * 2, 256, 0, s>>>(a->d_state, a->rs, reinterpret_cast<const uint32_t* const*>(a->tab(4, 0)), a->nranks, a->rank);
     }
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
-    if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
-    k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
-    if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
+    if (a->evap_forked) {
+        WR_CUDA(cudaStreamWaitEvent(s, a->ev_join, 0));
+        a->evap_forked = false;
+    } else {
+        if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
+        k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
+        if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
+    }
+    // the last apply launch also wipes, on overflow of the fixed-capacity table (flag raised by gen / merge), the blocks that
+    // did not make it into the list; k_deposit_serial then applies the iteration's deposits in the reference's own loop order
     for (int g = 0; g < a->rs_groups; g++)
         k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty, (uint32_t)g, g == a->rs_groups - 1 ? 1 : 0);
-    // overflow of the fixed-capacity table (flag raised by gen / merge): wipe what apply could not reach, deposit serially
-    k_rankset_wipe<<<kNumSMs * 2, 256, 0, s>>>(a->d_state, a->rs);
     k_deposit_serial<<<1, 1024, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->trail_ids_tab(), a->trail_dirs_tab(), a->cap, a->chunk, (int)a->goal, a->d_Ltab,
                                         a->d_onbest, a->rs.count + 3, a->d_tau, a->p.rho, a->d_dirty, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
     WR_CUDA(cudaGetLastError());
@@ -997,13 +1011,32 @@ static bool graph_enabled()
 
 // Everything of one iteration between the iteration parameters and the deposits: construction, [exchange of the step counts],
 // ranking, best path.
-static int launch_construct_and_rank(wr_acs* a)
+static int launch_construct_and_rank(wr_acs* a, bool rankset_iteration)
 {
     cudaStream_t s = a->stream;
     if (a->nranks > 1) WR_CUDA(cudaMemsetAsync(a->d_local_steps, 0xFF, (size_t)a->chunk * sizeof(int), s));   // -1: beyond the colony
     int st = launch_walk(a);
     if (st != WR_OK) return st;
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
+    a->evap_forked = false;
+    if (a->nranks > 1 && rankset_iteration && evap_overlap()) {
+        // The walk was the last reader of the field: its evaporation (:268-272) can start now, on a side stream, while this
+        // stream waits for the peers, ranks the colony and merges the rank sets; the ordered chains join it again.  (On one GPU
+        // the same overlap was measured and rejected: the chain of small kernels slows down under a saturated memory system and
+        // there is no barrier wait to hide behind.)
+        if (!a->side) {
+            WR_CUDA(cudaStreamCreateWithFlags(&a->side, cudaStreamNonBlocking));
+            WR_CUDA(cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming));
+            WR_CUDA(cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming));
+        }
+        WR_CUDA(cudaEventRecord(a->ev_fork, s));
+        WR_CUDA(cudaStreamWaitEvent(a->side, a->ev_fork, 0));
+        if (a->timer.enabled) cudaEventRecord(a->sk_next(), a->side);
+        k_evaporate_tiles<<<kNumSMs * 8, 256, 0, a->side>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
+        if (a->timer.enabled) cudaEventRecord(a->sk_next(), a->side);
+        WR_CUDA(cudaEventRecord(a->ev_join, a->side));
+        a->evap_forked = true;
+    }
     if (a->nranks > 1) {   // trails and step counts of every rank are complete and visible: barrier, then the global colony
         launch_barrier(a);
         const int total = a->chunk * a->nranks;
@@ -1034,7 +1067,7 @@ static int capture_steady_iteration(wr_acs* a, cudaGraphExec_t* out)
     launch_warm(a, true);
     k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, 1, a->d_upd_q, a->rs.count, 1, a->d_feedback,
                                  a->rs_generation, a->p.rho);
-    int st = launch_construct_and_rank(a);
+    int st = launch_construct_and_rank(a, true);
     if (st == WR_OK) st = launch_rankset_update(a);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(s, &graph);
@@ -1104,7 +1137,7 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
         k_iter_begin<<<1, 1, 0, s>>>(a->d_state, a->p.fixed_colony, a->colony_max, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->d_upd_q,
                                      a->rankset ? a->rs.count : nullptr, rs_now ? 1 : 0, a->d_feedback, a->rs_generation, a->p.rho);
         a->upd_q_zeroed = true;
-        int st = launch_construct_and_rank(a);
+        int st = launch_construct_and_rank(a, rs_now);
         if (st != WR_OK) return st;
         if (rs_now) st = launch_rankset_update(a);   // rank sets instead of sorted records (rankset.cuh)
         else if (sharded) { st = launch_record_update_sharded(a); a->warm_by_pull = true; }
@@ -1452,7 +1485,7 @@ static int preload_iteration_kernels()
 #define WR_PRELOAD(f) WR_CUDA(cudaFuncGetAttributes(&at, f))
     WR_PRELOAD(k_peer_barrier); WR_PRELOAD(k_gather_steps); WR_PRELOAD(k_rank_small); WR_PRELOAD(k_rank_chunks); WR_PRELOAD(k_rank_merge);
     WR_PRELOAD(k_rank_finish_prefix); WR_PRELOAD(k_best_copy_peer); WR_PRELOAD(k_best_copy); WR_PRELOAD(k_rankset_gen); WR_PRELOAD(k_rankset_publish);
-    WR_PRELOAD(k_rankset_merge); WR_PRELOAD(k_evaporate_tiles); WR_PRELOAD(k_rankset_apply); WR_PRELOAD(k_rankset_wipe); WR_PRELOAD(k_deposit_serial);
+    WR_PRELOAD(k_rankset_merge); WR_PRELOAD(k_evaporate_tiles); WR_PRELOAD(k_rankset_apply); WR_PRELOAD(k_deposit_serial);
     WR_PRELOAD((k_deposit_gen<false, true>)); WR_PRELOAD(k_tile_offsets); WR_PRELOAD(k_update_fused<true>); WR_PRELOAD(k_update_fused<false>);
     WR_PRELOAD(k_pull_finals); WR_PRELOAD(k_iter_begin); WR_PRELOAD(k_iter_end); WR_PRELOAD(k_path_warm); WR_PRELOAD(k_rankset_warm);
     WR_PRELOAD((k_walk2<false, true, 0>)); WR_PRELOAD((k_walk2<false, true, 1>)); WR_PRELOAD((k_walk2<false, true, 2>)); WR_PRELOAD((k_walk2<false, true, 3>));

@@ -25,6 +25,7 @@
 //   k_rankset_apply   one launch per group g, ascending: blocks of group g add their ranks' values to tau[slot] in
 //                     ascending rank order — across the launches a slot's chain runs group 0, 1, 2 ... = the reference's
 //                     additions in the reference's order — then the block and its key are wiped for the next iteration
+//                     (the last launch also sweeps the table after an overflow)
 #pragma once
 #include "acs_kernels.cuh"
 
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(128) k_rankset_gen(const IterState* st, const 
             const uint32_t mine = at + __popc(cm & ((1u << lane) - 1u));
             if (claimed) {
                 if (mine < rs.limit) rs.list[mine] = h;
-                else *over = 1u;   // beyond the claim limit: the block stays out of the list and is wiped by k_rankset_wipe
+                else *over = 1u;   // beyond the claim limit: the block stays out of the list and is wiped by the sweep of the last apply launch
             }
         }
         if (valid && h != 0xFFFFFFFFu) atomicOr(rs.rows + (size_t)h * kRsRowWords + word, bit);
@@ -261,19 +262,15 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
         }
     }
     if (last_group && blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = n;
-}
-
-// Overflow only: blocks claimed beyond the list (their indices were dropped) are found by a sweep of the whole table.
-__global__ void __launch_bounds__(256) k_rankset_wipe(const IterState* st, RankSet rs)
-{
-    if (!st->use_rankset || rs.count[3] == 0u) return;
-    const size_t R = (size_t)rs.rmask + 1;
-    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < R; h += (size_t)gridDim.x * blockDim.x) {
-        if (rs.key[h] == 0ull) continue;
-        uint4* row = reinterpret_cast<uint4*>(rs.rows + h * kRsRowWords);
+    if (last_group && overflow) {   // blocks claimed beyond the list (their indices were dropped): a sweep of the whole table finds them
+        const size_t R = (size_t)rs.rmask + 1;
+        for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < R; h += (size_t)gridDim.x * blockDim.x) {
+            if (rs.key[h] == 0ull) continue;
+            uint4* r4 = reinterpret_cast<uint4*>(rs.rows + h * kRsRowWords);
 #pragma unroll
-        for (int j = 0; j < 8; j++) row[j] = make_uint4(0u, 0u, 0u, 0u);
-        rs.key[h] = 0ull;
+            for (int j = 0; j < 8; j++) r4[j] = make_uint4(0u, 0u, 0u, 0u);
+            rs.key[h] = 0ull;
+        }
     }
 }
 
