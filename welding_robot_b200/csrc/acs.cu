@@ -314,6 +314,13 @@ struct IpcMapping {
     void* ptr = nullptr;
 };
 static std::vector<IpcMapping> g_ipc_maps;   // one per peer rank (a process drives one GPU)
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int device = -1;
+    bool in_use = false;
+};
+static std::vector<SideStream> g_side_streams;   // side streams of sharded handles, parked between handles
 
 static void free_colony_buffers(wr_acs* a)
 {
@@ -535,7 +542,11 @@ extern "C" int wr_acs_destroy(wr_acs* a)
     feedback_release(a->h_feedback);
     for (cudaEvent_t e : a->sk_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : a->rs_ev) if (e) cudaEventDestroy(e);
-    if (a->side) { cudaStreamSynchronize(a->side); cudaStreamDestroy(a->side); cudaEventDestroy(a->ev_fork); cudaEventDestroy(a->ev_join); }
+    if (a->side) {
+        cudaStreamSynchronize(a->side);
+        std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+        for (SideStream& ss : g_side_streams) if (ss.stream == a->side) ss.in_use = false;
+    }
     if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
     delete a;
     return WR_OK;
@@ -1024,10 +1035,19 @@ static int launch_construct_and_rank(wr_acs* a, bool rankset_iteration)
         // stream waits for the peers, ranks the colony and merges the rank sets; the ordered chains join it again.  (On one GPU
         // the same overlap was measured and rejected: the chain of small kernels slows down under a saturated memory system and
         // there is no barrier wait to hide behind.)
-        if (!a->side) {
-            WR_CUDA(cudaStreamCreateWithFlags(&a->side, cudaStreamNonBlocking));
-            WR_CUDA(cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming));
-            WR_CUDA(cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming));
+        if (!a->side) {   // parked between handles (searches created per request): creating a stream costs more than an iteration
+            std::lock_guard<std::mutex> lock(g_rs_cache_mu);
+            for (SideStream& ss : g_side_streams)
+                if (ss.stream && !ss.in_use && ss.device == a->device) { ss.in_use = true; a->side = ss.stream; a->ev_fork = ss.fork; a->ev_join = ss.join; break; }
+            if (!a->side) {
+                SideStream ss;
+                WR_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+                WR_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+                WR_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+                ss.device = a->device; ss.in_use = true;
+                g_side_streams.push_back(ss);
+                a->side = ss.stream; a->ev_fork = ss.fork; a->ev_join = ss.join;
+            }
         }
         WR_CUDA(cudaEventRecord(a->ev_fork, s));
         WR_CUDA(cudaStreamWaitEvent(a->side, a->ev_fork, 0));
