@@ -733,19 +733,19 @@ def launches_per_iteration(update_mode, colony=ANTS_PER_GPU, iters=5, sharded=Fa
     out as one CUDA graph launch still runs the same kernels)."""
     slot_bits = int(np.ceil(np.log2(CUBE ** 3 * 6)))
     sort = lambda bits: 3 * ((bits + 9) // 10)  # noqa: E731  hist + scan + scatter per pass of <= 10-bit digits (radix_sort.cu)
-    rank = 1 if colony <= 16384 else 3                           # k_rank_small | chunk sorts + merge + prefix finish
-    groups = (int(0.2 * colony) + 1 + 1023) // 1024              # apply launches of the rank-set path
+    rank = 1 if colony <= 8192 else 3                            # k_rank_small | chunk sorts + merge + prefix finish
+    groups = 1 if int(0.2 * colony) + 1 <= 1024 else 2           # rank-set path: apply (+ clear when the colony needs more than one rank group)
     # iter_begin, walk pass 1 + 2, ranking, best copy, iter_end (once per wr_acs_iterate call)
     n = 1 + 2 + rank + 1 + 1.0 / iters
     if sharded:
-        n += 2                                                   # barrier + gather of the step counts
+        n += 1                                                   # gather of the step counts (the barrier is inside)
     if update_mode == 2:
         return n + 1 + 2                                         # L2 warm-up, evaporate, atomic deposits
     if update_mode == 4:                                         # rank sets: L2 warm-up, gen, evaporate, apply x groups, wipe, serial fallback (both exit at once)
-        return n + 1 + 1 + 1 + groups + 2 + (3 if sharded else 0)   # sharded: + publish, barrier, merge
+        return n + 1 + 1 + 1 + groups + 1 + (2 if sharded else 0)   # sharded: + publish, merge (the barrier is inside)
     n += 1 + sort(slot_bits) + 2                                 # deposit gen, slot sort, tile offsets + fused
     if sharded:
-        n += 4 + 2                                               # partition pass, barrier + pull of the peers' final values (which is also the L2 warm-up)
+        n += 4 + 1                                               # partition pass, pull of the peers' final values (barrier inside; also the L2 warm-up)
     else:
         n += 1                                                   # L2 warm-up
     return n

@@ -124,7 +124,7 @@ struct wr_acs {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool evap_forked = false;
     void* comm = nullptr;             // NCCL communicator (wr_acs_comm_init): wr_acs_begin exchanges the peer slabs through it
-    uint32_t* d_epoch = nullptr;      // peer barrier: number of barriers this rank has passed since the slabs were exchanged
+    uint32_t* d_epoch = nullptr;      // [0] unused [1] = d_peer_err
     uint32_t* d_peer_err = nullptr;   // set by a barrier that timed out (a peer died): reported by wr_acs_sync
     unsigned long long barrier_timeout_ns = 20000000000ull;
     std::vector<void*> ipc_opened;
@@ -627,7 +627,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     WR_CUDA_A(dmalloc(&a->d_upd_q, 4 * sizeof(uint32_t), a->stream));
     {
         WR_CUDA_A(cudaFuncSetAttribute(k_rank_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmallSmem));
-        WR_CUDA_A(cudaFuncSetAttribute(k_rank_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmallSmem));
+        WR_CUDA_A(cudaFuncSetAttribute(k_rank_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankChunkSmem));
         const size_t ws = walk_smem(a);
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         if (a->K == kK26) WR_CUDA_A(cudaFuncSetAttribute(k_walk26<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
@@ -786,6 +786,7 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     a->rs_generation = (a->rs_generation + 1) & 0xFFFFu; a->rs_choice = 0; a->rs_enqueued = 0;
     drop_steady_graph(a);   // endpoints, heuristic table and generation are baked into the captured launches
     a->sk_used = 0; a->sk_ms = 0; a->sk_launches = 0;
+    a->peers_set = false;   // sharded: the barrier epochs restart with the iteration counter, so the slabs are exchanged (and their flag words zeroed) per search
     a->begun = true;
     a->timer.used = 0;
     for (float& m : a->timer.ms) m = 0;
@@ -873,12 +874,12 @@ static int launch_rank(wr_acs* a, const int* d_all_steps)
     cudaStream_t s = a->stream;
     const float* d_L = a->K == kK26 ? a->d_ant_L : nullptr;
     a->ants_in_b = false;
-    if (cm <= kRankSmallMax) {   // the whole ranking in one single-CTA kernel
+    if (cm <= 2 * kRankChunk) {   // the whole ranking in one single-CTA kernel
         k_rank_small<<<1, kRankSmallThreads, kRankSmallSmem, s>>>(a->d_state, d_all_steps, d_L, a->cap, a->rank_bits, a->d_Ltab, a->sort_ants.keys_a, a->sort_ants.vals_a,
                                                                    a->d_rec_off, a->d_order, a->d_best_n, a->d_best_ids, a->d_onbest);
-    } else {                     // chunks of 16384 ants sorted in parallel, merged by rank counting, prefix-only finish
-        const int nchunks = (cm + kRankSmallMax - 1) / kRankSmallMax;
-        k_rank_chunks<<<nchunks, kRankSmallThreads, kRankSmallSmem, s>>>(a->d_state, d_all_steps, d_L, a->cap, a->rank_bits, a->sort_ants.keys_b, a->sort_ants.vals_b);
+    } else {                     // chunks of 4096 ants sorted in parallel, merged by rank counting, prefix-only finish
+        const int nchunks = (cm + kRankChunk - 1) / kRankChunk;
+        k_rank_chunks<<<nchunks, kRankSmallThreads, kRankChunkSmem, s>>>(a->d_state, d_all_steps, d_L, a->cap, a->rank_bits, a->sort_ants.keys_b, a->sort_ants.vals_b);
         k_rank_merge<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, a->sort_ants.keys_b, a->sort_ants.vals_b, a->sort_ants.keys_a, a->sort_ants.vals_a, a->d_order);
         k_rank_finish_prefix<<<1, 1024, 0, s>>>(a->d_state, a->sort_ants.keys_a, a->sort_ants.vals_a, a->cap, a->d_Ltab, a->d_rec_off, a->w_max,
                                                 a->K == kK26 ? d_all_steps : nullptr, a->d_best_n, a->d_best_ids, a->d_onbest);
@@ -947,11 +948,13 @@ static int launch_update(wr_acs* a)
     return WR_OK;
 }
 
-// ---- peer barrier of a sharded colony (k_peer_barrier) -------------------------------------------------------------------
-static void launch_barrier(wr_acs* a)
+// ---- peer barrier of a sharded colony (acs_kernels.cuh: peer_barrier, executed inside the kernel that reads peer data) ----
+static PeerBarrier barrier_args(const wr_acs* a)
 {
-    k_peer_barrier<<<1, std::max(32, (a->nranks + 31) / 32 * 32), 0, a->stream>>>(reinterpret_cast<uint32_t* const*>(const_cast<void**>(a->tab(5, 0))), a->rank, a->nranks,
-                                                                                 a->d_epoch, a->d_peer_err, a->barrier_timeout_ns);
+    PeerBarrier b;
+    b.flags_tab = reinterpret_cast<uint32_t* const*>(const_cast<void**>(a->tab(5, 0)));
+    b.me = a->rank; b.nranks = a->nranks; b.err = a->d_peer_err; b.timeout_ns = a->barrier_timeout_ns;
+    return b;
 }
 
 // ---- the rank-set deposit path (rankset.cuh): build [+ publish | barrier | merge], evaporate, one apply launch per rank group ----
@@ -963,8 +966,7 @@ static int launch_rankset_update(wr_acs* a)
                                            a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr, first, a->chunk);
     if (a->nranks > 1) {
         k_rankset_publish<<<kNumSMs, 256, 0, s>>>(a->d_state, a->rs, a->pub_buf());
-        launch_barrier(a);
-        k_rankset_merge<<<kNumSMs * 2, 256, 0, s>>>(a->d_state, a->rs, reinterpret_cast<const uint32_t* const*>(a->tab(4, 0)), a->nranks, a->rank);
+        k_rankset_merge<<<kNumSMs * 2, 256, 0, s>>>(barrier_args(a), a->d_state, a->rs, reinterpret_cast<const uint32_t* const*>(a->tab(4, 0)), a->nranks, a->rank);
     }
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     if (a->evap_forked) {
@@ -975,10 +977,10 @@ static int launch_rankset_update(wr_acs* a)
         k_evaporate_tiles<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<float4*>(a->d_tau), a->ntiles, a->p.rho, a->d_dirty, stream_cs());
         if (a->timer.enabled) cudaEventRecord(a->sk_next(), s);
     }
-    // the last apply launch also wipes, on overflow of the fixed-capacity table (flag raised by gen / merge), the blocks that
-    // did not make it into the list; k_deposit_serial then applies the iteration's deposits in the reference's own loop order
-    for (int g = 0; g < a->rs_groups; g++)
-        k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty, (uint32_t)g, g == a->rs_groups - 1 ? 1 : 0);
+    // ordered chains (all rank groups in one launch), wipe; on overflow of the fixed-capacity table (flag raised by gen / merge)
+    // the chains are skipped, the whole table is swept and k_deposit_serial applies the deposits in the reference's own loop order
+    k_rankset_apply<<<kNumSMs * 4, 256, 0, s>>>(a->d_state, a->d_tau, a->rs, a->p.rho, a->d_dirty, a->rs_groups);
+    if (a->rs_groups > 1) k_rankset_clear<<<kNumSMs * 2, 256, 0, s>>>(a->d_state, a->rs);
     k_deposit_serial<<<1, 1024, 0, s>>>(a->d_state, rank_keys(a), rank_vals(a), a->trail_ids_tab(), a->trail_dirs_tab(), a->cap, a->chunk, (int)a->goal, a->d_Ltab,
                                         a->d_onbest, a->rs.count + 3, a->d_tau, a->p.rho, a->d_dirty, a->K, a->K == kK26 ? a->d_ant_steps : nullptr);
     WR_CUDA(cudaGetLastError());
@@ -1007,9 +1009,8 @@ static int launch_record_update_sharded(wr_acs* a)
     WR_CUDA(cudaMemsetAsync(fin, 0, 4 * sizeof(uint32_t), s));
     st = launch_fused(a, ck, cv, a->d_nq, fin);
     if (st != WR_OK) return st;
-    launch_barrier(a);   // every rank's list of final values is complete
-    k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(a->d_tau, walk_warm() ? a->d_heur : nullptr, reinterpret_cast<const uint32_t* const*>(a->tab(2, a->parity)),
-                                              a->nranks, a->rank, a->d_dirty, a->d_upd_q);
+    k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(barrier_args(a), a->d_state, a->d_tau, walk_warm() ? a->d_heur : nullptr,
+                                              reinterpret_cast<const uint32_t* const*>(a->tab(2, a->parity)), a->nranks, a->rank, a->d_dirty, a->d_upd_q);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -1057,11 +1058,10 @@ static int launch_construct_and_rank(wr_acs* a, bool rankset_iteration)
         WR_CUDA(cudaEventRecord(a->ev_join, a->side));
         a->evap_forked = true;
     }
-    if (a->nranks > 1) {   // trails and step counts of every rank are complete and visible: barrier, then the global colony
-        launch_barrier(a);
+    if (a->nranks > 1) {   // barrier (trails and step counts of every rank complete and visible), then the global colony
         const int total = a->chunk * a->nranks;
-        k_gather_steps<<<std::max(1, std::min((total + 255) / 256, kNumSMs * 2)), 256, 0, s>>>(reinterpret_cast<const int* const*>(a->tab(3, a->parity)), a->nranks, a->chunk,
-                                                                                                 a->d_ant_steps);
+        k_gather_steps<<<std::max(1, std::min((total + 255) / 256, kNumSMs)), 256, 0, s>>>(barrier_args(a), a->d_state, reinterpret_cast<const int* const*>(a->tab(3, a->parity)),
+                                                                                             a->nranks, a->chunk, a->d_ant_steps);
     }
     st = launch_rank(a, a->d_ant_steps);
     if (st != WR_OK) return st;
@@ -1503,9 +1503,9 @@ static int preload_iteration_kernels()
     if (done) return WR_OK;
     cudaFuncAttributes at;
 #define WR_PRELOAD(f) WR_CUDA(cudaFuncGetAttributes(&at, f))
-    WR_PRELOAD(k_peer_barrier); WR_PRELOAD(k_gather_steps); WR_PRELOAD(k_rank_small); WR_PRELOAD(k_rank_chunks); WR_PRELOAD(k_rank_merge);
+    WR_PRELOAD(k_gather_steps); WR_PRELOAD(k_rank_small); WR_PRELOAD(k_rank_chunks); WR_PRELOAD(k_rank_merge);
     WR_PRELOAD(k_rank_finish_prefix); WR_PRELOAD(k_best_copy_peer); WR_PRELOAD(k_best_copy); WR_PRELOAD(k_rankset_gen); WR_PRELOAD(k_rankset_publish);
-    WR_PRELOAD(k_rankset_merge); WR_PRELOAD(k_evaporate_tiles); WR_PRELOAD(k_rankset_apply); WR_PRELOAD(k_deposit_serial);
+    WR_PRELOAD(k_rankset_merge); WR_PRELOAD(k_evaporate_tiles); WR_PRELOAD(k_rankset_apply); WR_PRELOAD(k_rankset_clear); WR_PRELOAD(k_deposit_serial);
     WR_PRELOAD((k_deposit_gen<false, true>)); WR_PRELOAD(k_tile_offsets); WR_PRELOAD(k_update_fused<true>); WR_PRELOAD(k_update_fused<false>);
     WR_PRELOAD(k_pull_finals); WR_PRELOAD(k_iter_begin); WR_PRELOAD(k_iter_end); WR_PRELOAD(k_path_warm); WR_PRELOAD(k_rankset_warm);
     WR_PRELOAD((k_walk2<false, true, 0>)); WR_PRELOAD((k_walk2<false, true, 1>)); WR_PRELOAD((k_walk2<false, true, 2>)); WR_PRELOAD((k_walk2<false, true, 3>));

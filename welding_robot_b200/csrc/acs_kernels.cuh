@@ -78,6 +78,53 @@ __device__ __forceinline__ float pow_int(float x, int y)
     return ans;
 }
 
+// ------------------------------------------------------------------------------------------
+// Barrier between the ranks of a sharded colony, in peer memory (NVLink): every rank owns an array of epoch words, one
+// per source rank, in its slab.  Rank `me` writes the barrier's epoch into word `me` of every peer's array (system-scope
+// release: everything this rank's earlier kernels wrote — trails, step counts, published row blocks, final values — is
+// visible to whoever acquires the word), then waits until every peer's word in its own array has reached the epoch.
+// No host involvement, no collective library in the iteration loop.  The epoch is a function of the iteration counter
+// (two barriers per iteration: 2*iter + 1 after the walk, 2*iter + 2 before the deposits are merged), the words restart at
+// 0 with every exchange of the slabs (wr_acs_peer_export) — so the barrier needs no state of its own and lives INSIDE the
+// kernel that consumes what it protects: every CTA of that kernel signals (idempotent) and waits before it touches peer
+// data.  A peer that never arrives (its process died) would spin forever: after `timeout_ns` the CTA gives up, sets *err
+// and the host reports it at the next synchronisation.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct PeerBarrier {
+    uint32_t* const* flags_tab;   // [rank] -> that rank's epoch words
+    int me, nranks;
+    uint32_t* err;
+    unsigned long long timeout_ns;
+};
+
+// all threads of the CTA call it; `which` = 1 or 2 (the barrier of this iteration)
+__device__ __forceinline__ void peer_barrier(const PeerBarrier& b, const IterState* st, uint32_t which)
+{
+    const uint32_t e = 2u * (uint32_t)st->iter + which;
+    __threadfence_system();
+    for (int t = threadIdx.x; t < b.nranks; t += blockDim.x) {
+        if (t == b.me) continue;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags_tab[t] + b.me), "r"(e) : "memory");
+        const uint32_t* mine = b.flags_tab[b.me] + t;
+        const unsigned long long t0 = global_timer_ns();
+        while (true) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - e) >= 0) break;
+            if (global_timer_ns() - t0 > b.timeout_ns) { *b.err = 1u; break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void k_begin(IterState* st, float predict)
 {   // computeSolution :229-233
     st->iter = 0;
@@ -597,9 +644,10 @@ __global__ void k_save_result(const IterState* st, const int* __restrict__ best_
 // overwrites its own, so far only evaporated, copy.  bufs[p]: word 0 = count, records (slot, value bits) from word 4.
 // The same pass is the next walk's L2 warm-up (cf. k_path_warm): the slots that just received deposits are where the
 // colony walks next, so the tau lines are left dirty in L2 by the writes and the heuristic rows are touched here.
-__global__ void __launch_bounds__(256) k_pull_finals(float* tau, const float* __restrict__ heur, const uint32_t* const* __restrict__ bufs, int npeers, int me,
-                                                      uint8_t* dirty, uint32_t* upd_q)
+__global__ void __launch_bounds__(256) k_pull_finals(PeerBarrier pb, const IterState* st, float* tau, const float* __restrict__ heur,
+                                                      const uint32_t* const* __restrict__ bufs, int npeers, int me, uint8_t* dirty, uint32_t* upd_q)
 {
+    peer_barrier(pb, st, 2u);   // every rank's list of final values is complete
     uint32_t acc = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {   // tiles that received deposits on ANY rank (the slices are disjoint): the statistic k_iter_begin publishes
         uint32_t tiles = 0;
@@ -620,50 +668,11 @@ __global__ void __launch_bounds__(256) k_pull_finals(float* tau, const float* __
     if (acc == 0x9E3779B9u && npeers < 0) tau[0] = 0.0f;   // keeps the warm-up loads alive; never true
 }
 
-// ------------------------------------------------------------------------------------------
-// Barrier between the ranks of a sharded colony, in peer memory (NVLink): every rank owns an array of epoch words, one
-// per source rank, in its slab.  Rank `me` writes its new epoch into word `me` of every peer's array (system-scope
-// release: everything this rank's earlier kernels wrote — trails, step counts, published row blocks, final values — is
-// visible to whoever acquires the word), then waits until every peer's word in its own array has reached the epoch.
-// No host involvement, no collective library in the iteration loop.  One CTA; thread t talks to rank t.
-// A peer that never arrives (its process died) would spin forever: after `timeout_ns` the kernel gives up, sets *err and
-// the host reports it at the next synchronisation.
-// k_gather_steps (next launch) then copies every rank's step counts into the global colony array the ranking reads.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long global_timer_ns()
+// barrier 1 (every rank's walk is complete), then every rank's step counts -> the global colony array the ranking reads
+__global__ void __launch_bounds__(256) k_gather_steps(PeerBarrier pb, const IterState* st, const int* const* __restrict__ steps_tab, int nranks, int chunk,
+                                                      int* __restrict__ all_steps)
 {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-__global__ void __launch_bounds__(256) k_peer_barrier(uint32_t* const* __restrict__ flags_tab, int me, int nranks, uint32_t* epoch, uint32_t* err,
-                                                      unsigned long long timeout_ns)
-{
-    __shared__ uint32_t s_epoch;
-    const int t = threadIdx.x;
-    if (t == 0) s_epoch = *epoch + 1u;
-    __syncthreads();
-    const uint32_t e = s_epoch;
-    if (t < nranks && t != me) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags_tab[t] + me), "r"(e) : "memory");
-        const uint32_t* mine = flags_tab[me] + t;
-        const unsigned long long t0 = global_timer_ns();
-        while (true) {
-            uint32_t v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-            if ((int)(v - e) >= 0) break;
-            if (global_timer_ns() - t0 > timeout_ns) { *err = 1u; break; }
-            __nanosleep(200);
-        }
-    }
-    __syncthreads();
-    if (t == 0) *epoch = e;
-}
-
-__global__ void __launch_bounds__(256) k_gather_steps(const int* const* __restrict__ steps_tab, int nranks, int chunk, int* __restrict__ all_steps)
-{
+    peer_barrier(pb, st, 1u);
     const int total = nranks * chunk;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int r = i / chunk;

@@ -182,25 +182,27 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_small(IterState* st,
 }
 
 // ---- colonies beyond one CTA (C2 on eight GPUs: 32 768 ants; C3: 65 536) -----------------------------------------------------
-// k_rank_chunks: one CTA per chunk of kRankSmallMax ants sorts its chunk as above (chunks in parallel) -> chunk-sorted
+// k_rank_chunks: one CTA per chunk of kRankChunk ants sorts its chunk as above (chunks in parallel) -> chunk-sorted
 // (key, ant) lists in global memory.  k_rank_merge: an element's final position is its position in its own chunk plus, for
 // every other chunk, the number of elements that precede it there — keys <= its key in chunks of LOWER ant indices (ties go
 // to the lower index), keys < its key in the others: binary searches in L2-resident lists, one thread per element.
 // k_rank_finish_prefix: best decision, eligibility and record offsets; eligible ranks are a prefix of the sorted colony
 // (arrived ants first) no longer than w_max, so one CTA scans min(n, w_max + 1) elements instead of the colony.
+constexpr int kRankChunk = 4096;   // ants per chunk of the chunked path: short sorts, many CTAs in parallel
+constexpr size_t kRankChunkSmem = (size_t)12 * kRankChunk + (size_t)32 * 256 * sizeof(uint32_t);
 __global__ void __launch_bounds__(kRankSmallThreads) k_rank_chunks(const IterState* st, const int* __restrict__ ant_steps, const float* __restrict__ ant_L, int cap,
                                                                     int key_bits, uint32_t* __restrict__ ck, uint32_t* __restrict__ cv)
 {
     extern __shared__ __align__(16) uint32_t rs_smem[];
-    uint32_t* kbuf[2] = {rs_smem, rs_smem + kRankSmallMax};
-    uint16_t* vbase = reinterpret_cast<uint16_t*>(rs_smem + 2 * kRankSmallMax);
-    uint16_t* vbuf[2] = {vbase, vbase + kRankSmallMax};
-    uint32_t* whist = rs_smem + 3 * kRankSmallMax;
+    uint32_t* kbuf[2] = {rs_smem, rs_smem + kRankChunk};
+    uint16_t* vbase = reinterpret_cast<uint16_t*>(rs_smem + 2 * kRankChunk);
+    uint16_t* vbuf[2] = {vbase, vbase + kRankChunk};
+    uint32_t* whist = rs_smem + 3 * kRankChunk;
     __shared__ uint32_t warp_sum[32];
     const int n = st->colony;
-    const int first = blockIdx.x * kRankSmallMax;
+    const int first = blockIdx.x * kRankChunk;
     if (first >= n) return;
-    const int nc = min(kRankSmallMax, n - first);
+    const int nc = min(kRankChunk, n - first);
     const int src = rank_sort_chunk(kbuf, vbuf, whist, warp_sum, ant_steps, ant_L, first, nc, cap, key_bits);
     for (int i = threadIdx.x; i < nc; i += kRankSmallThreads) { ck[first + i] = kbuf[src][i]; cv[first + i] = (uint32_t)first + vbuf[src][i]; }
 }
@@ -212,13 +214,13 @@ __global__ void __launch_bounds__(256) k_rank_merge(const IterState* st, const u
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = ck[i];
-    const int mine = i / kRankSmallMax;
-    const int nchunks = (n + kRankSmallMax - 1) / kRankSmallMax;
-    int pos = i - mine * kRankSmallMax;
+    const int mine = i / kRankChunk;
+    const int nchunks = (n + kRankChunk - 1) / kRankChunk;
+    int pos = i - mine * kRankChunk;
     for (int c = 0; c < nchunks; c++) {
         if (c == mine) continue;
-        const uint32_t* k = ck + (size_t)c * kRankSmallMax;
-        int lo = 0, hi = min(kRankSmallMax, n - c * kRankSmallMax);
+        const uint32_t* k = ck + (size_t)c * kRankChunk;
+        int lo = 0, hi = min(kRankChunk, n - c * kRankChunk);
         if (c < mine) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] <= key) lo = mid + 1; else hi = mid; } }   // upper bound
         else { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < key) lo = mid + 1; else hi = mid; } }           // lower bound
         pos += lo;

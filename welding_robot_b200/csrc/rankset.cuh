@@ -22,10 +22,10 @@
 //   k_rankset_publish / k_rankset_merge   sharded colonies: the claimed blocks (key + 32 words) are copied to the peer
 //                     slab, and every rank ORs every peer's blocks into its own table
 //   k_evaporate_tiles (acs_kernels.cuh) tau *= rho over the dirty tiles, :268-272 — the one HBM stream of the update
-//   k_rankset_apply   one launch per group g, ascending: blocks of group g add their ranks' values to tau[slot] in
-//                     ascending rank order — across the launches a slot's chain runs group 0, 1, 2 ... = the reference's
-//                     additions in the reference's order — then the block and its key are wiped for the next iteration
-//                     (the last launch also sweeps the table after an overflow)
+//   k_rankset_apply   per slot, the block of its lowest group leads: it adds the ranks' values of group 0, 1, 2 ... to
+//                     tau[slot] in ascending rank order (the higher groups' blocks are looked up) = the reference's
+//                     additions in the reference's order; then the blocks and keys are wiped for the next iteration
+//                     (in the same kernel for one group, by k_rankset_clear otherwise)
 #pragma once
 #include "acs_kernels.cuh"
 
@@ -140,10 +140,11 @@ __global__ void __launch_bounds__(256) k_rankset_publish(const IterState* st, Ra
 
 // ... and OR every peer's published blocks into the local table (warp per block).  After this kernel the table, the
 // list and the overflow flag are identical on every rank (up to the order of the list, which nothing depends on).
-__global__ void __launch_bounds__(256) k_rankset_merge(const IterState* st, RankSet rs, const uint32_t* const* __restrict__ pubs, int npeers, int me)
+__global__ void __launch_bounds__(256) k_rankset_merge(PeerBarrier pb, const IterState* st, RankSet rs, const uint32_t* const* __restrict__ pubs, int npeers, int me)
 {
     constexpr unsigned FULL = 0xffffffffu;
     if (!st->use_rankset) return;
+    peer_barrier(pb, st, 2u);   // every rank has published its blocks
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     volatile uint32_t* over = rs.count + 3;
@@ -172,13 +173,30 @@ __global__ void __launch_bounds__(256) k_rankset_merge(const IterState* st, Rank
     }
 }
 
-// One launch per group, ascending.  Lane per block; a block with more than 64 ranks is handed to the whole warp: the 32
-// values of a word are fetched by the lanes at once and the dependent FADD chain runs on values exchanged by shuffle (a
-// converged colony puts ~0.2*colony ranks on every slot of the best path).  Absent ranks contribute +0, the identity.
-__global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, float* tau, RankSet rs, float rho, uint8_t* dirty, uint32_t group, int last_group)
+// block of `want` (key with its on-best bit), or 0xFFFFFFFF.  Read-only: nothing is wiped while k_rankset_apply looks up.
+__device__ __forceinline__ uint32_t rankset_find(const RankSet& rs, unsigned long long want, uint32_t h)
+{
+    for (uint32_t probes = 0; probes <= rs.rmask; probes++) {
+        const unsigned long long k = __ldcg(rs.key + h);
+        if (k == want) return h;
+        if (k == 0ull) return 0xFFFFFFFFu;
+        h = (h + 1) & rs.rmask;
+    }
+    return 0xFFFFFFFFu;
+}
+
+// The ordered chains, ONE launch for all rank groups.  A slot's chain must run group 0, 1, 2 ... (ascending ranks), so the
+// block of the slot's LOWEST group is the slot's leader and processes the whole chain, looking the higher groups' blocks up
+// in the table; the other blocks of the slot do nothing.  Lane per leader while the chain is one light block (a wandering
+// colony: ~10^5 slots with a handful of ranks each); a leader with more than 64 ranks in its block or with further groups
+// is handed to the whole warp: the 32 values of a word are fetched by the lanes at once and the dependent FADD chain runs on
+// values exchanged by shuffle (a converged colony puts ~0.2*colony ranks on every slot of the best path).  Absent ranks
+// contribute +0, the identity of the chain.
+// groups_max == 1 (colonies up to 5120 ants): no look-ups happen, so every block is wiped as soon as it is consumed;
+// otherwise k_rankset_clear follows (a wipe during the look-ups would cut other slots' probe chains).
+__global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, float* tau, RankSet rs, float rho, uint8_t* dirty, int groups_max)
 {
     if (!st->use_rankset) return;
-    if (group * (uint32_t)kRsGroupRanks >= (uint32_t)max(st->n_eligible, 1) && !last_group) return;
     const bool overflow = rs.count[3] != 0u;   // the table is incomplete: wipe only, k_deposit_serial applies the deposits
     const float base_new = __fmul_rn(st->base, rho);   // clean-tile field: a slot that still holds the sentinel is worth this after the evaporation
     constexpr unsigned FULL = 0xffffffffu;
@@ -186,29 +204,39 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
     const uint32_t n = min(rs.count[0], rs.limit);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    const float* vt = rs.vtab + 2 * (size_t)group * kRsGroupRanks;
+    const uint32_t groups = ((uint32_t)max(st->n_eligible, 1) + kRsGroupRanks - 1) / kRsGroupRanks;   // groups that can exist this iteration
+    const bool wipe_here = groups_max == 1;
     // Consecutive list entries go to consecutive WARPS (entry = base + lane*nwarps + warp): the first ant to run claims
     // the whole best path in one stretch of the list, and those are exactly the heavy blocks — one per warp, not 32.
-    for (uint32_t base = 0; base < n; base += nwarps * 32u) {   // warp-uniform trips
+    for (uint32_t base = 0; base < n && !(overflow && !wipe_here); base += nwarps * 32u) {   // warp-uniform trips
         const uint32_t e = base + (uint32_t)lane * nwarps + warp;
-        bool has = e < n;
-        uint32_t h = 0, slot = 0, flag = 0;
+        const bool has = e < n;
+        uint32_t h = 0, slot = 0, flag = 0, group = 0;
+        unsigned long long key = 0ull;
         if (has) {
             h = rs.list[e];
-            const unsigned long long k = rs.key[h];
-            slot = (uint32_t)k - 1u;
-            flag = (uint32_t)(k >> 63);
-            has = (((uint32_t)(k >> 32)) & 0x7FFFFFFFu) == group && k != 0ull;
+            key = rs.key[h];
+            slot = (uint32_t)key - 1u;
+            flag = (uint32_t)(key >> 63);
+            group = ((uint32_t)(key >> 32)) & 0x7FFFFFFFu;
         }
         uint32_t* row = rs.rows + (size_t)h * kRsRowWords;
+        bool leader = has && !overflow;
+        bool more = false;   // the slot has blocks of higher groups
+        if (leader && groups > 1) {
+            const unsigned long long kbase = key & ~(0x7FFFFFFFull << 32);   // slot + on-best bit
+            for (uint32_t g = group; g-- > 0 && leader;) leader = rankset_find(rs, kbase | ((unsigned long long)g << 32), rankset_hash(slot, g) >> rs.shift) == 0xFFFFFFFFu;
+            for (uint32_t g = group + 1; g < groups && leader && !more; g++) more = rankset_find(rs, kbase | ((unsigned long long)g << 32), rankset_hash(slot, g) >> rs.shift) != 0xFFFFFFFFu;
+        }
         int pc = 0;
         uint4 q[8];
-        if (has) {
+        if (leader && !more) {
 #pragma unroll
             for (int j = 0; j < 8; j++) { q[j] = reinterpret_cast<const uint4*>(row)[j]; pc += __popc(q[j].x) + __popc(q[j].y) + __popc(q[j].z) + __popc(q[j].w); }
         }
-        const bool heavy = has && pc > 64 && !overflow;
-        if (has && !heavy && !overflow) {
+        const bool heavy = leader && (more || pc > 64);
+        if (leader && !heavy) {
+            const float* vt = rs.vtab + 2 * (size_t)group * kRsGroupRanks;
             float x = tau_or_base(tau[slot], base_new);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -230,39 +258,78 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
         while (hm) {
             const int src = __ffs(hm) - 1;
             hm &= hm - 1;
-            const uint32_t hs = __shfl_sync(FULL, h, src);
             const uint32_t ss = __shfl_sync(FULL, slot, src);
             const uint32_t fs = __shfl_sync(FULL, flag, src);
-            const uint32_t* rrow = rs.rows + (size_t)hs * kRsRowWords;
+            const uint32_t g0 = __shfl_sync(FULL, group, src);
+            uint32_t hs = __shfl_sync(FULL, h, src);
+            const unsigned long long kbase = (unsigned long long)(ss + 1u) | ((unsigned long long)fs << 63);
             float x = tau_or_base(tau[ss], base_new);
-            const uint32_t mine = rrow[lane];   // the row: one coalesced load, lane j holds word j
-            for (int j0 = 0; j0 < kRsRowWords; j0 += 4) {   // four words per round: their value loads are in flight together
-                uint32_t m[4];
-                float v[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    m[j] = __shfl_sync(FULL, mine, j0 + j);
-                    v[j] = ((m[j] >> lane) & 1u) ? vt[2 * ((j0 + j) * 32 + lane) + fs] : 0.0f;
+            for (uint32_t g = g0; g < groups; g++) {   // warp-uniform
+                if (g != g0) {
+                    uint32_t f = 0xFFFFFFFFu;
+                    if (lane == 0) f = rankset_find(rs, kbase | ((unsigned long long)g << 32), rankset_hash(ss, g) >> rs.shift);
+                    hs = __shfl_sync(FULL, f, 0);
+                    if (hs == 0xFFFFFFFFu) continue;
                 }
+                const float* vt = rs.vtab + 2 * (size_t)g * kRsGroupRanks;
+                const uint32_t mine = rs.rows[(size_t)hs * kRsRowWords + lane];   // the row: one coalesced load, lane j holds word j
+                for (int j0 = 0; j0 < kRsRowWords; j0 += 4) {   // four words per round: their value loads are in flight together
+                    uint32_t m[4];
+                    float v[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (m[j] == 0u) continue;   // warp-uniform
+                    for (int j = 0; j < 4; j++) {
+                        m[j] = __shfl_sync(FULL, mine, j0 + j);
+                        v[j] = ((m[j] >> lane) & 1u) ? vt[2 * ((j0 + j) * 32 + lane) + fs] : 0.0f;
+                    }
 #pragma unroll
-                    for (int i = 0; i < 32; i++) x = __fadd_rn(x, __shfl_sync(FULL, v[j], i));
+                    for (int j = 0; j < 4; j++) {
+                        if (m[j] == 0u) continue;   // warp-uniform
+#pragma unroll
+                        for (int i = 0; i < 32; i++) x = __fadd_rn(x, __shfl_sync(FULL, v[j], i));
+                    }
                 }
             }
             if (lane == 0) { tau[ss] = x; dirty[ss / (uint32_t)kUpdTile] = 1; }
         }
         __syncwarp();
-        if (has) {   // leave the table empty for the next iteration; remember the slot for the walk's L2 warm-up
+        if (has && wipe_here) {   // leave the table empty for the next iteration; remember the slot for the walk's L2 warm-up
 #pragma unroll
             for (int j = 0; j < 8; j++) reinterpret_cast<uint4*>(row)[j] = make_uint4(0u, 0u, 0u, 0u);
             rs.key[h] = 0ull;
             rs.touched[e] = slot;
         }
     }
-    if (last_group && blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = n;
-    if (last_group && overflow) {   // blocks claimed beyond the list (their indices were dropped): a sweep of the whole table finds them
+    if (!wipe_here) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = n;
+    if (overflow) {   // blocks claimed beyond the list (their indices were dropped): a sweep of the whole table finds them
+        const size_t R = (size_t)rs.rmask + 1;
+        for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < R; h += (size_t)gridDim.x * blockDim.x) {
+            if (rs.key[h] == 0ull) continue;
+            uint4* r4 = reinterpret_cast<uint4*>(rs.rows + h * kRsRowWords);
+#pragma unroll
+            for (int j = 0; j < 8; j++) r4[j] = make_uint4(0u, 0u, 0u, 0u);
+            rs.key[h] = 0ull;
+        }
+    }
+}
+
+// groups_max > 1: after the chains, every listed block and its key are wiped for the next iteration (and, after an overflow,
+// the blocks that did not make it into the list: a sweep of the whole table finds them)
+__global__ void __launch_bounds__(256) k_rankset_clear(const IterState* st, RankSet rs)
+{
+    if (!st->use_rankset) return;
+    const uint32_t n = min(rs.count[0], rs.limit);
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t e = warp; e < n; e += nwarps) {   // warp per block: one coalesced 128-byte store
+        const uint32_t h = rs.list[e];
+        const unsigned long long k = rs.key[h];
+        rs.rows[(size_t)h * kRsRowWords + lane] = 0u;
+        __syncwarp();
+        if (lane == 0) { rs.touched[e] = (uint32_t)k - 1u; rs.key[h] = 0ull; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = n;
+    if (rs.count[3] != 0u) {
         const size_t R = (size_t)rs.rmask + 1;
         for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < R; h += (size_t)gridDim.x * blockDim.x) {
             if (rs.key[h] == 0ull) continue;
