@@ -53,6 +53,7 @@ def sync():
 
 
 out = {"world": world, "sweep": {}, "trajectory": []}
+out["traj_threshold"] = os.environ.get("WR_TRAJ_ON")
 for thr in (["1000", "2000", "4000", "8000", "16000", "30000"] if len(sys.argv) < 2 else [t for t in sys.argv[1:] if t != "none"]):
     os.environ["WR_RANKSET_ON"] = thr
     for rep in range(2):
@@ -65,7 +66,10 @@ for thr in (["1000", "2000", "4000", "8000", "16000", "30000"] if len(sys.argv) 
         st = a.updateStats()
         del a
     out["sweep"][thr] = {"seconds_150_iterations": dt, "rank_set_iterations": st["rankset_iterations"]}
-del os.environ["WR_RANKSET_ON"]
+if os.environ.get("WR_TRAJ_ON"):
+    os.environ["WR_RANKSET_ON"] = os.environ["WR_TRAJ_ON"]
+else:
+    os.environ.pop("WR_RANKSET_ON", None)
 a, step = make()
 a.setTiming(True)
 prev = a.kernelMs()

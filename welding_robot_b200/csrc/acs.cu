@@ -628,6 +628,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     {
         WR_CUDA_A(cudaFuncSetAttribute(k_rank_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmallSmem));
         WR_CUDA_A(cudaFuncSetAttribute(k_rank_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankChunkSmem));
+        WR_CUDA_A(cudaFuncSetAttribute(k_rank_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * kRankChunk * (int)sizeof(uint16_t)));
         const size_t ws = walk_smem(a);
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
         if (a->K == kK26) WR_CUDA_A(cudaFuncSetAttribute(k_walk26<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
@@ -880,7 +881,9 @@ static int launch_rank(wr_acs* a, const int* d_all_steps)
     } else {                     // chunks of 4096 ants sorted in parallel, merged by rank counting, prefix-only finish
         const int nchunks = (cm + kRankChunk - 1) / kRankChunk;
         k_rank_chunks<<<nchunks, kRankSmallThreads, kRankChunkSmem, s>>>(a->d_state, d_all_steps, d_L, a->cap, a->rank_bits, a->sort_ants.keys_b, a->sort_ants.vals_b);
-        k_rank_merge<<<(cm + 255) / 256, 256, 0, s>>>(a->d_state, a->sort_ants.keys_b, a->sort_ants.vals_b, a->sort_ants.keys_a, a->sort_ants.vals_a, a->d_order);
+        const int stage = std::min(nchunks, 24);
+        k_rank_merge<<<(cm + kRankMergeThreads - 1) / kRankMergeThreads, kRankMergeThreads, (size_t)stage * kRankChunk * sizeof(uint16_t), s>>>(
+            a->d_state, a->sort_ants.keys_b, a->sort_ants.vals_b, a->sort_ants.keys_a, a->sort_ants.vals_a, a->d_order, a->K == kK26 ? 0 : 1);
         k_rank_finish_prefix<<<1, 1024, 0, s>>>(a->d_state, a->sort_ants.keys_a, a->sort_ants.vals_a, a->cap, a->d_Ltab, a->d_rec_off, a->w_max,
                                                 a->K == kK26 ? d_all_steps : nullptr, a->d_best_n, a->d_best_ids, a->d_onbest);
     }

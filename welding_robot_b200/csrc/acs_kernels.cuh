@@ -86,7 +86,7 @@ __device__ __forceinline__ float pow_int(float x, int y)
 // No host involvement, no collective library in the iteration loop.  The epoch is a function of the iteration counter
 // (two barriers per iteration: 2*iter + 1 after the walk, 2*iter + 2 before the deposits are merged), the words restart at
 // 0 with every exchange of the slabs (wr_acs_peer_export) — so the barrier needs no state of its own and lives INSIDE the
-// kernel that consumes what it protects: every CTA of that kernel signals (idempotent) and waits before it touches peer
+// kernel that consumes what it protects: its first CTAs signal (idempotent), every CTA waits before it touches peer
 // data.  A peer that never arrives (its process died) would spin forever: after `timeout_ns` the CTA gives up, sets *err
 // and the host reports it at the next synchronisation.
 // ------------------------------------------------------------------------------------------
@@ -108,10 +108,11 @@ struct PeerBarrier {
 __device__ __forceinline__ void peer_barrier(const PeerBarrier& b, const IterState* st, uint32_t which)
 {
     const uint32_t e = 2u * (uint32_t)st->iter + which;
-    __threadfence_system();
+    const bool signals = blockIdx.x < 4;   // the first CTAs to be dispatched signal (idempotent; four of them so that one is certainly resident early)
+    if (signals) __threadfence_system();
     for (int t = threadIdx.x; t < b.nranks; t += blockDim.x) {
         if (t == b.me) continue;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags_tab[t] + b.me), "r"(e) : "memory");
+        if (signals) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags_tab[t] + b.me), "r"(e) : "memory");
         const uint32_t* mine = b.flags_tab[b.me] + t;
         const unsigned long long t0 = global_timer_ns();
         while (true) {

@@ -207,27 +207,54 @@ __global__ void __launch_bounds__(kRankSmallThreads) k_rank_chunks(const IterSta
     for (int i = threadIdx.x; i < nc; i += kRankSmallThreads) { ck[first + i] = kbuf[src][i]; cv[first + i] = (uint32_t)first + vbuf[src][i]; }
 }
 
-__global__ void __launch_bounds__(256) k_rank_merge(const IterState* st, const uint32_t* __restrict__ ck, const uint32_t* __restrict__ cv,
-                                                     uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals, int* __restrict__ order_of_ant)
+// One CTA per 1024 consecutive elements of one chunk.  The other chunks' keys are staged in shared memory 16 bits wide (a
+// key is a step count <= cap + 1 < 65536, or — K = 26 — compared through global memory), so the 12-step binary searches
+// run at shared-memory latency instead of one L2 round trip per step.
+constexpr int kRankMergeThreads = 1024;
+__global__ void __launch_bounds__(kRankMergeThreads) k_rank_merge(const IterState* st, const uint32_t* __restrict__ ck, const uint32_t* __restrict__ cv,
+                                                                   uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals, int* __restrict__ order_of_ant,
+                                                                   int keys16)
 {
+    extern __shared__ __align__(16) uint16_t mk_smem[];   // [chunks that fit][kRankChunk]
     const int n = st->colony;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t key = ck[i];
-    const int mine = i / kRankChunk;
     const int nchunks = (n + kRankChunk - 1) / kRankChunk;
-    int pos = i - mine * kRankChunk;
-    for (int c = 0; c < nchunks; c++) {
-        if (c == mine) continue;
-        const uint32_t* k = ck + (size_t)c * kRankChunk;
-        int lo = 0, hi = min(kRankChunk, n - c * kRankChunk);
-        if (c < mine) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] <= key) lo = mid + 1; else hi = mid; } }   // upper bound
-        else { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < key) lo = mid + 1; else hi = mid; } }           // lower bound
-        pos += lo;
+    const int i = blockIdx.x * kRankMergeThreads + threadIdx.x;
+    const int mine = (blockIdx.x * kRankMergeThreads) / kRankChunk;   // CTA-uniform: kRankChunk is a multiple of the CTA size
+    constexpr int kStage = 24;                                         // chunks staged per round (192 KB)
+    uint32_t key = 0, ant = 0;
+    int pos = 0;
+    if (i < n) { key = ck[i]; ant = cv[i]; pos = i - mine * kRankChunk; }
+    for (int c0 = 0; c0 < nchunks; c0 += kStage) {
+        const int c1 = min(c0 + kStage, nchunks);
+        if (keys16) {
+            __syncthreads();
+            for (int j = threadIdx.x; j < (c1 - c0) * kRankChunk; j += kRankMergeThreads) {
+                const int g = c0 * kRankChunk + j;
+                mk_smem[j] = g < n ? (uint16_t)ck[g] : (uint16_t)0xFFFF;
+            }
+            __syncthreads();
+        }
+        if (i < n) {
+            for (int c = c0; c < c1; c++) {
+                if (c == mine) continue;
+                int lo = 0, hi = min(kRankChunk, n - c * kRankChunk);
+                if (keys16) {
+                    const uint16_t* k = mk_smem + (size_t)(c - c0) * kRankChunk;
+                    if (c < mine) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] <= key) lo = mid + 1; else hi = mid; } }   // upper bound
+                    else { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < key) lo = mid + 1; else hi = mid; } }           // lower bound
+                } else {
+                    const uint32_t* k = ck + (size_t)c * kRankChunk;
+                    if (c < mine) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] <= key) lo = mid + 1; else hi = mid; } }
+                    else { while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < key) lo = mid + 1; else hi = mid; } }
+                }
+                pos += lo;
+            }
+        }
     }
-    const uint32_t ant = cv[i];
-    out_keys[pos] = key; out_vals[pos] = ant;
-    order_of_ant[ant] = pos + 1;
+    if (i < n) {
+        out_keys[pos] = key; out_vals[pos] = ant;
+        order_of_ant[ant] = pos + 1;
+    }
 }
 
 __global__ void __launch_bounds__(1024) k_rank_finish_prefix(IterState* st, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int cap,
