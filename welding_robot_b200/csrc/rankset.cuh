@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
 #pragma unroll
             for (int j = 0; j < 8; j++) reinterpret_cast<uint4*>(row)[j] = make_uint4(0u, 0u, 0u, 0u);
             rs.key[h] = 0ull;
-            rs.touched[e] = slot;
+            if (!overflow) rs.touched[e] = slot;   // after an overflow the sweep below races with this loop: a key may already read 0
         }
     }
     if (!wipe_here) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = overflow ? 0u : n;   // no warm-up list after an overflow
     if (overflow) {   // blocks claimed beyond the list (their indices were dropped): a sweep of the whole table finds them
         const size_t R = (size_t)rs.rmask + 1;
         for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < R; h += (size_t)gridDim.x * blockDim.x) {
@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(256) k_rankset_clear(const IterState* st, Rank
 {
     if (!st->use_rankset) return;
     const uint32_t n = min(rs.count[0], rs.limit);
+    const bool overflow = rs.count[3] != 0u;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t e = warp; e < n; e += nwarps) {   // warp per block: one coalesced 128-byte store
@@ -326,10 +327,13 @@ __global__ void __launch_bounds__(256) k_rankset_clear(const IterState* st, Rank
         const unsigned long long k = rs.key[h];
         rs.rows[(size_t)h * kRsRowWords + lane] = 0u;
         __syncwarp();
-        if (lane == 0) { rs.touched[e] = (uint32_t)k - 1u; rs.key[h] = 0ull; }
+        if (lane == 0) {
+            if (!overflow) rs.touched[e] = (uint32_t)k - 1u;   // after an overflow the sweep below races with this loop: k may already read 0
+            rs.key[h] = 0ull;
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = n;
-    if (rs.count[3] != 0u) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = overflow ? 0u : n;   // no warm-up list after an overflow
+    if (overflow) {
         const size_t R = (size_t)rs.rmask + 1;
         for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < R; h += (size_t)gridDim.x * blockDim.x) {
             if (rs.key[h] == 0ull) continue;
