@@ -273,20 +273,18 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
                 }
                 const float* vt = rs.vtab + 2 * (size_t)g * kRsGroupRanks;
                 const uint32_t mine = rs.rows[(size_t)hs * kRsRowWords + lane];   // the row: one coalesced load, lane j holds word j
-                for (int j0 = 0; j0 < kRsRowWords; j0 += 4) {   // four words per round: their value loads are in flight together
-                    uint32_t m[4];
-                    float v[4];
+                // all of the block's values first (32 independent loads per lane, one round trip), then the chain runs on shuffles alone
+                float v[kRsRowWords];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        m[j] = __shfl_sync(FULL, mine, j0 + j);
-                        v[j] = ((m[j] >> lane) & 1u) ? vt[2 * ((j0 + j) * 32 + lane) + fs] : 0.0f;
-                    }
+                for (int w = 0; w < kRsRowWords; w++) {
+                    const uint32_t m = __shfl_sync(FULL, mine, w);
+                    v[w] = ((m >> lane) & 1u) ? vt[2 * (w * 32 + lane) + fs] : 0.0f;
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (m[j] == 0u) continue;   // warp-uniform
+                for (int w = 0; w < kRsRowWords; w++) {
+                    if (__shfl_sync(FULL, mine, w) == 0u) continue;   // warp-uniform
 #pragma unroll
-                        for (int i = 0; i < 32; i++) x = __fadd_rn(x, __shfl_sync(FULL, v[j], i));
-                    }
+                    for (int i = 0; i < 32; i++) x = __fadd_rn(x, __shfl_sync(FULL, v[w], i));
                 }
             }
             if (lane == 0) { tau[ss] = x; dirty[ss / (uint32_t)kUpdTile] = 1; }
