@@ -442,10 +442,10 @@ static int alloc_colony_buffers(wr_acs* a, int colony_max)
             WR_CUDA(cudaMemsetAsync(a->rs.rows, 0, R * kRsRowWords * sizeof(uint32_t), s));
             WR_CUDA(cudaMalloc(&a->rs.list, ((size_t)limit + 1) * sizeof(uint32_t)));
             WR_CUDA(cudaMalloc(&a->rs.touched, ((size_t)limit + 1) * sizeof(uint32_t)));
-            WR_CUDA(cudaMalloc(&a->rs.count, 4 * sizeof(uint32_t)));
+            WR_CUDA(cudaMalloc(&a->rs.count, 8 * sizeof(uint32_t)));
             WR_CUDA(cudaMalloc(&a->rs.vtab, (size_t)2 * (a->w_max + 1) * sizeof(float)));
         }
-        WR_CUDA(cudaMemsetAsync(a->rs.count, 0, 4 * sizeof(uint32_t), s));
+        WR_CUDA(cudaMemsetAsync(a->rs.count, 0, 8 * sizeof(uint32_t), s));
         a->rs_entries = R;
         a->rs.rmask = (uint32_t)(R - 1); a->rs.shift = 32 - log2R; a->rs.limit = limit;
         a->rs_groups = (a->w_max + kRsGroupRanks - 1) / kRsGroupRanks;

@@ -40,7 +40,8 @@ struct RankSet {
     uint32_t* rows;            // [R][32]
     uint32_t* list;            // [limit+1] blocks claimed (or merged in) this iteration
     uint32_t* touched;         // [limit+1] their slots (written by apply, read by the next walk's L2 warm-up)
-    uint32_t* count;           // [0] blocks in `list` [1] entries in `touched` (previous iteration) [2] always 0 [3] overflow flag
+    uint32_t* count;           // [0] blocks in `list` [1] blocks of the previous rank-set iteration (0xFFFFFFFF: it overflowed) [2] always 0
+                               // [3] overflow flag [4] entries in `touched`
     float* vtab;               // [w_max][2]  d(r, s) without / with the elitist term
     uint32_t rmask;            // R - 1
     int shift;                 // 32 - log2(R)
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(256) k_rankset_apply(const IterState* st, floa
         }
     }
     if (!wipe_here) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = overflow ? 0u : n;   // no warm-up list after an overflow
+    if (blockIdx.x == 0 && threadIdx.x == 0) { rs.count[1] = overflow ? 0xFFFFFFFFu : n; rs.count[4] = overflow ? 0u : n; }   // no warm-up list after an overflow
     if (overflow) {   // blocks claimed beyond the list (their indices were dropped): a sweep of the whole table finds them
         const size_t R = (size_t)rs.rmask + 1;
         for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < R; h += (size_t)gridDim.x * blockDim.x) {
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(256) k_rankset_clear(const IterState* st, Rank
             rs.key[h] = 0ull;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) rs.count[1] = overflow ? 0u : n;   // no warm-up list after an overflow
+    if (blockIdx.x == 0 && threadIdx.x == 0) { rs.count[1] = overflow ? 0xFFFFFFFFu : n; rs.count[4] = overflow ? 0u : n; }   // no warm-up list after an overflow
     if (overflow) {
         const size_t R = (size_t)rs.rmask + 1;
         for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < R; h += (size_t)gridDim.x * blockDim.x) {
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(256) k_rankset_warm(const uint32_t* __restrict
                                                        IterState* st)
 {
     if (!st->use_rankset) return;   // runs before k_iter_begin: the flag still describes the iteration that just ended
-    const uint32_t n = count[1];
+    const uint32_t n = count[4];
     uint32_t acc = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t node = touched[i] / 6u;
