@@ -14,6 +14,7 @@
 #include "acs_kernels.cuh"
 #include "walk2.cuh"
 #include "walk26.cuh"
+#include "walk3.cuh"
 #include "rank_small.cuh"
 #include "rankset.cuh"
 #include "batch.cuh"
@@ -477,6 +478,11 @@ static int walk_prefetch()
     static const int env = [] { const char* e = getenv("WR_WALK_PREFETCH"); return e ? atoi(e) : -1; }();   // -1: chosen per iteration (launch_walk)
     return env;
 }
+static int walk_version()
+{
+    static const int env = [] { const char* e = getenv("WR_WALK_V"); return e ? atoi(e) : 3; }();   // pass 1: 3 = k_walk3 (default), 2 = k_walk2
+    return env;
+}
 static int stream_cs()
 {
     static const int env = [] { const char* e = getenv("WR_STREAM_CS"); return e ? atoi(e) : 1; }();   // evict-first streaming of the tiles without deposits (default on)
@@ -638,6 +644,9 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk3<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk3<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk3<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         }
     }
     WR_CUDA_A(cudaStreamSynchronize(a->stream));
@@ -857,7 +866,13 @@ static int launch_walk(wr_acs* a)
     // instructions per step are pure issue cost (converged walk 0.346 -> 0.317 ms without them)
     int pf = walk_prefetch();
     if (pf < 0) pf = (a->rankset && a->rs_choice) ? 0 : 2;
-    launch_walk2<false>(w, alpha1, pf, blocks1, smem1, a->stream);
+    if (walk_version() == 3) {
+        if (!alpha1) k_walk3<false, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+        else if (pf) k_walk3<true, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+        else k_walk3<true, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+    } else {
+        launch_walk2<false>(w, alpha1, pf, blocks1, smem1, a->stream);
+    }
     // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
     w.table_log2 = a->gtable_log2;
     launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, kWalk2Lut + 128, a->stream);
@@ -1512,6 +1527,7 @@ static int preload_iteration_kernels()
     WR_PRELOAD((k_deposit_gen<false, true>)); WR_PRELOAD(k_tile_offsets); WR_PRELOAD(k_update_fused<true>); WR_PRELOAD(k_update_fused<false>);
     WR_PRELOAD(k_pull_finals); WR_PRELOAD(k_iter_begin); WR_PRELOAD(k_iter_end); WR_PRELOAD(k_path_warm); WR_PRELOAD(k_rankset_warm);
     WR_PRELOAD((k_walk2<false, true, 0>)); WR_PRELOAD((k_walk2<false, true, 1>)); WR_PRELOAD((k_walk2<false, true, 2>)); WR_PRELOAD((k_walk2<false, true, 3>));
+    WR_PRELOAD((k_walk3<true, 0>)); WR_PRELOAD((k_walk3<true, 1>)); WR_PRELOAD((k_walk3<false, 0>));
     WR_PRELOAD((k_walk2<false, false, 0>)); WR_PRELOAD((k_walk2<true, true, 0>)); WR_PRELOAD((k_walk2<true, false, 0>));
 #undef WR_PRELOAD
     int rc = sort_preload();
