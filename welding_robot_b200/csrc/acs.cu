@@ -468,6 +468,7 @@ static bool evap_overlap()
     static const bool on = [] { const char* e = getenv("WR_EVAP_OVERLAP"); return !e || atoi(e) != 0; }();
     return on;
 }
+static int preload_iteration_kernels();
 static bool batch_enabled()
 {
     static const bool on = [] { const char* e = getenv("WR_BATCH"); return !e || atoi(e) != 0; }();
@@ -572,6 +573,9 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
                "wr_acs_create: a grid axis exceeds 1024 nodes (k_walk2 packs node coordinates into 10 bits per axis)");
     WR_REQUIRE((unsigned long long)g->N * p->K < 0xFFFFFFFFull - kUpdTile, WR_ERR_INVALID, "wr_acs_create: grid too large for 32-bit slot ids");
     WR_REQUIRE(g->N >= 2, WR_ERR_INVALID, "wr_acs_create: grid too small");
+    // every kernel an iteration can launch is loaded now, once per device: CUDA loads kernels lazily at their first launch, which
+    // would otherwise land in the middle of a search (the rank-set kernels and the graph first run when the colony has converged)
+    { WR_CUDA(cudaSetDevice(g->device)); int rc = preload_iteration_kernels(); if (rc != WR_OK) return rc; }
     wr_acs* a = new wr_acs();
     a->g = g; a->p = *p; a->N = g->N;
     if (p->update_mode == WR_UPDATE_RANKSET) {   // the record path it alternates with (and falls back to) is FUSED
@@ -1517,8 +1521,10 @@ extern "C" int wr_acs_batch_stats(wr_acs* a, uint64_t out[4])
 // signal that this very thread has not enqueued yet.  So everything an iteration can launch is loaded up front.
 static int preload_iteration_kernels()
 {
-    static bool done = false;
-    if (done) return WR_OK;
+    static unsigned long long done = 0;   // one bit per device (modules are loaded per context)
+    int dev = 0;
+    WR_CUDA(cudaGetDevice(&dev));
+    if (done >> (dev & 63) & 1ull) return WR_OK;
     cudaFuncAttributes at;
 #define WR_PRELOAD(f) WR_CUDA(cudaFuncGetAttributes(&at, f))
     WR_PRELOAD(k_gather_steps); WR_PRELOAD(k_rank_small); WR_PRELOAD(k_rank_chunks); WR_PRELOAD(k_rank_merge);
@@ -1532,7 +1538,7 @@ static int preload_iteration_kernels()
 #undef WR_PRELOAD
     int rc = sort_preload();
     if (rc != WR_OK) return rc;
-    done = true;
+    done |= 1ull << (dev & 63);
     return WR_OK;
 }
 
