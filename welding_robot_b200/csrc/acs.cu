@@ -630,7 +630,8 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
     a->h_Ltab.pop_back();
     WR_CUDA_A(dmalloc(&a->d_best_n, sizeof(int), a->stream));
     WR_CUDA_A(cudaMemsetAsync(a->d_best_n, 0, sizeof(int), a->stream));
-    WR_CUDA_A(dmalloc(&a->d_best_ids, ((size_t)a->cap + 2) * sizeof(uint32_t), a->stream));
+    WR_CUDA_A(dmalloc(&a->d_best_ids, ((size_t)a->cap + 16) * sizeof(uint32_t), a->stream));   // k_walk3 reads ids up to 7 positions past the walk: every entry must be a node id
+    WR_CUDA_A(cudaMemsetAsync(a->d_best_ids, 0, ((size_t)a->cap + 16) * sizeof(uint32_t), a->stream));
     WR_CUDA_A(dmalloc(&a->d_best_dirs, (size_t)a->cap + 2, a->stream));
     WR_CUDA_A(dmalloc(&a->d_tile_off, ((size_t)a->ntiles + 2) * sizeof(uint32_t), a->stream));
     WR_CUDA_A(dmalloc(&a->d_dep_list, ((size_t)a->ntiles + 2) * sizeof(uint32_t), a->stream));
@@ -651,6 +652,7 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        WR_CUDA_A(cudaFuncSetAttribute(k_walk3<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         }
     }
     WR_CUDA_A(cudaStreamSynchronize(a->stream));
@@ -850,7 +852,7 @@ static int launch_walk(wr_acs* a)
     w.path_ids = a->d_path_ids; w.path_dirs = a->d_path_dirs;
     w.table_log2 = a->table_log2; w.table_entries = a->table_entries; w.overflow_list = a->d_overflow;
     w.gkeys = a->d_gkeys; w.gmasks = a->d_gmasks; w.gtab = a->d_gmasks; w.gtable_log2 = a->gtable_log2; w.resume = a->d_resume;
-    w.precision = g->precision; w.ant_L = a->d_ant_L;
+    w.precision = g->precision; w.ant_L = a->d_ant_L; w.best_ids = a->d_best_ids;
     if (a->K == kK26) {
         const size_t smem = walk_smem(a);
         const int per_sm = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 16));
@@ -871,7 +873,8 @@ static int launch_walk(wr_acs* a)
     int pf = walk_prefetch();
     if (pf < 0) pf = (a->rankset && a->rs_choice) ? 0 : 2;
     if (walk_version() == 3) {
-        if (!alpha1) k_walk3<false, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+        if (!alpha1 && pf) k_walk3<false, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+        else if (!alpha1) k_walk3<false, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
         else if (pf) k_walk3<true, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
         else k_walk3<true, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
     } else {
@@ -1533,7 +1536,7 @@ static int preload_iteration_kernels()
     WR_PRELOAD((k_deposit_gen<false, true>)); WR_PRELOAD(k_tile_offsets); WR_PRELOAD(k_update_fused<true>); WR_PRELOAD(k_update_fused<false>);
     WR_PRELOAD(k_pull_finals); WR_PRELOAD(k_iter_begin); WR_PRELOAD(k_iter_end); WR_PRELOAD(k_path_warm); WR_PRELOAD(k_rankset_warm);
     WR_PRELOAD((k_walk2<false, true, 0>)); WR_PRELOAD((k_walk2<false, true, 1>)); WR_PRELOAD((k_walk2<false, true, 2>)); WR_PRELOAD((k_walk2<false, true, 3>));
-    WR_PRELOAD((k_walk3<true, 0>)); WR_PRELOAD((k_walk3<true, 1>)); WR_PRELOAD((k_walk3<false, 0>));
+    WR_PRELOAD((k_walk3<true, 0>)); WR_PRELOAD((k_walk3<true, 1>)); WR_PRELOAD((k_walk3<false, 0>)); WR_PRELOAD((k_walk3<false, 1>));
     WR_PRELOAD((k_walk2<false, false, 0>)); WR_PRELOAD((k_walk2<true, true, 0>)); WR_PRELOAD((k_walk2<true, false, 0>));
 #undef WR_PRELOAD
     int rc = sort_preload();

@@ -65,6 +65,7 @@ struct WalkArgs {
     int4* resume;            // [chunk] state of an overflowed ant: {cur, steps, ntiles, bits of L (K = 26)}
     float precision;         // K = 26 (walk26.cuh): step lengths precision, precision*1.414f, precision*1.732f
     float* ant_L;            // K = 26: [chunk] length of the finished ant, +inf if it died (for K = 6 L is a function of steps)
+    const uint32_t* best_ids;   // k_walk3: nodes of the best path so far, [cap + 16], every entry a valid node id (gather prediction)
 };
 
 __device__ __forceinline__ float pow_int(float x, int y)

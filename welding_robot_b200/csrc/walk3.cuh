@@ -16,6 +16,14 @@
 //     move table answers); the tile count lives in a register fed by one vote — no winner branch, no shared-memory counter,
 //     no flag word to poll;
 //   * outcome bookkeeping (arrived / died why / capped) is reconstructed after the loop from (cur, steps, last candidate mask).
+//   * PREFETCH = 0 (the colony has converged: chosen by the same device feedback that selects the rank-set deposits): the
+//     gathers are PREDICTED.  The ncu capture of the first k_walk3 showed 46 % of the stall samples on the four instructions
+//     that wait for tau[cur] / heur[cur]: the ~28 ants of an SM advance in lockstep along the same path, whose rows (735 x 2
+//     lines of 128 B) do not fit L1, so every step somebody pays an L2 round trip.  But where a converged ant will stand at
+//     step t is known: node t of the best path so far.  Every trip loads the next four best-path node ids (one broadcast
+//     LDG.128) and this lane's tau / heur values of those nodes, a whole trip before they are needed; after a move the lane
+//     compares the node it reached with the predicted one and takes the values from registers, or — a deviating ant —
+//     issues the ordinary loads.  The values come from the same addresses either way, so every ant is bit-identical.
 // Ants whose table fills up are parked exactly like k_walk2's and resumed by k_walk2<GLOBAL = true> (pass 2, unchanged).
 #pragma once
 #include "walk2.cuh"
@@ -142,8 +150,21 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk3(WalkArgs a)
         float tau_v = __ldg(tau_k + (size_t)cur * 6);
         float heur_v = __ldg(heur_k + (size_t)cur * 6);
 
-        // one step at index T + J with the draw u; SLICE = which part of the next Philox block runs beside it
-        auto step = [&](const uint32_t J, const float u) {
+        // predicted rows (PREDICT): best-path positions T+1..T+3 (c*) and T+4..T+7 (n*), this lane's slot of each
+        constexpr bool PREDICT = PREFETCH == 0;
+        uint32_t c1 = 0, c2 = 0, c3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        float ct1 = 0.f, ct2 = 0.f, ct3 = 0.f, ch1 = 0.f, ch2 = 0.f, ch3 = 0.f;
+        float nt0 = 0.f, nt1 = 0.f, nt2 = 0.f, nt3 = 0.f, nh0 = 0.f, nh1 = 0.f, nh2 = 0.f, nh3 = 0.f;
+        if (PREDICT) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.best_ids));
+            c1 = q.y; c2 = q.z; c3 = q.w;
+            ct1 = __ldg(tau_k + (size_t)c1 * 6); ch1 = __ldg(heur_k + (size_t)c1 * 6);
+            ct2 = __ldg(tau_k + (size_t)c2 * 6); ch2 = __ldg(heur_k + (size_t)c2 * 6);
+            ct3 = __ldg(tau_k + (size_t)c3 * 6); ch3 = __ldg(heur_k + (size_t)c3 * 6);
+        }
+
+        // one step at index T + J with the draw u; (pn, pt, ph) = predicted next node and this lane's values of its row
+        auto step = [&](const uint32_t J, const float u, const uint32_t pn, const float pt_v, const float ph_v) {
             if (PREFETCH) {
                 long long nb = (long long)cur + stride_k;
                 nb = nb < 0 ? 0 : (nb > last_node ? last_node : nb);
@@ -191,8 +212,16 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk3(WalkArgs a)
             const uint32_t prev = (uint32_t)cur;
             cur += mv.x;
             P += (uint32_t)mv.y;
-            tau_v = __ldg(tau_k + (size_t)cur * 6);
-            heur_v = __ldg(heur_k + (size_t)cur * 6);
+            if (PREDICT) {
+                tau_v = pt_v; heur_v = ph_v;
+                if ((uint32_t)cur != pn) {   // off the best path (or a finished ant idling): the ordinary gathers
+                    tau_v = __ldg(tau_k + (size_t)cur * 6);
+                    heur_v = __ldg(heur_k + (size_t)cur * 6);
+                }
+            } else {
+                tau_v = __ldg(tau_k + (size_t)cur * 6);
+                heur_v = __ldg(heur_k + (size_t)cur * 6);
+            }
             // ---- side effects, all predicated -------------------------------------------------------------------------
             const bool stepok = pb != 0u;                      // implies live (a candidate needs a live ant)
             const bool win = pick && (pb >> k) == 1u;          // this lane's pick is the highest one
@@ -211,10 +240,21 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk3(WalkArgs a)
 
         while (__any_sync(FULL, live)) {
             pc0 = iter; pc1 = ant_global; pc2 = ((T >> 2) + 1u) | a.block_hi; pc3 = a.stream_word;
-            step(0u, u0); rounds(IC<0>{}, IC<3>{});
-            step(1u, u1); rounds(IC<3>{}, IC<6>{});
-            step(2u, u2); rounds(IC<6>{}, IC<9>{});
-            step(3u, u3); rounds(IC<9>{}, IC<10>{});
+            if (PREDICT) {   // ids of best-path positions T+4..T+7 (the same 16 bytes for every lane); consumed after step 0
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.best_ids + T + 4u));
+                n0 = q.x; n1 = q.y; n2 = q.z; n3 = q.w;
+            }
+            step(0u, u0, c1, ct1, ch1); rounds(IC<0>{}, IC<3>{});
+            if (PREDICT) {   // their rows: first needed by the last step of this trip
+                nt0 = __ldg(tau_k + (size_t)n0 * 6); nh0 = __ldg(heur_k + (size_t)n0 * 6);
+                nt1 = __ldg(tau_k + (size_t)n1 * 6); nh1 = __ldg(heur_k + (size_t)n1 * 6);
+                nt2 = __ldg(tau_k + (size_t)n2 * 6); nh2 = __ldg(heur_k + (size_t)n2 * 6);
+                nt3 = __ldg(tau_k + (size_t)n3 * 6); nh3 = __ldg(heur_k + (size_t)n3 * 6);
+            }
+            step(1u, u1, c2, ct2, ch2); rounds(IC<3>{}, IC<6>{});
+            step(2u, u2, c3, ct3, ch3); rounds(IC<6>{}, IC<9>{});
+            step(3u, u3, n0, nt0, nh0); rounds(IC<9>{}, IC<10>{});
+            if (PREDICT) { c1 = n1; c2 = n2; c3 = n3; ct1 = nt1; ct2 = nt2; ct3 = nt3; ch1 = nh1; ch2 = nh2; ch3 = nh3; }
             u0 = __fmul_rn(__int2float_rn((int)(pc0 >> 1)), 4.656612873077392578125e-10f);
             u1 = __fmul_rn(__int2float_rn((int)(pc1 >> 1)), 4.656612873077392578125e-10f);
             u2 = __fmul_rn(__int2float_rn((int)(pc2 >> 1)), 4.656612873077392578125e-10f);
