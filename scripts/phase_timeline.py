@@ -22,7 +22,7 @@ with contextlib.redirect_stdout(io.StringIO()):
 acs.setEndpoints(wl["start"], wl["goal"]); acs.begin(1.0)
 acs.setTiming(True)
 done, prev, prec = 0, None, 0
-for target in (1, 2, 3, 5, 10, 15, 20, 25, 30, 35, 40, 50, 60, 80, 120):
+for target in (1, 2, 3, 5, 10, 15, 20, 25, 30, 35, 40, 45, 50, 60, 80, 120):
     acs.iterate(target - done)
     ms = acs.kernelMs(); c = acs.counters()
     d = {k: (ms[k] - (prev[k] if prev else 0.0)) / (target - done) for k in ms}
