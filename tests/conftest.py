@@ -9,6 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# tests/test_gpu_shards_local.py runs several shards of one colony in ONE process: a shard's barrier kernel waits for kernels of the
+# other shards' streams, so those streams must not share a hardware work queue (default: 8 queues; the suite creates more streams than
+# that before it gets there).  Must be set before the CUDA context exists.  One process per GPU — the product layout — is not affected.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def pytest_configure(config):

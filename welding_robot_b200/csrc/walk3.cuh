@@ -46,7 +46,7 @@ __device__ __forceinline__ void philox_rounds(uint32_t& c0, uint32_t& c1, uint32
 }
 
 template <bool ALPHA1, int PREFETCH>
-__global__ void __launch_bounds__(kWalkThreads) k_walk3(WalkArgs a)
+__global__ void __launch_bounds__(kWalkThreads, 2) k_walk3(WalkArgs a)   // two CTAs per SM (shared memory); no register squeeze
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [0, 1024): move table indexed by the 6-bit pick ballot (see k_walk2); [1024, 1152): unused here; [1152, ...): tables [16][E]
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk3(WalkArgs a)
         if (k == 0) {   // addStartNode :81-86
             const uint32_t key = Pstart & kKeyMask;
             const uint32_t bit = (((Pstart & kPackLow) * kPackMul) >> 20) & 31u;
-            tab.store(tile_hash(key, (uint32_t)E), ((unsigned long long)key << 32) | (unsigned long long)(1u << bit));
+            tab.store(tile_hash(key, (uint32_t)E - 3u), ((unsigned long long)key << 32) | (unsigned long long)(1u << bit));
         }
         __syncwarp();
 
@@ -178,14 +178,42 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk3(WalkArgs a)
             const uint32_t key = Pk & kKeyMask;
             const uint32_t bitm = 1u << ((((Pk & kPackLow) * kPackMul) >> 20) & 31u);
             const bool open_k = heur_v != kClosedSlot;
-            unsigned slot = tile_hash(key, (uint32_t)E);
-            unsigned long long e = tab.load(slot);
-            while (open_k && (uint32_t)(e >> 32) != key && (uint32_t)(e >> 32) != 0u) {   // collisions are rare at load <= 3/4
-                slot = slot + 1 < (unsigned)E ? slot + 1 : 0u;
-                e = tab.load(slot);
+            // scans start in [0, E-4]: the first four entries of a scan need no wrap-around
+            unsigned slot = tile_hash(key, (uint32_t)E - 3u);
+            bool found;
+            uint32_t emask;
+            if (PREFETCH & 1) {
+                // wandering colony: tables are half full and a step's lookups are mostly of tiles that are NOT there (scan to the first
+                // empty entry), so the probe loop ran ~3 extra trips per warp-step (the longest of 24 scans), each a dependent
+                // LDS + branch.  Here the first four entries of the scan are fetched at once and resolved with selects.
+                unsigned long long e0, e1, e2, e3;
+                const uint32_t sa = tab.sa + slot * 8u;
+                asm volatile("ld.shared.b64 %0, [%4];\n\tld.shared.b64 %1, [%4+8];\n\tld.shared.b64 %2, [%4+16];\n\tld.shared.b64 %3, [%4+24];"
+                             : "=l"(e0), "=l"(e1), "=l"(e2), "=l"(e3) : "r"(sa) : "memory");
+                const uint32_t k0 = (uint32_t)(e0 >> 32), k1 = (uint32_t)(e1 >> 32), k2 = (uint32_t)(e2 >> 32), k3 = (uint32_t)(e3 >> 32);
+                const bool h0 = k0 == key, h1 = k1 == key, h2 = k2 == key, h3 = k3 == key;   // an entry is never behind an empty one of its own scan
+                const bool s0 = h0 || k0 == 0u, s1 = h1 || k1 == 0u, s2 = h2 || k2 == 0u, s3 = h3 || k3 == 0u;
+                found = h0 || h1 || h2 || h3;
+                emask = (h0 ? (uint32_t)e0 : 0u) | (h1 ? (uint32_t)e1 : 0u) | (h2 ? (uint32_t)e2 : 0u) | (h3 ? (uint32_t)e3 : 0u);
+                slot += s0 ? 0u : (s1 ? 1u : (s2 ? 2u : 3u));
+                if (open_k && !(s0 || s1 || s2 || s3)) {   // rare: keep scanning
+                    unsigned long long e;
+                    do {
+                        slot = slot + 1 < (unsigned)E ? slot + 1 : 0u;
+                        e = tab.load(slot);
+                    } while ((uint32_t)(e >> 32) != key && (uint32_t)(e >> 32) != 0u);
+                    found = (uint32_t)(e >> 32) == key;
+                    emask = found ? (uint32_t)e : 0u;
+                }
+            } else {
+                unsigned long long e = tab.load(slot);
+                while (open_k && (uint32_t)(e >> 32) != key && (uint32_t)(e >> 32) != 0u) {   // collisions are rare once the colony has converged
+                    slot = slot + 1 < (unsigned)E ? slot + 1 : 0u;
+                    e = tab.load(slot);
+                }
+                found = (uint32_t)(e >> 32) == key;
+                emask = found ? (uint32_t)e : 0u;
             }
-            const bool found = (uint32_t)(e >> 32) == key;
-            const uint32_t emask = found ? (uint32_t)e : 0u;
             const bool cand = live && open_k && !(emask & bitm);
             // ---- info = tau^alpha * (1 + beta*cos)  (:151-154) ------------------------------------------------------
             const float tau_now = tau_or_base(tau_v, base_now);
