@@ -653,7 +653,6 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
-        WR_CUDA_A(cudaFuncSetAttribute(k_walk3<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         }
     }
     WR_CUDA_A(cudaStreamSynchronize(a->stream));
@@ -874,8 +873,7 @@ static int launch_walk(wr_acs* a)
     int pf = walk_prefetch();
     if (pf < 0) pf = (a->rankset && a->rs_choice) ? 0 : 2;
     if (walk_version() == 3) {
-        if (alpha1 && pf == 3) k_walk3<true, 3><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-        else if (!alpha1 && pf) k_walk3<false, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+        if (!alpha1 && pf) k_walk3<false, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
         else if (!alpha1) k_walk3<false, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
         else if (pf) k_walk3<true, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
         else k_walk3<true, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
@@ -1538,7 +1536,7 @@ static int preload_iteration_kernels()
     WR_PRELOAD((k_deposit_gen<false, true>)); WR_PRELOAD(k_tile_offsets); WR_PRELOAD(k_update_fused<true>); WR_PRELOAD(k_update_fused<false>);
     WR_PRELOAD(k_pull_finals); WR_PRELOAD(k_iter_begin); WR_PRELOAD(k_iter_end); WR_PRELOAD(k_path_warm); WR_PRELOAD(k_rankset_warm);
     WR_PRELOAD((k_walk2<false, true, 0>)); WR_PRELOAD((k_walk2<false, true, 1>)); WR_PRELOAD((k_walk2<false, true, 2>)); WR_PRELOAD((k_walk2<false, true, 3>));
-    WR_PRELOAD((k_walk3<true, 0>)); WR_PRELOAD((k_walk3<true, 1>)); WR_PRELOAD((k_walk3<false, 0>)); WR_PRELOAD((k_walk3<false, 1>)); WR_PRELOAD((k_walk3<true, 3>));
+    WR_PRELOAD((k_walk3<true, 0>)); WR_PRELOAD((k_walk3<true, 1>)); WR_PRELOAD((k_walk3<false, 0>)); WR_PRELOAD((k_walk3<false, 1>));
     WR_PRELOAD((k_walk2<false, false, 0>)); WR_PRELOAD((k_walk2<true, true, 0>)); WR_PRELOAD((k_walk2<true, false, 0>));
 #undef WR_PRELOAD
     int rc = sort_preload();

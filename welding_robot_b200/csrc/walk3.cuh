@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) k_walk3(WalkArgs a)   // two 
         float heur_v = __ldg(heur_k + (size_t)cur * 6);
 
         // predicted rows (PREDICT): best-path positions T+1..T+3 (c*) and T+4..T+7 (n*), this lane's slot of each
-        constexpr bool PREDICT = PREFETCH != 1;   // 0: predicted gathers, 1: neighbour rows prefetched into L1, 3: both
+        constexpr bool PREDICT = PREFETCH == 0;   // 0: converged colony, predicted gathers; 1: wandering colony, neighbour rows prefetched
         uint32_t c1 = 0, c2 = 0, c3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
         float ct1 = 0.f, ct2 = 0.f, ct3 = 0.f, ch1 = 0.f, ch2 = 0.f, ch3 = 0.f;
         float nt0 = 0.f, nt1 = 0.f, nt2 = 0.f, nt3 = 0.f, nh0 = 0.f, nh1 = 0.f, nh2 = 0.f, nh3 = 0.f;
@@ -166,6 +166,10 @@ __global__ void __launch_bounds__(kWalkThreads, 2) k_walk3(WalkArgs a)   // two 
         // one step at index T + J with the draw u; (pn, pt, ph) = predicted next node and this lane's values of its row
         auto step = [&](const uint32_t J, const float u, const uint32_t pn, const float pt_v, const float ph_v) {
             if (PREFETCH & 1) {
+                // Measured and rejected instead of this prefetch: (a) prediction AND prefetch together (slower than either alone in
+                // its regime); (b) staging the six neighbours' rows in shared memory with cp.async and letting only the winning lane
+                // wait for its own copies — the wait (DEPBAR on the warp's scoreboard) is per WARP, so every step waited for the
+                // slowest of 144 copies: iteration 1 1.64 -> 1.94 ms.
                 long long nb = (long long)cur + stride_k;
                 nb = nb < 0 ? 0 : (nb > last_node ? last_node : nb);
                 const float* pt = a.tau + nb * 6;
