@@ -484,6 +484,11 @@ static int walk_version()
     static const int env = [] { const char* e = getenv("WR_WALK_V"); return e ? atoi(e) : 3; }();   // pass 1: 3 = k_walk3 (default), 2 = k_walk2
     return env;
 }
+static int batch_minb()
+{
+    static const int env = [] { const char* e = getenv("WR_BATCH_MINB"); XX
+    return env;
+}
 static int stream_cs()
 {
     static const int env = [] { const char* e = getenv("WR_STREAM_CS"); return e ? atoi(e) : 1; }();   // evict-first streaming of the tiles without deposits (default on)
@@ -1447,6 +1452,10 @@ extern "C" int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const in
     const size_t rank_smem = (size_t)12 * maxn + 32 * 256 * sizeof(uint32_t);
     WR_CUDA(cudaFuncSetAttribute(k_walk_batch<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     WR_CUDA(cudaFuncSetAttribute(k_walk_batch<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     WR_CUDA(cudaFuncSetAttribute(k_batch_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
     const int per_sm = std::max(1, std::min(16, (int)((227 * 1024) / (smem1 + 1024))));
     BatchArgs w;
@@ -1473,10 +1482,14 @@ extern "C" int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const in
         for (int it = 0; it < n_iterations; it++) {
             k_batch_iter_begin<<<(n + 255) / 256, 256, 0, s>>>(a->d_state, b->qs, n, a->p.fixed_colony, cm, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->p.rho);
             if (alpha1) {
-                k_walk_batch<false, true><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                if (walk_version() == 3 && batch_minb() == 6) k_walk_batch3<true, 6><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                else if (walk_version() == 3 && batch_minb() == 5) k_walk_batch3<true, 5><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                else if (walk_version() == 3) k_walk_batch3<true, 4><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                else k_walk_batch<false, true><<<blocks1, kWalkThreads, smem1, s>>>(w);
                 k_walk_batch<true, true><<<blocks2, kWalkThreads, kWalk2Lut + 128, s>>>(w);
             } else {
-                k_walk_batch<false, false><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                if (walk_version() == 3) k_walk_batch3<false, 4><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                else k_walk_batch<false, false><<<blocks1, kWalkThreads, smem1, s>>>(w);
                 k_walk_batch<true, false><<<blocks2, kWalkThreads, kWalk2Lut + 128, s>>>(w);
             }
             k_batch_rank<<<n, kRankSmallThreads, rank_smem, s>>>(a->d_state, b->qs, b->tab, b->steps, cm, maxn, a->cap, a->rank_bits, a->d_Ltab, b->ranked_keys, b->ranked_vals,

@@ -24,6 +24,7 @@
 #pragma once
 #include "rank_small.cuh"
 #include "walk2.cuh"
+#include "walk3.cuh"
 
 namespace wr {
 
@@ -438,6 +439,293 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
                 c_nocand += (result < 0 && reason == 1) ? 1 : 0;
                 c_fall += (result < 0 && reason == 2) ? 1 : 0;
                 c_cap += (result < 0 && reason == 3) ? 1 : 0;
+                c_steps += (unsigned long long)steps; c_ants++;
+            }
+            if (k == 0) a.ant_steps[(size_t)qi * a.colony_max + ant] = result;
+        }
+        __syncwarp();
+    }
+    if (k == 0) {
+        if (c_steps) atomicAdd(&st->cnt[0], c_steps);
+        if (c_ants) atomicAdd(&st->cnt[1], c_ants);
+        if (c_arrived) atomicAdd(&st->cnt[2], c_arrived);
+        if (c_nocand) atomicAdd(&st->cnt[3], c_nocand);
+        if (c_fall) atomicAdd(&st->cnt[4], c_fall);
+        if (c_cap) atomicAdd(&st->cnt[5], c_cap);
+        if (c_over) atomicAdd(&st->cnt[8], c_over);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass 1 of K2 over a batch, restructured like k_walk3 (walk3.cuh): the four ants of a warp are at the same step index, so
+// four steps per trip with the draw chosen at compile time, Philox for the next four steps computed in slices beside them, the
+// trail kept in registers and written eight steps at a time, the visited insert a predicated store by the lane whose pick is
+// the highest, the tile count fed by one vote, outcomes reconstructed after the loop.  The step's arithmetic — pheromone entry
+// or scalar, geometric factor, roulette — is k_walk_batch's, so every ant is bit-identical; pass 2 (parked ants) stays
+// k_walk_batch<GLOBAL = true>.  This kernel is issue-bound once a few hundred queries are in flight (60 % of the issue
+// slots), so the shorter instruction stream is throughput.
+// ------------------------------------------------------------------------------------------
+template <bool ALPHA1, int MINB>   // MINB: CTAs per SM the register allocation is bounded for (6 = all that the 34 KB tables allow: at most 80 registers)
+__global__ void __launch_bounds__(kWalkThreads, MINB) k_walk_batch3(BatchArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int4* move_lut = reinterpret_cast<int4*>(smem_raw);
+    unsigned long long* tab_s = reinterpret_cast<unsigned long long*>(smem_raw + kWalk2Lut + 128);
+    if (threadIdx.x < 64) {
+        const int pbv = threadIdx.x;
+        const int c = pbv ? 31 - __clz(pbv) : 0;
+        const int dx = (c == 3) - (c == 2), dy = (c == 4) - (c == 1), dz = (c == 5) - (c == 0);
+        move_lut[pbv] = pbv ? make_int4(dx + dy * a.rx + dz * a.rx * a.ry, dx + dy * 1024 + dz * 1048576, c, 0) : make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane & 24;
+    const int k = lane & 7;
+    const int g = threadIdx.x >> 3;
+    const int E = a.table_entries;
+    uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(move_lut);
+    TabRef<false> tab;
+    tab.gp = nullptr;
+    tab.sa = (uint32_t)__cvta_generic_to_shared(tab_s + (size_t)g * E);
+    uint32_t gmask = 0xFFu << gbase;
+    uint32_t lut_rot = (uint32_t)(gbase - 4) & 31u;
+    asm volatile("" : "+r"(lut_sa), "+r"(tab.sa), "+r"(gmask), "+r"(lut_rot));
+
+    const int rx = a.rx, rxy = a.rx * a.ry;
+    const int dxk = (k == 3) - (k == 2), dyk = (k == 4) - (k == 1), dzk = (k == 5) - (k == 0);
+    const uint32_t dPk = (uint32_t)(dxk + dyk * 1024 + dzk * 1048576);
+    const int kk6 = k < 6 ? k : 5;
+    const int axis_k = (k == 2 || k == 3) ? 0 : ((k == 1 || k == 4) ? 1 : 2);
+    const int dk = dxk + dyk + dzk;
+    const float* xs = a.coords;
+    const float* ys = xs + a.rx;
+    const float* zs = ys + a.ry;
+    const float* axis_tab = axis_k == 0 ? xs : (axis_k == 1 ? ys : zs);
+    const int axis_len = axis_k == 0 ? a.rx : (axis_k == 1 ? a.ry : a.rz);
+    uint32_t m4 = k <= 4 ? ~0u : 0u, m3 = k <= 3 ? ~0u : 0u, m2 = k <= 2 ? ~0u : 0u, m1 = k <= 1 ? ~0u : 0u, m0 = k <= 0 ? ~0u : 0u;
+    asm volatile("" : "+r"(m4), "+r"(m3), "+r"(m2), "+r"(m1), "+r"(m0));
+    constexpr uint32_t kKeyMask = kPackKey | kKeyTag;
+
+    IterState* st = a.st;
+    const uint32_t iter = (uint32_t)st->iter;
+    const float base_now = st->base;
+    const float beta = a.beta;
+    const unsigned n_items = (unsigned)(a.nq * a.items_per_query);
+    const uint32_t limit = (uint32_t)((E >> 2) * 3);
+    const int cap = a.cap;
+    int cap_k = k < 6 ? cap : 0;   // the two idle lanes of a group are never alive
+    asm volatile("" : "+r"(cap_k));
+    const uint32_t* ent = a.tab.ent;
+
+    unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
+
+    while (true) {
+        unsigned q0 = 0;
+        if (lane == 0) q0 = atomicAdd(&st->queue, 1u);
+        q0 = __shfl_sync(FULL, q0, 0);
+        if (q0 >= n_items) break;                                    // warp-uniform
+        const uint32_t qi = q0 / (unsigned)a.items_per_query;        // work item = (query, group of four ants)
+        const int ant = (int)(q0 - qi * (unsigned)a.items_per_query) * 4 + (lane >> 3);
+        const BatchQuery& bq = a.qs[qi];
+        const bool has = ant < bq.colony;
+        const int start = bq.start, goal = bq.goal;
+        const uint32_t stream_word = bq.stream_word, block_hi = bq.block_hi;
+        const uint32_t qhash = qi * 0x85EBCA6Bu + (qi << 13);
+        const float gxv = __ldg(xs + goal % rx), gyv = __ldg(ys + (goal % rxy) / rx), gzv = __ldg(zs + goal / rxy);
+
+        const uint32_t Pstart = pack_xyz(start % rx, (start % rxy) / rx, start / rxy) | kKeyTag;   // bit 31: the key tag rides along
+        for (int i = k; i < E; i += kGroup) tab.store(i, 0ull);
+        __syncwarp();
+        if (k == 0) {   // addStartNode :81-86
+            const uint32_t key = Pstart & kKeyMask;
+            const uint32_t bit = (((Pstart & kPackLow) * kPackMul) >> 20) & 31u;
+            tab.store(tile_hash(key, (uint32_t)E), ((unsigned long long)key << 32) | (unsigned long long)(1u << bit));
+        }
+        __syncwarp();
+
+        int cur = start, steps = 0;
+        uint32_t P = Pstart;
+        uint32_t ntiles = 1u, lastcb = 1u;
+        bool parked = false;
+        bool live = has && cap_k > 0;
+        uint32_t T = 0, kt = (uint32_t)k;
+        uint32_t rec_id = 0, rec_dir = 0;
+        const size_t ant_row = ((size_t)qi * a.colony_max + (size_t)(has ? ant : 0)) * cap;
+        uint32_t* pid = a.path_ids + ant_row;
+        uint8_t* pdir = a.path_dirs + ant_row;
+
+        float u0, u1, u2, u3;
+        {
+            uint32_t w0, w1, w2, w3;
+            philox4(iter, (uint32_t)ant, block_hi, stream_word, a.seed_lo, a.seed_hi, w0, w1, w2, w3);
+            u0 = __fmul_rn(__int2float_rn((int)(w0 >> 1)), 4.656612873077392578125e-10f);
+            u1 = __fmul_rn(__int2float_rn((int)(w1 >> 1)), 4.656612873077392578125e-10f);
+            u2 = __fmul_rn(__int2float_rn((int)(w2 >> 1)), 4.656612873077392578125e-10f);
+            u3 = __fmul_rn(__int2float_rn((int)(w3 >> 1)), 4.656612873077392578125e-10f);
+        }
+        uint32_t pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0;
+        auto rounds = [&](auto r0, auto r1) { philox_rounds<decltype(r0)::value, decltype(r1)::value>(pc0, pc1, pc2, pc3, a.seed_lo, a.seed_hi); };
+
+        // the loads of a step — pheromone entry (first probe), open mask, coordinates — go out as soon as the node is known
+        uint32_t want0, eh; uint2 ekey; uint32_t etau; uint32_t omask; float cxv, cyv, czv, nbv;
+        auto issue_loads = [&]() {
+            want0 = (uint32_t)cur + 1u;
+            eh = (((uint32_t)cur * 2654435761u) ^ qhash) >> a.tab.shift;
+            const uint32_t* e = ent + (size_t)eh * kBatchEntryWords;
+            ekey = __ldg(reinterpret_cast<const uint2*>(e));
+            etau = __ldg(e + 2 + kk6);
+            omask = (uint32_t)__ldg(a.open6 + cur);
+            const int x = (int)(P & 1023u), y = (int)((P >> 10) & 1023u), z = (int)((P >> 20) & 1023u);
+            cxv = __ldg(xs + x); cyv = __ldg(ys + y); czv = __ldg(zs + z);
+            const int ci = (axis_k == 0 ? x : (axis_k == 1 ? y : z)) + dk;
+            nbv = __ldg(axis_tab + min(max(ci, 0), axis_len - 1));
+        };
+        issue_loads();
+
+        auto step = [&](const uint32_t J, const float u) {
+            // ---- geometric factor of slot k, k_heuristic's expressions -------------------------------------------------
+            const bool open_k = k < 6 && ((omask >> k) & 1u);
+            const float ax = __fsub_rn(gxv, cxv), ay = __fsub_rn(gyv, cyv), az = __fsub_rn(gzv, czv);
+            const float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+            const float cc = axis_k == 0 ? cxv : (axis_k == 1 ? cyv : czv);
+            const float ac = axis_k == 0 ? ax : (axis_k == 1 ? ay : az);
+            const float d = __fsub_rn(nbv, cc);
+            float nb = fabsf(d);
+            if (!(nb >= 1e-18f && nb <= 1e18f) && nb != 0.0f) nb = slow_norm1(d);
+            const float heur_v = __fadd_rn(1.0f, __fmul_rn(beta, __fdiv_rn(__fmul_rn(ac, d), __fmul_rn(na, nb))));
+            // ---- pheromone of slot k: the node's entry, or the scalar if it has none -----------------------------------
+            uint32_t probes = 0;
+            while ((ekey.x != want0 || (ekey.y & 0x7FFFFFFFu) != qi) && (ekey.x | ekey.y) != 0u) {   // rare: linear probing at load <= 1/2
+                if (++probes > a.tab.tmask) { ekey = make_uint2(0u, 0u); break; }
+                eh = (eh + 1) & a.tab.tmask;
+                const uint32_t* e = ent + (size_t)eh * kBatchEntryWords;
+                ekey = __ldg(reinterpret_cast<const uint2*>(e));
+                etau = __ldg(e + 2 + kk6);
+            }
+            const float tau_v = (ekey.x | ekey.y) != 0u ? __uint_as_float(etau) : __uint_as_float(kSentinelBits);
+            // ---- neighbour k: tabu probe -------------------------------------------------------------------------------
+            const uint32_t Pk = P + dPk;
+            const uint32_t key = Pk & kKeyMask;
+            const uint32_t bitm = 1u << ((((Pk & kPackLow) * kPackMul) >> 20) & 31u);
+            unsigned slot = tile_hash(key, (uint32_t)E);
+            unsigned long long e = tab.load(slot);
+            while (open_k && (uint32_t)(e >> 32) != key && (uint32_t)(e >> 32) != 0u) {
+                slot = slot + 1 < (unsigned)E ? slot + 1 : 0u;
+                e = tab.load(slot);
+            }
+            const bool found = (uint32_t)(e >> 32) == key;
+            const uint32_t emask = found ? (uint32_t)e : 0u;
+            const bool cand = live && open_k && !(emask & bitm);
+            const float tau_now = tau_or_base(tau_v, base_now);
+            const float tpow = ALPHA1 ? tau_now : pow_int(tau_now, a.alpha);
+            const float info = cand ? __fmul_rn(tpow, heur_v) : 0.0f;
+            // ---- roulette in the reference's order (:155, :172-181) ---------------------------------------------------
+            const unsigned cb = __ballot_sync(FULL, cand) & gmask;
+            const float v0 = __shfl_sync(FULL, info, 0, 8), v1 = __shfl_sync(FULL, info, 1, 8), v2 = __shfl_sync(FULL, info, 2, 8);
+            const float v3 = __shfl_sync(FULL, info, 3, 8), v4 = __shfl_sync(FULL, info, 4, 8), v5 = __shfl_sync(FULL, info, 5, 8);
+            const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, v0), v1), v2), v3), v4), v5);
+            const float rnd = __fmul_rn(u, total);
+            float mine = __fadd_rn(0.0f, v5);
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v4) & m4));
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v3) & m3));
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v2) & m2));
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v1) & m1));
+            mine = __fadd_rn(mine, __uint_as_float(__float_as_uint(v0) & m0));
+            const bool pick = cand && (mine >= rnd);
+            const unsigned pball = __ballot_sync(FULL, pick);
+            int4 mv;   // a dead or finished ant has no pick and the table's entry 0 moves nowhere
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(mv.x), "=r"(mv.y), "=r"(mv.z), "=r"(mv.w) : "r"(lut_sa + (__funnelshift_r(pball, pball, lut_rot) & 0x3F0u)) : "memory");
+            const unsigned pb = (pball >> gbase) & 0x3Fu;
+            const uint32_t prev = (uint32_t)cur;
+            cur += mv.x;
+            P += (uint32_t)mv.y;
+            issue_loads();
+            // ---- side effects, all predicated --------------------------------------------------------------------------
+            const bool stepok = pb != 0u;
+            const bool win = pick && (pb >> k) == 1u;
+            if (win) tab.store(slot, ((unsigned long long)key << 32) | (unsigned long long)(emask | bitm));
+            if (stepok && kt == J) { rec_id = prev; rec_dir = (uint32_t)mv.z; }
+            const bool full = ntiles > limit;
+            const unsigned nt = __ballot_sync(FULL, win && !found) & gmask;
+            ntiles += nt ? 1u : 0u;
+            lastcb = live ? cb : lastcb;
+            steps = stepok ? (int)(T + J + 1u) : steps;
+            const bool go = stepok && cur != goal;
+            parked = parked || (go && full);
+            live = go && !full && (int)(T + J + 1u) < cap_k;
+            __syncwarp();
+        };
+
+        while (__any_sync(FULL, live)) {
+            pc0 = iter; pc1 = (uint32_t)ant; pc2 = ((T >> 2) + 1u) | block_hi; pc3 = stream_word;
+            step(0u, u0); rounds(IC<0>{}, IC<3>{});
+            step(1u, u1); rounds(IC<3>{}, IC<6>{});
+            step(2u, u2); rounds(IC<6>{}, IC<9>{});
+            step(3u, u3); rounds(IC<9>{}, IC<10>{});
+            u0 = __fmul_rn(__int2float_rn((int)(pc0 >> 1)), 4.656612873077392578125e-10f);
+            u1 = __fmul_rn(__int2float_rn((int)(pc1 >> 1)), 4.656612873077392578125e-10f);
+            u2 = __fmul_rn(__int2float_rn((int)(pc2 >> 1)), 4.656612873077392578125e-10f);
+            u3 = __fmul_rn(__int2float_rn((int)(pc3 >> 1)), 4.656612873077392578125e-10f);
+            if (T & 4u) {
+                const int base8 = (int)T - 4;
+                if (k < steps - base8) { pid[base8 + k] = rec_id; pdir[base8 + k] = (uint8_t)rec_dir; }
+            }
+            T += 4u;
+            kt ^= 4u;
+        }
+        if (T & 4u) {
+            const int base8 = (int)T - 4;
+            if (k < steps - base8) { pid[base8 + k] = rec_id; pdir[base8 + k] = (uint8_t)rec_dir; }
+        }
+        const bool arrived = has && steps > 0 && cur == goal;
+        const int result = arrived ? steps : (parked ? -2 : -1);
+        int reason = 0;
+        if (result == -1) reason = steps >= cap ? 3 : (lastcb == 0u ? 1 : 2);
+
+        {   // park the ants whose shared-memory table filled up (see k_walk_batch); HBM tables come from a pool
+            const bool pk = has && parked && !arrived;
+            const unsigned pm = __ballot_sync(FULL, pk && k == 0);
+            if (pm) {
+                int o = 0;
+                if (pk && k == 0) o = (int)atomicAdd(&st->overflow_n, 1u);
+                o = __shfl_sync(FULL, o, 0, 8);
+                const bool fits = (uint32_t)o < a.pool;
+                if (pk && !fits && k == 0) a.tab.count[1] = 1u;
+                const int Eg = 1 << a.gtable_log2;
+                for (unsigned rest = pm; rest; rest &= rest - 1) {
+                    const int src = __ffs(rest) - 1;
+                    const int oo = __shfl_sync(FULL, o, src);
+                    if ((uint32_t)oo >= a.pool) continue;   // warp-uniform
+                    uint4* z = reinterpret_cast<uint4*>(a.gtab + (size_t)oo * Eg);
+                    for (int i = lane; i < Eg / 2; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                __syncwarp();
+                if (pk && fits) {
+                    unsigned long long* ntab = a.gtab + (size_t)o * Eg;
+                    for (int i = k; i < E; i += kGroup) {
+                        const unsigned long long t = tab.load(i);
+                        if (t == 0ull) continue;
+                        unsigned sl = tile_hash((uint32_t)(t >> 32), (uint32_t)Eg);
+                        while (atomicCAS(&ntab[sl], 0ull, t) != 0ull) sl = (sl + 1) & (Eg - 1);
+                    }
+                    if (k == 0) {
+                        a.resume[o] = make_int4(cur, steps, 0, 0);
+                        a.overflow_list[o] = qi * (uint32_t)a.colony_max + (uint32_t)ant;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (has) {
+            if (result == -2) {
+                c_over++;
+            } else {
+                c_arrived += result >= 0 ? 1 : 0;
+                c_nocand += reason == 1 ? 1 : 0;
+                c_fall += reason == 2 ? 1 : 0;
+                c_cap += reason == 3 ? 1 : 0;
                 c_steps += (unsigned long long)steps; c_ants++;
             }
             if (k == 0) a.ant_steps[(size_t)qi * a.colony_max + ant] = result;
