@@ -50,6 +50,37 @@ int main(int argc, char** argv)
         SearchPath.counters(c);
         printf("[headless] stitched path: %zu points over %d segments; last search: %llu ant-steps, %llu ants\n", GlobalRoute.g_path_x.size(),
                GlobalRoute.path_segment_nums(), (unsigned long long)c[0], (unsigned long long)c[1]);
+        // ---- curve smoothing (main.cpp:287-352): degree-0 spline over the stitched path, then the constrained degree-2 spline over
+        //      its samples.  The demo samples both at wall-clock times (every >= 10 / >= 50 clock ticks); here at fixed times.
+        const int pt_num = (int)GlobalRoute.g_path_x.size();
+        if (pt_num >= 2) {
+            float start_pt[3] = {GlobalRoute.g_path_x[0], GlobalRoute.g_path_y[0], GlobalRoute.g_path_z[0]};
+            float end_pt[3] = {GlobalRoute.g_path_x[pt_num - 1], GlobalRoute.g_path_y[pt_num - 1], GlobalRoute.g_path_z[pt_num - 1]};
+            std::vector<float> rows((size_t)pt_num * 3);
+            std::vector<float*> ctrl(pt_num);
+            for (int i = 0; i < pt_num; i++) {
+                rows[3 * i] = GlobalRoute.g_path_x[i]; rows[3 * i + 1] = GlobalRoute.g_path_y[i]; rows[3 * i + 2] = GlobalRoute.g_path_z[i];
+                ctrl[i] = &rows[3 * i];
+            }
+            BS_Basic<float, 3, 0, 0, 0> smooth_curve(pt_num);
+            smooth_curve.SetParam(start_pt, end_pt, ctrl.data(), 150);
+            std::vector<float> t1, first;
+            for (int t = 10; t <= 160; t += 10) t1.push_back((float)t);
+            smooth_curve.getCurvePoints(t1, first);
+            const int n2 = (int)t1.size();
+            const float constrain = 0.05f;
+            float s2[9] = {start_pt[0], start_pt[1], start_pt[2], 0, 0, 0, 0, 0, 0}, e2[9] = {end_pt[0], end_pt[1], end_pt[2], 0, 0, 0, 0, 0, 0};
+            (void)constrain;   // main.cpp:329-331 fills columns 3..8 of the middle points with it; _CalcCPoints never reads them
+            std::vector<float*> ctrl2(n2);
+            for (int i = 0; i < n2; i++) ctrl2[i] = &first[3 * i];
+            BS_Basic<float, 3, 2, 2, 2> second_curve(n2);
+            second_curve.SetParam(s2, e2, ctrl2.data(), 6000);
+            std::vector<float> t2, smooth;
+            for (int t = 50; t <= 6050; t += 50) t2.push_back((float)t);
+            second_curve.getCurvePoints(t2, smooth);
+            printf("[headless] smoothed path: %zu points; first (%.6f, %.6f, %.6f), last (%.6f, %.6f, %.6f)\n", smooth.size() / 3, smooth[0], smooth[1], smooth[2],
+                   smooth[smooth.size() - 3], smooth[smooth.size() - 2], smooth[smooth.size() - 1]);
+        }
     } catch (const wr::Error& e) {
         fprintf(stderr, "[headless] %s (status %d)\n", e.what(), e.status);
         return 1;

@@ -29,6 +29,7 @@
 #include <iostream>
 #include <set>
 #include <stdexcept>
+#include <type_traits>
 #include <string>
 #include <utility>
 #include <vector>
@@ -645,5 +646,65 @@ private:
         wr::check(wr_gtsp_best(g_, 0, t.data(), &ne, &best_L));
         best_path.resize(ne);
         for (int i = 0; i < ne; i++) best_path[i] = std::make_pair(t[2 * i], t[2 * i + 1]);
+    }
+};
+
+// ---- BS_Basic (BSplineBasic.h:33-120): trajectory smoothing of the stitched path (main.cpp:287-352) ---------------------------
+// Same template parameters and SetParam as the reference (T = float, DIM = 3: what main.cpp instantiates); the curve is evaluated
+// for a whole vector of times in one kernel launch (getCurvePoints) — the demo's wall-clock sampling loop (main.cpp:309-320)
+// becomes a list of times.  getCurvePoint(u, ret) is kept for source compatibility (one launch per call).
+template <typename T, int DIM, int DEGREE, int CONST_LEVEL_INI, int CONST_LEVEL_FIN>
+class BS_Basic {
+    static_assert(std::is_same<T, float>::value && DIM == 3, "the GPU path implements BS_Basic<float, 3, ...> (main.cpp:299, :337)");
+
+public:
+    explicit BS_Basic(int num_middle) : NUM_MIDDLE(num_middle)
+    {
+        if (num_knots() < 2 * (DEGREE + 1)) printf("Invalid setup (num_knots, degree): %d, %d\n", num_knots(), DEGREE);   // :54-56
+    }
+    bool SetParam(T* init, T* fin, T** middle_pt, T fin_time)
+    {   // :70-76
+        init_.assign(init, init + DIM * (CONST_LEVEL_INI + 1));
+        fin_.assign(fin, fin + DIM * (CONST_LEVEL_FIN + 1));
+        mid_.resize((size_t)NUM_MIDDLE * DIM);
+        for (int i = 0; i < NUM_MIDDLE; i++)
+            for (int j = 0; j < DIM; j++) mid_[(size_t)i * DIM + j] = middle_pt[i][j];   // _CalcCPoints :441-447 copies DIM values per point
+        tf_ = fin_time;
+        knots_.assign(num_knots(), 0.f);
+        cps_.assign((size_t)num_cps() * DIM, 0.f);
+        return eval(nullptr, 0, nullptr, nullptr);
+    }
+    // getCurvePoint (:85-111) at every time of `u`; out: m rows of DIM; ok[i] (optional) = its return value
+    bool getCurvePoints(const std::vector<T>& u, std::vector<T>& out, std::vector<unsigned char>* ok = nullptr)
+    {
+        out.resize(u.size() * DIM);
+        std::vector<unsigned char> flags(u.size());
+        const bool r = eval(u.data(), (int)u.size(), out.data(), flags.data());
+        if (ok) *ok = flags;
+        return r;
+    }
+    bool getCurvePoint(T u, T* ret)
+    {
+        unsigned char f = 0;
+        T tmp[DIM];
+        for (int i = 0; i < DIM; i++) tmp[i] = ret[i];
+        if (!eval(&u, 1, tmp, &f) || !f) return false;
+        for (int i = 0; i < DIM; i++) ret[i] = tmp[i];
+        return true;
+    }
+    const std::vector<T>& knots() const { return knots_; }
+    const std::vector<T>& controlPoints() const { return cps_; }
+
+private:
+    int NUM_MIDDLE;
+    T tf_ = 0;
+    std::vector<T> init_, fin_, mid_, knots_, cps_;
+    int num_knots() const { return DEGREE + NUM_MIDDLE + 2 + CONST_LEVEL_INI + CONST_LEVEL_FIN + 1; }
+    int num_cps() const { return NUM_MIDDLE + 2 + CONST_LEVEL_INI + CONST_LEVEL_FIN; }
+    bool eval(const T* u, int m, T* out, unsigned char* ok)
+    {
+        wr::check(wr_bspline_eval(DEGREE, CONST_LEVEL_INI, CONST_LEVEL_FIN, init_.data(), fin_.data(), mid_.data(), NUM_MIDDLE, DIM, tf_, u, m, out, ok,
+                                  knots_.data(), cps_.data()));
+        return true;
     }
 };

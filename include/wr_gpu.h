@@ -245,6 +245,18 @@ int wr_gtsp_download_pheromone(wr_gtsp* g, int colony, double* out); /* n*n */
 int wr_gtsp_tau0(wr_gtsp* g, double* tau0);
 int wr_gtsp_kernel_ms(wr_gtsp* g, float out[3]); /* [0] info rebuild [1] construction [2] update */
 
+/* ------------------------------------------------------------------------------------------
+ * Trajectory smoothing — replaces BS_Basic<float, 3, DEGREE, CI, CF> (core/BSplineBasic.h) as
+ * main.cpp:299-300 and :337-338 use it: SetParam (:70-76) on the host, getCurvePoint (:85-111)
+ * for m sample times on the GPU.  init / fin: 3*(ci+1) / 3*(cf+1) floats (position, velocity,
+ * acceleration); middle: n_middle rows of middle_stride floats, the first three of each are used
+ * (main.cpp:325-334 passes rows of nine).  ok[i] (optional) = getCurvePoint's return value; the
+ * out row of a failed call keeps the caller's contents, as `res` does in the demo.  knots_out
+ * (degree+n_middle+ci+cf+3 floats) and cps_out ((n_middle+2+ci+cf)*3 floats) are optional.
+ * degree <= 5, ci, cf <= min(2, degree).  Host pointers. */
+int wr_bspline_eval(int degree, int ci, int cf, const float* init, const float* fin, const float* middle, int n_middle, int middle_stride,
+                    float fin_time, const float* u, int m, float* out, unsigned char* ok, float* knots_out, float* cps_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,7 @@ def lib():
         L.wro_gtsp_steps.restype = C.c_uint64
         L.wro_gtsp_steps.argtypes = [vp]
         L.wro_philox.argtypes = [vp, vp, vp]
+        L.wro_bspline.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -136,6 +137,7 @@ def ref():
         L.wrref_gtsp_pheromone.argtypes = [vp, vp]
         L.wrref_gtsp_tau0.restype = C.c_double
         L.wrref_gtsp_tau0.argtypes = [vp]
+        L.wrref_bspline.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp, vp, vp, vp]
         _ref = L
     return _ref
 
@@ -456,3 +458,23 @@ class RefGtsp:
 
     def tau0(self):
         return self.L.wrref_gtsp_tau0(self.h)
+
+
+def bspline(degree, ci, cf, init, fin, middle, fin_time, times, out=None, use_ref=False):
+    """BS_Basic<float, 3, degree, ci, cf>(len(middle)).SetParam(init, fin, middle, fin_time) + getCurvePoint at `times`
+    (BSplineBasic.h:70-111): the restatement, or — use_ref — the unmodified header behind oracle/_ref.
+    Returns (points [m][3], ok [m], knots, control points [ncp][3])."""
+    init = np.ascontiguousarray(init, np.float32).ravel(); fin = np.ascontiguousarray(fin, np.float32).ravel()
+    middle = np.ascontiguousarray(middle, np.float32)
+    n = middle.shape[0] if middle.size else 0
+    stride = middle.shape[1] if n else 3
+    u = np.ascontiguousarray(times, np.float32).ravel()
+    out = np.zeros((u.size, 3), np.float32) if out is None else np.ascontiguousarray(out, np.float32).copy()
+    ok = np.zeros(u.size, np.uint8)
+    knots = np.zeros(degree + n + 2 + ci + cf + 1, np.float32)
+    cps = np.zeros((n + 2 + ci + cf, 3), np.float32)
+    fn = ref().wrref_bspline if use_ref else lib().wro_bspline
+    rc = fn(degree, ci, cf, _p(init), _p(fin), _p(middle), n, stride, fin_time, _p(u), u.size, _p(out), _p(ok), _p(knots), _p(cps))
+    if rc != 0:
+        raise ValueError("bspline: unsupported (degree, ci, cf) = (%d, %d, %d)" % (degree, ci, cf))
+    return out, ok.astype(bool), knots, cps

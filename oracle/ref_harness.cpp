@@ -51,6 +51,20 @@ static void wrref_srand_hook(unsigned) {}
 #undef rand
 #undef srand
 
+// BSplineBasic.h (trajectory smoothing, main.cpp:287-352).  One more hook, for this header only: `new T[n]` hands out ZEROED
+// memory.  BS_Basic<T, DIM, 2, 2, 2> — the demo's second curve, main.cpp:337 — reads c_mat[1][3] in _CalcConstrainedCPoints
+// (BSplineBasic.h:403-404), an element _BasisFunsDers never writes for DEGREE = 2 (it fills DEGREE + 1 = 3 entries of a row of
+// CONST_LEVEL_FIN + 2 = 4): an uninitialised heap read.  In a fresh process glibc returns zero pages, so 0 is what the demo sees;
+// the hook makes that outcome deterministic, and the restatement and the GPU path define the element as 0.
+struct wrref_zero_t {};
+static wrref_zero_t wrref_zero;
+inline void* operator new[](size_t n, wrref_zero_t&) { return calloc(1, n ? n : 1); }
+#define new new (wrref_zero)
+#define private public
+#include "core/BSplineBasic.h"
+#undef private
+#undef new
+
 namespace {
 struct Quiet {  // the reference prints progress with printf/cout; keep test logs clean
     int saved = -1;
@@ -344,5 +358,40 @@ int wrref_gtsp_pheromone(void* h, double* out)
     return n;
 }
 double wrref_gtsp_tau0(void* h) { return ((ACS_GTSP*)h)->pheromone_0; }
+
+// BS_Basic<float, 3, DEGREE, CI, CF>::SetParam + getCurvePoint (BSplineBasic.h:70-120) at m times.  init / fin hold
+// 3 * (CI + 1) / 3 * (CF + 1) floats (position, velocity, acceleration); middle points are rows of `mid_stride` floats of which the
+// first three are used (main.cpp:325-334 passes rows of nine).  ok[i] = getCurvePoint's return value; out rows of a failed call keep
+// their previous contents, as `res` does in the demo.  Returns 0, or -1 for a (DEGREE, CI, CF) this harness does not instantiate.
+}  // extern "C"
+template <int DEG, int CI, int CF>
+static int bspline_run(const float* init, const float* fin, const float* middle, int n_mid, int mid_stride, float tf, const float* u, int m, float* out,
+                       unsigned char* ok, float* knots, float* cps)
+{
+    std::vector<float> a(init, init + 3 * (CI + 1)), b(fin, fin + 3 * (CF + 1));
+    std::vector<std::vector<float>> rows(n_mid);
+    std::vector<float*> mp(n_mid);
+    for (int i = 0; i < n_mid; i++) { rows[i].assign(middle + (size_t)i * mid_stride, middle + (size_t)i * mid_stride + 3); mp[i] = rows[i].data(); }
+    BS_Basic<float, 3, DEG, CI, CF> c(n_mid);
+    c.SetParam(a.data(), b.data(), mp.data(), tf);
+    if (knots) for (int i = 0; i < c.NumKnots_; i++) knots[i] = c.Knots_[i];
+    if (cps) for (int i = 0; i < c.NumCPs_; i++) for (int j = 0; j < 3; j++) cps[3 * i + j] = c.CPoints_[i][j];
+    for (int i = 0; i < m; i++) {
+        const bool r = c.getCurvePoint(u[i], out + 3 * i);
+        if (ok) ok[i] = r ? 1 : 0;
+    }
+    return 0;
+}
+extern "C" {
+int wrref_bspline(int degree, int ci, int cf, const float* init, const float* fin, const float* middle, int n_mid, int mid_stride, float tf,
+                  const float* u, int m, float* out, unsigned char* ok, float* knots, float* cps)
+{
+    Quiet q;
+#define WRREF_BS(D, A, B) if (degree == D && ci == A && cf == B) return bspline_run<D, A, B>(init, fin, middle, n_mid, mid_stride, tf, u, m, out, ok, knots, cps)
+    WRREF_BS(0, 0, 0); WRREF_BS(1, 0, 0); WRREF_BS(2, 0, 0); WRREF_BS(3, 0, 0); WRREF_BS(2, 1, 1); WRREF_BS(3, 1, 1);
+    WRREF_BS(2, 2, 2); WRREF_BS(3, 2, 2); WRREF_BS(4, 2, 2); WRREF_BS(5, 2, 2); WRREF_BS(3, 2, 1); WRREF_BS(3, 0, 2);
+#undef WRREF_BS
+    return -1;
+}
 
 }  // extern "C"

@@ -666,3 +666,155 @@ extern "C" double wro_gtsp_tau0(const wro_gtsp* g) { return g->tau0; }
 extern "C" uint64_t wro_gtsp_steps(const wro_gtsp* g) { return g->steps; }
 
 extern "C" void wro_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { wr_philox4x32_10(ctr, key, out); }
+
+// ---- trajectory smoothing: BS_Basic<float, 3, DEGREE, CI, CF> (core/BSplineBasic.h) ---------------------------------------------
+// SetParam (:70-76) + getCurvePoint (:85-111) for m times, with run-time degree / constraint levels.  Float arithmetic in the
+// reference's order (compiled with -ffp-contract=off).  The one element the reference reads without ever writing it
+// (c_mat[idx][CF + 2 - h] for DEGREE < CF + 1, :403) is 0 here, as in oracle/ref_harness.cpp's zeroing `new`; the bisection of
+// _findSpan is bounded (64 trips -> the call fails) where the reference would not terminate.
+namespace {
+struct Spline {
+    int degree, ci, cf, nk, ncp;
+    std::vector<float> K, C;   // knots, control points [ncp][3]
+    float left(int i, int j, float u) const { return u - K[i + 1 - j]; }     // _Left :339
+    float right(int i, int j, float u) const { return K[i + j] - u; }        // _Right :341
+    bool find_span(int& ret, float u) const
+    {   // :345-379
+        if (u < K[0] || K[nk - 1] < u) return false;
+        const float dd = u - K[nk - 1];
+        const float sq = dd * dd;
+        if ((double)sq < 1.e-10) {   // SP_IS_EQUAL :8
+            for (int i = nk - 2; i > -1; --i)
+                if (K[i] < u && u <= K[i + 1]) { ret = i; return true; }
+            return false;
+        }
+        int low = 0, high = nk - 1, mid = (low + high) >> 1, trips = 0;
+        while (u < K[mid] || u >= K[mid + 1]) {
+            if (++trips > 64) return false;
+            if (u < K[mid]) high = mid; else low = mid;
+            mid = (low + high) >> 1;
+        }
+        ret = mid;
+        return true;
+    }
+    // _BasisFunsDers(ders, u, n) :195-201 + :203-291; ders rows have `cols` entries, zero where the reference writes nothing
+    void basis_ders(std::vector<float>& ders, int cols, float u, int n) const
+    {
+        int span;
+        if (!find_span(span, u)) return;
+        const int p = degree;
+        std::vector<float> ndu((size_t)(p + 1) * (p + 1), 0.0f), a((size_t)2 * (p + 1), 0.0f);
+        auto ND = [&](int i, int j) -> float& { return ndu[(size_t)i * (p + 1) + j]; };
+        auto A = [&](int i, int j) -> float& { return a[(size_t)i * (p + 1) + j]; };
+        ND(0, 0) = 1.0f;
+        for (int j = 1; j <= p; ++j) {
+            float saved = 0.0f;
+            for (int r = 0; r < j; ++r) {
+                const float l = left(span, j - r, u), rr = right(span, r + 1, u);
+                ND(j, r) = rr + l;
+                const float temp = ND(r, j - 1) / ND(j, r);
+                ND(r, j) = saved + rr * temp;
+                saved = l * temp;
+            }
+            ND(j, j) = saved;
+        }
+        for (int j = 0; j <= p; ++j) ders[j] = ND(j, p);
+        for (int r = 0; r <= p; ++r) {
+            int s1 = 0, s2 = 1;
+            A(0, 0) = 1.0f;
+            for (int k = 1; k <= n; ++k) {
+                float d = 0.0f;
+                const int rk = r - k, pk = p - k;
+                if (r >= k) { A(s2, 0) = A(s1, 0) / ND(pk + 1, rk); d = A(s2, 0) * ND(rk, pk); }
+                const int j1 = rk >= -1 ? 1 : -rk, j2 = (r - 1 <= pk) ? k - 1 : p - r;
+                for (int j = j1; j <= j2; ++j) {
+                    A(s2, j) = (A(s1, j) - A(s1, j - 1)) / ND(pk + 1, rk + j);
+                    d += A(s2, j) * ND(rk + j, pk);
+                }
+                if (r <= pk) { A(s2, k) = -A(s1, k - 1) / ND(pk + 1, r); d += A(s2, k) * ND(r, pk); }
+                ders[(size_t)k * cols + r] = d;
+                const int t = s1; s1 = s2; s2 = t;
+            }
+        }
+        int r = p;
+        for (int k = 1; k <= n; ++k) {
+            for (int j = 0; j <= p; ++j) ders[(size_t)k * cols + j] *= r;
+            r *= (p - k);
+        }
+    }
+};
+}  // namespace
+
+extern "C" int wro_bspline(int degree, int ci, int cf, const float* init, const float* fin, const float* middle, int n_mid, int mid_stride, float tf,
+                           const float* u, int m, float* out, unsigned char* ok, float* knots, float* cps)
+{
+    if (degree < 0 || degree > 8 || ci < 0 || cf < 0 || ci > degree || cf > degree) return -1;
+    Spline sp;
+    sp.degree = degree; sp.ci = ci; sp.cf = cf;
+    sp.nk = degree + n_mid + 2 + ci + cf + 1;
+    sp.ncp = n_mid + 2 + ci + cf;
+    sp.K.assign(sp.nk, 0.0f);
+    sp.C.assign((size_t)sp.ncp * 3, 0.0f);
+    {   // _CalcKnot :149-164
+        int i = 0;
+        const int nmid = sp.nk - 2 * degree - 2;
+        const float step = tf / (nmid + 1);
+        for (int j = 0; j < degree + 1; ++j) sp.K[i++] = 0.0f;
+        for (int j = 0; j < nmid; ++j) { sp.K[i] = sp.K[i - 1] + step; ++i; }
+        for (int j = 0; j < degree + 1; ++j) sp.K[i++] = tf;
+    }
+    {   // _CalcConstrainedCPoints :381-427
+        for (int d = 0; d < 3; ++d) { sp.C[d] = init[d]; sp.C[(size_t)(sp.ncp - 1) * 3 + d] = fin[d]; }
+        const int cols = std::max(std::max(ci, cf) + 2, degree + 1);
+        std::vector<float> dm((size_t)(ci + 1) * cols, 0.0f);
+        sp.basis_ders(dm, cols, 0.0f, ci);
+        for (int j = 1; j < ci + 1; ++j)
+            for (int k = 0; k < 3; ++k) {
+                float c = init[j * 3 + k];
+                for (int h = j; h > 0; --h) c -= dm[(size_t)j * cols + h - 1] * sp.C[(size_t)(h - 1) * 3 + k];
+                sp.C[(size_t)j * 3 + k] = c / dm[(size_t)j * cols + j];
+            }
+        std::vector<float> cm((size_t)(cf + 1) * cols, 0.0f);
+        sp.basis_ders(cm, cols, tf, cf);
+        int idx = 1;
+        for (int j = sp.ncp - 2; j > sp.ncp - 2 - cf; --j) {
+            for (int k = 0; k < 3; ++k) {
+                float c = fin[idx * 3 + k];
+                for (int h = idx; h > 0; --h) c -= cm[(size_t)idx * cols + cf + 2 - h] * sp.C[(size_t)(sp.ncp - h) * 3 + k];
+                sp.C[(size_t)j * 3 + k] = c / cm[(size_t)idx * cols + cf + 1 - idx];
+            }
+            ++idx;
+        }
+    }
+    for (int i = 0; i < n_mid; ++i)   // _CalcCPoints :441-447
+        for (int d = 0; d < 3; ++d) sp.C[(size_t)(ci + 1 + i) * 3 + d] = middle[(size_t)i * mid_stride + d];
+    if (knots) memcpy(knots, sp.K.data(), sizeof(float) * sp.K.size());
+    if (cps) memcpy(cps, sp.C.data(), sizeof(float) * sp.C.size());
+    for (int i = 0; i < m; ++i) {   // getCurvePoint :85-111
+        float t = u[i];
+        if (t < sp.K[0]) t = sp.K[0];
+        else if (t > sp.K[sp.nk - 1]) t = sp.K[sp.nk - 1];
+        int span;
+        if (!sp.find_span(span, t)) { if (ok) ok[i] = 0; continue; }
+        std::vector<float> N(degree + 1, 0.0f);
+        float temp = 0.0f;
+        N[0] = 1.0f;
+        for (int j = 1; j <= degree; ++j) {   // _BasisFuns :316-338
+            float saved = 0.0f;
+            for (int r = 0; r < j; ++r) {
+                const float l = sp.left(span, j - r, t), rr = sp.right(span, r + 1, t);
+                if ((rr + l) != 0) temp = N[r] / (rr + l);
+                N[r] = saved + rr * temp;
+                saved = l * temp;
+            }
+            N[j] = saved;
+        }
+        for (int d = 0; d < 3; ++d) {
+            float c = 0.0f;
+            for (int q = 0; q <= degree; ++q) c += N[q] * sp.C[(size_t)(span - degree + q) * 3 + d];
+            out[3 * i + d] = c;
+        }
+        if (ok) ok[i] = 1;
+    }
+    return 0;
+}

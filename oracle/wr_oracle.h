@@ -97,6 +97,11 @@ void wro_gtsp_pheromone(const wro_gtsp* g, double* out);
 double wro_gtsp_tau0(const wro_gtsp* g);
 uint64_t wro_gtsp_steps(const wro_gtsp* g);
 
+/* ---- trajectory smoothing: BS_Basic<float, 3, degree, ci, cf> SetParam + getCurvePoint at m times (BSplineBasic.h:70-111);
+ * mirrors wrref_bspline.  Returns 0, -1 for an unsupported setup. */
+int wro_bspline(int degree, int ci, int cf, const float* init, const float* fin, const float* middle, int n_mid, int mid_stride, float tf,
+                const float* u, int m, float* out, unsigned char* ok, float* knots, float* cps);
+
 /* ---- Philox KAT hook ---- */
 void wro_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

@@ -41,8 +41,37 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+BSPLINE_CASES = [(0, 0, 0, 57, 150.0), (2, 2, 2, 16, 6000.0), (3, 2, 2, 40, 100.0), (3, 0, 0, 9, 10.0), (1, 0, 0, 5, 1.0), (2, 1, 1, 33, 77.7),
+                 (5, 2, 2, 64, 1000.0), (3, 2, 1, 12, 3.5)]
+
+
+def bspline_inputs(case):
+    """The inputs of a B-spline fixture, a pure function of the case (tests rebuild them instead of storing them)."""
+    d, ci, cf, n, tf = case
+    rng = np.random.default_rng(1000 * d + 100 * ci + 10 * cf + n)
+    mid = (rng.random((n, 9), dtype=np.float32) * 2 - 1)                      # rows of nine, like main.cpp:325-334
+    init = np.concatenate([mid[0, :3], (rng.random(3 * ci) - 0.5)]).astype(np.float32)
+    fin = np.concatenate([mid[-1, :3], (rng.random(3 * cf) - 0.5)]).astype(np.float32)
+    u = np.concatenate([np.linspace(-0.05 * tf, 1.05 * tf, 257), [0.0, tf, tf * (1 - 1e-7), np.nan]]).astype(np.float32)
+    pre = rng.random((u.size, 3), dtype=np.float32)                           # what `ret` holds before the call (kept by a failed call)
+    return init, fin, mid, tf, u, pre
+
+
+def bspline_fixtures():
+    """BS_Basic<float, 3, D, CI, CF> of the UNMODIFIED core/BSplineBasic.h: knots, control points, curve points, return values."""
+    assert O.have_ref(), "oracle/_ref/libwrref.so missing: run make -C oracle"
+    out = {}
+    for i, case in enumerate(BSPLINE_CASES):
+        init, fin, mid, tf, u, pre = bspline_inputs(case)
+        pts, ok, knots, cps = O.bspline(case[0], case[1], case[2], init, fin, mid, tf, u, out=pre, use_ref=True)
+        out["pts%d" % i] = pts; out["ok%d" % i] = ok; out["knots%d" % i] = knots; out["cps%d" % i] = cps
+        print("bspline", case, "ok", int(ok.sum()), "of", ok.size)
+    np.savez_compressed(os.path.join(HERE, "ref_bspline.npz"), **out)
+
+
 def main():
     assert O.have_ref(), "oracle/_ref/libwrref.so missing: run make -C oracle"
+    bspline_fixtures()
     meshes = {n: O.Ref.stl_read("%s/%s.stl" % (REF_FILES, n)) for n in ("cubic", "test", "simplified_piece", "origin_piece")}
     np.savez_compressed(os.path.join(HERE, "meshes.npz"), **meshes)
     kat = {"seed": SEED, "grids": [], "steps": [], "gtsp": []}
@@ -137,5 +166,7 @@ def main():
     print("wrote fixtures to", HERE)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1:] == ["bspline"]:
+    bspline_fixtures()
+elif __name__ == "__main__":
     main()

@@ -151,3 +151,22 @@ def test_keyed_mode_is_order_independent_and_deterministic(oracle, meshes):
         runs.append((A.pheromone(), A.best(), A.counters()))
     assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1][2] == runs[1][1][2]
     assert runs[2][2]["dead_step_cap"] > 0 and runs[0][2]["dead_step_cap"] == 0
+
+
+def test_bspline_matches_reference_fixture(oracle):
+    """BS_Basic<float, 3, D, CI, CF> (core/BSplineBasic.h): knots, control points, curve points and return values of the
+    restatement against what the unmodified header produced (tests/golden/ref_bspline.npz), bit for bit incl. the NaN time,
+    the out-of-range times (clamped) and fin_time itself (the SP_IS_EQUAL branch of _findSpan)."""
+    import os
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_golden as MG
+    fx = np.load(os.path.join(GOLDEN, "ref_bspline.npz"))
+    for i, case in enumerate(MG.BSPLINE_CASES):
+        init, fin, mid, tf, u, pre = MG.bspline_inputs(case)
+        pts, ok, knots, cps = oracle.bspline(case[0], case[1], case[2], init, fin, mid, tf, u, out=pre)
+        assert np.array_equal(knots.view(np.uint32), fx["knots%d" % i].view(np.uint32)), case
+        assert np.array_equal(cps.view(np.uint32), fx["cps%d" % i].view(np.uint32)), case
+        assert np.array_equal(ok, fx["ok%d" % i]), case
+        assert np.array_equal(pts.view(np.uint32), fx["pts%d" % i].view(np.uint32)), case

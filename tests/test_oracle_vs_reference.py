@@ -98,3 +98,21 @@ def test_gtsp_live(O):
     assert T.iterate(30, early_stop=True) == ran
     assert np.array_equal(T.best()[0], Rg.best()[0]) and T.best()[1] == Rg.best()[1]
     assert np.array_equal(T.pheromone().view(np.uint64), Rg.pheromone().view(np.uint64))
+
+
+def test_bspline_restatement_equals_reference_header(oracle):
+    """Live: random valid setups of every (DEGREE, CI, CF) the harness instantiates, restatement == unmodified BSplineBasic.h."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.default_rng(3)
+    bits = lambda a: a.view(np.uint32) if a.dtype == np.float32 else a   # noqa: E731
+    for (d, ci, cf) in [(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (2, 1, 1), (3, 1, 1), (2, 2, 2), (3, 2, 2), (4, 2, 2), (5, 2, 2), (3, 2, 1), (3, 0, 2)]:
+        for n, tf in [(max(1, d + 1 - ci - cf), 1.0), (57, 150.0), (1000, 123.456)]:
+            mid = rng.random((n, 9), dtype=np.float32) * 2 - 1
+            init = np.concatenate([mid[0, :3], rng.random(3 * ci) - 0.5]).astype(np.float32)
+            fin = np.concatenate([mid[-1, :3], rng.random(3 * cf) - 0.5]).astype(np.float32)
+            u = np.concatenate([np.linspace(-1, tf * 1.01, 301), [0, tf, tf * (1 - 1e-7), np.nan]]).astype(np.float32)
+            pre = rng.random((u.size, 3), dtype=np.float32)
+            a = oracle.bspline(d, ci, cf, init, fin, mid, tf, u, out=pre)
+            b = oracle.bspline(d, ci, cf, init, fin, mid, tf, u, out=pre, use_ref=True)
+            assert all(np.array_equal(bits(x), bits(y)) for x, y in zip(a, b)), (d, ci, cf, n, tf)

@@ -656,3 +656,51 @@ class ACS_GTSP:
                 lib().wr_gtsp_destroy(self._g)
         except Exception:
             pass
+
+
+class BS_Basic:
+    """Mirror of BS_Basic<float, 3, DEGREE, CONST_LEVEL_INI, CONST_LEVEL_FIN> (core/BSplineBasic.h:33-120), the trajectory
+    smoothing of main.cpp:287-352: SetParam on the host, curve points for a whole array of times in one kernel launch
+    (wr_bspline_eval).  The demo samples at wall-clock times (main.cpp:309-320); here the caller names the times."""
+
+    def __init__(self, num_middle, degree=0, const_level_ini=0, const_level_fin=0):
+        self.NUM_MIDDLE = int(num_middle)
+        self.DEGREE, self.CI, self.CF = int(degree), int(const_level_ini), int(const_level_fin)
+        self.NumKnots_ = self.DEGREE + self.NUM_MIDDLE + 2 + self.CI + self.CF + 1       # :39-40
+        self.NumCPs_ = self.NUM_MIDDLE + 2 + self.CI + self.CF                           # :41
+        self._set = False
+
+    def SetParam(self, init, fin, middle_pt, fin_time):
+        """:70-76.  init / fin: 3 * (level + 1) floats; middle_pt: [NUM_MIDDLE][>= 3] (the first three columns are used)."""
+        self._init = np.ascontiguousarray(init, dtype=np.float32).ravel()
+        self._fin = np.ascontiguousarray(fin, dtype=np.float32).ravel()
+        if self._init.size < 3 * (self.CI + 1) or self._fin.size < 3 * (self.CF + 1):
+            raise ValueError("init / fin need 3 * (constraint level + 1) floats")
+        self._mid = np.ascontiguousarray(middle_pt, dtype=np.float32).reshape(self.NUM_MIDDLE, -1) if self.NUM_MIDDLE else np.zeros((0, 3), np.float32)
+        self._tf = float(fin_time)
+        self.Knots_ = np.zeros(self.NumKnots_, np.float32)
+        self.CPoints_ = np.zeros((self.NumCPs_, 3), np.float32)
+        self._call(np.zeros(0, np.float32))
+        self._set = True
+        return True
+
+    def _call(self, u, out=None):
+        u = np.ascontiguousarray(u, dtype=np.float32).ravel()
+        if out is None:
+            out = np.zeros((u.size, 3), np.float32)
+        ok = np.zeros(u.size, np.uint8)
+        check(lib().wr_bspline_eval(self.DEGREE, self.CI, self.CF, ptr(self._init), ptr(self._fin), ptr(self._mid), self.NUM_MIDDLE,
+                                    self._mid.shape[1] if self.NUM_MIDDLE else 3, self._tf, ptr(u), u.size, ptr(out), ptr(ok),
+                                    ptr(self.Knots_), ptr(self.CPoints_)))
+        return out, ok.astype(bool)
+
+    def getCurvePoints(self, times, out=None):
+        """getCurvePoint (:85-111) at every time of `times`: ([m][3] points, [m] success flags).  A failed sample keeps the row of
+        `out` it was given (zeros without `out`), as the reference leaves `ret` untouched."""
+        if not self._set:
+            raise RuntimeError("SetParam first")
+        return self._call(times, out)
+
+    def getCurvePoint(self, u):
+        pts, ok = self.getCurvePoints([u])
+        return bool(ok[0]), pts[0]
