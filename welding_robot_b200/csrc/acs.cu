@@ -502,7 +502,7 @@ static int walk_warm()
 }
 static size_t walk_smem(const wr_acs* a)
 {
-    if (a->K == kK26) return ((size_t)kWalk26Ants << a->table_log2) * 12;
+    if (a->K == kK26) return ((size_t)kWalk26Ants << a->table_log2) * 12 + kWalk26pExtra;   // + k_walk26p's move table and exchange rows
     return kWalk2Lut + 128 + (size_t)kAntsPerCta * a->table_entries * sizeof(unsigned long long);
 }
 
@@ -648,7 +648,10 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
         WR_CUDA_A(cudaFuncSetAttribute(k_rank_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * kRankChunk * (int)sizeof(uint16_t)));
         const size_t ws = walk_smem(a);
         if (ws > 227 * 1024) { set_error("wr_acs_create: walk shared memory %zu B exceeds 227 KB", ws); wr_acs_destroy(a); return WR_ERR_INVALID; }
-        if (a->K == kK26) WR_CUDA_A(cudaFuncSetAttribute(k_walk26<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        if (a->K == kK26) {
+            WR_CUDA_A(cudaFuncSetAttribute(k_walk26<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+            WR_CUDA_A(cudaFuncSetAttribute(k_walk26p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+        }
         else {
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
@@ -863,7 +866,8 @@ static int launch_walk(wr_acs* a)
         const size_t smem = walk_smem(a);
         const int per_sm = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 16));
         const int blocks = std::max(1, std::min((a->chunk + kWalk26Ants - 1) / kWalk26Ants, kNumSMs * per_sm));
-        k_walk26<false><<<blocks, kWalk26Threads, smem, a->stream>>>(w);
+        if (walk_version() == 3 && g->rx <= 1024 && g->ry <= 1024 && g->rz <= 1024) k_walk26p<<<blocks, kWalk26Threads, smem, a->stream>>>(w);
+        else k_walk26<false><<<blocks, kWalk26Threads, smem, a->stream>>>(w);
         w.table_log2 = a->gtable_log2;
         k_walk26<true><<<std::max(1, std::min((a->chunk + kWalk26Ants - 1) / kWalk26Ants, kNumSMs * 4)), kWalk26Threads, 0, a->stream>>>(w);
         WR_CUDA(cudaGetLastError());
