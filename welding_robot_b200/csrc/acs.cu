@@ -479,17 +479,6 @@ static int walk_prefetch()
     static const int env = [] { const char* e = getenv("WR_WALK_PREFETCH"); return e ? atoi(e) : -1; }();   // -1: chosen per iteration (launch_walk)
     return env;
 }
-static int walk_version()
-{
-    static const int env = [] { const char* e = getenv("WR_WALK_V"); return e ? atoi(e) : 3; }();   // pass 1: 3 = k_walk3 (default), 2 = k_walk2
-    return env;
-}
-static int batch_minb()
-{
-    // k_walk_batch3's register bound in CTAs per SM: 5 (102 registers; measured best on C5: 2027 queries/s), 6 (80, spills: 1934), 4 (120: 1854)
-    static const int env = [] { const char* e = getenv("WR_BATCH_MINB"); return e ? atoi(e) : 5; }();
-    return env;
-}
 static int stream_cs()
 {
     static const int env = [] { const char* e = getenv("WR_STREAM_CS"); return e ? atoi(e) : 1; }();   // evict-first streaming of the tiles without deposits (default on)
@@ -653,11 +642,6 @@ extern "C" int wr_acs_create(wr_grid* g, const wr_acs_params* p, wr_acs** out)
             WR_CUDA_A(cudaFuncSetAttribute(k_walk26p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         }
         else {
-        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
-        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
-        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
-        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
-        WR_CUDA_A(cudaFuncSetAttribute(k_walk2<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
         WR_CUDA_A(cudaFuncSetAttribute(k_walk3<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
@@ -819,19 +803,6 @@ extern "C" int wr_acs_begin(wr_acs* a, float predict)
     return WR_OK;
 }
 
-template <bool GLOBAL>
-static void launch_walk2(const WalkArgs& w, bool alpha1, int prefetch, int blocks, size_t smem, cudaStream_t s)
-{
-    if (alpha1) {
-        if (prefetch == 1) k_walk2<GLOBAL, true, 1><<<blocks, kWalkThreads, smem, s>>>(w);
-        else if (prefetch == 2) k_walk2<GLOBAL, true, 2><<<blocks, kWalkThreads, smem, s>>>(w);
-        else if (prefetch == 3) k_walk2<GLOBAL, true, 3><<<blocks, kWalkThreads, smem, s>>>(w);
-        else k_walk2<GLOBAL, true, 0><<<blocks, kWalkThreads, smem, s>>>(w);
-    } else {
-        k_walk2<GLOBAL, false, 0><<<blocks, kWalkThreads, smem, s>>>(w);
-    }
-}
-
 // before k_iter_begin: pull the rows under last iteration's deposits into L2 (see k_path_warm)
 static void launch_warm(wr_acs* a, bool prev_rankset)
 {
@@ -866,7 +837,7 @@ static int launch_walk(wr_acs* a)
         const size_t smem = walk_smem(a);
         const int per_sm = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 16));
         const int blocks = std::max(1, std::min((a->chunk + kWalk26Ants - 1) / kWalk26Ants, kNumSMs * per_sm));
-        if (walk_version() == 3 && g->rx <= 1024 && g->ry <= 1024 && g->rz <= 1024) k_walk26p<<<blocks, kWalk26Threads, smem, a->stream>>>(w);
+        if (g->rx <= 1024 && g->ry <= 1024 && g->rz <= 1024) k_walk26p<<<blocks, kWalk26Threads, smem, a->stream>>>(w);
         else k_walk26<false><<<blocks, kWalk26Threads, smem, a->stream>>>(w);
         w.table_log2 = a->gtable_log2;
         k_walk26<true><<<std::max(1, std::min((a->chunk + kWalk26Ants - 1) / kWalk26Ants, kNumSMs * 4)), kWalk26Threads, 0, a->stream>>>(w);
@@ -882,17 +853,14 @@ static int launch_walk(wr_acs* a)
     // instructions per step are pure issue cost (converged walk 0.346 -> 0.317 ms without them)
     int pf = walk_prefetch();
     if (pf < 0) pf = (a->rankset && a->rs_choice) ? 0 : 2;
-    if (walk_version() == 3) {
-        if (!alpha1 && pf) k_walk3<false, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-        else if (!alpha1) k_walk3<false, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-        else if (pf) k_walk3<true, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-        else k_walk3<true, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
-    } else {
-        launch_walk2<false>(w, alpha1, pf, blocks1, smem1, a->stream);
-    }
+    if (!alpha1 && pf) k_walk3<false, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+    else if (!alpha1) k_walk3<false, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+    else if (pf) k_walk3<true, 1><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
+    else k_walk3<true, 0><<<blocks1, kWalkThreads, smem1, a->stream>>>(w);
     // pass 2: resume the ants that parked on a full shared-memory table (usually none: the kernel exits at once)
     w.table_log2 = a->gtable_log2;
-    launch_walk2<true>(w, alpha1, 0, a->walk2_blocks, kWalk2Lut + 128, a->stream);
+    if (alpha1) k_walk2<true><<<a->walk2_blocks, kWalkThreads, kWalk2Lut, a->stream>>>(w);
+    else k_walk2<false><<<a->walk2_blocks, kWalkThreads, kWalk2Lut, a->stream>>>(w);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
 }
@@ -1455,12 +1423,8 @@ extern "C" int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const in
     const bool alpha1 = a->p.alpha == 1;
     const int maxn = (std::max(cm, 32) + 31) / 32 * 32;
     const size_t rank_smem = (size_t)12 * maxn + 32 * 256 * sizeof(uint32_t);
-    WR_CUDA(cudaFuncSetAttribute(k_walk_batch<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    WR_CUDA(cudaFuncSetAttribute(k_walk_batch<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    WR_CUDA(cudaFuncSetAttribute(k_walk_batch3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     WR_CUDA(cudaFuncSetAttribute(k_batch_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
     const int per_sm = std::max(1, std::min(16, (int)((227 * 1024) / (smem1 + 1024))));
     BatchArgs w;
@@ -1487,15 +1451,11 @@ extern "C" int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const in
         for (int it = 0; it < n_iterations; it++) {
             k_batch_iter_begin<<<(n + 255) / 256, 256, 0, s>>>(a->d_state, b->qs, n, a->p.fixed_colony, cm, a->g->precision, a->p.tau0, it > 0 ? 1 : 0, a->p.rho);
             if (alpha1) {
-                if (walk_version() == 3 && batch_minb() == 6) k_walk_batch3<true, 6><<<blocks1, kWalkThreads, smem1, s>>>(w);
-                else if (walk_version() == 3 && batch_minb() == 5) k_walk_batch3<true, 5><<<blocks1, kWalkThreads, smem1, s>>>(w);
-                else if (walk_version() == 3) k_walk_batch3<true, 4><<<blocks1, kWalkThreads, smem1, s>>>(w);
-                else k_walk_batch<false, true><<<blocks1, kWalkThreads, smem1, s>>>(w);
-                k_walk_batch<true, true><<<blocks2, kWalkThreads, kWalk2Lut + 128, s>>>(w);
+                k_walk_batch3<true><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                k_walk_batch<true><<<blocks2, kWalkThreads, kWalk2Lut, s>>>(w);
             } else {
-                if (walk_version() == 3) k_walk_batch3<false, 4><<<blocks1, kWalkThreads, smem1, s>>>(w);
-                else k_walk_batch<false, false><<<blocks1, kWalkThreads, smem1, s>>>(w);
-                k_walk_batch<true, false><<<blocks2, kWalkThreads, kWalk2Lut + 128, s>>>(w);
+                k_walk_batch3<false><<<blocks1, kWalkThreads, smem1, s>>>(w);
+                k_walk_batch<false><<<blocks2, kWalkThreads, kWalk2Lut, s>>>(w);
             }
             k_batch_rank<<<n, kRankSmallThreads, rank_smem, s>>>(a->d_state, b->qs, b->tab, b->steps, cm, maxn, a->cap, a->rank_bits, a->d_Ltab, b->ranked_keys, b->ranked_vals,
                                                                   b->path_ids, b->path_dirs, b->best_ids, b->best_dirs);
@@ -1553,9 +1513,8 @@ static int preload_iteration_kernels()
     WR_PRELOAD(k_rankset_merge); WR_PRELOAD(k_evaporate_tiles); WR_PRELOAD(k_rankset_apply); WR_PRELOAD(k_rankset_clear); WR_PRELOAD(k_deposit_serial);
     WR_PRELOAD((k_deposit_gen<false, true>)); WR_PRELOAD(k_tile_offsets); WR_PRELOAD(k_update_fused<true>); WR_PRELOAD(k_update_fused<false>);
     WR_PRELOAD(k_pull_finals); WR_PRELOAD(k_iter_begin); WR_PRELOAD(k_iter_end); WR_PRELOAD(k_path_warm); WR_PRELOAD(k_rankset_warm);
-    WR_PRELOAD((k_walk2<false, true, 0>)); WR_PRELOAD((k_walk2<false, true, 1>)); WR_PRELOAD((k_walk2<false, true, 2>)); WR_PRELOAD((k_walk2<false, true, 3>));
     WR_PRELOAD((k_walk3<true, 0>)); WR_PRELOAD((k_walk3<true, 1>)); WR_PRELOAD((k_walk3<false, 0>)); WR_PRELOAD((k_walk3<false, 1>));
-    WR_PRELOAD((k_walk2<false, false, 0>)); WR_PRELOAD((k_walk2<true, true, 0>)); WR_PRELOAD((k_walk2<true, false, 0>));
+    WR_PRELOAD((k_walk2<true>)); WR_PRELOAD((k_walk2<false>));
 #undef WR_PRELOAD
     int rc = sort_preload();
     if (rc != WR_OK) return rc;

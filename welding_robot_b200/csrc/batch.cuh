@@ -173,16 +173,14 @@ __global__ void k_batch_iter_begin(IterState* st, BatchQuery* qs, int nq, int fi
 }
 
 // ------------------------------------------------------------------------------------------
-// K2 over a batch.  See walk2.cuh for the step itself; differences are marked BATCH.
+// K2 over a batch, pass 2: the ants that pass 1 (k_walk_batch3 below) parked on a full shared-memory table, resumed with their
+// HBM tables from the pool.  See walk2.cuh for the step itself; differences are marked BATCH.
 // ------------------------------------------------------------------------------------------
-template <bool GLOBAL, bool ALPHA1>
+template <bool ALPHA1>
 __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int4* move_lut = reinterpret_cast<int4*>(smem_raw);
-    uint32_t* ntiles_s = reinterpret_cast<uint32_t*>(smem_raw + kWalk2Lut);
-    volatile uint32_t* flag_s = reinterpret_cast<volatile uint32_t*>(smem_raw + kWalk2Lut + 64);
-    unsigned long long* tab_s = reinterpret_cast<unsigned long long*>(smem_raw + kWalk2Lut + 128);
     if (threadIdx.x < 64) {
         const int pbv = threadIdx.x;
         const int c = pbv ? 31 - __clz(pbv) : 0;
@@ -195,14 +193,12 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
     const int lane = threadIdx.x & 31;
     const int gbase = lane & 24;
     const int k = lane & 7;
-    const int g = threadIdx.x >> 3;
-    const int E = GLOBAL ? (1 << a.gtable_log2) : a.table_entries;
+    const int E = 1 << a.gtable_log2;
     uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(move_lut);
-    TabRef<GLOBAL> tab;
+    TabRef<true> tab;
     tab.gp = a.gtab;
-    tab.sa = (uint32_t)__cvta_generic_to_shared(tab_s + (size_t)g * E);
-    uint32_t flag_sa = (uint32_t)__cvta_generic_to_shared(smem_raw + kWalk2Lut + 64 + 4 * g);
-    asm volatile("" : "+r"(lut_sa), "+r"(tab.sa), "+r"(flag_sa));
+    tab.sa = 0;
+    asm volatile("" : "+r"(lut_sa));
 
     const int rx = a.rx, rxy = a.rx * a.ry;
     const int dxk = (k == 3) - (k == 2), dyk = (k == 4) - (k == 1), dzk = (k == 5) - (k == 0);
@@ -223,33 +219,24 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
     const uint32_t iter = (uint32_t)st->iter;
     const float base_now = st->base;
     const float beta = a.beta;
-    const unsigned n_items = GLOBAL ? st->overflow_n : (unsigned)(a.nq * a.items_per_query);
-    const uint32_t limit = (uint32_t)((E >> 2) * 3);
+    const unsigned n_items = st->overflow_n;   // the ants pass 1 parked
     const int cap = a.cap;
     const uint32_t* ent = a.tab.ent;
 
-    unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
+    unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0;
 
     while (true) {
         unsigned q0 = 0;
-        if (lane == 0) q0 = atomicAdd(GLOBAL ? &st->queue2 : &st->queue, GLOBAL ? 4u : 1u);
+        if (lane == 0) q0 = atomicAdd(&st->queue2, 4u);
         q0 = __shfl_sync(FULL, q0, 0);
         if (q0 >= n_items) break;                                    // warp-uniform
-        // BATCH: pass 1: work item = (query, group of four ants), the query is warp-uniform; pass 2: four parked ants of any queries
-        uint32_t qi; int ant; bool has;
-        unsigned slot_o = 0;
-        if (GLOBAL) {
-            slot_o = q0 + (unsigned)(lane >> 3);
-            has = slot_o < n_items;
-            const uint32_t ga = has ? a.overflow_list[slot_o] : 0u;
-            qi = ga / (uint32_t)a.colony_max; ant = (int)(ga - qi * (uint32_t)a.colony_max);
-        } else {
-            qi = q0 / (unsigned)a.items_per_query;
-            ant = (int)(q0 - qi * (unsigned)a.items_per_query) * 4 + (lane >> 3);
-            has = true;
-        }
+        // BATCH: four parked ants of any queries
+        const unsigned slot_o = q0 + (unsigned)(lane >> 3);
+        const bool has = slot_o < n_items;
+        const uint32_t ga = has ? a.overflow_list[slot_o] : 0u;
+        const uint32_t qi = ga / (uint32_t)a.colony_max;
+        const int ant = (int)(ga - qi * (uint32_t)a.colony_max);
         const BatchQuery& bq = a.qs[qi];
-        if (!GLOBAL) has = ant < bq.colony;
         const int start = bq.start, goal = bq.goal;
         const uint32_t stream_word = bq.stream_word, block_hi = bq.block_hi;
         const uint32_t qhash = qi * 0x85EBCA6Bu + (qi << 13);
@@ -267,23 +254,12 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
             u2 = __fmul_rn(__int2float_rn((int)(w2 >> 1)), 4.656612873077392578125e-10f);
             u3 = __fmul_rn(__int2float_rn((int)(w3 >> 1)), 4.656612873077392578125e-10f);
         };
-        if (GLOBAL) {
-            tab.gp = a.gtab + (size_t)(has ? slot_o : 0) * E;
-            if (has) {
-                const int4 r = a.resume[slot_o];
-                cur = r.x; steps = r.y;
-                P = pack_xyz(cur % rx, (cur % rxy) / rx, cur / rxy);
-                draw4((uint32_t)steps >> 2);
-            }
-        } else {
-            for (int i = k; i < E; i += kGroup) tab.store(i, 0ull);
-            if (k == 0) { ntiles_s[g] = 1u; flag_s[g] = 0u; }
-            __syncwarp();
-            if (k == 0) {   // addStartNode :81-86
-                const uint32_t key = (P & kPackKey) | kKeyTag;
-                const uint32_t bit = (((P & kPackLow) * kPackMul) >> 20) & 31u;
-                tab.store(tile_hash(key, (uint32_t)E), ((unsigned long long)key << 32) | (unsigned long long)(1u << bit));
-            }
+        tab.gp = a.gtab + (size_t)(has ? slot_o : 0) * E;
+        if (has) {   // resume: the visited set already lives in HBM table slot_o
+            const int4 r = a.resume[slot_o];
+            cur = r.x; steps = r.y;
+            P = pack_xyz(cur % rx, (cur % rxy) / rx, cur / rxy);
+            draw4((uint32_t)steps >> 2);
         }
         __syncwarp();
 
@@ -311,8 +287,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
         issue_loads();
 
         auto step = [&]() {
-            uint32_t flag = 0;
-            if (!GLOBAL) asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(flag) : "r"(flag_sa) : "memory");
             if (live && (steps & 3) == 0) draw4((uint32_t)steps >> 2);
             const float u = (steps & 2) ? ((steps & 1) ? u3 : u2) : ((steps & 1) ? u1 : u0);
             // ---- BATCH: geometric factor of slot k, k_heuristic's expressions ----------------------------------------
@@ -377,70 +351,24 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
                 tab.store(slot, ((unsigned long long)key << 32) | (unsigned long long)(emask | bitm));
                 pid[at] = (uint32_t)prev;
                 pdir[at] = (uint8_t)c;
-                if (!GLOBAL && !found) {
-                    uint32_t n;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n) : "r"(flag_sa - 64u) : "memory");
-                    n++;
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_sa - 64u), "r"(n) : "memory");
-                    if (n > limit) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(flag_sa), "r"(1u) : "memory");
-                }
             }
             const bool arrived = stepok && cur == goal;
-            const bool over = !GLOBAL && stepok && !arrived && flag != 0u;
-            const bool capped = stepok && !arrived && !over && steps >= cap;
-            result = arrived ? steps : (over ? -2 : result);
+            const bool capped = stepok && !arrived && steps >= cap;
+            result = arrived ? steps : result;
             reason = capped ? 3 : reason;
-            live = stepok && !arrived && !over && !capped;
+            live = stepok && !arrived && !capped;
             __syncwarp();
         };
         while (__any_sync(FULL, live)) {
             step();
             step();
         }
-        if (!GLOBAL) {   // park the ants whose shared-memory table filled up (see walk2.cuh); BATCH: HBM tables come from a pool
-            const bool parked = has && result == -2;
-            const unsigned pm = __ballot_sync(FULL, parked && k == 0);
-            if (pm) {
-                int o = 0;
-                if (parked && k == 0) o = (int)atomicAdd(&st->overflow_n, 1u);
-                o = __shfl_sync(FULL, o, 0, 8);
-                const bool fits = (uint32_t)o < a.pool;
-                if (parked && !fits && k == 0) a.tab.count[1] = 1u;   // pool exhausted: the batch is re-run in smaller pieces
-                const int Eg = 1 << a.gtable_log2;
-                for (unsigned rest = pm; rest; rest &= rest - 1) {
-                    const int src = __ffs(rest) - 1;
-                    const int oo = __shfl_sync(FULL, o, src);
-                    if ((uint32_t)oo >= a.pool) continue;   // warp-uniform
-                    uint4* z = reinterpret_cast<uint4*>(a.gtab + (size_t)oo * Eg);
-                    for (int i = lane; i < Eg / 2; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
-                }
-                __syncwarp();
-                if (parked && fits) {
-                    unsigned long long* ntab = a.gtab + (size_t)o * Eg;
-                    for (int i = k; i < E; i += kGroup) {
-                        const unsigned long long t = tab.load(i);
-                        if (t == 0ull) continue;
-                        unsigned sl = tile_hash((uint32_t)(t >> 32), (uint32_t)Eg);
-                        while (atomicCAS(&ntab[sl], 0ull, t) != 0ull) sl = (sl + 1) & (Eg - 1);
-                    }
-                    if (k == 0) {
-                        a.resume[o] = make_int4(cur, steps, 0, 0);
-                        a.overflow_list[o] = qi * (uint32_t)a.colony_max + (uint32_t)ant;
-                    }
-                }
-                __syncwarp();
-            }
-        }
         if (has) {
-            if (result == -2) {
-                c_over++;
-            } else {
-                c_arrived += result >= 0 ? 1 : 0;
-                c_nocand += (result < 0 && reason == 1) ? 1 : 0;
-                c_fall += (result < 0 && reason == 2) ? 1 : 0;
-                c_cap += (result < 0 && reason == 3) ? 1 : 0;
-                c_steps += (unsigned long long)steps; c_ants++;
-            }
+            c_arrived += result >= 0 ? 1 : 0;
+            c_nocand += (result < 0 && reason == 1) ? 1 : 0;
+            c_fall += (result < 0 && reason == 2) ? 1 : 0;
+            c_cap += (result < 0 && reason == 3) ? 1 : 0;
+            c_steps += (unsigned long long)steps; c_ants++;
             if (k == 0) a.ant_steps[(size_t)qi * a.colony_max + ant] = result;
         }
         __syncwarp();
@@ -452,7 +380,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
         if (c_nocand) atomicAdd(&st->cnt[3], c_nocand);
         if (c_fall) atomicAdd(&st->cnt[4], c_fall);
         if (c_cap) atomicAdd(&st->cnt[5], c_cap);
-        if (c_over) atomicAdd(&st->cnt[8], c_over);
     }
 }
 
@@ -465,8 +392,10 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk_batch(BatchArgs a)
 // k_walk_batch<GLOBAL = true>.  This kernel is issue-bound once a few hundred queries are in flight (60 % of the issue
 // slots), so the shorter instruction stream is throughput.
 // ------------------------------------------------------------------------------------------
-template <bool ALPHA1, int MINB>   // MINB: CTAs per SM the register allocation is bounded for (6 = all that the 34 KB tables allow: at most 80 registers)
-__global__ void __launch_bounds__(kWalkThreads, MINB) k_walk_batch3(BatchArgs a)
+// Register allocation bounded for five CTAs per SM (102 registers): measured best on C5 — 2027 queries/s, against 1934 with six
+// (80 registers, spills) and 1854 with four (120).
+template <bool ALPHA1>
+__global__ void __launch_bounds__(kWalkThreads, 5) k_walk_batch3(BatchArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int4* move_lut = reinterpret_cast<int4*>(smem_raw);

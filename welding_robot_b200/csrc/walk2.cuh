@@ -1,32 +1,23 @@
-// K2, the ant-construction kernel (selectNext ACSRank_3D.hpp:134-193 + the ant loop :252-265).
+// K2, pass 2 — and the pieces every walk kernel shares (selectNext ACSRank_3D.hpp:134-193 + the ant loop :252-265).
 //
-// One ant per 8-lane group (6 neighbour lanes + 2 idle), 4 ants per warp, 16 per CTA; persistent warps pull 4 ants at a
-// time from a device-side queue and step them in LOCKSTEP, so every warp collective runs with the full mask (sub-warp
-// masks held in registers make the compiler emit a MATCH/REDUX/WARPSYNC sequence per collective — the first kernel
-// measured 421 instructions per warp-step that way).  A step is straight-line predicated code: an ant that has arrived
-// or died idles until its three warp mates are done.
-//
-// Lane k < 6 owns neighbour slot k: it loads tau[cur][k] and the tabulated geometric factor heur[cur][k] (the six lanes
-// of a group read 24 contiguous bytes per array: one request each), probes the visited set for its neighbour and
-// evaluates tau^alpha * (1 + beta*cos).  The roulette needs the reference's exact summation order (ascending for
-// `total`, descending for `prob_sum`), so the six scores are exchanged with width-8 shuffles and every lane re-adds them
-// sequentially — two chains of 6 dependent FADDs.  Non-candidates carry info = +0, the identity of the chain.
-// A walk is a chain of dependent steps, so a colony of a few thousand ants is bound by the latency of one step, not by
-// bandwidth; what this kernel is about is the length of the per-step instruction stream (~180 warp-instructions):
+// The ant-construction step as every K = 6 kernel runs it: one ant per 8-lane group (6 neighbour lanes + 2 idle), 4 ants per
+// warp stepping in LOCKSTEP so that every warp collective runs with the full mask.  Lane k < 6 owns neighbour slot k: it loads
+// tau[cur][k] and the tabulated geometric factor heur[cur][k] (the six lanes of a group read 24 contiguous bytes per array),
+// probes the visited set for its neighbour and evaluates tau^alpha * (1 + beta*cos).  The roulette needs the reference's exact
+// summation order (ascending for `total`, descending for `prob_sum`), so the six scores are exchanged with width-8 shuffles and
+// every lane re-adds them sequentially — two chains of 6 dependent FADDs.  Non-candidates carry info = +0, the identity.
 //   * node coordinates live in ONE packed register  P = z<<20 | y<<10 | x  (a move is one add; needs dims <= 1024,
 //     wr_acs_create rejects larger grids);
 //   * the visited set ("tabu", std::set at :70) is an open-addressed table of 64-bit entries
-//     (1<<31 | tile key) << 32 | 32-bit mask  over 4x4x2-node tiles in shared memory: one LDS.64 per probe, one STS.64
-//     per insert, key = P & ~lowbits (one LOP3).  A lattice walk re-visits the same few tiles, so 768 entries (6 KB) hold
-//     walks of thousands of steps;
-//   * the chosen lane does everything that belongs to the move in one branch: visited insert, trail append
-//     (addNextNode :73-79), tile count; the table-full flag travels through shared memory instead of a vote;
-//   * an ant whose table reaches 3/4 moves its visited set to a table in HBM sized for the step cap (parallel CAS
-//     inserts), parks its state after the lockstep loop and is RESUMED by pass 2 (GLOBAL = true) from the step it
-//     stopped at — exact, because its draws are a pure function of (search, iteration, ant, step).  Two launches keep
-//     shared-memory addressing on the common path (a run-time switch costs 8-13 % per step);
-//   * the uniform draws of four steps are converted to float once per Philox call; alpha == 1 (the reference's
-//     literal, :319) is a template parameter; the step cap is checked off the critical path.
+//     (1<<31 | tile key) << 32 | 32-bit mask  over 4x4x2-node tiles: one 64-bit load per probe, one store per insert;
+//   * the move comes from a 64-entry table indexed by the pick ballot.
+// Pass 1 of every iteration is k_walk3 (walk3.cuh; k_walk_batch3 for concurrent searches) with the tables in shared memory.  An
+// ant whose shared-memory table reaches 3/4 moves its visited set to a table in HBM sized for the step cap, parks {node, steps}
+// and is RESUMED by the kernel below, k_walk2, from the very step it stopped at — exact, because its draws are a pure function
+// of (search, iteration, ant, step).  Two launches keep shared-memory addressing on the common path (a run-time switch cost
+// 8-13 % per step); pass 2 usually finds nothing to do and exits at once.
+// (Round 1-2 history: k_walk2 also was pass 1 until k_walk3 replaced it — 164 -> 127 instructions per warp-step, see
+// profiles/r2_walk3_*; that generic form, its L1/L2 prefetch modes and the register look-ahead experiment are gone.)
 #pragma once
 #include "acs_kernels.cuh"
 
@@ -82,17 +73,13 @@ __global__ void __launch_bounds__(256) k_path_warm(const IterState* st, const ui
     if (acc == 0x9E3779B9u && n < 0) const_cast<IterState*>(st)->cnt[8] = 0;   // keeps the loads alive; never true
 }
 
-template <bool GLOBAL, bool ALPHA1, int PREFETCH>
+template <bool ALPHA1>
 __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [0, 1024): move table indexed by the 6-bit pick ballot: the winner is its highest set bit c (the roulette scans
     //            5 -> 0) -> {node-id stride, packed-coordinate delta, c, -}; one LDS.128 replaces find-leading-one + index math
-    // [1024, 1088): tiles in each ant's table; [1088, 1152): table reached 3/4; [1152, ...): tables [16][E]
     int4* move_lut = reinterpret_cast<int4*>(smem_raw);
-    uint32_t* ntiles_s = reinterpret_cast<uint32_t*>(smem_raw + kWalk2Lut);
-    volatile uint32_t* flag_s = reinterpret_cast<volatile uint32_t*>(smem_raw + kWalk2Lut + 64);
-    unsigned long long* tab_s = reinterpret_cast<unsigned long long*>(smem_raw + kWalk2Lut + 128);
     if (threadIdx.x < 64) {
         const int pbv = threadIdx.x;
         const int c = pbv ? 31 - __clz(pbv) : 0;
@@ -105,15 +92,13 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
     const int lane = threadIdx.x & 31;
     const int gbase = lane & 24;
     const int k = lane & 7;
-    const int g = threadIdx.x >> 3;
-    const int E = GLOBAL ? (1 << a.gtable_log2) : a.table_entries;   // entries of the table this kernel probes
+    const int E = 1 << a.gtable_log2;   // entries of an HBM table
     uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(move_lut);
-    TabRef<GLOBAL> tab;
+    TabRef<true> tab;
     tab.gp = a.gtab;
-    tab.sa = (uint32_t)__cvta_generic_to_shared(tab_s + (size_t)g * E);
-    uint32_t flag_sa = (uint32_t)__cvta_generic_to_shared(smem_raw + kWalk2Lut + 64 + 4 * g);
+    tab.sa = 0;
     // opaque to the optimiser: otherwise it re-derives the shared-window base (S2UR + ULEA) inside the step loop
-    asm volatile("" : "+r"(lut_sa), "+r"(tab.sa), "+r"(flag_sa));
+    asm volatile("" : "+r"(lut_sa));
 
     const int rx = a.rx, rxy = a.rx * a.ry;
     const int dxk = (k == 3) - (k == 2), dyk = (k == 4) - (k == 1), dzk = (k == 5) - (k == 0);
@@ -123,8 +108,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
     // idle lanes (k = 6, 7) read a constant "closed" marker with a zero row stride, so `open` is one compare for every lane
     const float* heur_k_base = k < 6 ? a.heur + k : a.closed_marker;
     const int heur_row = k < 6 ? 6 : 0;
-    const long long stride_k = (long long)(dxk + dyk * rx + dzk * rxy);
-    const long long last_node = (long long)rxy * a.rz - 1;
     // lane masks of the descending prefix chain: lane k adds v_j only for j >= k
     uint32_t m4 = k <= 4 ? ~0u : 0u, m3 = k <= 3 ? ~0u : 0u, m2 = k <= 2 ? ~0u : 0u, m1 = k <= 1 ? ~0u : 0u, m0 = k <= 0 ? ~0u : 0u;
     asm volatile("" : "+r"(m4), "+r"(m3), "+r"(m2), "+r"(m1), "+r"(m0));   // keep them as register masks (one LOP3 each) instead of re-derived predicates
@@ -132,25 +115,21 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
     const uint32_t Pstart = pack_xyz(a.start % rx, (a.start % rxy) / rx, a.start / rxy);
 
     IterState* st = a.st;
-    const int colony = st->colony;
     const uint32_t iter = (uint32_t)st->iter;
     const float base_now = st->base;   // clean-tile field: what a slot that never received a deposit is worth this iteration
-    int local_n = min(max(colony - a.shard_first, 0), a.shard_chunk);
-    if (GLOBAL) local_n = (int)st->overflow_n;
-    const uint32_t limit = (uint32_t)((E >> 2) * 3);
+    const int local_n = (int)st->overflow_n;   // the ants pass 1 parked
     const int cap = a.cap, goal = a.goal;
 
-    unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0, c_over = 0;
-    uint32_t sink = 0, pre0 = 0, pre1 = 0, pre2 = 0, pre3 = 0;
+    unsigned long long c_steps = 0, c_ants = 0, c_arrived = 0, c_nocand = 0, c_fall = 0, c_cap = 0;
 
     while (true) {
         unsigned q0 = 0;
-        if (lane == 0) q0 = atomicAdd(GLOBAL ? &st->queue2 : &st->queue, 4u);
+        if (lane == 0) q0 = atomicAdd(&st->queue2, 4u);
         q0 = __shfl_sync(FULL, q0, 0);
         if (q0 >= (unsigned)local_n) break;                                    // warp-uniform
         const unsigned q = q0 + (unsigned)(lane >> 3);
         const bool has = q < (unsigned)local_n;
-        const int ant_local = has ? (GLOBAL ? (int)a.overflow_list[q] : (int)q) : 0;
+        const int ant_local = has ? (int)a.overflow_list[q] : 0;
         const uint32_t ant_global = (uint32_t)(a.shard_first + ant_local);
 
         int cur = a.start, steps = 0;
@@ -165,23 +144,13 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
             u2 = __fmul_rn(__int2float_rn((int)(w2 >> 1)), 4.656612873077392578125e-10f);
             u3 = __fmul_rn(__int2float_rn((int)(w3 >> 1)), 4.656612873077392578125e-10f);
         };
-        if (GLOBAL) {   // resume a parked ant: its visited set already lives in HBM table q
-            tab.gp = a.gtab + (size_t)(has ? q : 0) * E;
-            if (has) {
-                const int4 r = a.resume[q];
-                cur = r.x; steps = r.y;
-                P = pack_xyz(cur % rx, (cur % rxy) / rx, cur / rxy);
-                draw4((uint32_t)steps >> 2);
-            }
-        } else {
-            for (int i = k; i < E; i += kGroup) tab.store(i, 0ull);
-            if (k == 0) { ntiles_s[g] = 1u; flag_s[g] = 0u; }
-            __syncwarp();
-            if (k == 0) {   // addStartNode :81-86
-                const uint32_t key = (P & kPackKey) | kKeyTag;
-                const uint32_t bit = (((P & kPackLow) * kPackMul) >> 20) & 31u;
-                tab.store(tile_hash(key, (uint32_t)E), ((unsigned long long)key << 32) | (unsigned long long)(1u << bit));
-            }
+        // resume a parked ant: its visited set already lives in HBM table q
+        tab.gp = a.gtab + (size_t)(has ? q : 0) * E;
+        if (has) {
+            const int4 r = a.resume[q];
+            cur = r.x; steps = r.y;
+            P = pack_xyz(cur % rx, (cur % rxy) / rx, cur / rxy);
+            draw4((uint32_t)steps >> 2);
         }
         __syncwarp();
 
@@ -197,21 +166,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
         float heur_v = __ldg(heur_k_base + (size_t)cur * heur_row);
 
         auto step = [&]() {
-            if (PREFETCH) {   // the row of neighbour k is the next step's row if k wins: pull both arrays' lines towards the SM now
-                long long nb = (long long)cur + stride_k;
-                nb = nb < 0 ? 0 : (nb > last_node ? last_node : nb);
-                const float* pt = a.tau + nb * 6;
-                const float* ph = a.heur + nb * 6;
-                if (PREFETCH == 1) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pt));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ph));
-                } else {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pt));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ph));
-                }
-            }
-            uint32_t flag = 0;
-            if (!GLOBAL) asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(flag) : "r"(flag_sa) : "memory");
             // ---- Philox: one call yields the draws of 4 consecutive steps (live ants of a warp are in lockstep) ----
             if (live && (steps & 3) == 0) draw4((uint32_t)steps >> 2);
             const float u = (steps & 2) ? ((steps & 1) ? u3 : u2) : ((steps & 1) ? u1 : u0);
@@ -263,74 +217,28 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
                 tab.store(slot, ((unsigned long long)key << 32) | (unsigned long long)(emask | bitm));
                 pid[at] = (uint32_t)prev;
                 pdir[at] = (uint8_t)c;
-                if (!GLOBAL && !found) {   // tile count lives next to the flag: [flag_sa - 64]
-                    uint32_t n;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n) : "r"(flag_sa - 64u) : "memory");
-                    n++;
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_sa - 64u), "r"(n) : "memory");
-                    if (n > limit) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(flag_sa), "r"(1u) : "memory");
-                }
             }
             const bool arrived = stepok && cur == goal;              // :182-186
-            const bool over = !GLOBAL && stepok && !arrived && flag != 0u;
-            const bool capped = stepok && !arrived && !over && steps >= cap;   // a deviation the oracle mirrors; the reference is unbounded
-            result = arrived ? steps : (over ? -2 : result);
+            const bool capped = stepok && !arrived && steps >= cap;   // a deviation the oracle mirrors; the reference is unbounded
+            result = arrived ? steps : result;
             reason = capped ? 3 : reason;
-            live = stepok && !arrived && !over && !capped;
+            live = stepok && !arrived && !capped;
             __syncwarp();
         };
         while (__any_sync(FULL, live)) {   // two steps per trip: halves the cost of the loop's vote + branch; a finished ant just idles
             step();
             step();
         }
-        // ---- park the ants whose shared-memory table filled up: move the visited set to an HBM table sized for the step
-        //      cap and record where to resume; pass 2 (GLOBAL) continues them from the very step they stopped at ---------
-        if (!GLOBAL) {
-            const bool parked = has && result == -2;
-            const unsigned pm = __ballot_sync(FULL, parked && k == 0);
-            if (pm) {   // warp-uniform, rare
-                int o = 0;
-                if (parked && k == 0) o = (int)atomicAdd(&st->overflow_n, 1u);
-                o = __shfl_sync(FULL, o, 0, 8);
-                const int Eg = 1 << a.gtable_log2;
-                for (unsigned rest = pm; rest; rest &= rest - 1) {   // zero each parked ant's HBM table with the whole warp
-                    const int src = __ffs(rest) - 1;
-                    const int oo = __shfl_sync(FULL, o, src);
-                    uint4* z = reinterpret_cast<uint4*>(a.gtab + (size_t)oo * Eg);
-                    for (int i = lane; i < Eg / 2; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
-                }
-                __syncwarp();
-                if (parked) {
-                    unsigned long long* ntab = a.gtab + (size_t)o * Eg;
-                    for (int i = k; i < E; i += kGroup) {
-                        const unsigned long long t = tab.load(i);
-                        if (t == 0ull) continue;
-                        unsigned sl = tile_hash((uint32_t)(t >> 32), (uint32_t)Eg);
-                        while (atomicCAS(&ntab[sl], 0ull, t) != 0ull) sl = (sl + 1) & (Eg - 1);
-                    }
-                    if (k == 0) {
-                        a.resume[o] = make_int4(cur, steps, 0, 0);
-                        a.overflow_list[o] = (uint32_t)ant_local;
-                    }
-                }
-                __syncwarp();
-            }
-        }
         if (has) {
-            if (result == -2) {
-                c_over++;   // its steps are counted by pass 2
-            } else {
-                c_arrived += result >= 0 ? 1 : 0;
-                c_nocand += (result < 0 && reason == 1) ? 1 : 0;
-                c_fall += (result < 0 && reason == 2) ? 1 : 0;
-                c_cap += (result < 0 && reason == 3) ? 1 : 0;
-                c_steps += (unsigned long long)steps; c_ants++;
-            }
+            c_arrived += result >= 0 ? 1 : 0;
+            c_nocand += (result < 0 && reason == 1) ? 1 : 0;
+            c_fall += (result < 0 && reason == 2) ? 1 : 0;
+            c_cap += (result < 0 && reason == 3) ? 1 : 0;
+            c_steps += (unsigned long long)steps; c_ants++;
             if (k == 0) a.ant_steps[ant_local] = result;
         }
         __syncwarp();
     }
-    if (PREFETCH == 3 && (sink ^ pre0 ^ pre1 ^ pre2 ^ pre3) == 0x9E3779B9u && a.cap < 0) st->cnt[8] = 0;   // keeps the look-ahead loads alive; never true
     if (k == 0) {
         if (c_steps) atomicAdd(&st->cnt[0], c_steps);
         if (c_ants) atomicAdd(&st->cnt[1], c_ants);
@@ -338,7 +246,6 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk2(WalkArgs a)
         if (c_nocand) atomicAdd(&st->cnt[3], c_nocand);
         if (c_fall) atomicAdd(&st->cnt[4], c_fall);
         if (c_cap) atomicAdd(&st->cnt[5], c_cap);
-        if (c_over) atomicAdd(&st->cnt[8], c_over);
     }
 }
 
