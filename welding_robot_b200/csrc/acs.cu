@@ -1417,7 +1417,7 @@ extern "C" int wr_acs_search_batch(wr_acs* a, const int64_t* start_ids, const in
     rc = alloc_batch(a, nq, cm, &qc);
     if (rc != WR_OK) return rc;
     wr_batch* b = a->batch;
-    const int entries = batch_table_entries(256);
+    const int entries = batch_table_entries(320);   // 42 KB per CTA: five CTAs per SM, like the register bound (C5: 256 -> 1898, 320 -> 2095, 384 -> 1989, 512 -> 1636 queries/s)
     const size_t smem1 = kWalk2Lut + 128 + (size_t)kAntsPerCta * entries * sizeof(unsigned long long);
     WR_REQUIRE(smem1 <= 227 * 1024, WR_ERR_INVALID, "wr_acs_search_batch: WR_BATCH_TABLE too large");
     const bool alpha1 = a->p.alpha == 1;
