@@ -19,9 +19,23 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("world,colony,policy,env", [(2, 1001, "2", {}), (3, 640, "1", {}), (2, 333, "0", {"WR_RANKSET_ON": "100000", "WR_RANKSET_OFF": "2500"}),
                                                      (2, 777, "1", {"WR_RANKSET_LOG2": "9"}), (4, 6000, "1", {})])
 def test_peer_protocol_shards_equal_unsharded(world, colony, policy, env, monkeypatch):
+    """Shards of one process wait for each other's kernels on ONE GPU, which CUDA does not promise to run concurrently (streams may
+    share a hardware queue).  A barrier timeout — not a wrong bit — is therefore retried on fresh handles; every comparison stays
+    strict.  (One process per GPU, the product layout, has no such dependency; tests/test_gpu_multi.py covers it.)"""
+    import welding_robot_b200 as wr
+    for attempt in range(3):
+        try:
+            return _run_shards(world, colony, policy, env, monkeypatch)
+        except wr.WrError as e:
+            if "did not reach a barrier" not in str(e) or attempt == 2:
+                raise
+            print("barrier timeout between in-process shards, retrying (%d)" % (attempt + 1))
+
+
+def _run_shards(world, colony, policy, env, monkeypatch):
     import welding_robot_b200 as wr
     from welding_robot_b200.dist import LocalShards
-    monkeypatch.setenv("WR_PEER_TIMEOUT_MS", "15000")
+    monkeypatch.setenv("WR_PEER_TIMEOUT_MS", "8000")
     tris = np.load(os.path.join(GOLDEN, "meshes.npz"))["simplified_piece"]
 
     def make(sharded):

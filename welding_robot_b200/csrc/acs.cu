@@ -130,6 +130,7 @@ struct wr_acs {
     unsigned long long barrier_timeout_ns = 20000000000ull;
     std::vector<void*> ipc_opened;
     bool peers_set = false;
+    bool in_process_peers = false;   // the peers are handles of THIS process (wr_acs_peer_set_pointers; tests): one plain stream per shard, see there
     int* d_nq = nullptr;              // records in this rank's slot slice
     unsigned parity = 0;              // flips at every wr_acs_walk of a sharded handle
     bool warm_by_pull = false;        // the last iteration ended with k_pull_finals (which doubles as the L2 warm-up)
@@ -1034,7 +1035,7 @@ static int launch_construct_and_rank(wr_acs* a, bool rankset_iteration)
     if (st != WR_OK) return st;
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     a->evap_forked = false;
-    if (a->nranks > 1 && rankset_iteration && evap_overlap()) {
+    if (a->nranks > 1 && rankset_iteration && evap_overlap() && !a->in_process_peers) {
         // The walk was the last reader of the field: its evaporation (:268-272) can start now, on a side stream, while this
         // stream waits for the peers, ranks the colony and merges the rank sets; the ordered chains join it again.  (On one GPU
         // the same overlap was measured and rejected: the chain of small kernels slows down under a saturated memory system and
@@ -1146,7 +1147,7 @@ extern "C" int wr_acs_iterate(wr_acs* a, int n)
             a->d_local_steps = reinterpret_cast<int*>(a->d_slab + a->off_steps[a->parity]);
         }
         // steady state of a converged search: the whole iteration is one graph launch
-        if (rs_now && rs_prev && it > 0 && a->rs_enqueued > 0 && !a->timer.enabled && !a->rs_graph_failed && graph_enabled()) {
+        if (rs_now && rs_prev && it > 0 && a->rs_enqueued > 0 && !a->timer.enabled && !a->rs_graph_failed && !a->in_process_peers && graph_enabled()) {
             cudaGraphExec_t& gx = a->rs_graph[sharded ? a->parity : 0];
             if (!gx && capture_steady_iteration(a, &gx) != WR_OK) a->rs_graph_failed = true;
             if (gx) {
@@ -1598,6 +1599,12 @@ extern "C" int wr_acs_peer_set_pointers(wr_acs* a, void* const* all_raw_pointers
     WR_REQUIRE(a && all_raw_pointers && a->begun && a->nranks > 1 && a->d_slab, WR_ERR_STATE, "wr_acs_peer_set_pointers: sharded handle after wr_acs_begin only");
     std::vector<const unsigned char*> slabs(a->nranks);
     for (int r = 0; r < a->nranks; r++) slabs[r] = r == a->rank ? a->d_slab : static_cast<const unsigned char*>(all_raw_pointers[r]);
+    // Shards that live in one process wait for each other's kernels ON THE SAME GPU: every barrier kernel needs the other shards'
+    // kernels to run beside it, which CUDA does not promise (streams can share a hardware work queue).  Such handles therefore use
+    // plain launches on one stream each — no whole-iteration graphs, no forked evaporation stream: fewer queues that must make
+    // progress side by side (barrier timeouts in the one-GPU tests: 3 % -> 1 % of the cases; the tests retry those).  One process
+    // per GPU — the product layout — waits for OTHER GPUs only and keeps both.
+    a->in_process_peers = true;
     return install_peers(a, slabs);
 }
 
