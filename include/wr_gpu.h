@@ -186,9 +186,10 @@ int wr_acs_stream_kernel_ms(wr_acs* a, float* ms, int* launches);
  * 2 = device-to-device copy of the pheromone field (in-run copy ceiling).  The field is
  * multiplied by rho each time (which 0/1), so call it on a scratch search only. */
 int wr_acs_bench_kernel(wr_acs* a, int which, int reps, float* ms_per_launch);
-/* use an existing CUDA stream (cudaStream_t as void*); default: a private non-blocking stream.  A sharded handle whose
- * collectives are issued by somebody else (torch.distributed / NCCL on the caller's stream) MUST run on that stream:
- * the protocol orders kernels and collectives by stream order alone (welding_robot_b200/dist.py binds it itself). */
+/* use an existing CUDA stream (cudaStream_t as void*); default: a private non-blocking stream.  (Round 1's sharded protocol issued
+ * collectives from the host and needed the handle on the collectives' stream — the advisor's finding; since round 2 the exchange
+ * of a sharded iteration lives inside the library's kernels, so any stream will do.  The default streams cannot be captured into
+ * the steady-state CUDA graph: a handle on one of them runs plain launches.) */
 int wr_acs_set_stream(wr_acs* a, void* cuda_stream);
 
 /* ---- ant sharding across ranks: one process per GPU ------------------------------------------------

@@ -12,7 +12,7 @@ def matrix(n, seed):
     return np.array([[float("%.6f" % v) for v in row] for row in D])   # as a graph file would carry it
 
 
-@pytest.mark.parametrize("n,iters,batch", [(8, 12, 3), (33, 6, 4), (64, 5, 3), (256, 2, 2)])
+@pytest.mark.parametrize("n,iters,batch", [(8, 12, 3), (33, 6, 4), (64, 5, 3), (200, 4, 2), (256, 10, 3)])
 def test_gtsp_matches_oracle(oracle, n, iters, batch):
     import welding_robot_b200 as wr
     D = matrix(n, n)
