@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(kWalkThreads, 2) k_walk3(WalkArgs a)   // two 
         // one step at index T + J with the draw u; (pn, pt, ph) = predicted next node and this lane's values of its row
         auto step = [&](const uint32_t J, const float u, const uint32_t pn, const float pt_v, const float ph_v) {
             if (PREFETCH & 1) {
+                // (Also measured and rejected, for both modes: one Philox evaluation per 32 steps by letting lane k of a group compute
+                // block 8 w + k and shuffling the four draws of a trip out of lane (trip & 7) — 16 instructions per step fewer, yet the
+                // walk got 3 % slower and C5 10 %: four more shuffles at the head of every trip, three uniform branches, +8 registers.)
                 // Measured and rejected instead of this prefetch: (a) prediction AND prefetch together (slower than either alone in
                 // its regime); (b) staging the six neighbours' rows in shared memory with cp.async and letting only the winning lane
                 // wait for its own copies — the wait (DEPBAR on the warp's scoreboard) is per WARP, so every step waited for the
