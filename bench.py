@@ -652,7 +652,7 @@ def run_ours(args):
         return
     hbm, hbm_src = peaks()
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram__bytes_read+write per launch from the committed ncu --set full captures
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")   # dram__bytes_read+write per launch from the committed ncu --set full captures
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
@@ -686,11 +686,13 @@ def run_ours(args):
         "deposit_path": {"rank_set_iterations": rs_iters, "record_iterations": iters_done - rs_iters, "last": upd_stats} if args.update_mode == 4 else None,
         "kernel_ms_per_iteration": {k: v / iters_done for k, v in kms.items()},
         "kernel_ms_source": "replay of the timed iterations on a fresh handle with per-phase events (the timed region itself runs without them)",
-        "roofline": {"kernel": "k_walk2 (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
-                     "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk2", traffic.get("k_walk")),
+        "roofline": {"kernel": "k_walk3 (K2 ant construction; dominant by time)", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
+                     "frac": walk_gbs / hbm, "traffic": traffic.get("k_walk3"),
                      "traffic_source": "static: dram__bytes_read+write per launch from the committed `ncu --set full` capture (profiles/), not measured in this run",
                      "peak_source": hbm_src,
-                     "limiter": "step latency x longest ant, then instruction issue (not HBM: the gathers hit L2); see DESIGN.md section 4",
+                     "limiter": "(longest ant's steps) x (latency of one warp's dependent instruction chain: 132 warp-instructions per step at 3.9 cycles, "
+                                "28 % of the issue slots, 10 % of the warp slots in the round-2 ncu capture) - not HBM (1.5 MB of DRAM traffic per converged launch), "
+                                "not issue; see DESIGN.md section 4",
                      "algorithmic_bytes_per_launch": WALK_BYTES_PER_STEP * (local_steps / iters_done),
                      "note": "30 B algorithmic per ant-step; a walk is a chain of dependent gathers, so with 4096 ants the kernel is "
                              "latency-bound, not bandwidth-bound (see DESIGN.md)"},
