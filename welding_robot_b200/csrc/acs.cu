@@ -953,6 +953,13 @@ static int launch_update(wr_acs* a)
 }
 
 // ---- peer barrier of a sharded colony (acs_kernels.cuh: peer_barrier, executed inside the kernel that reads peer data) ----
+// Grid of a kernel that contains a peer barrier.  Its CTAs spin until every rank has signalled, and a rank signals from the first
+// CTAs of the same kernel.  With one process per GPU the spinning CTAs own their GPU.  Shards of ONE process share a GPU: a grid
+// that fills the SMs' thread or register slots while it spins keeps the other shards' kernels — the ones it waits for — from
+// being scheduled at all (seen as barrier timeouts in 1-3 % of the one-GPU test cases, e.g. two spinning k_rankset_merge CTAs per
+// SM leave no room for another shard's 1024-thread k_rank_small).  Such handles spin with a handful of CTAs.
+static int barrier_grid(const wr_acs* a, int blocks) { return a->in_process_peers ? std::min(blocks, 16) : blocks; }
+
 static PeerBarrier barrier_args(const wr_acs* a)
 {
     PeerBarrier b;
@@ -970,7 +977,7 @@ static int launch_rankset_update(wr_acs* a)
                                            a->rs, a->K, a->K == kK26 ? a->d_ant_steps : nullptr, first, a->chunk);
     if (a->nranks > 1) {
         k_rankset_publish<<<kNumSMs, 256, 0, s>>>(a->d_state, a->rs, a->pub_buf());
-        k_rankset_merge<<<kNumSMs * 2, 256, 0, s>>>(barrier_args(a), a->d_state, a->rs, reinterpret_cast<const uint32_t* const*>(a->tab(4, 0)), a->nranks, a->rank);
+        k_rankset_merge<<<barrier_grid(a, kNumSMs * 2), 256, 0, s>>>(barrier_args(a), a->d_state, a->rs, reinterpret_cast<const uint32_t* const*>(a->tab(4, 0)), a->nranks, a->rank);
     }
     if (a->timer.enabled) cudaEventRecord(a->timer.next(), s);
     if (a->evap_forked) {
@@ -1013,7 +1020,7 @@ static int launch_record_update_sharded(wr_acs* a)
     WR_CUDA(cudaMemsetAsync(fin, 0, 4 * sizeof(uint32_t), s));
     st = launch_fused(a, ck, cv, a->d_nq, fin);
     if (st != WR_OK) return st;
-    k_pull_finals<<<kNumSMs * 2, 256, 0, s>>>(barrier_args(a), a->d_state, a->d_tau, walk_warm() ? a->d_heur : nullptr,
+    k_pull_finals<<<barrier_grid(a, kNumSMs * 2), 256, 0, s>>>(barrier_args(a), a->d_state, a->d_tau, walk_warm() ? a->d_heur : nullptr,
                                               reinterpret_cast<const uint32_t* const*>(a->tab(2, a->parity)), a->nranks, a->rank, a->d_dirty, a->d_upd_q);
     WR_CUDA(cudaGetLastError());
     return WR_OK;
@@ -1064,7 +1071,7 @@ static int launch_construct_and_rank(wr_acs* a, bool rankset_iteration)
     }
     if (a->nranks > 1) {   // barrier (trails and step counts of every rank complete and visible), then the global colony
         const int total = a->chunk * a->nranks;
-        k_gather_steps<<<std::max(1, std::min((total + 255) / 256, kNumSMs)), 256, 0, s>>>(barrier_args(a), a->d_state, reinterpret_cast<const int* const*>(a->tab(3, a->parity)),
+        k_gather_steps<<<barrier_grid(a, std::max(1, std::min((total + 255) / 256, kNumSMs))), 256, 0, s>>>(barrier_args(a), a->d_state, reinterpret_cast<const int* const*>(a->tab(3, a->parity)),
                                                                                              a->nranks, a->chunk, a->d_ant_steps);
     }
     st = launch_rank(a, a->d_ant_steps);
@@ -1600,10 +1607,9 @@ extern "C" int wr_acs_peer_set_pointers(wr_acs* a, void* const* all_raw_pointers
     std::vector<const unsigned char*> slabs(a->nranks);
     for (int r = 0; r < a->nranks; r++) slabs[r] = r == a->rank ? a->d_slab : static_cast<const unsigned char*>(all_raw_pointers[r]);
     // Shards that live in one process wait for each other's kernels ON THE SAME GPU: every barrier kernel needs the other shards'
-    // kernels to run beside it, which CUDA does not promise (streams can share a hardware work queue).  Such handles therefore use
-    // plain launches on one stream each — no whole-iteration graphs, no forked evaporation stream: fewer queues that must make
-    // progress side by side (barrier timeouts in the one-GPU tests: 3 % -> 1 % of the cases; the tests retry those).  One process
-    // per GPU — the product layout — waits for OTHER GPUs only and keeps both.
+    // kernels to be scheduled beside it.  Such handles spin with small grids (barrier_grid) and use plain launches on one stream
+    // each — no whole-iteration graphs, no forked evaporation stream — so that as little as possible must be resident at once.
+    // One process per GPU — the product layout — waits for OTHER GPUs only and keeps full grids, graphs and the overlap.
     a->in_process_peers = true;
     return install_peers(a, slabs);
 }
