@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kWalk26Threads) k_walk26(WalkArgs a)
         keys = reinterpret_cast<uint32_t*>(mbase + (size_t)kWalk26Ants * E) + (size_t)w * E;
     }
 
-    const int rx = a.rx, ry = a.ry, rz = a.rz;
+    const int rx = a.rx, ry = a.ry;
     const int rxy = rx * ry;
     const int TX = (rx + 3) >> 2, TY = (ry + 3) >> 2;
     const bool active = lane < kK26;

@@ -1,7 +1,7 @@
-// K2, pass 1, third generation: k_walk2's step (walk2.cuh; selectNext ACSRank_3D.hpp:134-193 + the ant loop :252-265) with
+// K2, pass 1: the ant-construction step described in walk2.cuh (selectNext ACSRank_3D.hpp:134-193 + the ant loop :252-265) with
 // everything that is not the roulette itself taken off the warp's dependent instruction chain.
 //
-// What the round-2 capture of k_walk2 showed (profiles/r2_walk2_ncu.md): 1.7 warps per scheduler, 27 % of the issue slots, 6.3
+// What the mid-round-2 capture of the previous pass-1 kernel showed (profiles/r2_walk2_ncu.md): 1.7 warps per scheduler, 27 % of the issue slots, 6.3
 // cycles per issued instruction — the kernel's time is (longest ant's steps) x (latency of ONE warp's instruction chain), every
 // instruction of a step costs its full dependent latency, and nothing else on the scheduler hides it.  So this kernel removes
 // instructions and branches from the step, and moves work that has no consumer inside the step to where a stall would be:
@@ -24,7 +24,9 @@
 //     LDG.128) and this lane's tau / heur values of those nodes, a whole trip before they are needed; after a move the lane
 //     compares the node it reached with the predicted one and takes the values from registers, or — a deviating ant —
 //     issues the ordinary loads.  The values come from the same addresses either way, so every ant is bit-identical.
-// Ants whose table fills up are parked exactly like k_walk2's and resumed by k_walk2<GLOBAL = true> (pass 2, unchanged).
+//   * PREFETCH = 1 (the colony still wanders): the six neighbours' rows are prefetched a step ahead, and a visited-table look-up
+//     fetches four entries at once (no probe loop: most look-ups there are of tiles that are not present yet).
+// Ants whose table fills up move their visited set to a table in HBM, park {node, steps} and are resumed by k_walk2 (pass 2).
 #pragma once
 #include "walk2.cuh"
 
