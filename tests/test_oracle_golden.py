@@ -170,3 +170,24 @@ def test_bspline_matches_reference_fixture(oracle):
         assert np.array_equal(cps.view(np.uint32), fx["cps%d" % i].view(np.uint32)), case
         assert np.array_equal(ok, fx["ok%d" % i]), case
         assert np.array_equal(pts.view(np.uint32), fx["pts%d" % i].view(np.uint32)), case
+
+
+def test_bspline_oracle_properties(oracle):
+    """Properties of the restated BS_Basic that need no fixture: a degree-0 curve returns its control points (start point twice, then
+    the path, BSplineBasic.h:381-384 + :441-447); a clamped curve starts at the first and ends at the last point; times outside
+    [0, fin_time] are clamped (:88-92); equal control points give that point back (partition of unity up to rounding)."""
+    rng = np.random.default_rng(12)
+    path = np.cumsum(rng.random((40, 3)), axis=0).astype(np.float32)
+    pts, ok, knots, cps = oracle.bspline(0, 0, 0, path[0], path[-1], path, 150.0, np.zeros(0, np.float32))
+    mids = ((knots[:-1] + knots[1:]) * np.float32(0.5)).astype(np.float32)
+    pts, ok, _, _ = oracle.bspline(0, 0, 0, path[0], path[-1], path, 150.0, mids)
+    assert ok.all() and np.array_equal(pts, cps) and np.array_equal(cps[0], path[0]) and np.array_equal(cps[1:-1], path)
+    for d in (1, 2, 3, 5):
+        pts, ok, knots, cps = oracle.bspline(d, 0, 0, path[0], path[-1], path, 10.0, np.array([-3.0, 0.0, 10.0, 99.0], np.float32))
+        assert ok.all()
+        # (to rounding: the reference's basis functions give N_0(0) = K * (1 / K), one ulp short of 1)
+        assert np.array_equal(pts[0], pts[1]) and np.allclose(pts[1], path[0], rtol=1e-6, atol=0)      # before 0 -> clamped to the start
+        assert np.array_equal(pts[2], pts[3]) and np.allclose(pts[3], path[-1], rtol=1e-6, atol=0)     # after fin_time -> clamped to the end
+        same = np.tile(np.float32([0.25, -1.5, 3.0]), (20, 1))
+        q, ok2, _, _ = oracle.bspline(d, 0, 0, same[0], same[0], same, 7.0, np.linspace(0, 7, 57).astype(np.float32))
+        assert ok2.all() and np.allclose(q, same[0], rtol=0, atol=2e-6)
