@@ -874,7 +874,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)   # the timed region then is iterations 26-125 of the search, as in the driver's `--steps 20 --warmup 5`
     ap.add_argument("--iters", type=int, default=5, help="ACS iterations per step")
     ap.add_argument("--workload", default="C2", choices=["C2", "C3"], help="C2 = the bench workload; C3 = the 512^3 scaling case (exploration run)")
     ap.add_argument("--ants", type=int, default=0, help="ants per GPU (default: the workload's colony; other values are exploration runs)")
