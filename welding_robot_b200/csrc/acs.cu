@@ -487,7 +487,10 @@ static int stream_cs()
 }
 static int walk_warm()
 {
-    static const int env = [] { const char* e = getenv("WR_WALK_WARM"); return e ? atoi(e) : 1; }();
+    // The L2 warm-up of the rows under the last deposits (k_path_warm / k_rankset_warm) paid in round 1, when every step's gather
+    // was a demand load; with the gathers predicted a trip ahead (converged colony) or prefetched a step ahead (wandering colony)
+    // it no longer does: off, value 7.42 -> 7.46e9, converged iteration 0.3185 -> 0.3154 ms, e2e 3.27 -> 3.31e9.  WR_WALK_WARM=1 restores it.
+    static const int env = [] { const char* e = getenv("WR_WALK_WARM"); return e ? atoi(e) : 0; }();
     return env;
 }
 static size_t walk_smem(const wr_acs* a)
