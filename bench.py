@@ -741,15 +741,16 @@ def launches_per_iteration(update_mode, colony=ANTS_PER_GPU, iters=5, sharded=Fa
     n = 1 + 2 + rank + 1 + 1.0 / iters
     if sharded:
         n += 1                                                   # gather of the step counts (the barrier is inside)
+    warm = 1 if os.environ.get("WR_WALK_WARM", "0") not in ("", "0") else 0   # the L2 warm-up kernel (off by default since round 2)
     if update_mode == 2:
-        return n + 1 + 2                                         # L2 warm-up, evaporate, atomic deposits
-    if update_mode == 4:                                         # rank sets: L2 warm-up, gen, evaporate, apply x groups, wipe, serial fallback (both exit at once)
-        return n + 1 + 1 + 1 + groups + 1 + (2 if sharded else 0)   # sharded: + publish, merge (the barrier is inside)
+        return n + warm + 2                                      # [L2 warm-up], evaporate, atomic deposits
+    if update_mode == 4:                                         # rank sets: [L2 warm-up], gen, evaporate, apply x groups, wipe, serial fallback (both exit at once)
+        return n + warm + 1 + 1 + groups + 1 + (2 if sharded else 0)   # sharded: + publish, merge (the barrier is inside)
     n += 1 + sort(slot_bits) + 2                                 # deposit gen, slot sort, tile offsets + fused
     if sharded:
-        n += 4 + 1                                               # partition pass, pull of the peers' final values (barrier inside; also the L2 warm-up)
+        n += 4 + 1                                               # partition pass, pull of the peers' final values (barrier inside)
     else:
-        n += 1                                                   # L2 warm-up
+        n += warm                                                # [L2 warm-up]
     return n
 
 
