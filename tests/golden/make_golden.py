@@ -13,6 +13,9 @@ Outputs (all under tests/golden/):
   ref_acs.npz       whole searches of the unmodified reference on the C1 weld-point set
                     (SURVEY.md §8d): best path ids + length per pair, SHA-256 of the full
                     pheromone field after 1/2/10 iterations, under the sequential Philox stream
+  ref_bspline.npz   BS_Basic<float, 3, D, CI, CF> of the unmodified core/BSplineBasic.h for eight setups: knots, control
+                    points, curve points and return values at 261 times each (`python tests/golden/make_golden.py bspline`
+                    regenerates only this file; the inputs are a pure function of the case, see bspline_inputs)
 Everything here is produced by reference code, not by the oracle restatement; the tests then
 hold the oracle (and through it the GPU) to these values on machines without /root/reference.
 """
